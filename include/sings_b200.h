@@ -1,0 +1,149 @@
+/*
+ * sings_b200.h -- C ABI of libsings_b200.so: the B200 (sm_100a) implementation of SinGS's
+ * per-frame avatar hot path (SMPL linear-blend-skinning of every Gaussian, then the 3DGS
+ * differentiable tile rasterizer, forward and backward).
+ *
+ * Boundary rules:
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host";
+ *  - the library never allocates or frees: the caller sizes scratch with sgs_raster_sizes()
+ *    / sgs_sort_scratch_bytes() and passes raw pointers (torch tensors' data_ptr());
+ *  - every entry point takes the CUDA stream to launch on, is re-entrant, keeps no global
+ *    state, and never synchronises the host (except with debug != 0);
+ *  - return value: 0 = ok, < 0 = argument error (SGS_ERR_*), > 0 = a cudaError_t;
+ *    sgs_error_string() decodes both.
+ * All floating point is IEEE binary32; matrices are 16 contiguous floats read column-major
+ * (which is why SinGS passes transposed torch matrices, datasets/utils.py:37-39).
+ *
+ * Each entry point cites the reference interface it replaces (paths under /root/reference).
+ */
+#ifndef SINGS_B200_H
+#define SINGS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sgs_stream_t; /* cudaStream_t */
+
+#define SGS_ERR_BAD_ARG -1
+#define SGS_ERR_BAD_SH_DEGREE -2
+#define SGS_ERR_BAD_JOINTS -3
+#define SGS_ERR_MISALIGNED -4
+#define SGS_ERR_CAPACITY -5
+
+int sgs_version(void);
+const char* sgs_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * Rasterizer.  Replaces the pybind extension `diff_gaussian_rasterization._C`
+ * (rasterize_gaussians / rasterize_gaussians_backward / mark_visible) that
+ * sings/rec/renderer/gs_renderer_single.py:6-9,84-95 and gs_renderer_multiple.py:6-9,95-121
+ * reach through GaussianRasterizer.forward.
+ * ------------------------------------------------------------------------------------- */
+
+/* Scratch sizes in bytes for P Gaussians, a W x H image and room for L_cap (tile,Gaussian)
+ * pairs: geom (per-Gaussian records), binning (keys/values/ranges/look-back state),
+ * img (final_T, n_contrib), acc (backward accumulator).  Replaces the three resize
+ * callbacks of [upstream] rasterize_points.cu (geomBuffer / binningBuffer / imgBuffer). */
+int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
+                     size_t* binning_bytes, size_t* img_bytes, size_t* acc_bytes);
+
+/* Byte offsets of the inspectable arrays inside the scratch buffers (for parity tests):
+ * info[0]=counters (int32[32] in binning: [0]=num_rendered, [1]=overflow), [1]=keys_unsorted,
+ * [2]=vals_unsorted, [3]=keys_sorted, [4]=vals_sorted (point_list), [5]=ranges (uint2[tiles]),
+ * [6]=final_T (img), [7]=n_contrib (img), [8]=tiles, [9]=end_bit, [10]=passes,
+ * [11]=record floats per Gaussian (geom). */
+int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info);
+
+/* Forward: replaces _C.rasterize_gaussians ([upstream] rasterize_points.cu
+ * RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward).  Exactly one of
+ * shs (P,M,3) / colors_precomp (P,3) and one of (scales (P,3) + rotations (P,4)) /
+ * cov3D_precomp (P,6) is non-null.  out_color (3,H,W) and radii (P) are fully written.
+ * out_alpha / out_depth (H,W) are optional (null to skip).  host_counters (host, pinned,
+ * 2 ints, optional) receives {num_rendered, overflow} by an async copy on `stream`; if
+ * overflow != 0 the pair list did not fit L_cap: grow the binning buffer and call again. */
+int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* campos,
+                       float tanfovx, float tanfovy, const float* shs, int prefiltered,
+                       long long L_cap, void* geom, void* binning, void* img, float* out_color,
+                       int* radii, float* out_alpha, float* out_depth, int* host_counters,
+                       sgs_stream_t stream, int debug);
+
+/* Backward: replaces _C.rasterize_gaussians_backward ([upstream] Rasterizer::backward).
+ * geom/binning/img are the buffers the forward filled; acc is scratch (acc_bytes).  All
+ * outputs are fully written: dL_dmeans3D (P,3), dL_dmeans2D (P,3), dL_dcolors (P,3),
+ * dL_dopacity (P,1), dL_dcov3D (P,6), dL_dsh (P,M,3) [null when colours were precomputed],
+ * dL_dscales (P,3), dL_drots (P,4). */
+int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                        const float* colors_precomp, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos,
+                        float tanfovx, float tanfovy, const float* shs, const int* radii,
+                        const float* dL_dout_color, long long L_cap, const void* geom,
+                        const void* binning, const void* img, void* acc, float* dL_dmeans3D,
+                        float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                        float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                        sgs_stream_t stream, int debug);
+
+/* Replaces _C.mark_visible ([upstream] Rasterizer::markVisible). present: (P) bytes. */
+int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     unsigned char* present, sgs_stream_t stream);
+
+/* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
+ * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]
+ * rasterizer_impl.cu).  The result is in (keys,vals) when *result_in_tmp (host) == 0, else
+ * in (keys_tmp, vals_tmp). */
+size_t sgs_sort_scratch_bytes(long long n);
+int sgs_sort_pairs_u64(unsigned long long* keys, unsigned int* vals,
+                       unsigned long long* keys_tmp, unsigned int* vals_tmp, void* scratch,
+                       size_t scratch_bytes, long long n, int end_bit, int* result_in_tmp,
+                       sgs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Deformer.  Replaces the torch ops of sings/rec/models/sings_hybrid.py:398-428 (forward)
+ * and :525-552 (forward_chunk): lbs_extra (sings/rec/utils/body_model/lbs.py:16-74),
+ * matrix_to_quaternion / quaternion_multiply (sings/rec/utils/geometry/rotations.py:98-149,
+ * 393-407), and the pose -> A chain batch_rodrigues + batch_rigid_transform
+ * (sings/rec/utils/body_model/smpl.py:415-446,462-513).
+ * ------------------------------------------------------------------------------------- */
+
+/* pose (B,J,3) axis-angle, rest (J,3) rest joints, parents (J) int32 (parents[0] = -1,
+ * parents[j] < j), inv_A_t2cano (J,16) or null -> A_out (B,J,16) row-major 4x4
+ * = A_t2pose @ inv_A_t2cano; G_out (B,J,12) optional (needed by the backward). */
+int sgs_pose_to_A(const float* pose, const float* rest, const int* parents,
+                  const float* inv_A_t2cano, int B, int J, float* A_out, float* G_out,
+                  sgs_stream_t stream);
+int sgs_pose_to_A_bwd(const float* pose, const float* rest, const int* parents,
+                      const float* inv_A_t2cano, const float* G, const float* dL_dA, int B, int J,
+                      float* dL_dpose, sgs_stream_t stream);
+
+/* Fused LBS forward for B frames.  A (B,J,16); xyz_canon (N,3); W (N,J); rot_canon (N,9) or
+ * null (identity, the isotropic case); scales (N,3); smpl_scale (B) or null; transl (B,3) or
+ * null; ext_* (trans (B,3), rot (B,9), scale (B)) all null or all set.
+ * Outputs xyz (B,N,3), rotq (B,N,4), scales_out (B,N,3), T_out (B,N,16) or null. */
+int sgs_lbs_fwd(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                const float* rot_canon, const float* scales, const float* smpl_scale,
+                const float* transl, const float* ext_trans, const float* ext_rot,
+                const float* ext_scale, float* xyz_out, float* rotq_out, float* scales_out,
+                float* T_out, sgs_stream_t stream);
+
+/* Backward of sgs_lbs_fwd for upstream gradients g_xyz, g_rotq, g_scales and (optional,
+ * null if T was not used) g_T (B,N,16).  Written:
+ * d_xyz_canon (N,3), d_rot_canon (N,9) or null, d_scales (N,3).  Accumulated into
+ * (caller zero-fills): d_A (B,J,16), d_smpl_scale (B) or null, d_transl (B,3) or null. */
+int sgs_lbs_bwd(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                const float* rot_canon, const float* scales, const float* smpl_scale,
+                const float* transl, const float* ext_trans, const float* ext_rot,
+                const float* ext_scale, const float* g_xyz, const float* g_rotq,
+                const float* g_scales, const float* g_T, float* d_xyz_canon, float* d_rot_canon,
+                float* d_scales, float* d_A, float* d_smpl_scale, float* d_transl,
+                sgs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINGS_B200_H */

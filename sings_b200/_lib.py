@@ -1,0 +1,86 @@
+"""ctypes binding of libsings_b200.so (C ABI: include/sings_b200.h).
+
+There is no CPU path and no fallback: if the CUDA library is missing or a call fails, the
+caller gets an exception.  `build()` compiles the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsings_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+_lib = None
+
+c_f32p = C.c_void_p   # device pointers travel as integers
+_vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+
+_SIGNATURES = {
+    "sgs_version": (C.c_int, []),
+    "sgs_error_string": (C.c_char_p, [_i]),
+    "sgs_raster_sizes": (_i, [_i, _i, _i, _ll, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "sgs_raster_layout_info": (_i, [_i, _i, _i, _ll, C.POINTER(_ll)]),
+    "sgs_raster_forward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp,
+                                _vp, _f, _f, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _i]),
+    "sgs_raster_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
+                                 _f, _f, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _i]),
+    "sgs_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp]),
+    "sgs_sort_scratch_bytes": (_sz, [_ll]),
+    "sgs_sort_pairs_u64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _ll, _i, C.POINTER(_i), _vp]),
+    "sgs_pose_to_A": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sgs_pose_to_A_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "sgs_lbs_fwd": (_i, [_i, _i, _i] + [_vp] * 15),
+    "sgs_lbs_bwd": (_i, [_i, _i, _i] + [_vp] * 21),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+class SgsError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (sings_b200/csrc/Makefile)."""
+    if force:
+        subprocess.check_call(["make", "-s", "-C", CSRC, "clean"])
+    out = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise SgsError("building libsings_b200.so failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SgsError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  sings_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().sgs_error_string(code).decode()
+        raise SgsError(f"{what}: {msg} (code {code})" if what else f"{msg} (code {code})")
+
+
+def ptr(t) -> int | None:
+    """data_ptr of a CUDA tensor (or None)."""
+    if t is None:
+        return None
+    return t.data_ptr()

@@ -1,0 +1,226 @@
+// api.cu -- the C ABI of libsings_b200.so (include/sings_b200.h).
+#include "../../include/sings_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "kernels_lbs.h"
+
+using namespace sgs;
+
+extern "C" {
+
+int sgs_version(void) { return 100; }
+
+const char* sgs_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case SGS_ERR_BAD_ARG: return "sings_b200: bad argument";
+        case SGS_ERR_BAD_SH_DEGREE: return "sings_b200: SH degree must be 0..3 and M >= (D+1)^2";
+        case SGS_ERR_BAD_JOINTS: return "sings_b200: joint count must be 1..64";
+        case SGS_ERR_MISALIGNED: return "sings_b200: pointer not 16-byte aligned";
+        case SGS_ERR_CAPACITY: return "sings_b200: capacity exceeded";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "sings_b200: unknown error";
+}
+
+int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
+                     size_t* binning_bytes, size_t* img_bytes, size_t* acc_bytes) {
+    if (P < 0 || W <= 0 || H <= 0 || L_cap < 0) return SGS_ERR_BAD_ARG;
+    RasterLayout l = raster_layout(P, W, H, L_cap);
+    if (geom_bytes) *geom_bytes = l.geom_bytes;
+    if (binning_bytes) *binning_bytes = l.bin_bytes;
+    if (img_bytes) *img_bytes = l.img_bytes;
+    if (acc_bytes) *acc_bytes = align_up((size_t)(P > 0 ? P : 1) * ACC_FLOATS * 4, 256);
+    return 0;
+}
+
+int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info) {
+    if (!info || P < 0 || W <= 0 || H <= 0 || L_cap < 0) return SGS_ERR_BAD_ARG;
+    RasterLayout l = raster_layout(P, W, H, L_cap);
+    info[0] = (long long)l.cnt_off;
+    info[1] = (long long)l.keys0_off;
+    info[2] = (long long)l.vals0_off;
+    info[3] = (long long)((l.passes & 1) ? l.keys1_off : l.keys0_off);
+    info[4] = (long long)((l.passes & 1) ? l.vals1_off : l.vals0_off);
+    info[5] = (long long)l.ranges_off;
+    info[6] = (long long)l.finalT_off;
+    info[7] = (long long)l.ncontrib_off;
+    info[8] = l.tiles;
+    info[9] = l.end_bit;
+    info[10] = l.passes;
+    info[11] = REC_FLOATS;
+    return 0;
+}
+
+static int fill_geom_args(GeomArgs& a, int P, int D, int M, int W, int H, const float* means3D,
+                          const float* colors_precomp, const float* opacities,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* view, const float* proj,
+                          const float* campos, float tanfovx, float tanfovy, const float* shs,
+                          int prefiltered) {
+    if (P < 0 || W <= 0 || H <= 0) return SGS_ERR_BAD_ARG;
+    if (P > 0) {
+        if ((shs == nullptr) == (colors_precomp == nullptr)) return SGS_ERR_BAD_ARG;
+        if ((cov3D_precomp == nullptr) == (scales == nullptr || rotations == nullptr)) return SGS_ERR_BAD_ARG;
+        if (shs && (D < 0 || D > 3 || M < (D + 1) * (D + 1))) return SGS_ERR_BAD_SH_DEGREE;
+        if (rotations && ((uintptr_t)rotations & 15)) return SGS_ERR_MISALIGNED;
+        if (!means3D || !view || !proj || !campos) return SGS_ERR_BAD_ARG;
+    }
+    a.P = P; a.D = shs ? D : 0; a.M = M; a.W = W; a.H = H;
+    a.tanfovx = tanfovx; a.tanfovy = tanfovy; a.scale_modifier = scale_modifier;
+    a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities;
+    a.shs = shs; a.colors_precomp = colors_precomp; a.cov3D_precomp = cov3D_precomp;
+    a.view = view; a.proj = proj; a.campos = campos; a.prefiltered = prefiltered;
+    return 0;
+}
+
+int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* campos,
+                       float tanfovx, float tanfovy, const float* shs, int prefiltered,
+                       long long L_cap, void* geom, void* binning, void* img, float* out_color,
+                       int* radii, float* out_alpha, float* out_depth, int* host_counters,
+                       sgs_stream_t stream_, int debug) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GeomArgs a;
+    int rc = fill_geom_args(a, P, D, M, W, H, means3D, colors_precomp, opacities, scales,
+                            scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                            campos, tanfovx, tanfovy, shs, prefiltered);
+    if (rc) return rc;
+    if (!bg || !geom || !binning || !img || !out_color || (P > 0 && (!radii || !opacities)) || L_cap < 1)
+        return SGS_ERR_BAD_ARG;
+    if (L_cap >= (1ll << 30)) return SGS_ERR_CAPACITY;
+    if (((uintptr_t)geom & 15) || ((uintptr_t)binning & 15) || ((uintptr_t)img & 15)) return SGS_ERR_MISALIGNED;
+    RasterLayout lay = raster_layout(P, W, H, L_cap);
+    char* g = (char*)geom; char* b = (char*)binning; char* im = (char*)img;
+    rc = launch_geometry(a, lay, L_cap, radii, g, b, stream);
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    if (P > 0) {
+        rc = launch_radix_sort(lay, L_cap, b, stream, debug);
+        if (rc) return rc;
+        rc = launch_tile_ranges(lay, L_cap, b, stream);
+        if (rc) return rc;
+        if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    }
+    rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    if (host_counters)
+        SGS_CUDA_OK(cudaMemcpyAsync(host_counters, b + lay.cnt_off, 2 * sizeof(int),
+                                    cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                        const float* colors_precomp, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos,
+                        float tanfovx, float tanfovy, const float* shs, const int* radii,
+                        const float* dL_dout_color, long long L_cap, const void* geom,
+                        const void* binning, const void* img, void* acc, float* dL_dmeans3D,
+                        float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                        float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                        sgs_stream_t stream_, int debug) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GeomBwdArgs b;
+    int rc = fill_geom_args(b.fwd, P, D, M, W, H, means3D, colors_precomp, nullptr, scales,
+                            scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                            campos, tanfovx, tanfovy, shs, 0);
+    if (rc) return rc;
+    if (!bg || !geom || !binning || !img || !acc || !dL_dout_color || !dL_dmeans3D || !dL_dmeans2D ||
+        !dL_dcolors || !dL_dopacity || (P > 0 && !radii) || (shs && !dL_dsh) || L_cap < 1)
+        return SGS_ERR_BAD_ARG;
+    if (((uintptr_t)acc & 15) || (dL_drots && ((uintptr_t)dL_drots & 15))) return SGS_ERR_MISALIGNED;
+    if (P == 0) return 0;
+    RasterLayout lay = raster_layout(P, W, H, L_cap);
+    SGS_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * 4, stream));
+    rc = launch_blend_bwd(lay, W, H, (const char*)geom, (const char*)binning, (const char*)img, bg,
+                          dL_dout_color, (float*)acc, stream);
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    b.radii = radii; b.acc = (const float*)acc;
+    b.dL_dmeans3D = dL_dmeans3D; b.dL_dmeans2D = dL_dmeans2D; b.dL_dcolors = dL_dcolors;
+    b.dL_dopacity = dL_dopacity; b.dL_dcov3D = dL_dcov3D; b.dL_dsh = dL_dsh;
+    b.dL_dscales = dL_dscales; b.dL_drots = dL_drots;
+    rc = launch_geometry_bwd(b, (const char*)geom, stream);
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     unsigned char* present, sgs_stream_t stream) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return SGS_ERR_BAD_ARG;
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }
+
+int sgs_sort_pairs_u64(unsigned long long* keys, unsigned int* vals,
+                       unsigned long long* keys_tmp, unsigned int* vals_tmp, void* scratch,
+                       size_t scratch_bytes, long long n, int end_bit, int* result_in_tmp,
+                       sgs_stream_t stream) {
+    if (n > 0 && (!keys || !vals || !keys_tmp || !vals_tmp || !scratch)) return SGS_ERR_BAD_ARG;
+    return launch_sort_pairs_u64(keys, vals, keys_tmp, vals_tmp, (char*)scratch, scratch_bytes, n,
+                                 end_bit, result_in_tmp, (cudaStream_t)stream);
+}
+
+int sgs_pose_to_A(const float* pose, const float* rest, const int* parents,
+                  const float* inv_A_t2cano, int B, int J, float* A_out, float* G_out,
+                  sgs_stream_t stream) {
+    if (B < 0 || (B > 0 && (!pose || !rest || !parents || !A_out))) return SGS_ERR_BAD_ARG;
+    return launch_pose_to_A(pose, rest, parents, inv_A_t2cano, B, J, A_out, G_out, (cudaStream_t)stream);
+}
+
+int sgs_pose_to_A_bwd(const float* pose, const float* rest, const int* parents,
+                      const float* inv_A_t2cano, const float* G, const float* dL_dA, int B, int J,
+                      float* dL_dpose, sgs_stream_t stream) {
+    if (B < 0 || (B > 0 && (!pose || !rest || !parents || !G || !dL_dA || !dL_dpose))) return SGS_ERR_BAD_ARG;
+    return launch_pose_to_A_bwd(pose, rest, parents, inv_A_t2cano, G, dL_dA, B, J, dL_dpose, (cudaStream_t)stream);
+}
+
+static int fill_lbs(LbsArgs& a, int B, int N, int J, const float* A, const float* xyz, const float* W,
+                    const float* rot, const float* scales, const float* smpl_scale, const float* transl,
+                    const float* ext_trans, const float* ext_rot, const float* ext_scale) {
+    if (B < 0 || N < 0) return SGS_ERR_BAD_ARG;
+    if (B > 0 && N > 0 && (!A || !xyz || !W || !scales)) return SGS_ERR_BAD_ARG;
+    const int n_ext = (ext_trans != nullptr) + (ext_rot != nullptr) + (ext_scale != nullptr);
+    if (n_ext != 0 && n_ext != 3) return SGS_ERR_BAD_ARG;
+    a.B = B; a.N = N; a.J = J; a.A = A; a.xyz = xyz; a.W = W; a.rot = rot; a.scales = scales;
+    a.smpl_scale = smpl_scale; a.transl = transl;
+    a.ext_trans = ext_trans; a.ext_rot = ext_rot; a.ext_scale = ext_scale;
+    return 0;
+}
+
+int sgs_lbs_fwd(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                const float* rot_canon, const float* scales, const float* smpl_scale,
+                const float* transl, const float* ext_trans, const float* ext_rot,
+                const float* ext_scale, float* xyz_out, float* rotq_out, float* scales_out,
+                float* T_out, sgs_stream_t stream) {
+    LbsArgs a;
+    int rc = fill_lbs(a, B, N, J, A, xyz_canon, W, rot_canon, scales, smpl_scale, transl, ext_trans, ext_rot, ext_scale);
+    if (rc) return rc;
+    if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
+    LbsOut o{xyz_out, rotq_out, scales_out, T_out};
+    return launch_lbs_fwd(a, o, (cudaStream_t)stream);
+}
+
+int sgs_lbs_bwd(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                const float* rot_canon, const float* scales, const float* smpl_scale,
+                const float* transl, const float* ext_trans, const float* ext_rot,
+                const float* ext_scale, const float* g_xyz, const float* g_rotq,
+                const float* g_scales, const float* g_T, float* d_xyz_canon, float* d_rot_canon,
+                float* d_scales, float* d_A, float* d_smpl_scale, float* d_transl,
+                sgs_stream_t stream) {
+    LbsArgs a;
+    int rc = fill_lbs(a, B, N, J, A, xyz_canon, W, rot_canon, scales, smpl_scale, transl, ext_trans, ext_rot, ext_scale);
+    if (rc) return rc;
+    if (B > 0 && N > 0 && (!g_xyz || !g_rotq || !g_scales || !d_xyz_canon || !d_scales || !d_A)) return SGS_ERR_BAD_ARG;
+    LbsGrads g{g_xyz, g_rotq, g_scales, g_T, d_xyz_canon, d_rot_canon, d_scales, d_A, d_smpl_scale, d_transl};
+    return launch_lbs_bwd(a, g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

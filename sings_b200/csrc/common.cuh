@@ -1,0 +1,178 @@
+// common.cuh -- shared device helpers for the sm_100a kernels of sings_b200.
+//
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false
+// -fmad=false is part of the numeric contract: the only fused multiply-adds are
+// the explicit fmaf()/__fmaf_rn() calls, so the forward pass matches the C oracle bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgs {
+
+constexpr int TILE = 16;            // 16x16 pixel tiles ([upstream] config.h BLOCK_X/BLOCK_Y)
+constexpr int TILE_PIX = TILE * TILE;
+
+// ---- error plumbing: entry points return 0, a negative argument error, or a cudaError_t ----
+#define SGS_CUDA_OK(expr)                                   \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) return (int)_e;              \
+    } while (0)
+
+#define SGS_LAUNCH_OK()                                     \
+    do {                                                    \
+        cudaError_t _e = cudaGetLastError();                \
+        if (_e != cudaSuccess) return (int)_e;              \
+    } while (0)
+
+// debug mode: synchronise and check after each stage ([upstream] CHECK_CUDA(debug))
+#define SGS_STAGE_OK(debug, stream)                         \
+    do {                                                    \
+        SGS_LAUNCH_OK();                                    \
+        if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream)); \
+    } while (0)
+
+#ifndef SGS_ERR_BAD_ARG          // same values as include/sings_b200.h
+#define SGS_ERR_BAD_ARG -1
+#define SGS_ERR_BAD_SH_DEGREE -2
+#define SGS_ERR_BAD_JOINTS -3
+#define SGS_ERR_MISALIGNED -4
+#define SGS_ERR_CAPACITY -5
+#endif
+
+// ---- counters block at the head of the zeroed scratch region (int32 slots) ----
+enum : int {
+    CNT_NUM_RENDERED = 0,   // L = sum of tiles touched (written by the geometry kernel)
+    CNT_OVERFLOW = 1,       // set when L exceeded the binning capacity
+    CNT_SCAN_TICKET = 2,    // block ticket of the geometry kernel
+    CNT_VISIBLE = 3,        // number of Gaussians with radii > 0 (statistics)
+    CNT_SORT_TICKET0 = 8,   // + pass: block ticket of each radix pass (8 slots)
+    CNT_SLOTS = 32,
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- scoped loads/stores for the decoupled look-back status words ----
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- streaming (read-once) 128-bit global load, no L1 allocation ----
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---- cp.async (LDGSTS): 16-byte global -> shared, L2 only ----
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- TMA 1-D bulk copy (cp.async.bulk) + mbarrier: contiguous global chunk -> shared ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(s), "r"(parity)
+        : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                             unsigned long long* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(gmem_src), "r"(bytes), "r"(b)
+        : "memory");
+}
+
+// ---- vector reduction to global memory (sm_90+): one L2 atomic for four floats ----
+__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// exp(x) for x <= 0, bit-identical to oracle/c/raster_oracle.c expneg (numeric contract)
+__device__ __forceinline__ float expneg(float x) {
+    if (x < -80.0f) return 0.0f;
+    float n = rintf(__fmul_rn(x, 1.44269504088896341f));
+    float f = __fmaf_rn(n, -0.693359375f, x);
+    f = __fmaf_rn(n, 2.12194440e-4f, f);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, f, 1.3981999507e-3f);
+    p = __fmaf_rn(p, f, 8.3334519073e-3f);
+    p = __fmaf_rn(p, f, 4.1665795894e-2f);
+    p = __fmaf_rn(p, f, 1.6666665459e-1f);
+    p = __fmaf_rn(p, f, 5.0000001201e-1f);
+    float z = __fmul_rn(f, f);
+    float r = __fadd_rn(__fmaf_rn(p, z, f), 1.0f);
+    return __int_as_float(__float_as_int(r) + (__float2int_rn(n) << 23));
+}
+
+// column-major 4x4 times (x,y,z,1), row r  ([upstream] auxiliary.h transformPoint4x3/4x4)
+__device__ __forceinline__ float xform_row(const float* m, int r, float x, float y, float z) {
+    float t = __fmul_rn(m[r], x);
+    t = __fmaf_rn(m[4 + r], y, t);
+    t = __fmaf_rn(m[8 + r], z, t);
+    return __fadd_rn(t, m[12 + r]);
+}
+
+}  // namespace sgs

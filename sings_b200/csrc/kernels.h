@@ -1,0 +1,96 @@
+// kernels.h -- host-side launch functions of the individual .cu files (internal, C++).
+// The public boundary is the C ABI in include/sings_b200.h, implemented in api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgs {
+
+// floats per Gaussian in the geometry record consumed by the blend kernels
+constexpr int REC_FLOATS = 12;
+// record layout: [0]=pixel x, [1]=pixel y, [2]=-0.5*conic.a, [3]=-conic.b, [4]=-0.5*conic.c,
+// [5]=opacity, [6]=pmin (power below which alpha < 1/255 for sure), [7]=r, [8]=g, [9]=b,
+// [10]=view depth, [11]=flags (bit 0..2: colour channel clamped at 0)
+
+// floats per Gaussian in the blend-backward accumulator
+constexpr int ACC_FLOATS = 12;
+// accumulator layout: [0]=dL/dmean2D.x, [1]=.y, [2]=dL/dconic.a, [3]=dL/dconic.b (un-doubled),
+// [4]=dL/dconic.c, [5]=dL/dopacity, [6..8]=dL/dcolor rgb, [9..11] unused
+
+constexpr int SORT_ITEMS = 8;              // keys per thread in one radix tile
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_TILE = SORT_ITEMS * SORT_THREADS;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 8;
+
+struct RasterLayout {
+    // geometry state (per Gaussian)
+    size_t rec_off, geom_bytes;
+    // zeroed scratch + binning state
+    size_t cnt_off, hist_off, scan_off, sortstat_off, ranges_off, zero_bytes;
+    size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
+    // image state
+    size_t finalT_off, ncontrib_off, img_bytes;
+    int scan_blocks, sort_blocks, tiles, gx, gy, end_bit, passes;
+};
+
+RasterLayout raster_layout(int P, int W, int H, long long L_cap);
+int higher_msb(unsigned n);
+
+struct GeomArgs {
+    int P, D, M, W, H;
+    float tanfovx, tanfovy, scale_modifier;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* colors_precomp;
+    const float* cov3D_precomp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int prefiltered;
+};
+
+int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
+                    char* geom, char* bin, cudaStream_t stream);
+
+int launch_radix_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
+                      int debug);
+// stand-alone sort (A/B against CUB): sorts n pairs on key bits [0,end_bit)
+int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned long long* keys_tmp,
+                          unsigned* vals_tmp, char* scratch, size_t scratch_bytes, long long n,
+                          int end_bit, int* result_in_tmp, cudaStream_t stream);
+size_t sort_scratch_bytes(long long n);
+
+int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
+
+int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
+                     char* img, const float* bg, float* out_color, float* out_alpha,
+                     float* out_depth, cudaStream_t stream);
+
+int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
+                     const char* img, const float* bg, const float* dL_dpix, float* acc,
+                     cudaStream_t stream);
+
+struct GeomBwdArgs {
+    GeomArgs fwd;
+    const int* radii;
+    const float* acc;          // (P, ACC_FLOATS) from the blend backward
+    float* dL_dmeans3D;        // (P,3)
+    float* dL_dmeans2D;        // (P,3)
+    float* dL_dcolors;         // (P,3)  (meaningful when colors_precomp was given)
+    float* dL_dopacity;        // (P,1)
+    float* dL_dcov3D;          // (P,6)
+    float* dL_dsh;             // (P,M,3) or null
+    float* dL_dscales;         // (P,3)
+    float* dL_drots;           // (P,4)
+};
+int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t stream);
+
+int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
+                        cudaStream_t stream);
+
+}  // namespace sgs

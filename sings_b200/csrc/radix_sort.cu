@@ -1,0 +1,239 @@
+// radix_sort.cu -- hand-written onesweep LSD radix sort of (u64 key, u32 value) pairs.
+//
+// Replaces cub::DeviceRadixSort::SortPairs as called by the reference's rasterizer
+// ([upstream] rasterizer_impl.cu: keys = tile<<32 | depth bits, values = Gaussian ids, bits
+// [0, 32+getHigherMsb(tiles)); SURVEY.md A.1/A.3, K6 of section 2.4).  A stable LSD radix sort
+// has a unique answer, so the sorted arrays are bit-identical to CUB's.
+//
+// One kernel per 8-bit digit ("onesweep"): the digit histograms of ALL passes are produced
+// up front (fused into the key-emitting geometry kernel, or by histogram_kernel for the
+// stand-alone entry point); each pass ranks its tile stably (warp match_any + per-warp
+// counters), obtains the tile's global digit offsets by decoupled look-back over the
+// preceding tiles, and scatters through shared memory so global stores are digit-run
+// coalesced.  Tiles are taken in ticket order (forward progress of the look-back).
+// The item count is read from device memory, so the launch needs no host round trip.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sgs {
+
+constexpr unsigned ST_AGG = 1u << 30;
+constexpr unsigned ST_INCL = 2u << 30;
+constexpr unsigned ST_FLAG = 3u << 30;
+constexpr unsigned ST_VAL = ~ST_FLAG;
+
+struct SortPass {
+    const unsigned long long* keys_in;
+    const unsigned* vals_in;
+    unsigned long long* keys_out;
+    unsigned* vals_out;
+    const unsigned* hist;   // 256 bins of this pass
+    unsigned* status;       // [tiles][256] look-back words of this pass (zeroed)
+    int* ticket;            // zeroed
+    const int* n_ptr;       // item count on the device (may be null -> n_cap)
+    long long n_cap;
+    int shift;
+    unsigned mask;          // (1 << bits of this digit) - 1; < 255 only in a partial last pass
+};
+
+// exclusive scan of one value per thread over a 256-thread block
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_tmp, int lane, int warp) {
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    unsigned off = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++)
+        if (w < warp) off += s_tmp[w];
+    __syncthreads();
+    return off + incl - v;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass a) {
+    __shared__ unsigned s_cnt[SORT_THREADS / 32][RADIX];
+    __shared__ unsigned s_bexcl[RADIX];
+    __shared__ unsigned s_gbase[RADIX];
+    __shared__ unsigned long long s_keys[SORT_TILE];
+    __shared__ unsigned s_vals[SORT_TILE];
+    __shared__ unsigned s_tmp[SORT_THREADS / 32];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long n = a.n_ptr ? (long long)*a.n_ptr : a.n_cap;
+    if (n > a.n_cap) n = a.n_cap;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1);
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) s_cnt[w][tid] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const long long start = (long long)tile * SORT_TILE;
+    if (start >= n) return;
+    const int n_valid = (int)min((long long)SORT_TILE, n - start);
+
+    // ---- load, warp-striped: warp w owns items [w*256, w*256+256), item i of lane l = i*32+l ----
+    unsigned long long key[SORT_ITEMS];
+    unsigned val[SORT_ITEMS];
+    unsigned rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        int local = warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        bool ok = local < n_valid;
+        key[i] = ok ? a.keys_in[start + local] : ~0ull;
+        val[i] = ok ? a.vals_in[start + local] : 0u;
+    }
+    // ---- stable rank inside the warp's segment ----
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        unsigned d = (unsigned)(key[i] >> a.shift) & a.mask;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        unsigned old = 0;
+        if (lane == leader) {
+            old = s_cnt[warp][d];
+            s_cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + __popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- per digit (thread d): exclusive scan over warps, tile count ----
+    unsigned count = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; w++) {
+        unsigned t = s_cnt[w][tid];
+        s_cnt[w][tid] = count;
+        count += t;
+    }
+    // ---- decoupled look-back over preceding tiles, one digit per thread ----
+    unsigned* row = a.status + (size_t)tile * RADIX;
+    st_relaxed_u32(&row[tid], (tile == 0 ? ST_INCL : ST_AGG) | count);
+    unsigned prev = 0;
+    if (tile > 0) {
+        for (int j = tile - 1;; j--) {
+            const unsigned* p = a.status + (size_t)j * RADIX + tid;
+            unsigned s = ld_relaxed_u32(p);
+            while ((s & ST_FLAG) == 0) s = ld_relaxed_u32(p);
+            prev += s & ST_VAL;
+            if ((s & ST_FLAG) == ST_INCL) break;
+        }
+        st_relaxed_u32(&row[tid], ST_INCL | (prev + count));
+    }
+    // ---- digit bases: global (from the up-front histogram) and inside the tile ----
+    unsigned gexcl = block_excl_scan(a.hist[tid], s_tmp, lane, warp);
+    unsigned bexcl = block_excl_scan(count, s_tmp, lane, warp);
+    s_gbase[tid] = gexcl + prev;
+    s_bexcl[tid] = bexcl;
+    __syncthreads();
+    // ---- reorder through shared memory into tile-sorted order ----
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        unsigned d = (unsigned)(key[i] >> a.shift) & a.mask;
+        unsigned pos = s_bexcl[d] + s_cnt[warp][d] + rank[i];
+        s_keys[pos] = key[i];
+        s_vals[pos] = val[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+        int p = tid + k * SORT_THREADS;
+        if (p < n_valid) {
+            unsigned long long kk = s_keys[p];
+            unsigned d = (unsigned)(kk >> a.shift) & a.mask;
+            size_t dst = (size_t)s_gbase[d] + (unsigned)(p - (int)s_bexcl[d]);
+            a.keys_out[dst] = kk;
+            a.vals_out[dst] = s_vals[p];
+        }
+    }
+}
+
+// digit histograms of all passes in one read of the keys (stand-alone entry point only)
+__global__ void __launch_bounds__(256) histogram_kernel(const unsigned long long* keys, long long n,
+                                                        int passes, int end_bit, unsigned* hist) {
+    __shared__ unsigned s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long k = keys[i];
+        for (int p = 0; p < passes; p++) {
+            int bits = min(RADIX_BITS, end_bit - p * RADIX_BITS);
+            atomicAdd(&s_hist[p * RADIX + (unsigned)((k >> (p * RADIX_BITS)) & ((1u << bits) - 1u))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* k1, unsigned* v1,
+                      const unsigned* hist, unsigned* status, int* tickets, const int* n_ptr,
+                      long long n_cap, int passes, int end_bit, int blocks, cudaStream_t stream,
+                      int debug) {
+    for (int p = 0; p < passes; p++) {
+        SortPass a;
+        a.keys_in = (p & 1) ? k1 : k0;
+        a.vals_in = (p & 1) ? v1 : v0;
+        a.keys_out = (p & 1) ? k0 : k1;
+        a.vals_out = (p & 1) ? v0 : v1;
+        a.hist = hist + (size_t)p * RADIX;
+        a.status = status + (size_t)p * blocks * RADIX;
+        a.ticket = tickets + p;
+        a.n_ptr = n_ptr;
+        a.n_cap = n_cap;
+        a.shift = p * RADIX_BITS;
+        a.mask = (1u << min(RADIX_BITS, end_bit - p * RADIX_BITS)) - 1u;
+        onesweep_pass_kernel<<<blocks, SORT_THREADS, 0, stream>>>(a);
+        SGS_STAGE_OK(debug, stream);
+    }
+    return 0;
+}
+
+int launch_radix_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
+                      int debug) {
+    if (L_cap >= (1ll << 30)) return SGS_ERR_CAPACITY;
+    int* counters = reinterpret_cast<int*>(bin + lay.cnt_off);
+    return run_passes(reinterpret_cast<unsigned long long*>(bin + lay.keys0_off),
+                      reinterpret_cast<unsigned*>(bin + lay.vals0_off),
+                      reinterpret_cast<unsigned long long*>(bin + lay.keys1_off),
+                      reinterpret_cast<unsigned*>(bin + lay.vals1_off),
+                      reinterpret_cast<const unsigned*>(bin + lay.hist_off),
+                      reinterpret_cast<unsigned*>(bin + lay.sortstat_off),
+                      counters + CNT_SORT_TICKET0, counters + CNT_NUM_RENDERED, L_cap, lay.passes,
+                      lay.end_bit, lay.sort_blocks, stream, debug);
+}
+
+size_t sort_scratch_bytes(long long n) {
+    size_t blocks = (size_t)((n + SORT_TILE - 1) / SORT_TILE);
+    if (blocks < 1) blocks = 1;
+    return align_up(CNT_SLOTS * 4, 256) + align_up((size_t)MAX_PASSES * RADIX * 4, 256) +
+           align_up((size_t)MAX_PASSES * blocks * RADIX * 4, 256);
+}
+
+int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned long long* keys_tmp,
+                          unsigned* vals_tmp, char* scratch, size_t scratch_bytes, long long n,
+                          int end_bit, int* result_in_tmp, cudaStream_t stream) {
+    if (n < 0 || end_bit < 1 || end_bit > 64 || n >= (1ll << 30)) return SGS_ERR_BAD_ARG;
+    if (scratch_bytes < sort_scratch_bytes(n)) return SGS_ERR_CAPACITY;
+    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int blocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    if (result_in_tmp) *result_in_tmp = passes & 1;
+    if (n == 0) return 0;
+    SGS_CUDA_OK(cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), stream));
+    int* tickets = reinterpret_cast<int*>(scratch);
+    unsigned* hist = reinterpret_cast<unsigned*>(scratch + align_up(CNT_SLOTS * 4, 256));
+    unsigned* status = reinterpret_cast<unsigned*>(scratch + align_up(CNT_SLOTS * 4, 256) +
+                                                   align_up((size_t)MAX_PASSES * RADIX * 4, 256));
+    int hb = (int)min((long long)148 * 8, (n + 255) / 256);
+    histogram_kernel<<<hb, 256, 0, stream>>>(keys, n, passes, end_bit, hist);
+    SGS_LAUNCH_OK();
+    return run_passes(keys, vals, keys_tmp, vals_tmp, hist, status, tickets, nullptr, n, passes,
+                      end_bit, blocks, stream, 0);
+}
+
+}  // namespace sgs

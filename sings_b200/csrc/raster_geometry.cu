@@ -1,0 +1,372 @@
+// raster_geometry.cu -- fused forward "geometry" stage of the rasterizer:
+//   preprocess (cull, 3D cov, EWA 2D cov, conic, radius, tile rect, SH->RGB)
+//   + tiles-touched prefix sum (single-pass chained scan, decoupled look-back)
+//   + (tile|depth) key / Gaussian-id emission for every touched tile
+//   + the digit histograms of all radix passes,
+// in ONE pass over HBM.  Replaces, with identical results, the reference's
+//   [upstream] forward.cu preprocessCUDA, cub::DeviceScan::InclusiveSum,
+//   rasterizer_impl.cu duplicateWithKeys (K3+K4+K5 of section 2.4),
+// reached from /root/reference/sings/rec/renderer/gs_renderer_single.py:87-95.
+//
+// Layout: one CTA = 256 consecutive Gaussians, taken in ticket order so the chained scan can
+// never wait on a CTA that has not started.  SH rows (192 B each at M=16) are staged with
+// 16-byte cp.async into padded shared rows; the other attributes are read directly.
+// Emission is load-balanced over the CTA (binary search of the block-local offsets), so key
+// and value stores are fully coalesced.
+#include "geom_math.cuh"
+#include "kernels.h"
+
+namespace sgs {
+
+constexpr int GEO_THREADS = 256;
+constexpr unsigned long long FLAG_AGG = 1ull << 62;
+constexpr unsigned long long FLAG_INCL = 2ull << 62;
+constexpr unsigned long long FLAG_MASK = 3ull << 62;
+
+int higher_msb(unsigned n) {
+    unsigned msb = 16, step = 16;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return (int)msb;
+}
+
+RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
+    RasterLayout l{};
+    l.gx = (W + TILE - 1) / TILE;
+    l.gy = (H + TILE - 1) / TILE;
+    l.tiles = l.gx * l.gy;
+    l.end_bit = 32 + higher_msb((unsigned)l.tiles);
+    l.passes = (l.end_bit + RADIX_BITS - 1) / RADIX_BITS;
+    l.scan_blocks = (P + GEO_THREADS - 1) / GEO_THREADS;
+    if (l.scan_blocks < 1) l.scan_blocks = 1;
+    l.sort_blocks = (int)((L_cap + SORT_TILE - 1) / SORT_TILE);
+    if (l.sort_blocks < 1) l.sort_blocks = 1;
+    // geometry state
+    l.rec_off = 0;
+    l.geom_bytes = align_up((size_t)(P > 0 ? P : 1) * REC_FLOATS * 4, 256);
+    // binning state: zeroed region first
+    size_t o = 0;
+    l.cnt_off = o;      o += align_up(CNT_SLOTS * 4, 256);
+    l.hist_off = o;     o += align_up((size_t)MAX_PASSES * RADIX * 4, 256);
+    l.scan_off = o;     o += align_up((size_t)l.scan_blocks * 8, 256);
+    l.sortstat_off = o; o += align_up((size_t)l.passes * l.sort_blocks * RADIX * 4, 256);
+    l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
+    l.zero_bytes = o;
+    size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
+    l.keys0_off = o;    o += align_up(cap * 8, 256);
+    l.keys1_off = o;    o += align_up(cap * 8, 256);
+    l.vals0_off = o;    o += align_up(cap * 4, 256);
+    l.vals1_off = o;    o += align_up(cap * 4, 256);
+    l.bin_bytes = o;
+    // image state
+    size_t pix = (size_t)W * H;
+    l.finalT_off = 0;
+    l.ncontrib_off = align_up(pix * 4, 256);
+    l.img_bytes = l.ncontrib_off + align_up(pix * 4, 256);
+    return l;
+}
+
+struct GeoOut {
+    int* radii;
+    float* rec;
+    int* counters;
+    unsigned* hist;
+    unsigned long long* scan_status;
+    unsigned long long* keys;
+    unsigned* vals;
+    long long L_cap;
+    int passes;
+    int gx, gy;
+    float fx, fy;
+};
+
+// NVEC: float4 per SH row staged to shared memory; 0 = colours precomputed.
+// VEC16: SH rows are 16-byte aligned (M*3 % 4 == 0 and base aligned) -> 16-byte cp.async.
+template <int D, bool HAS_SH, bool VEC16>
+__global__ void __launch_bounds__(GEO_THREADS)
+geometry_kernel(GeomArgs a, GeoOut o) {
+    constexpr int NB = (D + 1) * (D + 1);
+    constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
+    constexpr int S4 = HAS_SH ? sh_stride4(NVEC) : 0;
+    extern __shared__ float4 s_sh[];                 // GEO_THREADS * S4 float4
+    __shared__ float s_cam[36];
+    __shared__ unsigned s_incl[GEO_THREADS];         // block-local inclusive tile offsets
+    __shared__ int4 s_rect[GEO_THREADS];             // x0, y0, width, depth bits
+    __shared__ unsigned s_warp[GEO_THREADS / 32];
+    __shared__ unsigned s_hist[MAX_PASSES * RADIX];
+    __shared__ int s_ticket;
+    __shared__ unsigned long long s_prefix;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(&o.counters[CNT_SCAN_TICKET], 1);
+    if (tid < 16) s_cam[tid] = a.view[tid];
+    else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
+    else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
+    for (int i = tid; i < o.passes * RADIX; i += GEO_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const int chunk = s_ticket;
+    const int base = chunk * GEO_THREADS;
+    const int idx = base + tid;
+    const bool in_range = idx < a.P;
+    const float* V = s_cam;
+    const float* Mx = s_cam + 16;
+
+    // ---- stage this CTA's SH rows (asynchronously; consumed after the geometry math) ----
+    if constexpr (HAS_SH) {
+        const int rows = min(GEO_THREADS, a.P - base);
+        const size_t row_floats = (size_t)a.M * 3;
+        if (VEC16) {
+            const int total = rows * NVEC;
+            for (int f = tid; f < total; f += GEO_THREADS) {
+                int row = f / NVEC, col = f - row * NVEC;
+                cp_async16(&s_sh[row * S4 + col], a.shs + (size_t)(base + row) * row_floats + col * 4);
+            }
+        } else {
+            float* s_f = reinterpret_cast<float*>(s_sh);
+            const int total = rows * NB * 3;
+            for (int f = tid; f < total; f += GEO_THREADS) {
+                int row = f / (NB * 3), col = f - row * (NB * 3);
+                cp_async4(&s_f[row * S4 * 4 + col], a.shs + (size_t)(base + row) * row_floats + col);
+            }
+        }
+        cp_async_commit();
+    }
+
+    // ---- per-Gaussian geometry ----
+    unsigned tiles = 0;
+    int rad = 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    float px = 0, py = 0, pz = 0, depth = 0, ix = 0, iy = 0;
+    float conA = 0, conB = 0, conC = 0, opac = 0;
+    if (in_range) {
+        px = a.means3D[3 * idx]; py = a.means3D[3 * idx + 1]; pz = a.means3D[3 * idx + 2];
+        depth = xform_row(V, 2, px, py, pz);
+        if (depth > 0.2f) {      // [upstream] in_frustum: p_view.z <= 0.2 culls
+            float pvx = xform_row(V, 0, px, py, pz), pvy = xform_row(V, 1, px, py, pz);
+            float phx = xform_row(Mx, 0, px, py, pz), phy = xform_row(Mx, 1, px, py, pz);
+            float phw = xform_row(Mx, 3, px, py, pz);
+            float pw = DIV(1.0f, ADD(phw, 0.0000001f));
+            float ppx = MUL(phx, pw), ppy = MUL(phy, pw);
+            float c3[6];
+            if (a.cov3D_precomp) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[6 * (size_t)idx + k];
+            } else {
+                float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+                cov3d_from_scale_rot(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2],
+                                     a.scale_modifier, q.x, q.y, q.z, q.w, c3);
+            }
+            Cov2D cv;
+            cov2d(pvx, pvy, depth, o.fx, o.fy, a.tanfovx, a.tanfovy, c3, V, cv);
+            float det = FMA(cv.a, cv.c, -MUL(cv.b, cv.b));
+            if (det != 0.0f) {
+                float det_inv = DIV(1.0f, det);
+                conA = MUL(cv.c, det_inv); conB = MUL(-cv.b, det_inv); conC = MUL(cv.a, det_inv);
+                float mid = MUL(0.5f, ADD(cv.a, cv.c));
+                float sq = SQRT(fmaxf(0.1f, FMA(mid, mid, -det)));
+                float l1 = ADD(mid, sq), l2 = SUB(mid, sq);
+                rad = __float2int_rz(ceilf(MUL(3.0f, SQRT(fmaxf(l1, l2)))));
+                ix = MUL(FMA(ADD(ppx, 1.0f), (float)a.W, -1.0f), 0.5f);   // ndc2Pix
+                iy = MUL(FMA(ADD(ppy, 1.0f), (float)a.H, -1.0f), 0.5f);
+                get_rect(ix, iy, rad, o.gx, o.gy, x0, y0, x1, y1);
+                tiles = (unsigned)((x1 - x0) * (y1 - y0));
+                if (tiles == 0) rad = 0;
+                opac = a.opacities[idx];
+            }
+        }
+    }
+
+    // ---- colour: SH -> RGB (or precomputed) and the blend record ----
+    if constexpr (HAS_SH) cp_async_wait_all();
+    __syncthreads();
+    if (tiles > 0) {
+        float rgb[3];
+        unsigned flags = 0;
+        if constexpr (HAS_SH) {
+            float dx = SUB(px, V[32]), dy = SUB(py, V[33]), dz = SUB(pz, V[34]);
+            float len = SQRT(FMA(dz, dz, FMA(dy, dy, MUL(dx, dx))));
+            float inv = DIV(1.0f, len);
+            float b[NB];
+            sh_basis<D>(MUL(dx, inv), MUL(dy, inv), MUL(dz, inv), b);
+            float sh[NVEC * 4];
+            const float4* row = s_sh + tid * S4;
+#pragma unroll
+            for (int j = 0; j < NVEC; j++) {
+                float4 v = row[j];
+                sh[4 * j] = v.x; sh[4 * j + 1] = v.y; sh[4 * j + 2] = v.z; sh[4 * j + 3] = v.w;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float acc = MUL(b[0], sh[ch]);
+#pragma unroll
+                for (int k = 1; k < NB; k++) acc = FMA(b[k], sh[3 * k + ch], acc);
+                acc = ADD(acc, 0.5f);
+                if (acc < 0.0f) flags |= 1u << ch;
+                rgb[ch] = fmaxf(acc, 0.0f);
+            }
+        } else {
+            rgb[0] = a.colors_precomp[3 * idx]; rgb[1] = a.colors_precomp[3 * idx + 1];
+            rgb[2] = a.colors_precomp[3 * idx + 2];
+        }
+        // pmin: any power below it gives alpha = opacity*exp(power) < 1/255 with a 1 % margin,
+        // so the blend kernels may skip the pair without evaluating exp (pure optimisation).
+        float pmin = opac > 0.0f ? -(__logf(255.0f * opac) + 0.01f) : __int_as_float(0x7f800000);
+        float4* rec = reinterpret_cast<float4*>(o.rec) + (size_t)idx * 3;
+        rec[0] = make_float4(ix, iy, MUL(-0.5f, conA), -conB);
+        rec[1] = make_float4(MUL(-0.5f, conC), opac, pmin, rgb[0]);
+        rec[2] = make_float4(rgb[1], rgb[2], depth, __uint_as_float(flags));
+    }
+    if (in_range) o.radii[idx] = rad;
+
+    // ---- block scan of tiles touched ----
+    unsigned incl = tiles;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    s_rect[tid] = make_int4(x0, y0, x1 - x0, __float_as_int(depth));
+    __syncthreads();
+    unsigned warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < GEO_THREADS / 32; w++) {
+        unsigned v = s_warp[w];
+        if (w < warp) warp_off += v;
+        block_total += v;
+    }
+    incl += warp_off;
+    s_incl[tid] = incl;
+
+    // ---- chained scan across CTAs (decoupled look-back, one warp) ----
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (lane == 0)
+            st_relaxed_u64(&o.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
+        if (chunk > 0) {
+            int look = chunk - 1;
+            while (true) {
+                int j = look - lane;
+                unsigned long long s = j >= 0 ? ld_relaxed_u64(&o.scan_status[j]) : FLAG_INCL;
+                while (__any_sync(0xffffffffu, (s & FLAG_MASK) == 0)) {
+                    if ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&o.scan_status[j]);
+                }
+                unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
+                unsigned long long val = s & ~FLAG_MASK;
+                int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                unsigned long long v = lane <= first ? val : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&o.scan_status[chunk], FLAG_INCL | (excl + block_total));
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            unsigned long long total = excl + block_total;
+            if (chunk == (int)gridDim.x - 1)
+                o.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+            if (total > (unsigned long long)o.L_cap) o.counters[CNT_OVERFLOW] = 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- emit (tile|depth) keys and Gaussian ids: [upstream] duplicateWithKeys ----
+    const unsigned long long prefix = s_prefix;
+    for (unsigned e = tid; e < block_total; e += GEO_THREADS) {
+        int lo = 0, hi = GEO_THREADS - 1;          // first g with s_incl[g] > e
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_incl[mid] > e) hi = mid; else lo = mid + 1;
+        }
+        const int g = lo;
+        const int4 r = s_rect[g];
+        const unsigned first = g ? s_incl[g - 1] : 0u;
+        const unsigned k = e - first;
+        const unsigned ty = k / (unsigned)r.z, tx = k - ty * (unsigned)r.z;
+        const unsigned tile_id = (unsigned)(r.y + (int)ty) * (unsigned)o.gx + (unsigned)(r.x + (int)tx);
+        const unsigned long long key = ((unsigned long long)tile_id << 32) | (unsigned)r.w;
+        const unsigned long long pos = prefix + e;
+        if (pos < (unsigned long long)o.L_cap) {
+            o.keys[pos] = key;
+            o.vals[pos] = (unsigned)(base + g);
+            for (int p = 0; p < o.passes; p++)
+                atomicAdd(&s_hist[p * RADIX + (unsigned)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < o.passes * RADIX; i += GEO_THREADS) {
+        unsigned c = s_hist[i];
+        if (c) atomicAdd(&o.hist[i], c);
+    }
+}
+
+template <int D, bool HAS_SH>
+static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec16, cudaStream_t st) {
+    size_t smem = HAS_SH ? (size_t)GEO_THREADS * sh_stride4(sh_nvec(D)) * 16 : 0;
+    if (vec16) {
+        auto k = geometry_kernel<D, HAS_SH, true>;
+        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, GEO_THREADS, smem, st>>>(a, o);
+    } else {
+        auto k = geometry_kernel<D, HAS_SH, false>;
+        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<blocks, GEO_THREADS, smem, st>>>(a, o);
+    }
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
+                    char* geom, char* bin, cudaStream_t stream) {
+    // one memset clears counters, histograms, scan + sort look-back status and tile ranges
+    SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
+    if (a.P <= 0) return 0;
+    GeoOut o;
+    o.radii = radii;
+    o.rec = reinterpret_cast<float*>(geom + lay.rec_off);
+    o.counters = reinterpret_cast<int*>(bin + lay.cnt_off);
+    o.hist = reinterpret_cast<unsigned*>(bin + lay.hist_off);
+    o.scan_status = reinterpret_cast<unsigned long long*>(bin + lay.scan_off);
+    o.keys = reinterpret_cast<unsigned long long*>(bin + lay.keys0_off);
+    o.vals = reinterpret_cast<unsigned*>(bin + lay.vals0_off);
+    o.L_cap = L_cap;
+    o.passes = lay.passes;
+    o.gx = lay.gx; o.gy = lay.gy;
+    o.fx = (float)a.W / (2.0f * a.tanfovx);
+    o.fy = (float)a.H / (2.0f * a.tanfovy);
+    const bool has_sh = a.colors_precomp == nullptr;
+    if (!has_sh) return launch_geo_t<0, false>(a, o, lay.scan_blocks, false, stream);
+    const bool vec16 = ((a.M * 3) % 4 == 0) && (((uintptr_t)a.shs & 15) == 0) &&
+                       (a.M * 3 >= sh_nvec(a.D) * 4);
+    switch (a.D) {
+        case 0: return launch_geo_t<0, true>(a, o, lay.scan_blocks, vec16, stream);
+        case 1: return launch_geo_t<1, true>(a, o, lay.scan_blocks, vec16, stream);
+        case 2: return launch_geo_t<2, true>(a, o, lay.scan_blocks, vec16, stream);
+        case 3: return launch_geo_t<3, true>(a, o, lay.scan_blocks, vec16, stream);
+        default: return SGS_ERR_BAD_SH_DEGREE;
+    }
+}
+
+// [upstream] rasterizer_impl.cu checkFrustum (markVisible)
+__global__ void mark_visible_kernel(int P, const float* means3D, const float* view, unsigned char* present) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float z = xform_row(view, 2, means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]);
+    present[i] = z > 0.2f;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
+                        cudaStream_t stream) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace sgs

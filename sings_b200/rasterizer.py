@@ -1,0 +1,297 @@
+"""Host side of the rasterizer: torch.autograd wrapper over the C ABI (include/sings_b200.h).
+
+Mirrors the Python surface of the reference's third-party rasterizer -- the classic
+`diff_gaussian_rasterization` API that SinGS is written against
+(/root/reference/sings/rec/renderer/gs_renderer_single.py:6-9, 69-95;
+gs_renderer_multiple.py:6-9, 95-121): `GaussianRasterizationSettings` with exactly those 12
+fields, `GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs | colors_precomp,
+scales + rotations | cov3D_precomp) -> (color (3,H,W), radii (P,))`, `markVisible`, and the
+gradient order `(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+cov3Ds_precomp, None)`.
+
+Differences by design (B200-first, results identical):
+  * the forward never blocks on a device->host copy to size buffers: the (tile, Gaussian)
+    pair list is written into a capacity-sized buffer; the pair count and an overflow flag
+    come back through pinned memory.  Default ("checked") mode waits for that flag once per
+    forward and transparently re-runs with a larger buffer if it overflowed; `set_async(True)`
+    defers the check to `check_pending()` / the next forward (no host sync at all).
+  * scratch is torch-owned (`torch.empty(uint8)`), sized by `sgs_raster_sizes`; the library
+    never allocates.
+  * alpha (= 1 - final transmittance) and expected depth are available from
+    `GaussianRasterizer.forward_aux(...)` without changing the 2-tuple contract.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_ASYNC = os.environ.get("SGS_ASYNC", "0") == "1"
+_cap_hint: dict = {}           # device index -> pair-list capacity learned from earlier frames
+_pinned: dict = {}             # device index -> (pinned int32 [slots,2], next slot)
+_pending: list = []            # async mode: (event, pinned row, L_cap) not yet checked
+_SLOTS = 256
+last_num_rendered = 0          # informational: pair count of the last checked forward
+
+
+def set_async(flag: bool) -> None:
+    """Async mode: forward() performs no host synchronisation; a pair-list overflow is raised
+    by check_pending() (called at the start of every forward) instead of being repaired."""
+    global _ASYNC
+    _ASYNC = bool(flag)
+
+
+def _pinned_row(dev: int):
+    buf, nxt = _pinned.get(dev, (None, 0))
+    if buf is None:
+        buf = torch.zeros(_SLOTS, 2, dtype=torch.int32).pin_memory()
+    _pinned[dev] = (buf, (nxt + 1) % _SLOTS)
+    return buf[nxt]
+
+
+def check_pending(block: bool = False) -> None:
+    """Async mode: examine finished forwards; raise if one overflowed its pair-list capacity."""
+    global last_num_rendered
+    keep = []
+    for ev, row, cap, dev in _pending:
+        if block:
+            ev.synchronize()
+        if ev.query():
+            L, ovf = int(row[0]), int(row[1])
+            last_num_rendered = L
+            _cap_hint[dev] = max(_cap_hint.get(dev, 0), int(L * 1.3) + 4096)
+            if ovf:
+                _pending.clear()
+                raise _lib.SgsError(
+                    f"rasterizer pair list overflowed (needed {L}, capacity {cap}) in async mode; "
+                    "the frame is incomplete. Capacity has been raised; re-render the frame.")
+        else:
+            keep.append((ev, row, cap, dev))
+    _pending[:] = keep
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool = False     # accepted for forward compatibility; must stay False
+
+
+def _f32c(t: Optional[torch.Tensor], name: str, dev) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != dev:
+        raise ValueError(f"{name} must live on {dev}, got {t.device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _sizes(P, W, H, L_cap):
+    s = [C.c_size_t() for _ in range(4)]
+    _lib.check(_lib.lib().sgs_raster_sizes(P, W, H, L_cap, *[C.byref(x) for x in s]), "sgs_raster_sizes")
+    return [int(x.value) for x in s]
+
+
+def layout_info(P, W, H, L_cap) -> dict:
+    """Offsets of the inspectable arrays inside the scratch buffers (parity tests)."""
+    info = (C.c_longlong * 16)()
+    _lib.check(_lib.lib().sgs_raster_layout_info(P, W, H, L_cap, info), "sgs_raster_layout_info")
+    keys = ["counters", "keys_unsorted", "vals_unsorted", "keys_sorted", "vals_sorted", "ranges",
+            "final_T", "n_contrib", "tiles", "end_bit", "passes", "rec_floats"]
+    return {k: int(info[i]) for i, k in enumerate(keys)}
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings, want_aux):
+        L_ = _lib.lib()
+        rs = raster_settings
+        if getattr(rs, "antialiasing", False):
+            raise NotImplementedError("antialiasing=True is not part of the classic API SinGS uses")
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise _lib.SgsError("sings_b200 rasterizer needs CUDA tensors (no CPU fallback)")
+        dev = means3D.device
+        P = means3D.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        m3 = _f32c(means3D, "means3D", dev)
+        if m3 is None:
+            m3 = torch.zeros(0, 3, device=dev)
+        shc = _f32c(sh, "shs", dev)
+        col = _f32c(colors_precomp, "colors_precomp", dev)
+        opa = _f32c(opacities, "opacities", dev)
+        sca = _f32c(scales, "scales", dev)
+        rot = _f32c(rotations, "rotations", dev)
+        cov = _f32c(cov3Ds_precomp, "cov3D_precomp", dev)
+        bg = _f32c(rs.bg, "bg", dev)
+        view = _f32c(rs.viewmatrix, "viewmatrix", dev)
+        proj = _f32c(rs.projmatrix, "projmatrix", dev)
+        campos = _f32c(rs.campos, "campos", dev)
+        M = shc.shape[1] if shc is not None else 0
+        D = int(rs.sh_degree)
+        if P > 0:
+            if (shc is None) == (col is None):
+                raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+            if (cov is None) == (sca is None or rot is None):
+                raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+            if opa is None or opa.numel() != P:
+                raise ValueError("opacities must have one value per Gaussian")
+        stream = torch.cuda.current_stream(dev)
+        di = dev.index if dev.index is not None else torch.cuda.current_device()
+        if _ASYNC:
+            check_pending()
+        L_cap = max(_cap_hint.get(di, 0), 4 * P, 1 << 16)
+        color = torch.empty(3, H, W, device=dev, dtype=torch.float32)
+        radii = torch.empty(P, device=dev, dtype=torch.int32)
+        alpha = torch.empty(H, W, device=dev, dtype=torch.float32) if want_aux else None
+        depth = torch.empty(H, W, device=dev, dtype=torch.float32) if want_aux else None
+        global last_num_rendered
+        while True:
+            gb, bb, ib, _ = _sizes(P, W, H, L_cap)
+            geom = torch.empty(gb, device=dev, dtype=torch.uint8)
+            binning = torch.empty(bb, device=dev, dtype=torch.uint8)
+            img = torch.empty(ib, device=dev, dtype=torch.uint8)
+            row = _pinned_row(di)
+            try:
+                rc = L_.sgs_raster_forward(
+                    P, D, M, W, H, _lib.ptr(bg), _lib.ptr(m3), _lib.ptr(col), _lib.ptr(opa),
+                    _lib.ptr(sca), float(rs.scale_modifier), _lib.ptr(rot), _lib.ptr(cov),
+                    _lib.ptr(view), _lib.ptr(proj), _lib.ptr(campos), float(rs.tanfovx),
+                    float(rs.tanfovy), _lib.ptr(shc), int(bool(rs.prefiltered)), L_cap,
+                    _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img), _lib.ptr(color),
+                    _lib.ptr(radii), _lib.ptr(alpha), _lib.ptr(depth), row.data_ptr(),
+                    stream.cuda_stream, int(bool(rs.debug)))
+                _lib.check(rc, "sgs_raster_forward")
+            except Exception:
+                if rs.debug:
+                    torch.save((means3D, sh, colors_precomp, opacities, scales, rotations,
+                                cov3Ds_precomp, tuple(rs)), "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            if _ASYNC:
+                _pending.append((ev, row, L_cap, di))
+                break
+            ev.synchronize()
+            L, ovf = int(row[0]), int(row[1])
+            last_num_rendered = L
+            _cap_hint[di] = max(_cap_hint.get(di, 0), int(L * 1.3) + 4096)
+            if not ovf:
+                break
+            L_cap = _cap_hint[di]
+        ctx.raster_settings = rs
+        ctx.L_cap = L_cap
+        ctx.dims = (P, D, M, W, H)
+        ctx.has = (shc is not None, col is not None, cov is not None)
+        ctx.opac_shape = tuple(opacities.shape) if opacities is not None else (P, 1)
+        ctx.save_for_backward(m3, shc, col, sca, rot, cov, radii, geom, binning, img, bg, view,
+                              proj, campos)
+        ctx.mark_non_differentiable(radii)
+        if want_aux:
+            ctx.mark_non_differentiable(alpha, depth)
+            return color, radii, alpha, depth
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, *_unused):
+        L_ = _lib.lib()
+        rs = ctx.raster_settings
+        P, D, M, W, H = ctx.dims
+        (m3, shc, col, sca, rot, cov, radii, geom, binning, img, bg, view, proj,
+         campos) = ctx.saved_tensors
+        dev = m3.device
+        g = grad_out_color
+        if g.dtype != torch.float32:
+            g = g.float()
+        g = g.contiguous()
+        stream = torch.cuda.current_stream(dev)
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        d_means3D, d_means2D, d_colors, d_opac = e(P, 3), e(P, 3), e(P, 3), e(P, 1)
+        d_cov = e(P, 6)
+        d_sh = e(P, M, 3) if shc is not None else None
+        d_scales, d_rots = e(P, 3), e(P, 4)
+        acc_bytes = _sizes(P, W, H, ctx.L_cap)[3]
+        acc = torch.empty(acc_bytes, device=dev, dtype=torch.uint8)
+        try:
+            rc = L_.sgs_raster_backward(
+                P, D, M, W, H, _lib.ptr(bg), _lib.ptr(m3), _lib.ptr(col), _lib.ptr(sca),
+                float(rs.scale_modifier), _lib.ptr(rot), _lib.ptr(cov), _lib.ptr(view),
+                _lib.ptr(proj), _lib.ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
+                _lib.ptr(shc), _lib.ptr(radii), _lib.ptr(g), ctx.L_cap, _lib.ptr(geom),
+                _lib.ptr(binning), _lib.ptr(img), _lib.ptr(acc), _lib.ptr(d_means3D),
+                _lib.ptr(d_means2D), _lib.ptr(d_colors), _lib.ptr(d_opac), _lib.ptr(d_cov),
+                _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), stream.cuda_stream,
+                int(bool(rs.debug)))
+            _lib.check(rc, "sgs_raster_backward")
+        except Exception:
+            if rs.debug:
+                torch.save((m3, radii, col, sca, rot, cov, g, shc, tuple(rs)), "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            raise
+        has_sh, has_col, has_cov = ctx.has
+        return (d_means3D, d_means2D, d_sh if has_sh else None, d_colors if has_col else None,
+                d_opac.reshape(ctx.opac_shape), None if has_cov else d_scales, None if has_cov else d_rots,
+                d_cov if has_cov else None, None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings, want_aux=False):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings, want_aux)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask of Gaussians in front of the near plane (view z > 0.2)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = positions.detach().float().contiguous()
+            view = rs.viewmatrix.float().contiguous()
+            out = torch.empty(pos.shape[0], device=pos.device, dtype=torch.uint8)
+            _lib.check(_lib.lib().sgs_mark_visible(
+                pos.shape[0], pos.data_ptr(), view.data_ptr(), out.data_ptr(),
+                torch.cuda.current_stream(pos.device).cuda_stream), "sgs_mark_visible")
+            return out.bool()
+
+    def _check(self, shs, colors_precomp, scales, rotations, cov3D_precomp):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        self._check(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, self.raster_settings, False)
+
+    def forward_aux(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                    rotations=None, cov3D_precomp=None):
+        """Like forward(), plus alpha (H,W) = 1 - final_T and depth (H,W) = sum alpha_i T_i z_i
+        (both non-differentiable)."""
+        self._check(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, self.raster_settings, True)
