@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- deformed-avatar fwd+bwd frames/s (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W               # this repo's CUDA path
+    torchrun ... bench.py --gpus N --steps K --warmup W         # one rank per GPU, views sharded
+    python bench.py --impl reference --steps K --warmup W       # CPU arm (oracle port)
+
+A step = one pass of the hot path over one synthetic frame: pose -> A -> LBS of every
+Gaussian -> rasterize (1024^2, SH degree 3) -> dL/dimage -> rasterizer backward -> LBS
+backward -> densification statistics (+ the gradient all-reduce when N > 1).
+Workload = BASELINE.json configs[1]: 200k Gaussians, J=24, random pose, synthetic data.
+
+`value`  : device-resident inputs, AvatarStep (sync-free launch sequence), CUDA events.
+`e2e`    : the public API (sings_b200.deform + diff_gaussian_rasterization autograd) with HOST
+           buffers: per step pose/transl/dL-dimage are copied from pinned memory and the loss
+           is read back, all inside the timed region.
+L2      : inputs rotate over a ring of distinct avatars larger than the 126 MB L2.
+Nothing here reads /root/reference.  The CPU arm / cpu_baseline time the oracle port
+(oracle/lbs_oracle.py + oracle/c/raster_oracle.c, OpenMP) -- the only use of oracle/ here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GAUSS, H_IMG, W_IMG, SH_DEG, N_JOINTS = 200_000, 1024, 1024, 3, 24
+RING = 4
+WORKLOAD = "single B200: LBS + rasterize fwd+bwd, 200k Gaussians, SH degree 3, 1024x1024 view, random pose"
+METRIC = "deformed-avatar fwd+bwd frames/s @200k Gaussians 1024^2"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_frame_inputs(seed: int, n=N_GAUSS, H=H_IMG, W=W_IMG, J=N_JOINTS):
+    """numpy inputs of one avatar + one frame."""
+    from sings_b200 import synthetic as syn
+    av = syn.make_avatar(n, J, seed=seed)
+    pose = syn.random_pose(J, seed=seed + 2)
+    transl = syn.default_transl(H)
+    view = syn.make_view(H, W)
+    rng = np.random.default_rng(seed + 3)
+    G = rng.normal(size=(3, H, W)).astype(np.float32)
+    bg = np.ones(3, np.float32)
+    return av, pose, transl, view, G, bg
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference torch LBS restated + C rasterizer), all host threads
+# ------------------------------------------------------------------------------------------
+def cpu_frame(av, pose, transl, view, G, bg, D=SH_DEG):
+    import torch
+    from oracle import lbs_oracle as lo
+    from oracle import raster_oracle as ro
+    t = torch.from_numpy
+    xyz_c = t(av.xyz_canon).requires_grad_(True)
+    sc_c = t(av.scales).requires_grad_(True)
+    rot_c = t(av.rotmat_canon).requires_grad_(True)
+    pose_t = t(pose)[None].clone().requires_grad_(True)
+    tr = t(transl)[None].clone().requires_grad_(True)
+    A = lo.pose_to_A(pose_t, t(av.rest), av.parents, t(av.inv_A_t2cano))
+    xyz, q, sc, _ = lo.deform(A, xyz_c, t(av.lbs_weights), sc_c, rot_c, None, tr)
+    cam = ro.Camera(W=view.image_width, H=view.image_height, tanfovx=view.tanfovx, tanfovy=view.tanfovy,
+                    view=view.world_view_transform.reshape(-1), proj=view.full_proj_transform.reshape(-1),
+                    campos=view.camera_center)
+    st = ro.forward(cam, xyz[0].detach().numpy(), av.opacity, bg, shs=av.shs,
+                    scales=sc[0].detach().numpy(), rotations=q[0].detach().numpy(), sh_degree=D)
+    gr = ro.backward(st, G)
+    torch.autograd.backward([xyz, q, sc], [t(gr["means3D"])[None], t(gr["rotations"])[None], t(gr["scales"])[None]])
+    return st.num_rendered, float((st.color * G).sum())
+
+
+def run_cpu(steps: int, warmup: int, frames):
+    import torch
+    from oracle import raster_oracle as ro
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ro.set_threads(cores)
+    for i in range(warmup):
+        cpu_frame(*frames[i % len(frames)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_frame(*frames[i % len(frames)])
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = [build_frame_inputs(100)]
+    steps, warmup = args.steps, args.warmup
+    # bound the run to a few minutes: probe one frame, then cap the step count
+    t0 = time.perf_counter()
+    cpu_frame(*frames[0])
+    t1 = time.perf_counter() - t0
+    budget = 150.0
+    steps_run = max(1, min(steps, int(budget / max(t1, 1e-3))))
+    warm_run = min(warmup, 1)
+    fps, ms, cores = run_cpu(steps_run, warm_run, frames)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps_run, "warmup": warm_run, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": [H_IMG, W_IMG],
+                   "sh_degree": SH_DEG, "joints": N_JOINTS},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps_run} full frames (LBS fwd+bwd via the torch restatement of the "
+                                   f"reference's lbs_extra/rotations, rasterizer fwd+bwd via the OpenMP C oracle); "
+                                   f"the reference has no CPU rasterizer and its CUDA one is not vendored"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(N, J, M, L, W, H, n_vis, passes=6):
+    """Per-launch algorithmic bytes of each stage (DESIGN.md 'Algorithmic bytes')."""
+    pix, tiles = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    return {
+        "lbs_fwd": N * (100 + 4 * J),
+        "lbs_bwd": N * (148 + 4 * J),
+        "geometry": N * (236 + 75) + 8 * N + 20 * N + 12 * L,      # preprocess + scan + duplicateWithKeys
+        "sort": (8 + 24 * passes) * L,
+        "ranges": 8 * L + 8 * tiles,
+        "blend_fwd": 40 * L + 20 * pix + 8 * tiles,
+        "blend_bwd": 40 * L + 20 * pix + 36 * n_vis,
+        "geometry_bwd": (300 + 256) * n_vis,
+    }
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from sings_b200 import dp
+    from sings_b200.step import AvatarStep, FrameInputs
+
+    rank, local, world = dp.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    hbm_peak, peak_src = peaks()
+
+    # ---- workload: ring of distinct avatars (inputs larger than L2), each rank its own views
+    sets = []
+    for r in range(RING):
+        av, pose, transl, view, G, bg = build_frame_inputs(1000 * rank + 10 * r)
+        t = lambda a: torch.as_tensor(a, device=dev)
+        step = AvatarStep(t(av.xyz_canon), t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs),
+                          t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano),
+                          H_IMG, W_IMG, SH_DEG, timing=True)
+        fr = FrameInputs(pose=t(pose), transl=t(transl), viewmatrix=t(view.world_view_transform),
+                         projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(bg),
+                         tanfovx=view.tanfovx, tanfovy=view.tanfovy)
+        sets.append(dict(step=step, fr=fr, G=t(G), av=av, pose=pose, transl=transl, view=view, G_np=G, bg=bg))
+    exch = dp.GradExchange(N_GAUSS, sets[0]["step"].n_param_grads, dev) if world > 1 else None
+
+    def one_step(i, pending):
+        s = sets[i % RING]
+        st = s["step"]
+        if exch is not None and pending[i % RING] is not None:
+            pending[i % RING]()            # finish the all-reduce that last used this bucket
+            pending[i % RING] = None
+            st.grad_accum.zero_(); st.denom.zero_(); st.max_radii2D.zero_()
+        st.forward(s["fr"])
+        st.backward(s["G"])
+        if exch is not None:
+            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pending = [None] * RING
+    from sings_b200._lib import SgsError
+    for attempt in range(4):
+        for i in range(max(args.warmup, 3, RING)):
+            one_step(i, pending)
+        torch.cuda.synchronize()
+        try:
+            for s in sets:
+                s["L"] = s["step"].check_capacity()
+            break
+        except SgsError:          # pair list capacity grown; warm up again with the larger buffers
+            for s in sets:
+                try:
+                    s["step"].check_capacity()
+                except SgsError:
+                    pass
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i, pending)
+    for i in range(RING):
+        if pending[i] is not None:
+            pending[i]()
+            pending[i] = None
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    for s in sets:
+        s["step"].check_capacity()
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---- per-stage device times (CUDA events recorded inside the timed loop) ----
+    stage = {}
+    for s in sets:
+        for k, v in s["step"].stage_ms().items():
+            stage.setdefault(k, []).append(v)
+    stage = {k: float(np.mean(v)) for k, v in stage.items()}
+    Lm = float(np.mean([s["L"] for s in sets]))
+    n_vis = float(np.mean([int((s["step"].radii > 0).sum().item()) for s in sets]))
+    ab = algorithmic_bytes(N_GAUSS, N_JOINTS, 16, Lm, W_IMG, H_IMG, n_vis)
+    stages_out = {}
+    for k, b in ab.items():
+        ms = stage.get(k)
+        if ms and ms > 0:
+            gbs = b / (ms * 1e-3) / 1e9
+            stages_out[k] = {"ms": round(ms, 4), "alg_mb": round(b / 1e6, 2), "gbs": round(gbs, 1),
+                             "frac": round(gbs / hbm_peak, 4)}
+    dom = max((k for k in stages_out), key=lambda k: stages_out[k]["ms"])
+    hot = ["lbs_fwd", "geometry", "sort", "ranges"]
+    hot_b = sum(ab[k] for k in hot)
+    hot_ms = sum(stage[k] for k in hot)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": stages_out[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+        "frac": stages_out[dom]["frac"], "traffic": None, "peak_source": peak_src,
+        "stages": stages_out,
+        "lbs_preprocess_sort": {"alg_mb": round(hot_b / 1e6, 2), "ms": round(hot_ms, 4),
+                                "gbs": round(hot_b / (hot_ms * 1e-3) / 1e9, 1),
+                                "frac": round(hot_b / (hot_ms * 1e-3) / 1e9 / hbm_peak, 4)},
+        "frame_alg_mb": round(sum(ab.values()) / 1e6, 1),
+        "pairs_L": Lm, "visible": n_vis,
+    }
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, sets, dev, world, rank)
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        s = sets[0]
+        frames = [(s["av"], s["pose"], s["transl"], s["view"], s["G_np"], s["bg"])]
+        n_cpu = 2
+        fps, ms, cores = run_cpu(n_cpu, 1, frames)
+        cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                    "sample": f"{n_cpu} full frames of the same workload on the host (torch restatement of the "
+                              f"reference LBS + OpenMP C rasterizer oracle, fwd+bwd)"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": [H_IMG, W_IMG], "sh_degree": SH_DEG,
+                       "joints": N_JOINTS, "views_per_gpu_per_step": 1,
+                       "l2": f"inputs rotate over a ring of {RING} distinct avatars (~{RING * 70} MB of inputs) > 126 MB L2",
+                       "parallelism": f"dp{world} (views sharded, gradient bucket all-reduced)" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": 16 * args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, sets, dev, world, rank):
+    """Same metric through the public API with host buffers (pinned), per step:
+    H2D pose + transl + dL/dimage, forward, backward, D2H loss."""
+    import torch
+    import torch.distributed as dist
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from sings_b200 import deform
+
+    host = []
+    for s in sets:
+        av = s["av"]
+        t = lambda a: torch.as_tensor(a, device=dev)
+        params = dict(xyz=t(av.xyz_canon).requires_grad_(True), rot=t(av.rotmat_canon).requires_grad_(True),
+                      scales=t(av.scales).requires_grad_(True), opacity=t(av.opacity).requires_grad_(True),
+                      shs=t(av.shs).requires_grad_(True), W=t(av.lbs_weights), rest=t(av.rest),
+                      parents=torch.from_numpy(av.parents), inv_A=t(av.inv_A_t2cano))
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        host.append(dict(p=params, pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]),
+                         view=s["view"], bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
+                         pm=t(s["view"].full_proj_transform), cp=t(s["view"].camera_center)))
+    h2d = int(host[0]["pose"].numel() * 4 + host[0]["transl"].numel() * 4 + host[0]["G"].numel() * 4)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(i):
+        hs = host[i % RING]
+        p = hs["p"]
+        pose = hs["pose"].to(dev, non_blocking=True).requires_grad_(True)
+        transl = hs["transl"].to(dev, non_blocking=True).requires_grad_(True)
+        G = hs["G"].to(dev, non_blocking=True)
+        A = deform.pose_to_A(pose, p["rest"], p["parents"], p["inv_A"])
+        xyz, rotq, sc = deform.deform_gaussians(A, p["xyz"], p["W"], p["rot"], p["scales"], None, transl)
+        v = hs["view"]
+        rs = GaussianRasterizationSettings(
+            image_height=v.image_height, image_width=v.image_width, tanfovx=v.tanfovx, tanfovy=v.tanfovy,
+            bg=hs["bg"], scale_modifier=1.0, viewmatrix=hs["vm"], projmatrix=hs["pm"], sh_degree=SH_DEG,
+            campos=hs["cp"], prefiltered=False, debug=False)
+        means2D = torch.zeros_like(xyz, requires_grad=True)
+        img, radii = GaussianRasterizer(rs)(means3D=xyz, means2D=means2D, shs=p["shs"], opacities=p["opacity"],
+                                            scales=sc, rotations=rotq)
+        loss = (img * G).sum()
+        for q in (p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"]):
+            q.grad = None
+        loss.backward()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    n = max(10, min(args.steps, 200))
+    for i in range(3):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"value": world * n / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 4, "steps": n, "ms_per_step": ms / n,
+            "api": "sings_b200.deform.pose_to_A + deform_gaussians + diff_gaussian_rasterization.GaussianRasterizer (autograd)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

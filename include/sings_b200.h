@@ -36,6 +36,17 @@ typedef void* sgs_stream_t; /* cudaStream_t */
 int sgs_version(void);
 const char* sgs_error_string(int code);
 
+/* Stage timing (measurement only).  A timing handle owns n CUDA events; the rasterizer entry
+ * points record them at stage boundaries when given a handle (null = no recording):
+ *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit), [2] after the radix
+ *             sort, [3] after tile ranges, [4] after the blend;
+ *   backward: [5] start, [6] after the blend backward (incl. accumulator memset), [7] end.
+ * sgs_timing_elapsed_ms waits for event j and returns the time from event i to event j. */
+int sgs_timing_create(int n_events, void** handle);
+int sgs_timing_destroy(void* handle);
+int sgs_timing_record(void* handle, int i, sgs_stream_t stream);
+int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms);
+
 /* ---------------------------------------------------------------------------------------
  * Rasterizer.  Replaces the pybind extension `diff_gaussian_rasterization._C`
  * (rasterize_gaussians / rasterize_gaussians_backward / mark_visible) that
@@ -71,7 +82,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
                        float tanfovx, float tanfovy, const float* shs, int prefiltered,
                        long long L_cap, void* geom, void* binning, void* img, float* out_color,
                        int* radii, float* out_alpha, float* out_depth, int* host_counters,
-                       sgs_stream_t stream, int debug);
+                       sgs_stream_t stream, int debug, void* timing);
 
 /* Backward: replaces _C.rasterize_gaussians_backward ([upstream] Rasterizer::backward).
  * geom/binning/img are the buffers the forward filled; acc is scratch (acc_bytes).  All
@@ -87,11 +98,20 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
                         const void* binning, const void* img, void* acc, float* dL_dmeans3D,
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
-                        sgs_stream_t stream, int debug);
+                        sgs_stream_t stream, int debug, void* timing);
 
 /* Replaces _C.mark_visible ([upstream] Rasterizer::markVisible). present: (P) bytes. */
 int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      unsigned char* present, sgs_stream_t stream);
+
+/* Densification statistics of one rendered view, in place.  Replaces
+ * sings/rec/models/sings_hybrid.py:1013-1015 (add_densification_stats) and
+ * sings/rec/trainer/gs_trainer.py:487-490: for Gaussians with radii > 0,
+ * xyz_gradient_accum += ||grad_means2D[:, :2]||, denom += 1, max_radii2D = max(., radii).
+ * grad_means2D (P,3); radii (P) int32; the three outputs (P) float32. */
+int sgs_densify_stats(int P, const float* grad_means2D, const int* radii,
+                      float* xyz_gradient_accum, float* denom, float* max_radii2D,
+                      sgs_stream_t stream);
 
 /* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
  * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]

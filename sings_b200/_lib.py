@@ -20,15 +20,20 @@ _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 _SIGNATURES = {
     "sgs_version": (C.c_int, []),
     "sgs_error_string": (C.c_char_p, [_i]),
+    "sgs_timing_create": (_i, [_i, C.POINTER(_vp)]),
+    "sgs_timing_destroy": (_i, [_vp]),
+    "sgs_timing_record": (_i, [_vp, _i, _vp]),
+    "sgs_timing_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_f)]),
     "sgs_raster_sizes": (_i, [_i, _i, _i, _ll, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "sgs_raster_layout_info": (_i, [_i, _i, _i, _ll, C.POINTER(_ll)]),
     "sgs_raster_forward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                                 _vp, _f, _f, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _i]),
+                                _vp, _i, _vp]),
     "sgs_raster_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
                                  _f, _f, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _vp, _i]),
+                                 _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgs_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp]),
+    "sgs_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_sort_scratch_bytes": (_sz, [_ll]),
     "sgs_sort_pairs_u64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _ll, _i, C.POINTER(_i), _vp]),
     "sgs_pose_to_A": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -6,9 +6,50 @@
 
 using namespace sgs;
 
+struct Timing {
+    int n;
+    cudaEvent_t* ev;
+};
+static inline void tick(void* timing, int i, cudaStream_t s) {
+    if (!timing) return;
+    Timing* t = (Timing*)timing;
+    if (i < t->n) cudaEventRecord(t->ev[i], s);
+}
+
 extern "C" {
 
 int sgs_version(void) { return 100; }
+
+int sgs_timing_create(int n_events, void** handle) {
+    if (n_events < 1 || !handle) return SGS_ERR_BAD_ARG;
+    Timing* t = new Timing;
+    t->n = n_events;
+    t->ev = new cudaEvent_t[n_events];
+    for (int i = 0; i < n_events; i++) SGS_CUDA_OK(cudaEventCreate(&t->ev[i]));
+    *handle = t;
+    return 0;
+}
+int sgs_timing_destroy(void* handle) {
+    if (!handle) return 0;
+    Timing* t = (Timing*)handle;
+    for (int i = 0; i < t->n; i++) cudaEventDestroy(t->ev[i]);
+    delete[] t->ev;
+    delete t;
+    return 0;
+}
+int sgs_timing_record(void* handle, int i, sgs_stream_t stream) {
+    if (!handle || i < 0 || i >= ((Timing*)handle)->n) return SGS_ERR_BAD_ARG;
+    SGS_CUDA_OK(cudaEventRecord(((Timing*)handle)->ev[i], (cudaStream_t)stream));
+    return 0;
+}
+int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms) {
+    if (!handle || !ms) return SGS_ERR_BAD_ARG;
+    Timing* t = (Timing*)handle;
+    if (i < 0 || j < 0 || i >= t->n || j >= t->n) return SGS_ERR_BAD_ARG;
+    SGS_CUDA_OK(cudaEventSynchronize(t->ev[j]));
+    SGS_CUDA_OK(cudaEventElapsedTime(ms, t->ev[i], t->ev[j]));
+    return 0;
+}
 
 const char* sgs_error_string(int code) {
     switch (code) {
@@ -82,7 +123,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
                        float tanfovx, float tanfovy, const float* shs, int prefiltered,
                        long long L_cap, void* geom, void* binning, void* img, float* out_color,
                        int* radii, float* out_alpha, float* out_depth, int* host_counters,
-                       sgs_stream_t stream_, int debug) {
+                       sgs_stream_t stream_, int debug, void* timing) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GeomArgs a;
     int rc = fill_geom_args(a, P, D, M, W, H, means3D, colors_precomp, opacities, scales,
@@ -95,18 +136,25 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (((uintptr_t)geom & 15) || ((uintptr_t)binning & 15) || ((uintptr_t)img & 15)) return SGS_ERR_MISALIGNED;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     char* g = (char*)geom; char* b = (char*)binning; char* im = (char*)img;
+    tick(timing, 0, stream);
     rc = launch_geometry(a, lay, L_cap, radii, g, b, stream);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    tick(timing, 1, stream);
     if (P > 0) {
         rc = launch_radix_sort(lay, L_cap, b, stream, debug);
         if (rc) return rc;
+        tick(timing, 2, stream);
         rc = launch_tile_ranges(lay, L_cap, b, stream);
         if (rc) return rc;
         if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    } else {
+        tick(timing, 2, stream);
     }
+    tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
     if (rc) return rc;
+    tick(timing, 4, stream);
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     if (host_counters)
         SGS_CUDA_OK(cudaMemcpyAsync(host_counters, b + lay.cnt_off, 2 * sizeof(int),
@@ -123,7 +171,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
                         const void* binning, const void* img, void* acc, float* dL_dmeans3D,
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
-                        sgs_stream_t stream_, int debug) {
+                        sgs_stream_t stream_, int debug, void* timing) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GeomBwdArgs b;
     int rc = fill_geom_args(b.fwd, P, D, M, W, H, means3D, colors_precomp, nullptr, scales,
@@ -136,17 +184,20 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     if (((uintptr_t)acc & 15) || (dL_drots && ((uintptr_t)dL_drots & 15))) return SGS_ERR_MISALIGNED;
     if (P == 0) return 0;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
+    tick(timing, 5, stream);
     SGS_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * 4, stream));
     rc = launch_blend_bwd(lay, W, H, (const char*)geom, (const char*)binning, (const char*)img, bg,
                           dL_dout_color, (float*)acc, stream);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    tick(timing, 6, stream);
     b.radii = radii; b.acc = (const float*)acc;
     b.dL_dmeans3D = dL_dmeans3D; b.dL_dmeans2D = dL_dmeans2D; b.dL_dcolors = dL_dcolors;
     b.dL_dopacity = dL_dopacity; b.dL_dcov3D = dL_dcov3D; b.dL_dsh = dL_dsh;
     b.dL_dscales = dL_dscales; b.dL_drots = dL_drots;
     rc = launch_geometry_bwd(b, (const char*)geom, stream);
     if (rc) return rc;
+    tick(timing, 7, stream);
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     return 0;
 }
@@ -155,6 +206,14 @@ int sgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      unsigned char* present, sgs_stream_t stream) {
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return SGS_ERR_BAD_ARG;
     return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int sgs_densify_stats(int P, const float* grad_means2D, const int* radii, float* xyz_gradient_accum,
+                      float* denom, float* max_radii2D, sgs_stream_t stream) {
+    if (P < 0 || (P > 0 && (!grad_means2D || !radii || !xyz_gradient_accum || !denom || !max_radii2D)))
+        return SGS_ERR_BAD_ARG;
+    return launch_densify_stats(P, grad_means2D, radii, xyz_gradient_accum, denom, max_radii2D,
+                                (cudaStream_t)stream);
 }
 
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }

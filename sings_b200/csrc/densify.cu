@@ -1,0 +1,37 @@
+// densify.cu -- densification statistics of one rendered view, fused into one kernel.
+//
+// Replaces the torch ops of
+//   /root/reference/sings/rec/models/sings_hybrid.py:1013-1015 (add_densification_stats):
+//       xyz_gradient_accum[vis] += ||viewspace_points.grad[vis, :2]||_2 ;  denom[vis] += 1
+//   /root/reference/sings/rec/trainer/gs_trainer.py:487-490:
+//       max_radii2D[vis] = max(max_radii2D[vis], radii[vis])          with vis = radii > 0
+// These three per-Gaussian arrays are the data-parallel all-reduce payload besides the
+// parameter gradients (SUM for the first two, MAX for the third).  The norm is
+// taken per view BEFORE any cross-replica sum, as the reference does per step.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sgs {
+
+__global__ void densify_stats_kernel(int P, const float* __restrict__ grad2d, const int* __restrict__ radii,
+                                     float* __restrict__ accum, float* __restrict__ denom,
+                                     float* __restrict__ max_radii) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int r = radii[i];
+    if (r <= 0) return;
+    const float gx = grad2d[3 * (size_t)i], gy = grad2d[3 * (size_t)i + 1];
+    accum[i] += sqrtf(gx * gx + gy * gy);
+    denom[i] += 1.0f;
+    max_radii[i] = fmaxf(max_radii[i], (float)r);
+}
+
+int launch_densify_stats(int P, const float* grad2d, const int* radii, float* accum, float* denom,
+                         float* max_radii, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, grad2d, radii, accum, denom, max_radii);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace sgs

@@ -93,4 +93,7 @@ int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t str
 int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
                         cudaStream_t stream);
 
+int launch_densify_stats(int P, const float* grad2d, const int* radii, float* accum, float* denom,
+                         float* max_radii, cudaStream_t stream);
+
 }  // namespace sgs

@@ -1,0 +1,107 @@
+"""Data-parallel sharding of views / frames and the one exchange step of the hot path.
+
+The reference is single-process (no distributed code at all; one view per
+step, /root/reference/sings/rec/trainer/gs_trainer.py:214-244; frames independent in
+animate_chunk, :681-719).  A frame is an independent unit of work given replicated canonical
+Gaussians, so the path shards naturally:
+
+  * training step: view v -> rank v mod R; every rank runs the full hot path on its views;
+    ONE all-reduce(SUM) of the flat gradient bucket (canonical-parameter gradients +
+    this step's `xyz_gradient_accum` / `denom` increments, whose norms were taken per view
+    before the sum -- sings_hybrid.py:1013-1015) and ONE all-reduce(MAX) of `max_radii2D`
+    (gs_trainer.py:487-490);
+  * animation: contiguous frame ranges per rank, no collective per frame.
+
+One process per GPU, torch.distributed (NCCL over NVLink on the B200 box, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Training views of this rank: v with v mod world == rank."""
+    return list(range(rank, n_views, world))
+
+
+def shard_frames(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous animation frame range [lo, hi) of this rank (sizes differ by at most 1)."""
+    base, rem = divmod(n_frames, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradExchange:
+    """Owns the persistent densification statistics and performs the per-step exchange.
+
+    bucket: flat float32 tensor [param grads (n_param_grads) | accum increment (N) | denom
+    increment (N)]; max_radii: (N) this step's per-rank maximum screen radius.
+    """
+
+    def __init__(self, n_gaussians: int, n_param_grads: int, device, group=None,
+                 average_grads: bool = False):
+        self.N = n_gaussians
+        self.n_param_grads = n_param_grads
+        self.group = group
+        self.average = average_grads
+        z = lambda: torch.zeros(n_gaussians, device=device, dtype=torch.float32)
+        self.xyz_gradient_accum, self.denom, self.max_radii2D = z(), z(), z()
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def exchange(self, bucket: torch.Tensor, max_radii: torch.Tensor, async_op: bool = False):
+        """All-reduce one step's bucket (SUM) and radii (MAX) in place and fold the statistics
+        into the persistent accumulators.  With async_op=True returns a finish() callable so
+        the exchange overlaps whatever the caller launches next."""
+        handles = []
+        if self.world > 1:
+            handles.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            handles.append(dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
+
+        def finish():
+            for h in handles:
+                h.wait()
+            n = self.n_param_grads
+            if self.average and self.world > 1:
+                bucket[:n].div_(self.world)
+            self.xyz_gradient_accum += bucket[n:n + self.N]
+            self.denom += bucket[n + self.N:n + 2 * self.N]
+            torch.maximum(self.max_radii2D, max_radii, out=self.max_radii2D)
+            return bucket[:n]
+
+        return finish if async_op else finish()
+
+    def reset(self):
+        self.xyz_gradient_accum.zero_()
+        self.denom.zero_()
+        self.max_radii2D.zero_()
+
+
+def broadcast_parameters(tensors: Sequence[torch.Tensor], src: int = 0, group=None) -> None:
+    """Replicate the canonical Gaussians (and skinning weights) from rank `src`."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world) from the torchrun environment; initialises the default group
+    when WORLD_SIZE > 1 (backend nccl on CUDA, gloo otherwise)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world

@@ -177,7 +177,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovy), _lib.ptr(shc), int(bool(rs.prefiltered)), L_cap,
                     _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img), _lib.ptr(color),
                     _lib.ptr(radii), _lib.ptr(alpha), _lib.ptr(depth), row.data_ptr(),
-                    stream.cuda_stream, int(bool(rs.debug)))
+                    stream.cuda_stream, int(bool(rs.debug)), None)
                 _lib.check(rc, "sgs_raster_forward")
             except Exception:
                 if rs.debug:
@@ -239,7 +239,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _lib.ptr(binning), _lib.ptr(img), _lib.ptr(acc), _lib.ptr(d_means3D),
                 _lib.ptr(d_means2D), _lib.ptr(d_colors), _lib.ptr(d_opac), _lib.ptr(d_cov),
                 _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), stream.cuda_stream,
-                int(bool(rs.debug)))
+                int(bool(rs.debug)), None)
             _lib.check(rc, "sgs_raster_backward")
         except Exception:
             if rs.debug:

@@ -1,0 +1,197 @@
+"""AvatarStep -- the whole per-frame hot path (pose -> A -> LBS -> rasterize -> backward ->
+LBS backward -> densification statistics) as one preallocated, sync-free launch sequence.
+
+This is the fused fast path behind the two drop-in boundaries (`diff_gaussian_rasterization`
+and `sings_b200.deform`): same kernels, same results, but without per-call tensor allocation
+and autograd bookkeeping.  It corresponds to one iteration of the reference's hot loop between
+`human_gs.forward` and `loss.backward()` (/root/reference/sings/rec/trainer/gs_trainer.py:
+229-244, 400; sings_hybrid.py:398-428; gs_renderer_single.py:45-107) plus the statistics of
+gs_trainer.py:486-492.
+
+All canonical-parameter gradients land in ONE flat float32 bucket
+    [ d_xyz_canon (N,3) | d_scales (N,3) | d_rotmat_canon (N,9) | d_opacity (N) | d_shs (N,M,3)
+      | xyz_gradient_accum (N) | denom (N) ]
+so the data-parallel exchange is a single SUM all-reduce of the bucket and a MAX all-reduce
+of `max_radii2D` (sings_b200/dp.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rasterizer import _sizes
+
+
+@dataclass
+class FrameInputs:
+    """Per-frame inputs on the device (the reference's data dict)."""
+    pose: torch.Tensor          # (J,3) axis-angle (joint 0 = global orientation)
+    transl: torch.Tensor        # (3,)
+    viewmatrix: torch.Tensor    # (4,4) W2C^T
+    projmatrix: torch.Tensor    # (4,4) full projection
+    campos: torch.Tensor        # (3,)
+    bg: torch.Tensor            # (3,)
+    tanfovx: float
+    tanfovy: float
+    smpl_scale: Optional[torch.Tensor] = None   # (1,)
+
+
+class AvatarStep:
+    def __init__(self, xyz_canon, rotmat_canon, scales, opacity, shs, lbs_weights, rest_joints,
+                 parents, inv_A_t2cano, H: int, W: int, sh_degree: int, pair_capacity: int = 0,
+                 timing: bool = False):
+        dev = xyz_canon.device
+        if dev.type != "cuda":
+            raise _lib.SgsError("AvatarStep needs CUDA tensors (no CPU fallback)")
+        self.L = _lib.lib()
+        self.dev = dev
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        self.xyz_canon, self.rot_canon, self.scales = f(xyz_canon), f(rotmat_canon), f(scales)
+        self.opacity, self.shs, self.W_lbs = f(opacity), f(shs), f(lbs_weights)
+        self.rest, self.inv_A = f(rest_joints), f(inv_A_t2cano)
+        self.parents = parents.to(device=dev, dtype=torch.int32).contiguous()
+        self.N, self.J = self.xyz_canon.shape[0], self.W_lbs.shape[1]
+        self.M = self.shs.shape[1]
+        self.H, self.Wd, self.D = int(H), int(W), int(sh_degree)
+        N, J, M = self.N, self.J, self.M
+        e = lambda *s, dt=torch.float32: torch.empty(*s, device=dev, dtype=dt)
+        # forward intermediates
+        self.A = e(1, J, 4, 4)
+        self.G = e(1, J, 12)
+        self.xyz, self.rotq, self.sc = e(1, N, 3), e(1, N, 4), e(1, N, 3)
+        self.color = e(3, H, W)
+        self.radii = e(N, dt=torch.int32)
+        self.L_cap = int(pair_capacity) if pair_capacity else max(8 * N, 1 << 16)
+        self._alloc_scratch()
+        self.counters = torch.zeros(2, dtype=torch.int32).pin_memory()
+        # backward intermediates (rasterizer boundary gradients)
+        self.g_means3D, self.g_means2D, self.g_colors = e(N, 3), e(N, 3), e(N, 3)
+        self.g_cov = e(N, 6)
+        self.g_scales_r, self.g_rots = e(N, 3), e(N, 4)
+        # flat gradient bucket (see module docstring)
+        self.n_rot = 9 if self.rot_canon is not None else 0
+        sizes = [3 * N, 3 * N, self.n_rot * N, N, 3 * M * N, N, N]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        self.bucket = torch.zeros(int(offs[-1]), device=dev, dtype=torch.float32)
+        v = lambda i, *shape: self.bucket[int(offs[i]):int(offs[i + 1])].view(*shape)
+        self.d_xyz_canon, self.d_scales = v(0, N, 3), v(1, N, 3)
+        self.d_rot_canon = v(2, N, 3, 3) if self.n_rot else None
+        self.d_opacity, self.d_shs = v(3, N, 1), v(4, N, M, 3)
+        self.grad_accum, self.denom = v(5, N), v(6, N)
+        self.n_param_grads = int(offs[5])
+        self.max_radii2D = torch.zeros(N, device=dev, dtype=torch.float32)
+        # small per-frame gradients
+        self.d_A = torch.zeros(1, J, 4, 4, device=dev)
+        self.d_transl = torch.zeros(1, 3, device=dev)
+        self.d_pose = e(1, J, 3)
+        self.timing = None
+        if timing:
+            h = C.c_void_p()
+            _lib.check(self.L.sgs_timing_create(16, C.byref(h)), "sgs_timing_create")
+            self.timing = h
+
+    def _alloc_scratch(self):
+        gb, bb, ib, ab = _sizes(self.N, self.Wd, self.H, self.L_cap)
+        e = lambda n: torch.empty(n, device=self.dev, dtype=torch.uint8)
+        self.geom, self.binning, self.img, self.acc = e(gb), e(bb), e(ib), e(ab)
+
+    # ---------------------------------------------------------------------------------
+    def forward(self, fr: FrameInputs, stream=None):
+        """pose -> A -> LBS -> rasterize.  Returns the (3,H,W) image (a persistent buffer)."""
+        L_, p = self.L, _lib.ptr
+        st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        self._fr = fr
+        pose = fr.pose.reshape(1, self.J, 3)
+        tm = self.timing
+        if tm:
+            L_.sgs_timing_record(tm, 8, st)
+        _lib.check(L_.sgs_pose_to_A(p(pose), p(self.rest), p(self.parents), p(self.inv_A), 1, self.J,
+                                    p(self.A), p(self.G), st), "sgs_pose_to_A")
+        _lib.check(L_.sgs_lbs_fwd(1, self.N, self.J, p(self.A), p(self.xyz_canon), p(self.W_lbs),
+                                  p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
+                                  None, None, None, p(self.xyz), p(self.rotq), p(self.sc), None, st),
+                   "sgs_lbs_fwd")
+        if tm:
+            L_.sgs_timing_record(tm, 9, st)
+        _lib.check(L_.sgs_raster_forward(
+            self.N, self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.xyz), None, p(self.opacity),
+            p(self.sc), 1.0, p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos),
+            float(fr.tanfovx), float(fr.tanfovy), p(self.shs), 0, self.L_cap, p(self.geom),
+            p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
+            self.counters.data_ptr(), st, 0, tm), "sgs_raster_forward")
+        return self.color
+
+    def backward(self, dL_dimage: torch.Tensor, stream=None, stats: bool = True):
+        """Backward of forward() for dL/d(image) (3,H,W); fills the gradient bucket, d_pose,
+        d_transl and (stats=True) accumulates the densification statistics of this view."""
+        L_, p = self.L, _lib.ptr
+        st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        fr = self._fr
+        tm = self.timing
+        _lib.check(L_.sgs_raster_backward(
+            self.N, self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.xyz), None, p(self.sc), 1.0,
+            p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos), float(fr.tanfovx),
+            float(fr.tanfovy), p(self.shs), p(self.radii), p(dL_dimage), self.L_cap, p(self.geom),
+            p(self.binning), p(self.img), p(self.acc), p(self.g_means3D), p(self.g_means2D),
+            p(self.g_colors), p(self.d_opacity), p(self.g_cov), p(self.d_shs), p(self.g_scales_r),
+            p(self.g_rots), st, 0, tm), "sgs_raster_backward")
+        if tm:
+            L_.sgs_timing_record(tm, 10, st)
+        self.d_A.zero_()
+        self.d_transl.zero_()
+        pose = fr.pose.reshape(1, self.J, 3)
+        _lib.check(L_.sgs_lbs_bwd(1, self.N, self.J, p(self.A), p(self.xyz_canon), p(self.W_lbs),
+                                  p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
+                                  None, None, None, p(self.g_means3D), p(self.g_rots),
+                                  p(self.g_scales_r), None, p(self.d_xyz_canon), p(self.d_rot_canon),
+                                  p(self.d_scales), p(self.d_A), None, p(self.d_transl), st),
+                   "sgs_lbs_bwd")
+        _lib.check(L_.sgs_pose_to_A_bwd(p(pose), p(self.rest), p(self.parents), p(self.inv_A),
+                                        p(self.G), p(self.d_A), 1, self.J, p(self.d_pose), st),
+                   "sgs_pose_to_A_bwd")
+        if stats:
+            _lib.check(L_.sgs_densify_stats(self.N, p(self.g_means2D), p(self.radii),
+                                            p(self.grad_accum), p(self.denom), p(self.max_radii2D), st),
+                       "sgs_densify_stats")
+        if tm:
+            L_.sgs_timing_record(tm, 11, st)
+
+    def reset_stats(self):
+        self.grad_accum.zero_()
+        self.denom.zero_()
+        self.max_radii2D.zero_()
+
+    def check_capacity(self) -> int:
+        """After a synchronisation: (num_rendered); grows the pair list and raises if the last
+        forward overflowed (the frame must then be re-rendered)."""
+        L, ovf = int(self.counters[0]), int(self.counters[1])
+        if ovf:
+            self.L_cap = int(L * 1.3) + 4096
+            self._alloc_scratch()
+            raise _lib.SgsError(f"pair list overflowed (needed {L}); capacity raised to {self.L_cap}, re-render")
+        return L
+
+    def stage_ms(self) -> dict:
+        """Per-stage device times of the last forward+backward (needs timing=True)."""
+        if not self.timing:
+            raise _lib.SgsError("AvatarStep(timing=True) required")
+        out = {}
+        ms = C.c_float()
+        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("sort", 1, 2), ("ranges", 2, 3),
+                           ("blend_fwd", 3, 4), ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7),
+                           ("lbs_bwd", 10, 11), ("total", 8, 11)]:
+            _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
+            out[name] = float(ms.value)
+        return out
+
+    def __del__(self):
+        try:
+            if self.timing:
+                self.L.sgs_timing_destroy(self.timing)
+        except Exception:
+            pass

@@ -1,0 +1,131 @@
+"""GPU: drop-in integration.  The reference's renderer shim
+(/root/reference/sings/rec/renderer/gs_renderer_single.py:12-107) is restated here call for
+call (the GPU box has no /root/reference) and driven with the same `data` / `human_gs_out`
+dicts SinGS builds; plus AvatarStep (the fused fast path) against the autograd path."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_scene, oracle_camera, rel_err
+from oracle import raster_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_style_render(means3D, feats, opacity, scales, rotations, data, scaling_modifier=1.0,
+                           bg_color=None, active_sh_degree=0):
+    """The body of the reference's render(): same statements, same keyword names."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    if bg_color is None:
+        bg_color = torch.zeros(3, dtype=torch.float32, device="cuda")
+    screenspace_points = torch.zeros_like(means3D, dtype=means3D.dtype, requires_grad=True, device="cuda") + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    means2D = screenspace_points
+    tanfovx = math.tan(data['fovx'] * 0.5)
+    tanfovy = math.tan(data['fovy'] * 0.5)
+    shs, rgb = None, None
+    if len(feats.shape) == 2:
+        rgb = feats
+    else:
+        shs = feats
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(data['image_height']), image_width=int(data['image_width']), tanfovx=tanfovx,
+        tanfovy=tanfovy, bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=data['world_view_transform'],
+        projmatrix=data['full_proj_transform'], sh_degree=active_sh_degree, campos=data['camera_center'],
+        prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+    rendered_image, radii = rasterizer(means3D=means3D, means2D=means2D, shs=shs, opacities=opacity,
+                                       scales=scales, rotations=rotations, colors_precomp=rgb)
+    rendered_image = torch.clamp(rendered_image, 0.0, 1.0)
+    return {"render": rendered_image, "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0, "radii": radii}
+
+
+def test_renderer_shim_flow_and_densification_stats():
+    sc = make_scene(N=4000, H=160, W=96, seed=12)
+    view = sc["view"]
+    dev = "cuda"
+    t = lambda a, rg=False: torch.tensor(np.ascontiguousarray(a), device=dev, requires_grad=rg)
+    data = dict(fovx=view.fovx, fovy=view.fovy, image_height=view.image_height, image_width=view.image_width,
+                world_view_transform=t(view.world_view_transform), full_proj_transform=t(view.full_proj_transform),
+                camera_center=t(view.camera_center))
+    gs = dict(xyz=t(sc["means3D"], True), shs=t(sc["shs"], True), opacity=t(sc["opacity"], True),
+              scales=t(sc["scales"], True), rotq=t(sc["rotations"], True), active_sh_degree=2)
+    bg = torch.rand(3, device=dev)
+    pkg = reference_style_render(gs["xyz"], gs["shs"], gs["opacity"], gs["scales"], gs["rotq"], data,
+                                 bg_color=bg, active_sh_degree=gs["active_sh_degree"])
+    st = ro.forward(oracle_camera(view), sc["means3D"], sc["opacity"], bg.cpu().numpy(), shs=sc["shs"],
+                    scales=sc["scales"], rotations=sc["rotations"], sh_degree=2)
+    assert np.abs(pkg["render"].detach().cpu().numpy() - np.clip(st.color, 0, 1)).max() <= 1e-4
+    assert np.array_equal(pkg["visibility_filter"].cpu().numpy(), st.radii > 0)
+    G = torch.randn(3, view.image_height, view.image_width, device=dev)
+    (pkg["render"] * G).sum().backward()
+    clip_mask = ((st.color > 0) & (st.color < 1)).astype(np.float32)
+    gr = ro.backward(st, G.cpu().numpy() * clip_mask)
+    vs = pkg["viewspace_points"]
+    assert vs.grad is not None and rel_err(vs.grad.cpu().numpy(), gr["means2D"]) < 1e-3
+    # densification statistics (sings_hybrid.py:1013-1015, gs_trainer.py:487-490) via the fused kernel
+    from sings_b200 import _lib
+    N = 4000
+    accum = torch.zeros(N, device=dev); denom = torch.zeros(N, device=dev); maxr = torch.full((N,), 3.0, device=dev)
+    _lib.check(_lib.lib().sgs_densify_stats(N, vs.grad.data_ptr(), pkg["radii"].data_ptr(), accum.data_ptr(),
+                                            denom.data_ptr(), maxr.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    vis = pkg["visibility_filter"]
+    exp_acc = torch.zeros(N, device=dev)
+    exp_acc[vis] += torch.norm(vs.grad[vis, :2], dim=-1)
+    exp_max = torch.full((N,), 3.0, device=dev)
+    exp_max[vis] = torch.max(exp_max[vis], pkg["radii"][vis].float())
+    assert torch.allclose(accum, exp_acc, rtol=1e-6, atol=1e-12)
+    assert torch.equal(denom, vis.float()) and torch.equal(maxr, exp_max)
+
+
+def test_avatar_step_matches_autograd_path():
+    """AvatarStep (preallocated, sync-free C-ABI sequence) == deform + rasterizer autograd."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from helpers import raster_settings
+    from sings_b200 import deform
+    from sings_b200.step import AvatarStep, FrameInputs
+    sc = make_scene(N=6000, H=128, W=128, seed=15)
+    av, view = sc["avatar"], sc["view"]
+    dev = "cuda"
+    t = lambda a, rg=False: torch.tensor(np.ascontiguousarray(a), device=dev, requires_grad=rg)
+    bg = np.array([1.0, 1.0, 1.0], np.float32)
+    step = AvatarStep(t(av.xyz_canon), t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs),
+                      t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano),
+                      128, 128, 3, timing=True)
+    fr = FrameInputs(pose=t(sc["pose"]), transl=t(sc["transl"]), viewmatrix=t(view.world_view_transform),
+                     projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(bg),
+                     tanfovx=view.tanfovx, tanfovy=view.tanfovy)
+    G = torch.randn(3, 128, 128, device=dev)
+    img = step.forward(fr).clone()
+    step.backward(G)
+    torch.cuda.synchronize()
+    assert step.check_capacity() > 0
+    ms = step.stage_ms()
+    assert ms["total"] > 0 and ms["blend_fwd"] > 0
+    # autograd path
+    pose = t(sc["pose"], True)
+    xyz_c, rot_c, sc_c = t(av.xyz_canon, True), t(av.rotmat_canon, True), t(av.scales, True)
+    opa, shs, tr = t(av.opacity, True), t(av.shs, True), t(sc["transl"], True)
+    A = deform.pose_to_A(pose, t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano))
+    xyz, q, s = deform.deform_gaussians(A, xyz_c, t(av.lbs_weights), rot_c, sc_c, None, tr)
+    m2 = torch.zeros_like(xyz, requires_grad=True)
+    img2, radii = GaussianRasterizer(raster_settings(view, bg, 3))(means3D=xyz, means2D=m2, shs=shs,
+                                                                   opacities=opa, scales=s, rotations=q)
+    (img2 * G).sum().backward()
+    assert torch.equal(img, img2.detach())
+    assert torch.equal(step.radii, radii)
+    for a, b, name in [(step.d_xyz_canon, xyz_c.grad, "xyz"), (step.d_scales, sc_c.grad, "scales"),
+                       (step.d_rot_canon, rot_c.grad, "rot"), (step.d_opacity, opa.grad, "opacity"),
+                       (step.d_shs, shs.grad, "shs"), (step.d_pose[0], pose.grad, "pose"),
+                       (step.d_transl[0], tr.grad, "transl")]:
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4, name
+    vis = radii > 0
+    assert torch.equal(step.denom, vis.float())
+    assert torch.allclose(step.grad_accum[vis], torch.norm(m2.grad[vis, :2], dim=-1), rtol=1e-4, atol=1e-12)

@@ -1,0 +1,266 @@
+"""GPU parity tests of the rasterizer through the drop-in module / C ABI against the CPU
+oracle.  Bars (BASELINE.json north_star): sort keys, tile ranges, per-pixel contributor counts
+bit-exact; RGB / alpha / depth <= 1e-4 max-abs (fp32); gradients <= 1e-3 relative."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import inspect_state, make_scene, oracle_camera, raster_settings, rel_err
+from oracle import raster_oracle as ro
+
+pytestmark = pytest.mark.gpu
+IMG_TOL = 1e-4      # max-abs, fp32 (north_star)
+GRAD_TOL = 1e-3     # relative (north_star)
+
+
+def run_cuda(sc, bg, D, mode="sh", want_aux=True, scale_modifier=1.0, M=None):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = "cuda"
+    t = lambda a, rg=True: torch.tensor(np.ascontiguousarray(a), device=dev, requires_grad=rg)
+    N = sc["means3D"].shape[0]
+    leaves = dict(means3D=t(sc["means3D"]), opacities=t(sc["opacity"]))
+    leaves["means2D"] = torch.zeros(N, 3, device=dev, requires_grad=True)
+    if mode == "colors":
+        leaves["colors_precomp"] = t(sc["colors"])
+    else:
+        shs = sc["shs"] if M is None else sc["shs"][:, :M]
+        leaves["shs"] = t(shs)
+    if mode == "cov3d":
+        leaves["cov3D_precomp"] = t(sc["cov3D"])
+    else:
+        leaves["scales"], leaves["rotations"] = t(sc["scales"]), t(sc["rotations"])
+    rast = GaussianRasterizer(raster_settings(sc["view"], bg, D, scale_modifier=scale_modifier))
+    out = rast.forward_aux(**leaves) if want_aux else rast(**leaves)
+    return leaves, out
+
+
+def run_oracle(sc, bg, D, mode="sh", scale_modifier=1.0, M=None):
+    kw = {}
+    if mode == "colors":
+        kw["colors_precomp"] = sc["colors"]
+    else:
+        kw["shs"] = sc["shs"] if M is None else np.ascontiguousarray(sc["shs"][:, :M])
+    if mode == "cov3d":
+        kw["cov3D_precomp"] = sc["cov3D"]
+    else:
+        kw["scales"], kw["rotations"] = sc["scales"], sc["rotations"]
+    return ro.forward(oracle_camera(sc["view"]), sc["means3D"], sc["opacity"], bg, sh_degree=D,
+                      scale_modifier=scale_modifier, **kw)
+
+
+def check_forward(sc, st, out, bit_exact=True):
+    color, radii, alpha, depth = out
+    fn = color.grad_fn
+    saved = fn.saved_tensors
+    N = sc["means3D"].shape[0]
+    W, H = sc["view"].image_width, sc["view"].image_height
+    ins = inspect_state((saved[7], saved[8], saved[9]), N, W, H, fn.L_cap)
+    assert ins["overflow"] == 0
+    assert ins["num_rendered"] == st.num_rendered
+    assert np.array_equal(radii.cpu().numpy(), st.radii)
+    assert np.array_equal(ins["keys"], st.keys), "sorted (tile|depth) keys must be bit-exact"
+    assert np.array_equal(ins["point_list"], st.point_list), "sorted Gaussian ids must be bit-exact"
+    assert np.array_equal(ins["ranges"], st.ranges), "tile ranges must be bit-exact"
+    assert np.array_equal(ins["n_contrib"], st.n_contrib), "contributor counts must be bit-exact"
+    img = color.detach().cpu().numpy()
+    assert np.abs(img - st.color).max() <= IMG_TOL
+    assert np.abs(alpha.cpu().numpy() - st.alpha).max() <= IMG_TOL
+    assert np.abs(depth.cpu().numpy() - st.depth).max() <= IMG_TOL * max(1.0, float(st.depth.max()))
+    assert np.abs(ins["final_T"] - st.final_T).max() <= 1e-6
+    if bit_exact:       # the numeric contract makes the forward reproducible bit for bit
+        assert np.array_equal(img, st.color) and np.array_equal(ins["final_T"], st.final_T)
+    return ins
+
+
+def check_backward(sc, st, leaves, color, seed=1):
+    G = np.random.default_rng(seed).normal(size=st.color.shape).astype(np.float32)
+    (color * torch.tensor(G, device="cuda")).sum().backward()
+    torch.cuda.synchronize()
+    gr = ro.backward(st, G)
+    names = dict(means3D="means3D", means2D="means2D", opacities="opacities", shs="sh",
+                 colors_precomp="colors_precomp", scales="scales", rotations="rotations",
+                 cov3D_precomp="cov3Ds_precomp")
+    for k, t in leaves.items():
+        assert t.grad is not None, k
+        assert t.grad.shape == t.shape
+        e = rel_err(t.grad.cpu().numpy(), gr[names[k]])
+        assert e <= GRAD_TOL, f"grad {k}: rel err {e}"
+    assert float(leaves["means2D"].grad[:, 2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,H,W,D", [(3000, 128, 160, 3), (5000, 200, 136, 0), (1500, 70, 45, 2),
+                                     (2000, 64, 64, 1)])
+def test_sh_paths_forward_backward(N, H, W, D):
+    sc = make_scene(N=N, H=H, W=W, seed=N + D)
+    bg = np.array([0.2, 0.4, 0.6], np.float32)
+    st = run_oracle(sc, bg, D)
+    leaves, out = run_cuda(sc, bg, D)
+    check_forward(sc, st, out)
+    check_backward(sc, st, leaves, out[0])
+
+
+def test_precomputed_colors_and_cov3d():
+    sc = make_scene(N=2500, H=96, W=112, seed=21)
+    rng = np.random.default_rng(2)
+    sc["colors"] = rng.uniform(size=(2500, 3)).astype(np.float32)
+    bg = np.zeros(3, np.float32)
+    st = run_oracle(sc, bg, 0, mode="colors")
+    leaves, out = run_cuda(sc, bg, 0, mode="colors")
+    check_forward(sc, st, out)
+    check_backward(sc, st, leaves, out[0])
+    cov = st.cov3D.copy()
+    cov[cov.sum(1) == 0] = np.array([1e-4, 0, 0, 1e-4, 0, 1e-4], np.float32)
+    sc["cov3D"] = cov
+    st2 = run_oracle(sc, bg, 2, mode="cov3d")
+    leaves, out = run_cuda(sc, bg, 2, mode="cov3d")
+    check_forward(sc, st2, out)
+    check_backward(sc, st2, leaves, out[0])
+
+
+def test_unpadded_sh_rows_and_scale_modifier():
+    """M = 9 coefficients (rows not 16-byte multiples -> scalar staging path), modifier != 1."""
+    sc = make_scene(N=1800, H=80, W=96, seed=33)
+    bg = np.ones(3, np.float32)
+    st = run_oracle(sc, bg, 2, scale_modifier=1.3, M=9)
+    leaves, out = run_cuda(sc, bg, 2, scale_modifier=1.3, M=9)
+    check_forward(sc, st, out)
+    check_backward(sc, st, leaves, out[0])
+
+
+def test_isotropic_j52_scene_and_turnaround_view():
+    sc = make_scene(N=3000, H=112, W=112, J=52, seed=44, isotropic=True, yaw=2.1)
+    bg = np.array([0.9, 0.1, 0.3], np.float32)
+    st = run_oracle(sc, bg, 0)
+    assert st.num_rendered > 1000
+    leaves, out = run_cuda(sc, bg, 0)
+    check_forward(sc, st, out)
+    check_backward(sc, st, leaves, out[0])
+
+
+def test_empty_and_all_culled():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    sc = make_scene(N=64, H=48, W=48, seed=5)
+    bg = np.array([0.3, 0.6, 0.9], np.float32)
+    rs = raster_settings(sc["view"], bg, 0)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    img, radii = GaussianRasterizer(rs)(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1),
+                                        colors_precomp=z(0, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert radii.numel() == 0
+    assert torch.allclose(img, torch.tensor(bg, device="cuda")[:, None, None].expand(3, 48, 48))
+    # everything behind the camera
+    sc["means3D"][:, 2] = -5.0
+    st = run_oracle(sc, bg, 1)
+    leaves, out = run_cuda(sc, bg, 1)
+    assert st.num_rendered == 0
+    check_forward(sc, st, out)
+    (out[0].sum()).backward()
+    assert float(leaves["means3D"].grad.abs().max()) == 0.0
+    assert float(leaves["shs"].grad.abs().max()) == 0.0
+
+
+def test_errors_mirror_the_reference_wrapper():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    sc = make_scene(N=16, H=32, W=32, seed=6)
+    rs = raster_settings(sc["view"], np.zeros(3, np.float32), 0)
+    t = lambda a: torch.tensor(a, device="cuda")
+    r = GaussianRasterizer(rs)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=t(sc["means3D"]), means2D=t(sc["means3D"]), opacities=t(sc["opacity"]),
+          scales=t(sc["scales"]), rotations=t(sc["rotations"]))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=t(sc["means3D"]), means2D=t(sc["means3D"]), opacities=t(sc["opacity"]), shs=t(sc["shs"]))
+    with pytest.raises(ValueError, match="num_points, 3"):
+        r(means3D=t(sc["means3D"])[:, :2], means2D=t(sc["means3D"]), opacities=t(sc["opacity"]),
+          shs=t(sc["shs"]), scales=t(sc["scales"]), rotations=t(sc["rotations"]))
+
+
+def test_mark_visible():
+    from diff_gaussian_rasterization import GaussianRasterizer
+    sc = make_scene(N=500, H=32, W=32, seed=8)
+    sc["means3D"][::3, 2] = 0.1
+    rs = raster_settings(sc["view"], np.zeros(3, np.float32), 0)
+    vis = GaussianRasterizer(rs).markVisible(torch.tensor(sc["means3D"], device="cuda"))
+    assert np.array_equal(vis.cpu().numpy(), ro.mark_visible(sc["means3D"], oracle_camera(sc["view"]).view))
+
+
+def test_pair_list_overflow_is_repaired_and_async_mode_reports_it():
+    """Huge Gaussians touch every tile: the pair list outgrows the default capacity; checked mode
+    re-runs transparently, async mode raises at the next check."""
+    import sings_b200.rasterizer as R
+    sc = make_scene(N=20000, H=256, W=256, seed=10, scale_range=(0.2, 0.4))
+    bg = np.zeros(3, np.float32)
+    st = run_oracle(sc, bg, 0)
+    assert st.num_rendered > 4 * 20000 and st.num_rendered > (1 << 16)
+    R._cap_hint.clear()
+    leaves, out = run_cuda(sc, bg, 0)
+    check_forward(sc, st, out)
+    R._cap_hint.clear()
+    R.set_async(True)
+    try:
+        run_cuda(sc, bg, 0, want_aux=False)
+        with pytest.raises(Exception, match="overflowed"):
+            R.check_pending(block=True)
+        leaves, out = run_cuda(sc, bg, 0)           # capacity was raised: now complete
+        R.check_pending(block=True)
+        assert np.abs(out[0].detach().cpu().numpy() - st.color).max() <= IMG_TOL
+    finally:
+        R.set_async(False)
+        R._pending.clear()
+
+
+def test_standalone_sort_matches_stable_reference():
+    from sings_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n, end_bit in [(1, 45), (255, 13), (2049, 45), (1_000_003, 47), (300_000, 64)]:
+        hi = (1 << min(end_bit, 62)) - 1
+        keys = torch.randint(0, hi, (n,), device="cuda", dtype=torch.int64, generator=g)
+        if end_bit == 45:
+            keys[: n // 2] = keys[: n // 2] & ~0xFFFF      # many equal keys: stability matters
+        vals = torch.arange(n, device="cuda", dtype=torch.int32)
+        k0 = keys.clone()
+        kt, vt = torch.empty_like(keys), torch.empty_like(vals)
+        sb = L.sgs_sort_scratch_bytes(n)
+        scratch = torch.empty(sb, device="cuda", dtype=torch.uint8)
+        flag = ctypes.c_int(0)
+        _lib.check(L.sgs_sort_pairs_u64(keys.data_ptr(), vals.data_ptr(), kt.data_ptr(), vt.data_ptr(),
+                                        scratch.data_ptr(), sb, n, end_bit, ctypes.byref(flag),
+                                        torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        rk, rv = (kt, vt) if flag.value else (keys, vals)
+        mask = (1 << end_bit) - 1 if end_bit < 63 else -1
+        sk, si = torch.sort(k0 & mask if end_bit < 63 else k0, stable=True)
+        assert torch.equal(rk & mask if end_bit < 63 else rk, sk)
+        assert torch.equal(rv.long(), si)
+
+
+def test_full_size_config_c2_bit_exact_and_properties():
+    """BASELINE.json configs[1] at full size (200k Gaussians, 1024^2, SH 3): the oracle still
+    finishes in seconds, so the forward is compared bit for bit; plus size-independent
+    properties (ranges partition [0,L), sum tiles == L, sortedness, n_contrib <= list length)."""
+    sc = make_scene(N=200_000, H=1024, W=1024, seed=0, scale_range=(0.002, 0.012))
+    bg = np.ones(3, np.float32)
+    st = run_oracle(sc, bg, 3)
+    leaves, out = run_cuda(sc, bg, 3)
+    ins = check_forward(sc, st, out)
+    L = ins["num_rendered"]
+    assert L > 500_000
+    k = ins["keys"]
+    assert np.all(k[1:] >= k[:-1])
+    r = ins["ranges"].astype(np.int64)
+    assert int((r[:, 1] - r[:, 0]).sum()) == L
+    lens = (r[:, 1] - r[:, 0]).reshape(64, 64)
+    nmax = ins["n_contrib"].reshape(64, 16, 64, 16).max(axis=(1, 3))
+    assert np.all(nmax <= lens)
+    check_backward(sc, st, leaves, out[0])
+
+
+def test_stress_shape_2048_sort_key_width():
+    """configs[4]-shaped (scaled to 60k Gaussians): 2048^2 view -> 47-bit keys, 16384 tiles."""
+    sc = make_scene(N=60_000, H=2048, W=2048, seed=3, scale_range=(0.002, 0.012))
+    bg = np.zeros(3, np.float32)
+    st = run_oracle(sc, bg, 1)
+    leaves, out = run_cuda(sc, bg, 1)
+    check_forward(sc, st, out)
