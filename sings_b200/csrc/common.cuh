@@ -46,6 +46,7 @@ enum : int {
     CNT_OVERFLOW = 1,       // set when L exceeded the binning capacity
     CNT_SCAN_TICKET = 2,    // block ticket of the geometry kernel
     CNT_VISIBLE = 3,        // number of Gaussians with radii > 0 (statistics)
+    CNT_RANGES_DONE = 4,    // CTAs of the tile-range kernel that have finished
     CNT_SORT_TICKET0 = 8,   // + pass: block ticket of each radix pass (8 slots)
     CNT_SLOTS = 32,
 };

@@ -7,10 +7,12 @@
 namespace sgs {
 
 // floats per Gaussian in the geometry record consumed by the blend kernels
-constexpr int REC_FLOATS = 12;
+constexpr int REC_FLOATS = 16;
 // record layout: [0]=pixel x, [1]=pixel y, [2]=-0.5*conic.a, [3]=-conic.b, [4]=-0.5*conic.c,
 // [5]=opacity, [6]=pmin (power below which alpha < 1/255 for sure), [7]=r, [8]=g, [9]=b,
-// [10]=view depth, [11]=flags (bit 0..2: colour channel clamped at 0)
+// [10]=view depth, [11]=unused, [12]=t = -2 pmin with margin (footprint: d^T conic d <= t),
+// [13]=-b/c, [14]=-b/a (edge minimisers of the quadratic form), [15]=flags (bit 0..2: colour
+// channel clamped at 0)
 
 // floats per Gaussian in the blend-backward accumulator
 constexpr int ACC_FLOATS = 12;
@@ -28,7 +30,7 @@ struct RasterLayout {
     // geometry state (per Gaussian)
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
-    size_t cnt_off, hist_off, scan_off, sortstat_off, ranges_off, zero_bytes;
+    size_t cnt_off, hist_off, scan_off, sortstat_off, ranges_off, zero_bytes, order_off;
     size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;

@@ -55,6 +55,7 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.sortstat_off = o; o += align_up((size_t)l.passes * l.sort_blocks * RADIX * 4, 256);
     l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
     l.zero_bytes = o;
+    l.order_off = o;    o += align_up((size_t)l.tiles * 4, 256);
     size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
     l.keys0_off = o;    o += align_up(cap * 8, 256);
     l.keys1_off = o;    o += align_up(cap * 8, 256);
@@ -214,10 +215,17 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         // pmin: any power below it gives alpha = opacity*exp(power) < 1/255 with a 1 % margin,
         // so the blend kernels may skip the pair without evaluating exp (pure optimisation).
         float pmin = opac > 0.0f ? -(__logf(255.0f * opac) + 0.01f) : __int_as_float(0x7f800000);
-        float4* rec = reinterpret_cast<float4*>(o.rec) + (size_t)idx * 3;
+        // footprint {alpha >= 1/255} = {d^T conic d <= t}, t = -2 pmin (with a margin); the blend
+        // kernels compare it with the minimum of the quadratic form over a pixel block to skip
+        // blocks the Gaussian cannot reach (exact ellipse/rectangle test).
+        const float tq = -2.0f * pmin;
+        const float t_m = (tq == tq) ? tq * 1.002f + 0.02f : __int_as_float(0x7f800000);   // NaN: no culling
+        const float nb_c = -conB / conC, nb_a = -conB / conA;
+        float4* rec = reinterpret_cast<float4*>(o.rec) + (size_t)idx * 4;
         rec[0] = make_float4(ix, iy, MUL(-0.5f, conA), -conB);
         rec[1] = make_float4(MUL(-0.5f, conC), opac, pmin, rgb[0]);
-        rec[2] = make_float4(rgb[1], rgb[2], depth, __uint_as_float(flags));
+        rec[2] = make_float4(rgb[1], rgb[2], depth, 0.0f);
+        rec[3] = make_float4(t_m, nb_c, nb_a, __uint_as_float(flags));
     }
     if (in_range) o.radii[idx] = rad;
 

@@ -69,7 +69,7 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
         g2x = a0.x; g2y = a0.y;
         const float gxx = a0.z, gxy = a0.w, gyy = a1.x;
         gop = a1.y; gcol[0] = a1.z; gcol[1] = a1.w; gcol[2] = a2.x;
-        flags = __float_as_uint(rec[3 * (size_t)idx + 2].w);
+        flags = __float_as_uint(rec[4 * (size_t)idx + 3].w);
         px = a.means3D[3 * idx]; py = a.means3D[3 * idx + 1]; pz = a.means3D[3 * idx + 2];
         // ---- cov2D backward ----
         float c3[6];

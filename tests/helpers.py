@@ -67,6 +67,7 @@ def inspect_state(ctx_tensors, P, W, H, L_cap):
     out["ranges"] = b[info["ranges"]:info["ranges"] + 8 * info["tiles"]].view(np.uint32).reshape(-1, 2).copy()
     out["final_T"] = im[info["final_T"]:info["final_T"] + 4 * W * H].view(np.float32).reshape(H, W).copy()
     out["n_contrib"] = im[info["n_contrib"]:info["n_contrib"] + 4 * W * H].view(np.uint32).reshape(H, W).copy()
-    rec = geom.cpu().numpy()[:P * 48].view(np.float32).reshape(P, 12).copy()
+    nf = info["rec_floats"]
+    rec = geom.cpu().numpy()[:P * nf * 4].view(np.float32).reshape(P, nf).copy()
     out["rec"] = rec
     return out
