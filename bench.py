@@ -354,20 +354,47 @@ def run_e2e(args, sets, dev, world, rank):
         params = dict(xyz=t(av.xyz_canon).requires_grad_(True), rot=t(av.rotmat_canon).requires_grad_(True),
                       scales=t(av.scales).requires_grad_(True), opacity=t(av.opacity).requires_grad_(True),
                       shs=t(av.shs).requires_grad_(True), W=t(av.lbs_weights), rest=t(av.rest),
-                      parents=torch.from_numpy(av.parents), inv_A=t(av.inv_A_t2cano))
+                      parents=torch.from_numpy(av.parents).to(device=dev, dtype=torch.int32),
+                      inv_A=t(av.inv_A_t2cano))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         host.append(dict(p=params, pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]),
                          view=s["view"], bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
                          pm=t(s["view"].full_proj_transform), cp=t(s["view"].camera_center)))
     h2d = int(host[0]["pose"].numel() * 4 + host[0]["transl"].numel() * 4 + host[0]["G"].numel() * 4)
-    loss_host = torch.zeros(1).pin_memory()
+    # The input pipeline runs one step ahead on a copy stream (double-buffered device staging,
+    # like a data loader with pinned memory), the loss is read back through a ring of pinned
+    # slots one step late (like a logging trainer), and the rasterizer runs in async mode (the
+    # pair-list overflow flag is examined at the next forward instead of by a mid-step host
+    # sync).  Every H2D copy and every D2H read happens inside the timed region.
+    from sings_b200 import rasterizer as R
+    cur = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    NBUF = 2
+    stage = [dict(pose=torch.empty(N_JOINTS, 3, device=dev), transl=torch.empty(3, device=dev),
+                  G=torch.empty(3, H_IMG, W_IMG, device=dev), ready=torch.cuda.Event(),
+                  free=torch.cuda.Event()) for _ in range(NBUF)]
+    loss_host = torch.zeros(NBUF).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(NBUF)]
+    losses = []
 
-    def step(i):
-        hs = host[i % RING]
+    def prefetch(i):
+        hs, sb = host[i % RING], stage[i % NBUF]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sb["free"])          # the step that last used this buffer is done
+            sb["pose"].copy_(hs["pose"], non_blocking=True)
+            sb["transl"].copy_(hs["transl"], non_blocking=True)
+            sb["G"].copy_(hs["G"], non_blocking=True)
+            sb["ready"].record(copy_stream)
+
+    def step(i, n_total):
+        hs, sb = host[i % RING], stage[i % NBUF]
         p = hs["p"]
-        pose = hs["pose"].to(dev, non_blocking=True).requires_grad_(True)
-        transl = hs["transl"].to(dev, non_blocking=True).requires_grad_(True)
-        G = hs["G"].to(dev, non_blocking=True)
+        if i + 1 < n_total:
+            prefetch(i + 1)
+        cur.wait_event(sb["ready"])
+        pose = sb["pose"].detach().requires_grad_(True)
+        transl = sb["transl"].detach().requires_grad_(True)
+        G = sb["G"]
         A = deform.pose_to_A(pose, p["rest"], p["parents"], p["inv_A"])
         xyz, rotq, sc = deform.deform_gaussians(A, p["xyz"], p["W"], p["rot"], p["scales"], None, transl)
         v = hs["view"]
@@ -382,28 +409,46 @@ def run_e2e(args, sets, dev, world, rank):
         for q in (p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"]):
             q.grad = None
         loss.backward()
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[0])
+        sb["free"].record(cur)
+        loss_host[i % NBUF:i % NBUF + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ev[i % NBUF].record(cur)
+        if i >= 1:                                     # read the previous step's loss
+            loss_ev[(i - 1) % NBUF].synchronize()
+            losses.append(float(loss_host[(i - 1) % NBUF]))
+
+    def run(n):
+        for sb in stage:
+            sb["free"].record(cur)
+        prefetch(0)
+        for i in range(n):
+            step(i, n)
+        loss_ev[(n - 1) % NBUF].synchronize()
+        losses.append(float(loss_host[(n - 1) % NBUF]))
+        R.check_pending(block=True)
 
     n = max(10, min(args.steps, 200))
-    for i in range(3):
-        step(i)
+    run(RING)                # checked mode: sizes the pair-list capacity for every avatar of the ring
+    R.set_async(True)
+    run(RING)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    losses.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(n):
-        step(i)
+    run(n)
     e1.record()
     torch.cuda.synchronize()
+    R.set_async(False)
+    assert len(losses) == n and all(math.isfinite(x) for x in losses)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     return {"value": world * n / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": 4, "steps": n, "ms_per_step": ms / n,
+            "pipeline": "inputs prefetched one step ahead on a copy stream; loss read back one step late; "
+                        "all copies inside the timed region",
             "api": "sings_b200.deform.pose_to_A + deform_gaussians + diff_gaussian_rasterization.GaussianRasterizer (autograd)"}
 
 

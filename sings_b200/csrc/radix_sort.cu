@@ -21,6 +21,7 @@ constexpr unsigned ST_AGG = 1u << 30;
 constexpr unsigned ST_INCL = 2u << 30;
 constexpr unsigned ST_FLAG = 3u << 30;
 constexpr unsigned ST_VAL = ~ST_FLAG;
+constexpr int LOOKBACK_BATCH = 8;
 
 struct SortPass {
     const unsigned long long* keys_in;
@@ -113,14 +114,26 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass a)
     // ---- decoupled look-back over preceding tiles, one digit per thread ----
     unsigned* row = a.status + (size_t)tile * RADIX;
     st_relaxed_u32(&row[tid], (tile == 0 ? ST_INCL : ST_AGG) | count);
+    // The predecessors' words are fetched LOOKBACK_BATCH at a time (independent loads in
+    // flight together) and consumed in order: when every tile of a pass starts at once, tile
+    // k finds k-1 .. 1 still at AGGREGATE, and a walk of one dependent L2 round trip per
+    // predecessor would be the whole pass time.
     unsigned prev = 0;
     if (tile > 0) {
-        for (int j = tile - 1;; j--) {
-            const unsigned* p = a.status + (size_t)j * RADIX + tid;
-            unsigned s = ld_relaxed_u32(p);
-            while ((s & ST_FLAG) == 0) s = ld_relaxed_u32(p);
-            prev += s & ST_VAL;
-            if ((s & ST_FLAG) == ST_INCL) break;
+        bool found = false;
+        for (int j = tile - 1; !found; j -= LOOKBACK_BATCH) {
+            unsigned s[LOOKBACK_BATCH];
+#pragma unroll
+            for (int k = 0; k < LOOKBACK_BATCH; k++)
+                s[k] = j - k >= 0 ? ld_relaxed_u32(a.status + (size_t)(j - k) * RADIX + tid) : ST_INCL;
+#pragma unroll
+            for (int k = 0; k < LOOKBACK_BATCH; k++) {
+                if (found) continue;
+                unsigned v = s[k];
+                while ((v & ST_FLAG) == 0) v = ld_relaxed_u32(a.status + (size_t)(j - k) * RADIX + tid);
+                prev += v & ST_VAL;
+                found = (v & ST_FLAG) == ST_INCL;
+            }
         }
         st_relaxed_u32(&row[tid], ST_INCL | (prev + count));
     }

@@ -173,21 +173,32 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
 // ------------------------------------------------------------------------------------------
 // forward.  Warp-autonomous: every warp streams the tile's depth-sorted list by itself, 32
 // pairs at a time (one per lane, prefetched one chunk ahead), keeps the pairs that can reach
-// its own 8x4 pixel block (ballot), parks their records in a warp-private shared stage and
-// blends them in order.  No CTA barrier anywhere; a warp leaves as soon as its 32 pixels have
-// saturated.  The 8 warps of a CTA share a tile so the list is read from HBM/L2 once and
-// re-read from L1.
+// its own 8x4 pixel block (ballot) and appends their records, compacted, to a warp-private
+// ring in shared memory.  The ring is consumed FWD_U pairs at a time by a two-stage software
+// pipeline: EVAL computes the alphas of the next FWD_U pairs (independent chains: falloff,
+// exp, clamp) while COMPOSITE folds the previous FWD_U into the pixel state.  COMPOSITE is
+// branch-free and its only serial dependency per pair is one multiply (T), one predicate
+// (done) and the colour FMAs, so a lone warp on an SM -- the tail of the kernel is the tile
+// with the longest list -- still retires a pair every few cycles.  No CTA barrier anywhere;
+// a warp leaves as soon as its 32 pixels have saturated.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_PIX)
+constexpr int RING_SLOTS = 64;     // >= 32 + FWD_U
+
+struct FwdBatch {
+    float al[FWD_U], om[FWD_U], r[FWD_U], g[FWD_U], b[FWD_U], z[FWD_U];
+    unsigned pos[FWD_U];
+};
+
+__global__ void __launch_bounds__(TILE_PIX, 2)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ order,
                  const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
                  float* __restrict__ out_depth) {
-    __shared__ float4 s_q0[TILE_PIX / 32][2][32];
-    __shared__ float4 s_q1[TILE_PIX / 32][2][32];
-    __shared__ float4 s_q2[TILE_PIX / 32][2][32];
+    __shared__ float4 s_q0[TILE_PIX / 32][RING_SLOTS];     // x, y, -a/2, -b
+    __shared__ float4 s_q1[TILE_PIX / 32][RING_SLOTS];     // -c/2, opacity, pmin, r
+    __shared__ float4 s_q2[TILE_PIX / 32][RING_SLOTS];     // g, b, depth, list position + 1
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned tile = order[blockIdx.x];
@@ -201,74 +212,105 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2)), by1 = by0 + 3.0f;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
+    float4* const rq0 = s_q0[warp];
+    float4* const rq1 = s_q1[warp];
+    float4* const rq2 = s_q2[warp];
 
     bool done = !inside;
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dacc = 0.0f;
+    float T = 1.0f, T_fin = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dacc = 0.0f;
     unsigned last = 0;
+    unsigned head = 0, tail = 0;       // ring: consumed / produced pair counts (warp-uniform)
+
+    FwdBatch cur;                      // the batch waiting to be composited (starts empty)
+#pragma unroll
+    for (int u = 0; u < FWD_U; u++) {
+        cur.al[u] = 0.0f; cur.om[u] = 1.0f; cur.r[u] = cur.g[u] = cur.b[u] = cur.z[u] = 0.0f; cur.pos[u] = 0;
+    }
+
+    // alphas of ring entries [base, base + FWD_U); entries at or beyond `limit` are empty
+    auto eval = [&](FwdBatch& e, unsigned base, unsigned limit) {
+#pragma unroll
+        for (int u = 0; u < FWD_U; u++) {
+            const unsigned slot = (base + u) & (RING_SLOTS - 1);
+            const float4 q0 = rq0[slot];
+            const float4 q1 = rq1[slot];
+            const float4 q2 = rq2[slot];
+            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+            const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
+            const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
+            const float al = fminf(0.99f, __fmul_rn(q1.y, expneg(fminf(power, 0.0f))));
+            const bool ok = (base + u < limit) && !(power > 0.0f) && !(al < 1.0f / 255.0f);
+            e.al[u] = ok ? al : 0.0f;
+            e.om[u] = ok ? __fsub_rn(1.0f, al) : 1.0f;
+            e.r[u] = q1.w; e.g[u] = q2.x; e.b[u] = q2.y; e.z[u] = q2.z;
+            e.pos[u] = __float_as_uint(q2.w);
+        }
+    };
+    // fold a batch into the pixel state, in order.  T keeps multiplying after saturation
+    // (T_fin holds the reported value); an empty / rejected entry has al = 0, om = 1.
+    auto composite = [&](const FwdBatch& e) {
+#pragma unroll
+        for (int u = 0; u < FWD_U; u++) {
+            const float test_T = __fmul_rn(T, e.om[u]);
+            const bool hit = e.al[u] > 0.0f;
+            const bool kill = hit && !done && test_T < 0.0001f;
+            T_fin = kill ? T : T_fin;
+            done = done || kill;
+            const float wgt = done ? 0.0f : __fmul_rn(e.al[u], T);
+            C0 = __fmaf_rn(e.r[u], wgt, C0);
+            C1 = __fmaf_rn(e.g[u], wgt, C1);
+            C2 = __fmaf_rn(e.b[u], wgt, C2);
+            Dacc = __fmaf_rn(e.z[u], wgt, Dacc);
+            last = (hit && !done) ? e.pos[u] : last;
+            T = test_T;
+        }
+    };
+
+    // ring slots always hold finite records (an empty slot contributes colour * 0)
+    rq0[lane] = rq0[lane + 32] = make_float4(0, 0, 0, 0);
+    rq1[lane] = rq1[lane + 32] = make_float4(0, 0, 0, 0);
+    rq2[lane] = rq2[lane + 32] = make_float4(0, 0, 0, 0);
 
     Rec p;
     p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
     if (lane < len) p = load_rec(rec, __ldg(point_list + range.x + lane));
-    int buf = 0;
-    for (int pos = 0; pos < len; pos += 32, buf ^= 1) {
+    for (int pos = 0; pos < len; pos += 32) {
         if (__all_sync(0xffffffffu, done)) break;
         const bool rel = (pos + lane < len) && reaches_block(p.q0, p.q1, p.q3, bx0, bx1, by0, by1);
-        unsigned bits = __ballot_sync(0xffffffffu, rel);
-        s_q0[warp][buf][lane] = p.q0; s_q1[warp][buf][lane] = p.q1; s_q2[warp][buf][lane] = p.q2;
+        const unsigned bits = __ballot_sync(0xffffffffu, rel);
+        __syncwarp();                  // earlier ring reads are complete before slots are reused
+        if (rel) {
+            const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
+            rq0[slot] = p.q0;
+            rq1[slot] = p.q1;
+            rq2[slot] = make_float4(p.q2.x, p.q2.y, p.q2.z, __uint_as_float((unsigned)(pos + lane + 1)));
+        }
+        tail += __popc(bits);
         __syncwarp();
         if (pos + 32 + lane < len) p = load_rec(rec, __ldg(point_list + range.x + pos + 32 + lane));
-        if (done) continue;
-        // alpha of a pair depends only on the pair: FWD_U pairs are evaluated together as
-        // independent instruction chains; only the order-dependent part (T, colour) is serial.
-        while (bits) {
-            float pw[FWD_U], opa[FWD_U], red[FWD_U];
-            int jj[FWD_U];
-            bool any_ok = false;
-#pragma unroll
-            for (int u = 0; u < FWD_U; u++) {
-                const bool in = bits != 0;
-                const int j = in ? __ffs(bits) - 1 : 0;
-                bits &= bits - 1;
-                const float4 q0 = s_q0[warp][buf][j];     // x, y, -a/2, -b
-                const float4 q1 = s_q1[warp][buf][j];     // -c/2, opacity, pmin, r
-                const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-                const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
-                const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
-                const bool ok = in && !(power > 0.0f || power < q1.z);
-                pw[u] = ok ? power : 1.0f;          // a positive value marks "rejected"
-                opa[u] = q1.y; red[u] = q1.w; jj[u] = j;
-                any_ok |= ok;
-            }
-            if (!any_ok) continue;
-            float al[FWD_U];
-#pragma unroll
-            for (int u = 0; u < FWD_U; u++)
-                al[u] = fminf(0.99f, __fmul_rn(opa[u], expneg(fminf(pw[u], 0.0f))));
-#pragma unroll
-            for (int u = 0; u < FWD_U; u++) {
-                if (!(pw[u] <= 0.0f) || al[u] < 1.0f / 255.0f) continue;
-                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                if (test_T < 0.0001f) { done = true; break; }
-                const float4 q2 = s_q2[warp][buf][jj[u]];     // g, b, depth, -
-                const float wgt = __fmul_rn(al[u], T);
-                C0 = __fmaf_rn(red[u], wgt, C0);
-                C1 = __fmaf_rn(q2.x, wgt, C1);
-                C2 = __fmaf_rn(q2.y, wgt, C2);
-                Dacc = __fmaf_rn(q2.z, wgt, Dacc);
-                T = test_T;
-                last = (unsigned)(pos + jj[u] + 1);
-            }
-            if (done) break;
+        while (tail - head >= FWD_U) {
+            FwdBatch nxt;
+            eval(nxt, head, tail);
+            composite(cur);
+            cur = nxt;
+            head += FWD_U;
         }
+    }
+    {   // drain: the waiting batch, then the (partial) remainder of the ring
+        FwdBatch nxt;
+        eval(nxt, head, tail);
+        composite(cur);
+        composite(nxt);
     }
     if (inside) {
         const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
-        final_T[pix] = T;
+        const float Tr = done ? T_fin : T;       // a saturated pixel reports the T it stopped at
+        final_T[pix] = Tr;
         n_contrib[pix] = last;
-        out_color[pix] = __fmaf_rn(T, bg[0], C0);
-        out_color[plane + pix] = __fmaf_rn(T, bg[1], C1);
-        out_color[2 * plane + pix] = __fmaf_rn(T, bg[2], C2);
-        if (out_alpha) out_alpha[pix] = __fsub_rn(1.0f, T);
+        out_color[pix] = __fmaf_rn(Tr, bg[0], C0);
+        out_color[plane + pix] = __fmaf_rn(Tr, bg[1], C1);
+        out_color[2 * plane + pix] = __fmaf_rn(Tr, bg[2], C2);
+        if (out_alpha) out_alpha[pix] = __fsub_rn(1.0f, Tr);
         if (out_depth) out_depth[pix] = Dacc;
     }
 }

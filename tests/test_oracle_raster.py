@@ -54,9 +54,9 @@ def test_higher_msb_and_expneg():
     for x in xs:
         e, t = ro.expneg(float(np.float32(x))), math.exp(float(np.float32(x)))
         if x < -80:
-            assert e == 0.0
+            assert 0.0 < e < 2e-35          # clamped at exp(-80)
         else:
-            assert abs(e - t) <= 3e-7 * t
+            assert abs(e - t) <= 2.5e-7 * t
     assert ro.expneg(0.0) == 1.0
 
 
