@@ -38,8 +38,8 @@ const char* sgs_error_string(int code);
 
 /* Stage timing (measurement only).  A timing handle owns n CUDA events; the rasterizer entry
  * points record them at stage boundaries when given a handle (null = no recording):
- *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit), [2] after the radix
- *             sort, [3] after tile ranges, [4] after the blend;
+ *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit+tile counts), [12] after
+ *             tile ranges/order, [2] = [3] after the radix sort, [4] after the blend;
  *   backward: [5] start, [6] after the blend backward (incl. accumulator memset), [7] end.
  * sgs_timing_elapsed_ms waits for event j and returns the time from event i to event j. */
 int sgs_timing_create(int n_events, void** handle);

@@ -141,14 +141,15 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
+    rc = launch_tile_ranges(lay, b, stream);    // ranges + longest-first tile order from the counts
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    tick(timing, 12, stream);
     if (P > 0) {
         rc = launch_radix_sort(lay, L_cap, b, stream, debug);
         if (rc) return rc;
     }
     tick(timing, 2, stream);
-    rc = launch_tile_ranges(lay, L_cap, b, stream);    // also builds the longest-first tile order
-    if (rc) return rc;
-    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
     if (rc) return rc;

@@ -30,7 +30,7 @@ struct RasterLayout {
     // geometry state (per Gaussian)
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
-    size_t cnt_off, hist_off, scan_off, sortstat_off, ranges_off, zero_bytes, order_off;
+    size_t cnt_off, hist_off, scan_off, sortstat_off, tilecnt_off, zero_bytes, ranges_off, order_off;
     size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
@@ -67,7 +67,7 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
                           int end_bit, int* result_in_tmp, cudaStream_t stream);
 size_t sort_scratch_bytes(long long n);
 
-int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
+int launch_tile_ranges(const RasterLayout& lay, char* bin, cudaStream_t stream);
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,

@@ -58,12 +58,14 @@ __global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __
                                  const int* __restrict__ parents, const float* __restrict__ inv_A,
                                  int J, float* __restrict__ A_out, float* __restrict__ G_out) {
     extern __shared__ float s_local[];     // J x 12 local transforms
+    __shared__ int s_par[64];
     const int b = blockIdx.x, j = threadIdx.x;
     if (j < J) {
         float R[9];
         const float* p = pose + ((size_t)b * J + j) * 3;
         rodrigues(p[0], p[1], p[2], R);
         const int par = parents[j];
+        s_par[j] = par;
         float t[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) t[k] = rest[3 * j + k] - (par >= 0 ? rest[3 * par + k] : 0.0f);
@@ -77,7 +79,7 @@ __global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __
     if (j >= J) return;
     int chain[64];
     int depth = 0;
-    for (int k = j; k >= 0 && depth < 64; k = parents[k]) chain[depth++] = k;
+    for (int k = j; k >= 0 && depth < 64; k = s_par[k]) chain[depth++] = k;
     float G[12], tmp[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) G[k] = s_local[12 * chain[depth - 1] + k];
@@ -124,29 +126,36 @@ int launch_pose_to_A(const float* pose, const float* rest, const int* parents, c
     return 0;
 }
 
-// backward of pose_to_A_kernel: dL/dA (B,J,16) -> dL/dpose (B,J,3).  One CTA per frame.
-// Thread j seeds dL/dG_j, thread 0 walks the tree leaves-to-root (parents[j] < j), thread j
-// then differentiates its Rodrigues formula.
+// backward of pose_to_A_kernel: dL/dA (B,J,16) -> dL/dpose (B,J,3).  One CTA per frame, one
+// thread per joint.  Thread j seeds dL/dG_j; the kinematic tree is then walked leaves-to-root
+// one depth level at a time (a parent gathers dG_k L_k^T from its children, whose dG are
+// final after the previous level), each thread converts dL/dG_j to dL/dL_j with its parent's
+// G, and differentiates its Rodrigues formula.  Everything the walk touches is in shared memory.
 __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float* __restrict__ rest,
                                      const int* __restrict__ parents, const float* __restrict__ inv_A,
                                      const float* __restrict__ G_all, const float* __restrict__ dA,
                                      int J, float* __restrict__ d_pose) {
     extern __shared__ float s_mem[];
     float* s_L = s_mem;              // J x 12 local transforms
-    float* s_dG = s_mem + 12 * J;    // J x 12 dL/dG, then dL/dL
+    float* s_dG = s_mem + 12 * J;    // J x 12 dL/dG
+    float* s_G = s_mem + 24 * J;     // J x 12 global transforms (forward's G_out)
+    __shared__ int s_par[64], s_depth[64], s_maxd;
     const int b = blockIdx.x, j = threadIdx.x;
-    const float* G = G_all + (size_t)b * J * 12;
     float R[9];
+    if (j == 0) s_maxd = 0;
     if (j < J) {
         const float* p = pose + ((size_t)b * J + j) * 3;
         rodrigues(p[0], p[1], p[2], R);
         const int par = parents[j];
+        s_par[j] = par;
         float* L = s_L + 12 * j;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             L[4 * r] = R[3 * r]; L[4 * r + 1] = R[3 * r + 1]; L[4 * r + 2] = R[3 * r + 2];
             L[4 * r + 3] = rest[3 * j + r] - (par >= 0 ? rest[3 * par + r] : 0.0f);
         }
+#pragma unroll
+        for (int k = 0; k < 12; k++) s_G[12 * j + k] = G_all[((size_t)b * J + j) * 12 + k];
         // dOut -> dArel (through @ inv_A) -> dG
         float dO[12];
 #pragma unroll
@@ -177,34 +186,57 @@ __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float
         }
     }
     __syncthreads();
-    if (j == 0) {
-        for (int k = J - 1; k >= 1; k--) {
-            const int par = parents[k];
-            const float* Gp = G + 12 * par;
-            const float* L = s_L + 12 * k;
-            float* dG = s_dG + 12 * k;
-            float* dGp = s_dG + 12 * par;
-            float dL[12];
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 4; c++)
-                    dL[4 * r + c] = Gp[r] * dG[c] + Gp[4 + r] * dG[4 + c] + Gp[8 + r] * dG[8 + c];
-            for (int r = 0; r < 3; r++) {
-                for (int c = 0; c < 3; c++)
-                    dGp[4 * r + c] += dG[4 * r] * L[4 * c] + dG[4 * r + 1] * L[4 * c + 1] +
-                                      dG[4 * r + 2] * L[4 * c + 2] + dG[4 * r + 3] * L[4 * c + 3];
-                dGp[4 * r + 3] += dG[4 * r + 3];
-            }
-            for (int q = 0; q < 12; q++) dG[q] = dL[q];
-        }
+    int depth = 0;
+    if (j < J) {
+        for (int k = s_par[j]; k >= 0 && depth < 64; k = s_par[k]) depth++;
+        s_depth[j] = depth;
+        atomicMax(&s_maxd, depth);
     }
     __syncthreads();
+    const int maxd = s_maxd;
+    for (int d = maxd - 1; d >= 0; d--) {
+        if (j < J && depth == d) {
+            float acc[12];
+#pragma unroll
+            for (int q = 0; q < 12; q++) acc[q] = s_dG[12 * j + q];
+            for (int k = J - 1; k > j; k--) {           // children, highest index first
+                if (s_par[k] != j) continue;
+                const float* dG = s_dG + 12 * k;
+                const float* L = s_L + 12 * k;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        acc[4 * r + c] += dG[4 * r] * L[4 * c] + dG[4 * r + 1] * L[4 * c + 1] +
+                                          dG[4 * r + 2] * L[4 * c + 2] + dG[4 * r + 3] * L[4 * c + 3];
+                    acc[4 * r + 3] += dG[4 * r + 3];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 12; q++) s_dG[12 * j + q] = acc[q];
+        }
+        __syncthreads();
+    }
     if (j >= J) return;
-    // Rodrigues backward; E = dL/dR_j (rotation part of dL/dL_j; the root's L is G itself)
+    // E = dL/dR_j: rotation part of dL/dL_j = G_parent^T dL/dG_j (the root's L is G itself)
     float E[9];
+    {
+        const float* dG = s_dG + 12 * j;
+        const int par = s_par[j];
+        if (par >= 0) {
+            const float* Gp = s_G + 12 * par;
 #pragma unroll
-    for (int r = 0; r < 3; r++)
+            for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) E[3 * r + c] = s_dG[12 * j + 4 * r + c];
+                for (int c = 0; c < 3; c++)
+                    E[3 * r + c] = Gp[r] * dG[c] + Gp[4 + r] * dG[4 + c] + Gp[8 + r] * dG[8 + c];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) E[3 * r + c] = dG[4 * r + c];
+        }
+    }
     const float* p = pose + ((size_t)b * J + j) * 3;
     const float rx = p[0], ry = p[1], rz = p[2];
     const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
@@ -243,7 +275,7 @@ int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parent
                          float* d_pose, cudaStream_t stream) {
     if (B <= 0) return 0;
     if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
-    pose_to_A_bwd_kernel<<<B, 64, (size_t)J * 24 * 4, stream>>>(pose, rest, parents, inv_A, G, dA, J, d_pose);
+    pose_to_A_bwd_kernel<<<B, 64, (size_t)J * 36 * 4, stream>>>(pose, rest, parents, inv_A, G, dA, J, d_pose);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -327,34 +359,104 @@ __device__ __forceinline__ void quat_mul(const float* a, const float* b, float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// shared staging: joint transforms of all frames + this CTA's skinning-weight rows (TMA)
+// shared-memory tile of one CTA (256 consecutive Gaussians).  Every per-Gaussian array is a
+// contiguous block in global memory, so it is moved as a block: one TMA bulk copy
+// (cp.async.bulk + mbarrier) when the block is 16-byte aligned and a multiple of 16 bytes,
+// a cooperative coalesced copy otherwise (partial last CTA, unaligned views).  Threads then
+// read their own row from shared memory (strides 3, 4, 9, 12 words: bank-conflict free).
+// Results leave the same way (cp.async.bulk shared -> global, or coalesced stores).
 // ------------------------------------------------------------------------------------------
-struct LbsSmem {
+struct LbsTile {
     float4* A;        // [B][J][3]  rows 0..2 of each joint transform
+    float* frame;     // [B][16]: smpl_scale, transl(3), ext_scale, ext_trans(3), ext_quat(4)
     float* W;         // [256][J]
-    float* frame;     // [B][16]: smpl_scale, transl(3), ext_scale, ext_trans(3), ext_quat(4) ...
-    float* dT;        // backward only: [256][12]
+    float* xyz;       // [256][3]   (backward: reused for d_xyz at the end)
+    float* scl;       // [256][3]   (backward: reused for d_scales)
+    float* rot;       // [256][9]   (backward: reused for d_rot)
+    float* f_xyz;     // [256][3]   forward: output staging; backward: this frame's g_xyz
+    float* f_q;       // [256][4]
+    float* f_scl;     // [256][3]
+    float* dT;        // backward: [256][12]
+    float* part;      // backward: [8][J][12] per-warp partial dA
     unsigned long long* bar;
 };
 
-__device__ __forceinline__ void stage_inputs(const LbsArgs& a, LbsSmem& s, int base, int rows) {
-    const int tid = threadIdx.x;
-    const size_t w_bytes = (size_t)rows * a.J * 4;
-    const float* w_src = a.W + (size_t)base * a.J;
-    const bool tma_ok = ((uintptr_t)w_src & 15) == 0 && (w_bytes & 15) == 0;
-    if (tma_ok) {
-        if (tid == 0) {
-            mbar_init(s.bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(s.bar, (unsigned)w_bytes);
-            tma_bulk_g2s(s.W, w_src, (unsigned)w_bytes, s.bar);
-        }
-    } else {
-        for (int f = tid; f < rows * a.J; f += LBS_THREADS) s.W[f] = w_src[f];
+__host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bwd, LbsTile* t = nullptr,
+                                                 char* raw = nullptr) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 16); return at; };
+    const size_t oA = take((size_t)B * J * 3 * 16), oF = take((size_t)B * 16 * 4);
+    const size_t oW = take((size_t)LBS_THREADS * J * 4);
+    const size_t oX = take(LBS_THREADS * 12), oS = take(LBS_THREADS * 12);
+    const size_t oR = take(iso ? 0 : LBS_THREADS * 36);
+    const size_t oFX = take(LBS_THREADS * 12), oFQ = take(LBS_THREADS * 16), oFS = take(LBS_THREADS * 12);
+    const size_t oT = take(bwd ? LBS_THREADS * 48 : 0);
+    const size_t oP = take(bwd ? (size_t)(LBS_THREADS / 32) * J * 48 : 0);
+    const size_t oB = take(16);
+    if (t) {
+        t->A = reinterpret_cast<float4*>(raw + oA);  t->frame = reinterpret_cast<float*>(raw + oF);
+        t->W = reinterpret_cast<float*>(raw + oW);   t->xyz = reinterpret_cast<float*>(raw + oX);
+        t->scl = reinterpret_cast<float*>(raw + oS); t->rot = reinterpret_cast<float*>(raw + oR);
+        t->f_xyz = reinterpret_cast<float*>(raw + oFX); t->f_q = reinterpret_cast<float*>(raw + oFQ);
+        t->f_scl = reinterpret_cast<float*>(raw + oFS); t->dT = reinterpret_cast<float*>(raw + oT);
+        t->part = reinterpret_cast<float*>(raw + oP);
+        t->bar = reinterpret_cast<unsigned long long*>(raw + oB);
     }
+    return o;
+}
+
+__device__ __forceinline__ bool bulk_ok(const void* g, unsigned nfloats) {
+    return (((uintptr_t)g) & 15) == 0 && (nfloats & 3) == 0 && nfloats > 0;
+}
+
+// A set of block loads into shared memory completing on one mbarrier phase.  Usage (all
+// threads): begin(); add(...)...; end(); -- thread 0 arms the barrier with the byte total of
+// the TMA-eligible blocks and issues them, everyone copies the others, end() waits for both.
+struct BlockLoads {
+    unsigned long long* bar;
+    unsigned parity;
+    __device__ __forceinline__ void load(const float* const* src, float* const* dst, const unsigned* n, int count) {
+        const int tid = threadIdx.x;
+        if (tid == 0) {
+            unsigned bytes = 0;
+            for (int k = 0; k < count; k++)
+                if (bulk_ok(src[k], n[k])) bytes += n[k] * 4;
+            mbar_arrive_expect_tx(bar, bytes);
+            for (int k = 0; k < count; k++)
+                if (bulk_ok(src[k], n[k])) tma_bulk_g2s(dst[k], src[k], n[k] * 4, bar);
+        }
+        for (int k = 0; k < count; k++)
+            if (!bulk_ok(src[k], n[k]))
+                for (unsigned f = tid; f < n[k]; f += LBS_THREADS) dst[k][f] = src[k][f];
+    }
+    __device__ __forceinline__ void wait() {
+        __syncthreads();
+        mbar_wait(bar, parity);
+        parity ^= 1;
+    }
+};
+
+__device__ __forceinline__ void bulk_s2g(float* gmem_dst, const float* smem_src, unsigned bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(sa), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Store blocks from shared memory.  Call with all threads after the block's writers have
+// passed fence_proxy_async() + __syncthreads().  Thread 0 must call bulk_wait_read() (then a
+// __syncthreads) before the source is overwritten.
+__device__ __forceinline__ void block_store(float* dst, const float* src, unsigned nfloats) {
+    if (bulk_ok(dst, nfloats)) {
+        if (threadIdx.x == 0) bulk_s2g(dst, src, nfloats * 4);
+    } else {
+        for (unsigned f = threadIdx.x; f < nfloats; f += LBS_THREADS) dst[f] = src[f];
+    }
+}
+
+__device__ __forceinline__ void stage_frames(const LbsArgs& a, LbsTile& s) {
+    const int tid = threadIdx.x;
     for (int f = tid; f < a.B * a.J * 3; f += LBS_THREADS) {
         int bj = f / 3, r = f - bj * 3;
         s.A[f] = reinterpret_cast<const float4*>(a.A)[(size_t)bj * 4 + r];
@@ -371,28 +473,10 @@ __device__ __forceinline__ void stage_inputs(const LbsArgs& a, LbsSmem& s, int b
             for (int k = 0; k < 4; k++) fr[8 + k] = q[k];
         }
     }
-    __syncthreads();
-    if (tma_ok) mbar_wait(s.bar, 0);
-}
-
-__device__ __forceinline__ LbsSmem carve(char* raw, int B, int J, bool bwd) {
-    LbsSmem s;
-    size_t o = 0;
-    s.A = reinterpret_cast<float4*>(raw + o);   o += align_up((size_t)B * J * 3 * 16, 16);
-    s.W = reinterpret_cast<float*>(raw + o);    o += align_up((size_t)LBS_THREADS * J * 4, 16);
-    s.frame = reinterpret_cast<float*>(raw + o); o += align_up((size_t)B * 16 * 4, 16);
-    s.dT = reinterpret_cast<float*>(raw + o);   if (bwd) o += (size_t)LBS_THREADS * 12 * 4;
-    s.bar = reinterpret_cast<unsigned long long*>(raw + o);
-    return s;
-}
-
-static size_t lbs_smem_bytes(int B, int J, bool bwd) {
-    return align_up((size_t)B * J * 3 * 16, 16) + align_up((size_t)LBS_THREADS * J * 4, 16) +
-           align_up((size_t)B * 16 * 4, 16) + (bwd ? (size_t)LBS_THREADS * 12 * 4 : 0) + 16;
 }
 
 // T (3x4, row-major 12 floats) = sum_j w_j A[b][j]
-__device__ __forceinline__ void blend_T(const LbsSmem& s, int b, int J, int t, float* T) {
+__device__ __forceinline__ void blend_T(const LbsTile& s, int b, int J, int t, float* T) {
 #pragma unroll
     for (int k = 0; k < 12; k++) T[k] = 0.0f;
     const float4* Ab = s.A + (size_t)b * J * 3;
@@ -438,70 +522,102 @@ __device__ __forceinline__ void compose_rot(const float* T, const float* Rc, boo
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut o) {
     extern __shared__ __align__(16) char s_raw[];
-    LbsSmem s = carve(s_raw, a.B, a.J, false);
+    const bool iso = a.rot == nullptr;
+    LbsTile s;
+    lbs_tile_bytes(a.B, a.J, iso, false, &s, s_raw);
     const int tid = threadIdx.x;
     const int base = blockIdx.x * LBS_THREADS;
     const int rows = min(LBS_THREADS, a.N - base);
-    stage_inputs(a, s, base, rows);
+    if (tid == 0) {
+        mbar_init(s.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    BlockLoads ld{s.bar, 0};
+    {
+        const float* src[4] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
+                               iso ? nullptr : a.rot + (size_t)base * 9};
+        float* dst[4] = {s.W, s.xyz, s.scl, s.rot};
+        const unsigned n[4] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)rows * 9};
+        ld.load(src, dst, n, 4);
+    }
+    stage_frames(a, s);
+    ld.wait();
     const int n = base + tid;
-    if (n >= a.N) return;
-    const float x = a.xyz[3 * (size_t)n], y = a.xyz[3 * (size_t)n + 1], z = a.xyz[3 * (size_t)n + 2];
-    const float s0 = a.scales[3 * (size_t)n], s1 = a.scales[3 * (size_t)n + 1], s2 = a.scales[3 * (size_t)n + 2];
-    const bool iso = a.rot == nullptr;
-    float Rc[9];
-    if (!iso) {
+    const bool live = n < a.N;
+    float x = 0, y = 0, z = 0, s0 = 0, s1 = 0, s2 = 0;
+    float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (live) {
+        x = s.xyz[3 * tid]; y = s.xyz[3 * tid + 1]; z = s.xyz[3 * tid + 2];
+        s0 = s.scl[3 * tid]; s1 = s.scl[3 * tid + 1]; s2 = s.scl[3 * tid + 2];
+        if (!iso) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) Rc[k] = a.rot[9 * (size_t)n + k];
+            for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
+        }
     }
     for (int b = 0; b < a.B; b++) {
-        float T[12];
-        blend_T(s, b, a.J, tid, T);
-        const float* fr = s.frame + 16 * b;
-        float vx = T[0] * x + T[1] * y + T[2] * z + T[3];
-        float vy = T[4] * x + T[5] * y + T[6] * z + T[7];
-        float vz = T[8] * x + T[9] * y + T[10] * z + T[11];
-        float sc0 = s0, sc1 = s1, sc2 = s2;
-        if (a.smpl_scale) { vx *= fr[0]; vy *= fr[0]; vz *= fr[0]; sc0 *= fr[0]; sc1 *= fr[0]; sc2 *= fr[0]; }
-        if (a.transl) { vx += fr[1]; vy += fr[2]; vz += fr[3]; }
-        float Rp[9], q[4];
-        compose_rot(T, Rc, iso, Rp);
-        mat_to_quat(Rp, q);
-        if (a.ext_rot) {
-            const float* eR = a.ext_rot + 9 * b;
-            const float es = fr[4];
-            const float rx = eR[0] * vx + eR[1] * vy + eR[2] * vz;
-            const float ry = eR[3] * vx + eR[4] * vy + eR[5] * vz;
-            const float rz = eR[6] * vx + eR[7] * vy + eR[8] * vz;
-            vx = fr[5] + es * rx; vy = fr[6] + es * ry; vz = fr[7] + es * rz;
-            sc0 *= es; sc1 *= es; sc2 *= es;
-            float qo[4];
-            quat_mul(fr + 8, q, qo);
-            const float sg = qo[0] < 0.0f ? -1.0f : 1.0f;
+        if (live) {
+            float T[12];
+            blend_T(s, b, a.J, tid, T);
+            const float* fr = s.frame + 16 * b;
+            float vx = T[0] * x + T[1] * y + T[2] * z + T[3];
+            float vy = T[4] * x + T[5] * y + T[6] * z + T[7];
+            float vz = T[8] * x + T[9] * y + T[10] * z + T[11];
+            float sc0 = s0, sc1 = s1, sc2 = s2;
+            if (a.smpl_scale) { vx *= fr[0]; vy *= fr[0]; vz *= fr[0]; sc0 *= fr[0]; sc1 *= fr[0]; sc2 *= fr[0]; }
+            if (a.transl) { vx += fr[1]; vy += fr[2]; vz += fr[3]; }
+            float Rp[9], q[4];
+            compose_rot(T, Rc, iso, Rp);
+            mat_to_quat(Rp, q);
+            if (a.ext_rot) {
+                const float* eR = a.ext_rot + 9 * b;
+                const float es = fr[4];
+                const float rx = eR[0] * vx + eR[1] * vy + eR[2] * vz;
+                const float ry = eR[3] * vx + eR[4] * vy + eR[5] * vz;
+                const float rz = eR[6] * vx + eR[7] * vy + eR[8] * vz;
+                vx = fr[5] + es * rx; vy = fr[6] + es * ry; vz = fr[7] + es * rz;
+                sc0 *= es; sc1 *= es; sc2 *= es;
+                float qo[4];
+                quat_mul(fr + 8, q, qo);
+                const float sg = qo[0] < 0.0f ? -1.0f : 1.0f;
 #pragma unroll
-            for (int k = 0; k < 4; k++) q[k] = sg * qo[k];
+                for (int k = 0; k < 4; k++) q[k] = sg * qo[k];
+            }
+            s.f_xyz[3 * tid] = vx; s.f_xyz[3 * tid + 1] = vy; s.f_xyz[3 * tid + 2] = vz;
+            reinterpret_cast<float4*>(s.f_q)[tid] = make_float4(q[0], q[1], q[2], q[3]);
+            s.f_scl[3 * tid] = sc0; s.f_scl[3 * tid + 1] = sc1; s.f_scl[3 * tid + 2] = sc2;
+            if (o.T) {
+                const size_t on = (size_t)b * a.N + n;
+                float4* Tn = reinterpret_cast<float4*>(o.T) + on * 4;
+                Tn[0] = make_float4(T[0], T[1], T[2], T[3]);
+                Tn[1] = make_float4(T[4], T[5], T[6], T[7]);
+                Tn[2] = make_float4(T[8], T[9], T[10], T[11]);
+                // row 3 = sum_j w_j (0,0,0,1): the reference's T[3,3] is the weight-row sum
+                float wsum = 0.0f;
+                for (int j = 0; j < a.J; j++) wsum += s.W[(size_t)tid * a.J + j];
+                Tn[3] = make_float4(0.0f, 0.0f, 0.0f, wsum);
+            }
         }
-        const size_t on = (size_t)b * a.N + n;
-        o.xyz[3 * on] = vx; o.xyz[3 * on + 1] = vy; o.xyz[3 * on + 2] = vz;
-        reinterpret_cast<float4*>(o.rotq)[on] = make_float4(q[0], q[1], q[2], q[3]);
-        o.scales[3 * on] = sc0; o.scales[3 * on + 1] = sc1; o.scales[3 * on + 2] = sc2;
-        if (o.T) {
-            float4* Tn = reinterpret_cast<float4*>(o.T) + on * 4;
-            Tn[0] = make_float4(T[0], T[1], T[2], T[3]);
-            Tn[1] = make_float4(T[4], T[5], T[6], T[7]);
-            Tn[2] = make_float4(T[8], T[9], T[10], T[11]);
-            // row 3 = sum_j w_j (0,0,0,1): the reference's T[3,3] is the weight-row sum
-            float wsum = 0.0f;
-            for (int j = 0; j < a.J; j++) wsum += s.W[(size_t)tid * a.J + j];
-            Tn[3] = make_float4(0.0f, 0.0f, 0.0f, wsum);
+        fence_proxy_async();
+        __syncthreads();
+        const size_t ob = (size_t)b * a.N + base;
+        block_store(o.xyz + ob * 3, s.f_xyz, (unsigned)rows * 3);
+        block_store(o.rotq + ob * 4, s.f_q, (unsigned)rows * 4);
+        block_store(o.scales + ob * 3, s.f_scl, (unsigned)rows * 3);
+        if (tid == 0) {
+            bulk_commit();
+            if (b + 1 < a.B) bulk_wait_read();
         }
+        if (b + 1 < a.B) __syncthreads();
     }
+    if (tid == 0) bulk_wait_read();      // shared memory must outlive the outstanding bulk stores
 }
 
 int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
     if (a.N <= 0 || a.B <= 0) return 0;
     if (a.J < 1 || a.J > 64) return SGS_ERR_BAD_JOINTS;
-    if (((uintptr_t)a.A & 15) || ((uintptr_t)o.rotq & 15) || (o.T && ((uintptr_t)o.T & 15))) return SGS_ERR_MISALIGNED;
-    const size_t smem = lbs_smem_bytes(a.B, a.J, false);
+    if (((uintptr_t)a.A & 15) || (o.T && ((uintptr_t)o.T & 15))) return SGS_ERR_MISALIGNED;
+    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lbs_fwd_kernel<<<(a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream>>>(a, o);
@@ -514,27 +630,54 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(LbsArgs a, LbsGrads g) {
     extern __shared__ __align__(16) char s_raw[];
-    LbsSmem s = carve(s_raw, a.B, a.J, true);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const bool iso = a.rot == nullptr;
+    LbsTile s;
+    lbs_tile_bytes(a.B, a.J, iso, true, &s, s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int base = blockIdx.x * LBS_THREADS;
     const int rows = min(LBS_THREADS, a.N - base);
-    stage_inputs(a, s, base, rows);
+    if (tid == 0) {
+        mbar_init(s.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    BlockLoads ld{s.bar, 0};
+    {
+        const float* src[7] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
+                               iso ? nullptr : a.rot + (size_t)base * 9, g.g_xyz + (size_t)base * 3,
+                               g.g_rotq + (size_t)base * 4, g.g_scales + (size_t)base * 3};
+        float* dst[7] = {s.W, s.xyz, s.scl, s.rot, s.f_xyz, s.f_q, s.f_scl};
+        const unsigned n[7] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)rows * 9,
+                               (unsigned)rows * 3, (unsigned)rows * 4, (unsigned)rows * 3};
+        ld.load(src, dst, n, 7);
+    }
+    stage_frames(a, s);
+    ld.wait();
     const int n = base + tid;
     const bool live = n < a.N;
-    const bool iso = a.rot == nullptr;
     float x = 0, y = 0, z = 0, s0 = 0, s1 = 0, s2 = 0;
     float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (live) {
-        x = a.xyz[3 * (size_t)n]; y = a.xyz[3 * (size_t)n + 1]; z = a.xyz[3 * (size_t)n + 2];
-        s0 = a.scales[3 * (size_t)n]; s1 = a.scales[3 * (size_t)n + 1]; s2 = a.scales[3 * (size_t)n + 2];
+        x = s.xyz[3 * tid]; y = s.xyz[3 * tid + 1]; z = s.xyz[3 * tid + 2];
+        s0 = s.scl[3 * tid]; s1 = s.scl[3 * tid + 1]; s2 = s.scl[3 * tid + 2];
         if (!iso) {
 #pragma unroll
-            for (int k = 0; k < 9; k++) Rc[k] = a.rot[9 * (size_t)n + k];
+            for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
         }
     }
     float dx = 0, dy = 0, dz = 0, ds0 = 0, ds1 = 0, ds2 = 0;
     float dRc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int warp_rows = max(0, min(32, rows - warp * 32));
     for (int b = 0; b < a.B; b++) {
+        if (b > 0) {           // this frame's incoming gradients (frame 0 came with the tile)
+            __syncthreads();   // everyone is done with the previous frame's f_* blocks
+            const size_t ob = (size_t)b * a.N + base;
+            const float* src[3] = {g.g_xyz + ob * 3, g.g_rotq + ob * 4, g.g_scales + ob * 3};
+            float* dst[3] = {s.f_xyz, s.f_q, s.f_scl};
+            const unsigned nn[3] = {(unsigned)rows * 3, (unsigned)rows * 4, (unsigned)rows * 3};
+            ld.load(src, dst, nn, 3);
+            ld.wait();
+        }
         float dT[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) dT[k] = 0.0f;
@@ -544,10 +687,10 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(LbsArgs a, LbsGrad
             blend_T(s, b, a.J, tid, T);
             const float* fr = s.frame + 16 * b;
             const size_t on = (size_t)b * a.N + n;
-            float gx[3] = {g.g_xyz[3 * on], g.g_xyz[3 * on + 1], g.g_xyz[3 * on + 2]};
-            const float4 gq4 = reinterpret_cast<const float4*>(g.g_rotq)[on];
+            float gx[3] = {s.f_xyz[3 * tid], s.f_xyz[3 * tid + 1], s.f_xyz[3 * tid + 2]};
+            const float4 gq4 = reinterpret_cast<const float4*>(s.f_q)[tid];
             float gq[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
-            float gs[3] = {g.g_scales[3 * on], g.g_scales[3 * on + 1], g.g_scales[3 * on + 2]};
+            float gs[3] = {s.f_scl[3 * tid], s.f_scl[3 * tid + 1], s.f_scl[3 * tid + 2]};
             float Rp[9];
             compose_rot(T, Rc, iso, Rp);
             if (a.ext_rot) {
@@ -618,34 +761,73 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(LbsArgs a, LbsGrad
             const float t = warp_sum(gss);
             if (lane == 0) atomicAdd(g.d_smpl_scale + b, t);
         }
-        // ---- dA[b][j] = sum_n W[n][j] dT_n : CTA-level (J x 256) @ (256 x 12) ----
-        __syncthreads();
+        // ---- dA[b][j] = sum_n W[n][j] dT_n.  Each warp multiplies its own 32 rows: lane =
+        // joint (two joints per lane when J > 32), 12 accumulators per joint, the dT row is a
+        // broadcast LDS.128 x3 and the weight column a conflict-free LDS per row.  The eight
+        // per-warp partials are summed through shared memory; one atomic per CTA and entry.
+        float4* dTrow = reinterpret_cast<float4*>(s.dT) + tid * 3;
+        dTrow[0] = make_float4(dT[0], dT[1], dT[2], dT[3]);
+        dTrow[1] = make_float4(dT[4], dT[5], dT[6], dT[7]);
+        dTrow[2] = make_float4(dT[8], dT[9], dT[10], dT[11]);
+        __syncwarp();
+#pragma unroll 1
+        for (int jb = 0; jb < a.J; jb += 32) {
+            const int j = jb + lane;
+            float acc[12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) s.dT[tid * 12 + k] = dT[k];
+            for (int k = 0; k < 12; k++) acc[k] = 0.0f;
+            if (j < a.J) {
+                const float* wcol = s.W + (size_t)(warp * 32) * a.J + j;
+                const float4* drow = reinterpret_cast<const float4*>(s.dT) + (warp * 32) * 3;
+#pragma unroll 4
+                for (int l = 0; l < warp_rows; l++) {
+                    const float w = wcol[(size_t)l * a.J];
+                    const float4 d0 = drow[3 * l], d1 = drow[3 * l + 1], d2 = drow[3 * l + 2];
+                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]); acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]); acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                    acc[8] = fmaf(w, d2.x, acc[8]); acc[9] = fmaf(w, d2.y, acc[9]); acc[10] = fmaf(w, d2.z, acc[10]); acc[11] = fmaf(w, d2.w, acc[11]);
+                }
+                float4* pr = reinterpret_cast<float4*>(s.part) + ((size_t)warp * a.J + j) * 3;
+                pr[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                pr[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                pr[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+            }
+        }
         __syncthreads();
         for (int oidx = tid; oidx < a.J * 12; oidx += LBS_THREADS) {
-            const int j = oidx / 12, c = oidx - j * 12;
             float accv = 0.0f;
-            for (int t = 0; t < rows; t++) accv = fmaf(s.W[(size_t)t * a.J + j], s.dT[t * 12 + c], accv);
-            const int r = c >> 2, cc = c & 3;
-            atomicAdd(g.d_A + ((size_t)b * a.J + j) * 16 + 4 * r + cc, accv);
+#pragma unroll
+            for (int w = 0; w < LBS_THREADS / 32; w++) accv += s.part[(size_t)w * a.J * 12 + oidx];
+            const int j = oidx / 12, c = oidx - j * 12;
+            atomicAdd(g.d_A + ((size_t)b * a.J + j) * 16 + 4 * (c >> 2) + (c & 3), accv);
         }
     }
+    // ---- canonical-parameter gradients leave through the input blocks' shared memory ----
+    __syncthreads();
     if (live) {
-        g.d_xyz[3 * (size_t)n] = dx; g.d_xyz[3 * (size_t)n + 1] = dy; g.d_xyz[3 * (size_t)n + 2] = dz;
-        g.d_scales[3 * (size_t)n] = ds0; g.d_scales[3 * (size_t)n + 1] = ds1; g.d_scales[3 * (size_t)n + 2] = ds2;
-        if (g.d_rot) {
+        s.xyz[3 * tid] = dx; s.xyz[3 * tid + 1] = dy; s.xyz[3 * tid + 2] = dz;
+        s.scl[3 * tid] = ds0; s.scl[3 * tid + 1] = ds1; s.scl[3 * tid + 2] = ds2;
+        if (g.d_rot && !iso) {
 #pragma unroll
-            for (int k = 0; k < 9; k++) g.d_rot[9 * (size_t)n + k] = dRc[k];
+            for (int k = 0; k < 9; k++) s.rot[9 * tid + k] = dRc[k];
         }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    block_store(g.d_xyz + (size_t)base * 3, s.xyz, (unsigned)rows * 3);
+    block_store(g.d_scales + (size_t)base * 3, s.scl, (unsigned)rows * 3);
+    if (g.d_rot && !iso) block_store(g.d_rot + (size_t)base * 9, s.rot, (unsigned)rows * 9);
+    if (tid == 0) {
+        bulk_commit();
+        bulk_wait_read();
     }
 }
 
 int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
     if (a.N <= 0 || a.B <= 0) return 0;
     if (a.J < 1 || a.J > 64) return SGS_ERR_BAD_JOINTS;
-    if (((uintptr_t)a.A & 15) || ((uintptr_t)g.g_rotq & 15) || (g.g_T && ((uintptr_t)g.g_T & 15))) return SGS_ERR_MISALIGNED;
-    const size_t smem = lbs_smem_bytes(a.B, a.J, true);
+    if (((uintptr_t)a.A & 15) || (g.g_T && ((uintptr_t)g.g_T & 15))) return SGS_ERR_MISALIGNED;
+    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, true);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lbs_bwd_kernel<<<(a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream>>>(a, g);

@@ -6,8 +6,8 @@
 // reached from /root/reference/sings/rec/renderer/gs_renderer_single.py:87-95.
 //
 // One CTA per 16x16 tile, one thread per pixel.  B200-first structure (results unchanged):
-//  * tiles are processed longest-list-first (an order array built by the last CTA of the
-//    range kernel), so the few tiles with thousands of pairs do not form the tail;
+//  * tiles are processed longest-list-first (an order array built with the tile ranges from
+//    the per-tile pair counts), so the few tiles with thousands of pairs do not form the tail;
 //  * each warp owns an 8x4 pixel block; while staging a batch of 256 pairs every thread also
 //    computes, for its pair, which of the 8 pixel blocks the Gaussian's alpha >= 1/255 footprint
 //    can reach (ellipse bounding box AND bounding circle, conservative); each warp then
@@ -24,95 +24,94 @@
 namespace sgs {
 
 constexpr int ORDER_BUCKETS = 256;
-constexpr int BWD_U = 2;      // pairs whose alpha is evaluated together in the backward blend
+constexpr int BWD_U = 4;      // pairs per software-pipeline stage in the backward blend
 constexpr int FWD_U = 4;      // pairs evaluated together per pixel in the forward blend
 
-// [upstream] identifyTileRanges: ranges[tile] = [start, end) in the sorted list (pre-zeroed).
-// The last CTA to finish also builds `order`: tile ids sorted by descending list length
-// (counting sort on length/16, ties in arbitrary order).
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(const unsigned long long* __restrict__ keys, int* counters, long long n_cap,
-                   uint2* ranges, unsigned* __restrict__ order, int tiles) {
+// [upstream] identifyTileRanges, without a pass over the sorted list: the geometry kernel
+// counts the pairs of every tile while it emits them, so ranges[tile] = [start, end) is an
+// exclusive scan of the counts (an empty tile keeps (0, 0), like the reference's memset).
+// The same CTA builds `order`: tile ids sorted by descending list length (counting sort on
+// length/16, ties in arbitrary order) for the blend kernels' longest-first schedule.
+// One CTA of 1024 threads; runs right after the geometry kernel, before the sort.
+constexpr int ORDER_THREADS = 1024;
+
+__global__ void __launch_bounds__(ORDER_THREADS)
+tile_order_kernel(const unsigned* __restrict__ tile_count, uint2* __restrict__ ranges,
+                  unsigned* __restrict__ order, int tiles) {
     __shared__ unsigned s_cnt[ORDER_BUCKETS];
-    __shared__ unsigned s_tmp[8];
-    __shared__ int s_last;
-    const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        unsigned cur = (unsigned)(keys[i] >> 32);
-        if (i == 0) ranges[cur].x = 0;
-        else {
-            unsigned prev = (unsigned)(keys[i - 1] >> 32);
-            if (prev != cur) {
-                ranges[prev].y = (unsigned)i;
-                ranges[cur].x = (unsigned)i;
-            }
-        }
-        if (i == n - 1) ranges[cur].y = (unsigned)n;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&counters[CNT_RANGES_DONE], 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    __shared__ unsigned s_warp[ORDER_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_cnt[tid] = 0;
+    if (tid < ORDER_BUCKETS) s_cnt[tid] = 0;
     __syncthreads();
-    // bucket of every tile: independent (unrolled) L2 loads, then the shared-memory counts
-    constexpr int PER = 16;                       // tiles per thread per sweep (4096 tiles/sweep)
-    const uint2* vr = ranges;
-    for (int base = 0; base < tiles; base += 256 * PER) {
-        unsigned bk[PER];
-#pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const int t = base + u * 256 + tid;
-            uint2 rg = make_uint2(0, 0);
-            if (t < tiles) rg = __ldcg(vr + t);
-            bk[u] = ORDER_BUCKETS - 1 - min((rg.y - rg.x) >> 4, (unsigned)ORDER_BUCKETS - 1);
-        }
-#pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const bool ok = base + u * 256 + tid < tiles;
-            const unsigned peers = __match_any_sync(0xffffffffu, ok ? bk[u] : 0xffffffffu);
-            if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bk[u]], (unsigned)__popc(peers));
-        }
-    }
-    __syncthreads();
-    // exclusive scan of the 256 bucket counts
-    unsigned v = s_cnt[tid], incl = v;
+    // ---- ranges: thread t owns the contiguous tiles [t*per, (t+1)*per) ----
+    const int per = (tiles + ORDER_THREADS - 1) / ORDER_THREADS;
+    const int t0 = tid * per, t1 = min(t0 + per, tiles);
+    unsigned sum = 0;
+    for (int t = t0; t < t1; t++) sum += tile_count[t];
+    unsigned incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         unsigned x = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += x;
     }
-    if (lane == 31) s_tmp[warp] = incl;
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned off = 0;
-    for (int w = 0; w < warp; w++) off += s_tmp[w];
-    __syncthreads();
-    s_cnt[tid] = off + incl - v;
-    __syncthreads();
-    for (int base = 0; base < tiles; base += 256 * PER) {
-        unsigned bk[PER];
+    if (warp == 0) {
+        unsigned v = s_warp[lane], inc2 = v;
 #pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const int t = base + u * 256 + tid;
-            uint2 rg = make_uint2(0, 0);
-            if (t < tiles) rg = __ldcg(vr + t);
-            bk[u] = ORDER_BUCKETS - 1 - min((rg.y - rg.x) >> 4, (unsigned)ORDER_BUCKETS - 1);
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned x = __shfl_up_sync(0xffffffffu, inc2, d);
+            if (lane >= d) inc2 += x;
         }
+        s_warp[lane] = inc2 - v;
+    }
+    __syncthreads();
+    unsigned run = s_warp[warp] + incl - sum;
+    for (int t = t0; t < t1; t++) {
+        const unsigned c = tile_count[t];
+        ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+        run += c;
+    }
+    // ---- bucket sizes (warp-aggregated: most tiles are empty and share one bucket) ----
+    for (int base = 0; base < tiles; base += ORDER_THREADS) {
+        const int t = base + tid;
+        const bool ok = t < tiles;
+        const unsigned c = ok ? tile_count[t] : 0u;
+        const unsigned bk = ok ? ORDER_BUCKETS - 1 - min(c >> 4, (unsigned)ORDER_BUCKETS - 1) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, bk);
+        if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bk], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    // ---- exclusive scan of the 256 bucket counts (warps 0..7) ----
+    unsigned v = 0, binc = 0;
+    if (tid < ORDER_BUCKETS) {
+        v = s_cnt[tid];
+        binc = v;
 #pragma unroll
-        for (int u = 0; u < PER; u++) {
-            const int t = base + u * 256 + tid;
-            const bool ok = t < tiles;
-            const unsigned peers = __match_any_sync(0xffffffffu, ok ? bk[u] : 0xffffffffu);
-            const int leader = __ffs(peers) - 1;
-            unsigned slot = 0;
-            if (ok && lane == leader) slot = atomicAdd(&s_cnt[bk[u]], (unsigned)__popc(peers));
-            slot = __shfl_sync(0xffffffffu, slot, leader);
-            if (ok) order[slot + __popc(peers & lanemask_lt())] = (unsigned)t;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned x = __shfl_up_sync(0xffffffffu, binc, d);
+            if (lane >= d) binc += x;
         }
+        if (lane == 31) s_warp[warp] = binc;
+    }
+    __syncthreads();
+    if (tid < ORDER_BUCKETS) {
+        unsigned off = 0;
+        for (int w = 0; w < warp; w++) off += s_warp[w];
+        s_cnt[tid] = off + binc - v;
+    }
+    __syncthreads();
+    for (int base = 0; base < tiles; base += ORDER_THREADS) {
+        const int t = base + tid;
+        const bool ok = t < tiles;
+        const unsigned c = ok ? tile_count[t] : 0u;
+        const unsigned bk = ok ? ORDER_BUCKETS - 1 - min(c >> 4, (unsigned)ORDER_BUCKETS - 1) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, bk);
+        const int leader = __ffs(peers) - 1;
+        unsigned slot = 0;
+        if (ok && lane == leader) slot = atomicAdd(&s_cnt[bk], (unsigned)__popc(peers));
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (ok) order[slot + __popc(peers & lanemask_lt())] = (unsigned)t;
     }
 }
 
@@ -123,13 +122,10 @@ static inline const unsigned* sorted_vals(const RasterLayout& lay, const char* b
     return reinterpret_cast<const unsigned*>(bin + ((lay.passes & 1) ? lay.vals1_off : lay.vals0_off));
 }
 
-int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
-    int* counters = reinterpret_cast<int*>(bin + lay.cnt_off);
-    long long blocks = (L_cap + 255) / 256;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 4) blocks = 148 * 4;          // grid-stride: few CTAs take the "last CTA" path
-    tile_ranges_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-        sorted_keys(lay, bin), counters, L_cap, reinterpret_cast<uint2*>(bin + lay.ranges_off),
+int launch_tile_ranges(const RasterLayout& lay, char* bin, cudaStream_t stream) {
+    tile_order_kernel<<<1, ORDER_THREADS, 0, stream>>>(
+        reinterpret_cast<const unsigned*>(bin + lay.tilecnt_off),
+        reinterpret_cast<uint2*>(bin + lay.ranges_off),
         reinterpret_cast<unsigned*>(bin + lay.order_off), lay.tiles);
     SGS_LAUNCH_OK();
     return 0;
@@ -329,42 +325,43 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
 }
 
 // ------------------------------------------------------------------------------------------
-// backward.  Same warp-autonomous streaming, back to front, starting at the largest
-// contributor count among the warp's 32 pixels.  The nine per-pixel partial gradients of a
-// Gaussian are reduce-scattered across the warp (recursive halving: 14 shuffles instead of
-// 45) and leave as ONE reduction instruction (lanes 0..8 -> nine consecutive floats).
+// backward.  Same warp-autonomous streaming and ring queue, back to front, starting at the
+// largest contributor count among the warp's 32 pixels.  Two phases per warp:
+//  phase 1 (lane = pixel): the order-dependent part.  EVAL computes falloff G, alpha and
+//    1/(1-alpha) of the next BWD_U pairs while SEQ advances the pixel state (T, the colour
+//    behind the pair) over the previous BWD_U, branch-free.  Of everything the nine parameter
+//    gradients need, only TWO numbers per (pixel, pair) depend on the order: w = G dL/dalpha
+//    and d = alpha T.  SEQ parks them in a warp-private [pair][pixel] tile (row stride 33).
+//  phase 2 (lane = pair, every 32 queued pairs): each lane walks the 32 pixels of its pair's
+//    row and accumulates  sum w, w dx, w dy, w dx^2, w dx dy, w dy^2, d dL/dpix_rgb  in
+//    registers -- the reduction over pixels costs no shuffles at all -- then folds them into
+//    the nine gradients and issues 2 vector + 1 scalar reduction for its Gaussian.
 // ------------------------------------------------------------------------------------------
-// Sum eight values across the warp by recursive halving; lane l returns the total of v[l & 7].
-__device__ __forceinline__ float reduce_scatter8(float v0, float v1, float v2, float v3, float v4,
-                                                 float v5, float v6, float v7, int lane) {
-    const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
-    float k0 = h4 ? v4 : v0, k1 = h4 ? v5 : v1, k2 = h4 ? v6 : v2, k3 = h4 ? v7 : v3;
-    k0 += __shfl_xor_sync(0xffffffffu, h4 ? v0 : v4, 4);
-    k1 += __shfl_xor_sync(0xffffffffu, h4 ? v1 : v5, 4);
-    k2 += __shfl_xor_sync(0xffffffffu, h4 ? v2 : v6, 4);
-    k3 += __shfl_xor_sync(0xffffffffu, h4 ? v3 : v7, 4);
-    float m0 = h2 ? k2 : k0, m1 = h2 ? k3 : k1;
-    m0 += __shfl_xor_sync(0xffffffffu, h2 ? k0 : k2, 2);
-    m1 += __shfl_xor_sync(0xffffffffu, h2 ? k1 : k3, 2);
-    float r = h1 ? m1 : m0;
-    r += __shfl_xor_sync(0xffffffffu, h1 ? m0 : m1, 1);
-    r += __shfl_xor_sync(0xffffffffu, r, 8);
-    r += __shfl_xor_sync(0xffffffffu, r, 16);
-    return r;
-}
+constexpr int BWD_ROW = 33;        // padded row of the [pair][pixel] tiles: conflict-free both ways
 
-__global__ void __launch_bounds__(TILE_PIX)
+struct BwdBatch {
+    float al[BWD_U], G[BWD_U], om[BWD_U], inv[BWD_U], r[BWD_U], g[BWD_U], b[BWD_U];
+};
+
+struct BwdWarpSmem {
+    float4 q0[RING_SLOTS];          // x, y, -a/2, -b
+    float4 q1[RING_SLOTS];          // -c/2, opacity, list position (bits), r
+    float4 q2[RING_SLOTS];          // g, b, -, Gaussian id (bits)
+    float w[32 * BWD_ROW];          // G * dL/dalpha   [pair][pixel]
+    float d[32 * BWD_ROW];          // alpha * T       [pair][pixel]
+    float dp[3][32];                // dL/dpixel rgb of the warp's 32 pixels
+    unsigned id[2][32];             // Gaussian of each pair row (double-buffered by tile parity)
+};
+
+__global__ void __launch_bounds__(TILE_PIX, 2)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ order,
                  const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, float* __restrict__ acc) {
-    __shared__ float4 s_q0[TILE_PIX / 32][2][32];
-    __shared__ float4 s_q1[TILE_PIX / 32][2][32];
-    __shared__ float4 s_q2[TILE_PIX / 32][2][32];
-    __shared__ unsigned s_id[TILE_PIX / 32][2][32];
-
+    extern __shared__ __align__(16) char s_bwd_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[warp];
     const unsigned tile = order[blockIdx.x];
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
@@ -383,14 +380,98 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const int wlast = (int)__reduce_max_sync(0xffffffffu, last);
     if (wlast == 0) return;
     const float T_final = inside ? final_T[pix] : 0.0f;
-    float T = T_final;
     float dp0 = 0.0f, dp1 = 0.0f, dp2 = 0.0f;
     if (inside) { dp0 = dL_dpix[pix]; dp1 = dL_dpix[plane + pix]; dp2 = dL_dpix[2 * plane + pix]; }
-    const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    sm.dp[0][lane] = dp0; sm.dp[1][lane] = dp1; sm.dp[2][lane] = dp2;
+    const float nTf_bg = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+    // ring slots always hold finite records
+    sm.q0[lane] = sm.q0[lane + 32] = make_float4(0, 0, 0, 0);
+    sm.q1[lane] = sm.q1[lane + 32] = make_float4(0, 0, 0, 0);
+    sm.q2[lane] = sm.q2[lane + 32] = make_float4(0, 0, 0, 0);
 
-    float acc_r0 = 0, acc_r1 = 0, acc_r2 = 0;       // accum_rec
-    float last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0;
+    float T = T_final;
+    float B0 = 0.0f, B1 = 0.0f, B2 = 0.0f;     // colour accumulated behind the current pair
+    unsigned head = 0, tail = 0;               // ring: consumed / produced pair counts
+    unsigned row0 = 0;                         // first pair (consumption index) of the open [pair][pixel] tile; multiple of 32
+
+    BwdBatch cur;
+#pragma unroll
+    for (int u = 0; u < BWD_U; u++) {
+        cur.al[u] = 0.0f; cur.G[u] = 0.0f; cur.om[u] = 1.0f; cur.inv[u] = 1.0f;
+        cur.r[u] = cur.g[u] = cur.b[u] = 0.0f;
+    }
+
+    auto eval = [&](BwdBatch& e, unsigned base, unsigned limit) {
+#pragma unroll
+        for (int u = 0; u < BWD_U; u++) {
+            const unsigned slot = (base + u) & (RING_SLOTS - 1);
+            const float4 q0 = sm.q0[slot];
+            const float4 q1 = sm.q1[slot];
+            const float4 q2 = sm.q2[slot];
+            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+            const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
+            const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
+            const float G = expneg(fminf(power, 0.0f));
+            const float al = fminf(0.99f, __fmul_rn(q1.y, G));
+            const bool ok = (base + u < limit) && __float_as_uint(q1.z) < last && !(power > 0.0f) &&
+                            !(al < 1.0f / 255.0f);
+            e.al[u] = ok ? al : 0.0f;
+            e.G[u] = ok ? G : 0.0f;
+            e.om[u] = 1.0f - e.al[u];
+            e.inv[u] = __fdividef(1.0f, e.om[u]);
+            e.r[u] = q1.w; e.g[u] = q2.x; e.b[u] = q2.y;
+            if (lane == u) sm.id[((base + u) >> 5) & 1][(base + u) & 31] = __float_as_uint(q2.w);
+        }
+    };
+    // advance the pixel state over a batch whose first pair has consumption index `base`
+    auto seq = [&](const BwdBatch& e, unsigned base) {
+#pragma unroll
+        for (int u = 0; u < BWD_U; u++) {
+            T = T * e.inv[u];
+            const float dch = e.al[u] * T;
+            const float dot = (e.r[u] - B0) * dp0 + (e.g[u] - B1) * dp1 + (e.b[u] - B2) * dp2;
+            const float dLda = T * dot + nTf_bg * e.inv[u];
+            const unsigned row = (base + u) & 31;
+            sm.w[row * BWD_ROW + lane] = e.G[u] * dLda;
+            sm.d[row * BWD_ROW + lane] = dch;
+            B0 = e.al[u] * e.r[u] + e.om[u] * B0;
+            B1 = e.al[u] * e.g[u] + e.om[u] * B1;
+            B2 = e.al[u] * e.b[u] + e.om[u] * B2;
+        }
+    };
+    // phase 2 over the `cnt` (<= 32) pair rows of the open tile
+    auto reduce_rows = [&](unsigned cnt) {
+        __syncwarp();
+        if (lane < cnt) {
+            const unsigned id = sm.id[(row0 >> 5) & 1][lane];
+            const float4 q0 = __ldg(rec + 4 * (size_t)id);
+            const float4 q1 = __ldg(rec + 4 * (size_t)id + 1);
+            float S0 = 0, Sx = 0, Sy = 0, Sxx = 0, Sxy = 0, Syy = 0, Sr = 0, Sg = 0, Sb = 0;
+            const float* wr = sm.w + lane * BWD_ROW;
+            const float* dr = sm.d + lane * BWD_ROW;
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const float w = wr[k], d = dr[k];
+                const float dx = __fsub_rn(q0.x, bx0 + (float)(k & 7));
+                const float dy = __fsub_rn(q0.y, by0 + (float)(k >> 3));
+                const float wdx = w * dx, wdy = w * dy;
+                S0 += w;
+                Sx += wdx; Sy += wdy;
+                Sxx = fmaf(wdx, dx, Sxx); Sxy = fmaf(wdx, dy, Sxy); Syy = fmaf(wdy, dy, Syy);
+                Sr = fmaf(d, sm.dp[0][k], Sr); Sg = fmaf(d, sm.dp[1][k], Sg); Sb = fmaf(d, sm.dp[2][k], Sb);
+            }
+            // conic entries: a = -2*q0.z, b = -q0.w, c = -2*q1.x
+            const float ca = -2.0f * q0.z, cb = -q0.w, cc = -2.0f * q1.x, o = q1.y;
+            float* dst = acc + (size_t)id * ACC_FLOATS;
+            // accumulator slots 0..8: mean2D.x, .y, conic a, b, c, opacity, r, g, b
+            red_add_f4(dst, -o * ddelx_dx * (ca * Sx + cb * Sy), -o * ddely_dy * (cc * Sy + cb * Sx),
+                       -0.5f * o * Sxx, -0.5f * o * Sxy);
+            red_add_f4(dst + 4, -0.5f * o * Syy, S0, Sr, Sg);
+            atomicAdd(dst + 8, Sb);
+        }
+        __syncwarp();
+    };
 
     Rec p;
     unsigned pid = 0;
@@ -399,99 +480,58 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         pid = __ldg(point_list + range.x + (wlast - 1 - lane));
         p = load_rec(rec, pid);
     }
-    int buf = 0;
+    // `cur` starts as an empty batch at consumption index -BWD_U: its SEQ writes zeros into
+    // rows that real pairs overwrite before any reduction reads them.
+    unsigned pend = 0u - BWD_U;
     // chunk c covers list positions top-lane, top = wlast-1-32c: lane order = back-to-front order
-    for (int top = wlast - 1; top >= 0; top -= 32, buf ^= 1) {
+    for (int top = wlast - 1; top >= 0; top -= 32) {
         const bool rel = (top - lane >= 0) && reaches_block(p.q0, p.q1, p.q3, bx0, bx1, by0, by1);
-        unsigned bits = __ballot_sync(0xffffffffu, rel);
-        s_q0[warp][buf][lane] = p.q0; s_q1[warp][buf][lane] = p.q1; s_q2[warp][buf][lane] = p.q2;
-        s_id[warp][buf][lane] = pid;
+        const unsigned bits = __ballot_sync(0xffffffffu, rel);
+        __syncwarp();
+        if (rel) {
+            const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
+            sm.q0[slot] = p.q0;
+            sm.q1[slot] = make_float4(p.q1.x, p.q1.y, __uint_as_float((unsigned)(top - lane)), p.q1.w);
+            sm.q2[slot] = make_float4(p.q2.x, p.q2.y, 0.0f, __uint_as_float(pid));
+        }
+        tail += __popc(bits);
         __syncwarp();
         if (top - 32 - lane >= 0) {
             pid = __ldg(point_list + range.x + (top - 32 - lane));
             p = load_rec(rec, pid);
         }
-        while (bits) {
-            // stage 1: falloff and alpha of BWD_U pairs, independent chains
-            float Gs[BWD_U], als[BWD_U], dxs[BWD_U], dys[BWD_U];
-            int jj[BWD_U];
-            bool vs[BWD_U];
-            bool any_ok = false;
-#pragma unroll
-            for (int u = 0; u < BWD_U; u++) {
-                const bool in = bits != 0;
-                const int j = in ? __ffs(bits) - 1 : 0;
-                bits &= bits - 1;
-                const unsigned pos = (unsigned)(top - j);            // 0-based list position
-                const float4 q0 = s_q0[warp][buf][j];
-                const float4 q1 = s_q1[warp][buf][j];
-                const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-                const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
-                const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
-                vs[u] = in && pos < last && !(power > 0.0f) && !(power < q1.z);
-                Gs[u] = fminf(power, 0.0f);
-                als[u] = q1.y;
-                dxs[u] = dx; dys[u] = dy; jj[u] = j;
-                any_ok |= vs[u];
+        while (tail - head >= BWD_U) {
+            BwdBatch nxt;
+            eval(nxt, head, tail);
+            seq(cur, pend);
+            if (pend + BWD_U - row0 == 32) {       // the open tile is full (32 % BWD_U == 0)
+                reduce_rows(32);
+                row0 += 32;
             }
-            if (!__any_sync(0xffffffffu, any_ok)) continue;
-#pragma unroll
-            for (int u = 0; u < BWD_U; u++) {
-                Gs[u] = expneg(Gs[u]);
-                als[u] = fminf(0.99f, __fmul_rn(als[u], Gs[u]));
-                vs[u] = vs[u] && !(als[u] < 1.0f / 255.0f);
-            }
-            // stage 2: order-dependent state update, gradients, warp reduction
-#pragma unroll
-            for (int u = 0; u < BWD_U; u++) {
-                const bool valid = vs[u];
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                const int j = jj[u];
-                float g_mx = 0, g_my = 0, g_ca = 0, g_cb = 0, g_cc = 0, g_op = 0, g_r = 0, g_g = 0, g_b = 0;
-                if (valid) {
-                    const float4 q0 = s_q0[warp][buf][j];
-                    const float4 q1 = s_q1[warp][buf][j];
-                    const float4 q2 = s_q2[warp][buf][j];
-                    const float G = Gs[u], alpha = als[u], dx = dxs[u], dy = dys[u];
-                    const float inv1a = 1.0f / (1.0f - alpha);
-                    T = T * inv1a;
-                    const float dch = alpha * T;
-                    const float c0 = q1.w, c1 = q2.x, c2 = q2.y;
-                    acc_r0 = last_alpha * lc0 + (1.0f - last_alpha) * acc_r0;
-                    acc_r1 = last_alpha * lc1 + (1.0f - last_alpha) * acc_r1;
-                    acc_r2 = last_alpha * lc2 + (1.0f - last_alpha) * acc_r2;
-                    lc0 = c0; lc1 = c1; lc2 = c2;
-                    float dL_dalpha = (c0 - acc_r0) * dp0 + (c1 - acc_r1) * dp1 + (c2 - acc_r2) * dp2;
-                    g_r = dch * dp0; g_g = dch * dp1; g_b = dch * dp2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv1a) * bg_dot;
-                    const float dL_dG = q1.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    // conic entries: a = -2*q0.z, b = -q0.w, c = -2*q1.x
-                    const float ca = -2.0f * q0.z, cb = -q0.w, cc = -2.0f * q1.x;
-                    const float dG_ddelx = -gdx * ca - gdy * cb;
-                    const float dG_ddely = -gdy * cc - gdx * cb;
-                    g_mx = dL_dG * dG_ddelx * ddelx_dx;
-                    g_my = dL_dG * dG_ddely * ddely_dy;
-                    g_ca = -0.5f * gdx * dx * dL_dG;
-                    g_cb = -0.5f * gdx * dy * dL_dG;
-                    g_cc = -0.5f * gdy * dy * dL_dG;
-                    g_op = G * dL_dalpha;
-                }
-                // accumulator slots 0..8: mean2D.x, .y, conic a, b, c, opacity, r, g, b
-                const float r8 = reduce_scatter8(g_mx, g_my, g_ca, g_cb, g_cc, g_op, g_r, g_g, lane);
-                const float rb = warp_sum(g_b);
-                if (lane < 9) atomicAdd(acc + (size_t)s_id[warp][buf][j] * ACC_FLOATS + lane, lane < 8 ? r8 : rb);
-            }
+            cur = nxt;
+            pend = head;
+            head += BWD_U;
         }
+    }
+    {   // drain: the waiting batch, the partial remainder of the ring, the partial tile
+        BwdBatch nxt;
+        eval(nxt, head, tail);
+        seq(cur, pend);
+        if (pend + BWD_U - row0 == 32) {
+            reduce_rows(32);
+            row0 += 32;
+        }
+        if (tail > head) seq(nxt, head);
+        if (tail > row0) reduce_rows(tail - row0);
     }
 }
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      const char* img, const float* bg, const float* dL_dpix, float* acc,
                      cudaStream_t stream) {
-    blend_bwd_kernel<<<lay.tiles, TILE_PIX, 0, stream>>>(
+    const size_t smem = sizeof(BwdWarpSmem) * (TILE_PIX / 32);
+    SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    blend_bwd_kernel<<<lay.tiles, TILE_PIX, smem, stream>>>(
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.order_off), sorted_vals(lay, bin),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,

@@ -182,7 +182,7 @@ class AvatarStep:
             raise _lib.SgsError("AvatarStep(timing=True) required")
         out = {}
         ms = C.c_float()
-        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("sort", 1, 2), ("ranges", 2, 3),
+        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("ranges", 1, 12), ("sort", 12, 2),
                            ("blend_fwd", 3, 4), ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7),
                            ("lbs_bwd", 10, 11), ("total", 8, 11)]:
             _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
