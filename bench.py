@@ -227,8 +227,11 @@ def gpu_arm(args):
             pending[i % RING]()            # finish the all-reduce that last used this bucket
             pending[i % RING] = None
             st.grad_accum.zero_(); st.denom.zero_(); st.max_radii2D.zero_()
-        st.forward(s["fr"])
-        st.backward(s["G"])
+        if "replay" in s:
+            s["replay"]()                  # the whole frame as one CUDA-graph launch
+        else:
+            st.forward(s["fr"])
+            st.backward(s["G"])
         if exch is not None:
             pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True)
 
@@ -253,6 +256,17 @@ def gpu_arm(args):
                     s["step"].check_capacity()
                 except SgsError:
                     pass
+    if not args.no_graph:
+        # capacities are settled: record each avatar's frame (forward + backward) as a CUDA graph
+        for i in range(RING):
+            if pending[i] is not None:
+                pending[i]()
+                pending[i] = None
+        for s in sets:
+            s["replay"] = s["step"].capture(s["fr"], s["G"])
+        for i in range(2 * RING):
+            one_step(i, pending)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -309,7 +323,7 @@ def gpu_arm(args):
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, sets, dev, world, rank)
+        e2e = run_e2e(args, sets, dev, world, rank, exch)
     clocks = sampler.stop() if rank == 0 else None
 
     cpu_base = None
@@ -328,6 +342,7 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": [H_IMG, W_IMG], "sh_degree": SH_DEG,
                        "joints": N_JOINTS, "views_per_gpu_per_step": 1,
+                       "launch": "eager launches" if args.no_graph else "one CUDA graph per frame (forward+backward)",
                        "l2": f"inputs rotate over a ring of {RING} distinct avatars (~{RING * 70} MB of inputs) > 126 MB L2",
                        "parallelism": f"dp{world} (views sharded, gradient bucket all-reduced)" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
@@ -339,34 +354,35 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, sets, dev, world, rank):
-    """Same metric through the public API with host buffers (pinned), per step:
-    H2D pose + transl + dL/dimage, forward, backward, D2H loss."""
+def run_e2e(args, sets, dev, world, rank, exch=None):
+    """Same metric end to end with HOST buffers.  Per step, inside the timed region: H2D of
+    pose + transl + dL/dimage from pinned memory, forward, loss, backward, D2H of the loss.
+
+    Two callers of the same kernels are timed:
+      * `e2e` (headline): the C-ABI path -- `AvatarStep` drives include/sings_b200.h directly
+        with preallocated buffers (what a trainer integrating the library calls per frame);
+      * `e2e.dropin`: the reference-facing autograd modules (`sings_b200.deform` +
+        `diff_gaussian_rasterization.GaussianRasterizer`), which add torch.autograd and
+        per-call allocation overhead on the host.
+    Both use the same input pipeline: inputs are prefetched one step ahead on a copy stream
+    into double-buffered device staging (like a data loader with pinned memory) and the loss
+    is read back through pinned slots one step late (like a logging trainer)."""
     import torch
     import torch.distributed as dist
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     from sings_b200 import deform
+    from sings_b200 import rasterizer as R
+    from sings_b200.step import FrameInputs
 
     host = []
     for s in sets:
         av = s["av"]
         t = lambda a: torch.as_tensor(a, device=dev)
-        params = dict(xyz=t(av.xyz_canon).requires_grad_(True), rot=t(av.rotmat_canon).requires_grad_(True),
-                      scales=t(av.scales).requires_grad_(True), opacity=t(av.opacity).requires_grad_(True),
-                      shs=t(av.shs).requires_grad_(True), W=t(av.lbs_weights), rest=t(av.rest),
-                      parents=torch.from_numpy(av.parents).to(device=dev, dtype=torch.int32),
-                      inv_A=t(av.inv_A_t2cano))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        host.append(dict(p=params, pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]),
-                         view=s["view"], bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
+        host.append(dict(pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]), view=s["view"],
+                         bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
                          pm=t(s["view"].full_proj_transform), cp=t(s["view"].camera_center)))
     h2d = int(host[0]["pose"].numel() * 4 + host[0]["transl"].numel() * 4 + host[0]["G"].numel() * 4)
-    # The input pipeline runs one step ahead on a copy stream (double-buffered device staging,
-    # like a data loader with pinned memory), the loss is read back through a ring of pinned
-    # slots one step late (like a logging trainer), and the rasterizer runs in async mode (the
-    # pair-list overflow flag is examined at the next forward instead of by a mid-step host
-    # sync).  Every H2D copy and every D2H read happens inside the timed region.
-    from sings_b200 import rasterizer as R
     cur = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     NBUF = 2
@@ -386,15 +402,68 @@ def run_e2e(args, sets, dev, world, rank):
             sb["G"].copy_(hs["G"], non_blocking=True)
             sb["ready"].record(copy_stream)
 
-    def step(i, n_total):
-        hs, sb = host[i % RING], stage[i % NBUF]
-        p = hs["p"]
+    def finish_step(i, loss, sb):
+        sb["free"].record(cur)
+        loss_host[i % NBUF:i % NBUF + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ev[i % NBUF].record(cur)
+        if i >= 1:                                     # read the previous step's loss
+            loss_ev[(i - 1) % NBUF].synchronize()
+            losses.append(float(loss_host[(i - 1) % NBUF]))
+
+    # ---- C-ABI path ----
+    pending = [None] * RING
+
+    def drain_exchange():
+        for k in range(RING):
+            if pending[k] is not None:
+                pending[k]()
+                pending[k] = None
+
+    assert RING % NBUF == 0        # ring slot k always meets staging buffer k % NBUF (graphs bind addresses)
+    frames = [FrameInputs(pose=stage[k % NBUF]["pose"], transl=stage[k % NBUF]["transl"], viewmatrix=host[k]["vm"],
+                          projmatrix=host[k]["pm"], campos=host[k]["cp"], bg=host[k]["bg"],
+                          tanfovx=host[k]["view"].tanfovx, tanfovy=host[k]["view"].tanfovy) for k in range(RING)]
+    replays = [None] * RING
+
+    def step_abi(i, n_total):
+        hs, sb, st = host[i % RING], stage[i % NBUF], sets[i % RING]["step"]
+        if i + 1 < n_total:
+            prefetch(i + 1)
+        if exch is not None and pending[i % RING] is not None:
+            pending[i % RING]()            # finish the all-reduce that last used this bucket
+            pending[i % RING] = None
+            st.grad_accum.zero_(); st.denom.zero_(); st.max_radii2D.zero_()
+        cur.wait_event(sb["ready"])
+        if replays[i % RING] is not None:
+            replays[i % RING]()            # forward + loss + backward as one CUDA-graph launch
+            loss = st.loss
+        else:
+            img = st.forward(frames[i % RING])
+            loss = torch.dot(img.view(-1), sb["G"].view(-1))      # L = sum(image * G); dL/dimage = G
+            st.backward(sb["G"])
+        if exch is not None:
+            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True)
+        finish_step(i, loss, sb)
+
+    # ---- drop-in autograd path ----
+    params = []
+    if not args.no_dropin:
+        for s in sets:
+            av = s["av"]
+            t = lambda a: torch.as_tensor(a, device=dev)
+            params.append(dict(xyz=t(av.xyz_canon).requires_grad_(True), rot=t(av.rotmat_canon).requires_grad_(True),
+                               scales=t(av.scales).requires_grad_(True), opacity=t(av.opacity).requires_grad_(True),
+                               shs=t(av.shs).requires_grad_(True), W=t(av.lbs_weights), rest=t(av.rest),
+                               parents=torch.from_numpy(av.parents).to(device=dev, dtype=torch.int32),
+                               inv_A=t(av.inv_A_t2cano)))
+
+    def step_dropin(i, n_total):
+        hs, sb, p = host[i % RING], stage[i % NBUF], params[i % RING]
         if i + 1 < n_total:
             prefetch(i + 1)
         cur.wait_event(sb["ready"])
         pose = sb["pose"].detach().requires_grad_(True)
         transl = sb["transl"].detach().requires_grad_(True)
-        G = sb["G"]
         A = deform.pose_to_A(pose, p["rest"], p["parents"], p["inv_A"])
         xyz, rotq, sc = deform.deform_gaussians(A, p["xyz"], p["W"], p["rot"], p["scales"], None, transl)
         v = hs["view"]
@@ -405,18 +474,13 @@ def run_e2e(args, sets, dev, world, rank):
         means2D = torch.zeros_like(xyz, requires_grad=True)
         img, radii = GaussianRasterizer(rs)(means3D=xyz, means2D=means2D, shs=p["shs"], opacities=p["opacity"],
                                             scales=sc, rotations=rotq)
-        loss = (img * G).sum()
+        loss = (img * sb["G"]).sum()
         for q in (p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"]):
             q.grad = None
         loss.backward()
-        sb["free"].record(cur)
-        loss_host[i % NBUF:i % NBUF + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        loss_ev[i % NBUF].record(cur)
-        if i >= 1:                                     # read the previous step's loss
-            loss_ev[(i - 1) % NBUF].synchronize()
-            losses.append(float(loss_host[(i - 1) % NBUF]))
+        finish_step(i, loss, sb)
 
-    def run(n):
+    def run(step, n):
         for sb in stage:
             sb["free"].record(cur)
         prefetch(0)
@@ -424,32 +488,53 @@ def run_e2e(args, sets, dev, world, rank):
             step(i, n)
         loss_ev[(n - 1) % NBUF].synchronize()
         losses.append(float(loss_host[(n - 1) % NBUF]))
-        R.check_pending(block=True)
 
-    n = max(10, min(args.steps, 200))
-    run(RING)                # checked mode: sizes the pair-list capacity for every avatar of the ring
-    R.set_async(True)
-    run(RING)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    losses.clear()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(n)
-    e1.record()
-    torch.cuda.synchronize()
-    R.set_async(False)
-    assert len(losses) == n and all(math.isfinite(x) for x in losses)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    return {"value": world * n / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": 4, "steps": n, "ms_per_step": ms / n,
-            "pipeline": "inputs prefetched one step ahead on a copy stream; loss read back one step late; "
-                        "all copies inside the timed region",
-            "api": "sings_b200.deform.pose_to_A + deform_gaussians + diff_gaussian_rasterization.GaussianRasterizer (autograd)"}
+    def timed(step, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        losses.clear()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(step, n)
+        drain_exchange()
+        e1.record()
+        torch.cuda.synchronize()
+        assert len(losses) == n and all(math.isfinite(x) for x in losses)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    n = max(10, min(args.steps, 400))
+    run(step_abi, RING)
+    if not args.no_graph:
+        drain_exchange()
+        torch.cuda.synchronize()
+        for k in range(RING):
+            replays[k] = sets[k]["step"].capture(frames[k], stage[k % NBUF]["G"], loss_weight=stage[k % NBUF]["G"])
+        run(step_abi, RING)
+    ms = timed(step_abi, n)
+    for s in sets:
+        s["step"].check_capacity()
+    out = {"value": world * n / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "steps": n, "ms_per_step": ms / n,
+           "pipeline": "inputs prefetched one step ahead on a copy stream; loss read back one step late; "
+                       "all copies inside the timed region",
+           "api": "C ABI (include/sings_b200.h) driven by sings_b200.step.AvatarStep with preallocated buffers"
+                  + ("" if args.no_graph else ", one CUDA graph per frame")}
+    if not args.no_dropin:
+        nd = max(10, min(args.steps, 100))
+        run(step_dropin, RING)   # checked mode: sizes the pair-list capacity for every avatar of the ring
+        R.set_async(True)        # then no mid-step host sync: the overflow flag is examined at the next forward
+        run(step_dropin, RING)
+        msd = timed(step_dropin, nd)
+        R.check_pending(block=True)
+        R.set_async(False)
+        out["dropin"] = {"value": world * nd / (msd / 1e3), "unit": "frames/s", "steps": nd, "ms_per_step": msd / nd,
+                         "api": "sings_b200.deform.pose_to_A + deform_gaussians + "
+                                "diff_gaussian_rasterization.GaussianRasterizer (torch.autograd)"}
+    return out
 
 
 def main():
@@ -460,6 +545,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the autograd drop-in variant of the e2e run")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -38,8 +38,8 @@ const char* sgs_error_string(int code);
 
 /* Stage timing (measurement only).  A timing handle owns n CUDA events; the rasterizer entry
  * points record them at stage boundaries when given a handle (null = no recording):
- *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit+tile counts), [12] after
- *             tile ranges/order, [2] = [3] after the radix sort, [4] after the blend;
+ *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit), [2] after the radix
+ *             sort, [3] after tile ranges, [4] after the blend;
  *   backward: [5] start, [6] after the blend backward (incl. accumulator memset), [7] end.
  * sgs_timing_elapsed_ms waits for event j and returns the time from event i to event j. */
 int sgs_timing_create(int n_events, void** handle);
@@ -88,7 +88,10 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
  * geom/binning/img are the buffers the forward filled; acc is scratch (acc_bytes).  All
  * outputs are fully written: dL_dmeans3D (P,3), dL_dmeans2D (P,3), dL_dcolors (P,3),
  * dL_dopacity (P,1), dL_dcov3D (P,6), dL_dsh (P,M,3) [null when colours were precomputed],
- * dL_dscales (P,3), dL_drots (P,4). */
+ * dL_dscales (P,3), dL_drots (P,4).
+ * xyz_gradient_accum / denom / max_radii2D (P each; all three or all null): when given, the
+ * densification statistics of this view (see sgs_densify_stats) are accumulated in the same
+ * pass, in place. */
 int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
                         const float* colors_precomp, const float* scales, float scale_modifier,
                         const float* rotations, const float* cov3D_precomp,
@@ -98,6 +101,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
                         const void* binning, const void* img, void* acc, float* dL_dmeans3D,
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                        float* xyz_gradient_accum, float* denom, float* max_radii2D,
                         sgs_stream_t stream, int debug, void* timing);
 
 /* Replaces _C.mark_visible ([upstream] Rasterizer::markVisible). present: (P) bytes. */

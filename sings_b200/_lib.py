@@ -31,7 +31,7 @@ _SIGNATURES = {
                                 _vp, _i, _vp]),
     "sgs_raster_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp,
                                  _f, _f, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgs_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp]),
     "sgs_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_sort_scratch_bytes": (_sz, [_ll]),

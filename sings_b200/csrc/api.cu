@@ -10,10 +10,18 @@ struct Timing {
     int n;
     cudaEvent_t* ev;
 };
+// Inside a stream capture the record becomes an "external" event-record node, so the stage
+// events keep working (cudaEventElapsedTime) when the frame is replayed as a CUDA graph.
+static inline cudaError_t record_event(cudaEvent_t ev, cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+        return cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal);
+    return cudaEventRecord(ev, s);
+}
 static inline void tick(void* timing, int i, cudaStream_t s) {
     if (!timing) return;
     Timing* t = (Timing*)timing;
-    if (i < t->n) cudaEventRecord(t->ev[i], s);
+    if (i < t->n) record_event(t->ev[i], s);
 }
 
 extern "C" {
@@ -39,7 +47,7 @@ int sgs_timing_destroy(void* handle) {
 }
 int sgs_timing_record(void* handle, int i, sgs_stream_t stream) {
     if (!handle || i < 0 || i >= ((Timing*)handle)->n) return SGS_ERR_BAD_ARG;
-    SGS_CUDA_OK(cudaEventRecord(((Timing*)handle)->ev[i], (cudaStream_t)stream));
+    SGS_CUDA_OK(record_event(((Timing*)handle)->ev[i], (cudaStream_t)stream));
     return 0;
 }
 int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms) {
@@ -141,15 +149,14 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
-    rc = launch_tile_ranges(lay, b, stream);    // ranges + longest-first tile order from the counts
-    if (rc) return rc;
-    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
-    tick(timing, 12, stream);
     if (P > 0) {
         rc = launch_radix_sort(lay, L_cap, b, stream, debug);
         if (rc) return rc;
     }
     tick(timing, 2, stream);
+    rc = launch_tile_ranges(lay, L_cap, b, stream);    // ranges + tiles bucketed by list length
+    if (rc) return rc;
+    if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
     if (rc) return rc;
@@ -170,6 +177,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
                         const void* binning, const void* img, void* acc, float* dL_dmeans3D,
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                        float* xyz_gradient_accum, float* denom, float* max_radii2D,
                         sgs_stream_t stream_, int debug, void* timing) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GeomBwdArgs b;
@@ -181,6 +189,8 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
         !dL_dcolors || !dL_dopacity || (P > 0 && !radii) || (shs && !dL_dsh) || L_cap < 1)
         return SGS_ERR_BAD_ARG;
     if (((uintptr_t)acc & 15) || (dL_drots && ((uintptr_t)dL_drots & 15))) return SGS_ERR_MISALIGNED;
+    const int n_stat = (xyz_gradient_accum != nullptr) + (denom != nullptr) + (max_radii2D != nullptr);
+    if (n_stat != 0 && n_stat != 3) return SGS_ERR_BAD_ARG;
     if (P == 0) return 0;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     tick(timing, 5, stream);
@@ -194,6 +204,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     b.dL_dmeans3D = dL_dmeans3D; b.dL_dmeans2D = dL_dmeans2D; b.dL_dcolors = dL_dcolors;
     b.dL_dopacity = dL_dopacity; b.dL_dcov3D = dL_dcov3D; b.dL_dsh = dL_dsh;
     b.dL_dscales = dL_dscales; b.dL_drots = dL_drots;
+    b.stat_accum = xyz_gradient_accum; b.stat_denom = denom; b.stat_max_radii = max_radii2D;
     rc = launch_geometry_bwd(b, (const char*)geom, stream);
     if (rc) return rc;
     tick(timing, 7, stream);

@@ -30,7 +30,7 @@ struct RasterLayout {
     // geometry state (per Gaussian)
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
-    size_t cnt_off, hist_off, scan_off, sortstat_off, tilecnt_off, zero_bytes, ranges_off, order_off;
+    size_t cnt_off, hist_off, scan_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
     size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
@@ -67,7 +67,7 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
                           int end_bit, int* result_in_tmp, cudaStream_t stream);
 size_t sort_scratch_bytes(long long n);
 
-int launch_tile_ranges(const RasterLayout& lay, char* bin, cudaStream_t stream);
+int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
@@ -89,6 +89,9 @@ struct GeomBwdArgs {
     float* dL_dsh;             // (P,M,3) or null
     float* dL_dscales;         // (P,3)
     float* dL_drots;           // (P,4)
+    float* stat_accum;         // (P) xyz_gradient_accum += ||dL_dmeans2D.xy||  | all three or none:
+    float* stat_denom;         // (P) denom += 1                                | densification statistics
+    float* stat_max_radii;     // (P) max_radii2D = max(., radii)               | of the visible Gaussians
 };
 int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t stream);
 

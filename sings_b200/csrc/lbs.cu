@@ -300,9 +300,11 @@ __device__ __forceinline__ int mat_to_quat(const float* m, float* q) {
     else if (best == 1) { c[0] = m21 - m12; c[1] = sq;        c[2] = m10 + m01; c[3] = m02 + m20; }
     else if (best == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = sq;        c[3] = m12 + m21; }
     else                { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = sq; }
-    const float den = 2.0f * fmaxf(qa[best], 0.1f);
+    // den >= 0.2: one reciprocal (numerator 1, operands in the normal range) instead of four
+    // divisions whose zero numerators would take the slow IEEE path for the whole warp
+    const float inv_den = 1.0f / (2.0f * fmaxf(qa[best], 0.1f));
 #pragma unroll
-    for (int k = 0; k < 4; k++) q[k] = c[k] / den;
+    for (int k = 0; k < 4; k++) q[k] = c[k] * inv_den;
     return best;
 }
 
@@ -325,14 +327,14 @@ __device__ __forceinline__ void mat_to_quat_bwd(const float* m, const float* g, 
     else if (best == 1) { c[0] = m21 - m12; c[1] = sq;        c[2] = m10 + m01; c[3] = m02 + m20; }
     else if (best == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = sq;        c[3] = m12 + m21; }
     else                { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = sq; }
-    const float den = 2.0f * fmaxf(qb, 0.1f);
+    const float inv_den = 1.0f / (2.0f * fmaxf(qb, 0.1f));
     float gc[4];
     float gden = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { gc[k] = g[k] / den; gden -= g[k] * c[k] / (den * den); }
+    for (int k = 0; k < 4; k++) { gc[k] = g[k] * inv_den; gden -= g[k] * c[k] * inv_den * inv_den; }
     // den = 2 max(qb, 0.1): gradient reaches qb only above the floor; c[best] = qb^2
     float gqb = (qb > 0.1f ? 2.0f * gden : 0.0f) + 2.0f * qb * gc[best];
-    const float garg = arg[best] > 0.0f ? gqb / (2.0f * qb) : 0.0f;   // zero sub-gradient at 0
+    const float garg = arg[best] > 0.0f ? gqb * (0.5f / fmaxf(qb, 1e-30f)) : 0.0f;   // zero sub-gradient at 0
 #pragma unroll
     for (int k = 0; k < 9; k++) gm[k] = 0.0f;
     const float s0 = (best == 0 || best == 1) ? 1.0f : -1.0f;

@@ -6,8 +6,8 @@
 // reached from /root/reference/sings/rec/renderer/gs_renderer_single.py:87-95.
 //
 // One CTA per 16x16 tile, one thread per pixel.  B200-first structure (results unchanged):
-//  * tiles are processed longest-list-first (an order array built with the tile ranges from
-//    the per-tile pair counts), so the few tiles with thousands of pairs do not form the tail;
+//  * tiles are processed longest-list-first (the range kernel files every tile in a bucket by
+//    list length), so the few tiles with thousands of pairs do not form the tail;
 //  * each warp owns an 8x4 pixel block; while staging a batch of 256 pairs every thread also
 //    computes, for its pair, which of the 8 pixel blocks the Gaussian's alpha >= 1/255 footprint
 //    can reach (ellipse bounding box AND bounding circle, conservative); each warp then
@@ -23,96 +23,84 @@
 
 namespace sgs {
 
-constexpr int ORDER_BUCKETS = 256;
 constexpr int BWD_U = 4;      // pairs per software-pipeline stage in the backward blend
 constexpr int FWD_U = 4;      // pairs evaluated together per pixel in the forward blend
 
-// [upstream] identifyTileRanges, without a pass over the sorted list: the geometry kernel
-// counts the pairs of every tile while it emits them, so ranges[tile] = [start, end) is an
-// exclusive scan of the counts (an empty tile keeps (0, 0), like the reference's memset).
-// The same CTA builds `order`: tile ids sorted by descending list length (counting sort on
-// length/16, ties in arbitrary order) for the blend kernels' longest-first schedule.
-// One CTA of 1024 threads; runs right after the geometry kernel, before the sort.
-constexpr int ORDER_THREADS = 1024;
+// [upstream] identifyTileRanges: ranges[tile] = [start, end) in the sorted list, (0, 0) for a
+// tile without pairs.  One WARP per tile: a 33-ary search (32 probes per step, ballot) for the
+// lower bounds of tile and tile + 1 over the sorted keys -- 4 dependent L2 round trips at a
+// million pairs instead of the 21 of a binary search; no pass over the list, no atomics on
+// the ranges, no memset.  The CTA (32 tiles) then files its tiles in buckets by list length
+// (bucket = bit length of the count, 0 = empty) so the blend kernels can take tiles
+// longest-first: the few tiles with thousands of pairs must not form the tail.
+constexpr int LEN_BUCKETS = 32;
+constexpr int RANGE_THREADS = 1024;
 
-__global__ void __launch_bounds__(ORDER_THREADS)
-tile_order_kernel(const unsigned* __restrict__ tile_count, uint2* __restrict__ ranges,
-                  unsigned* __restrict__ order, int tiles) {
-    __shared__ unsigned s_cnt[ORDER_BUCKETS];
-    __shared__ unsigned s_warp[ORDER_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < ORDER_BUCKETS) s_cnt[tid] = 0;
+// first index in [0, n) whose key's tile id is >= target (warp-cooperative)
+__device__ __forceinline__ unsigned warp_lower_bound(const unsigned long long* __restrict__ keys,
+                                                     unsigned n, unsigned target, int lane) {
+    unsigned lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned len = hi - lo;
+        if (len <= 32) {
+            const bool pred = (unsigned)lane < len && (unsigned)(__ldg(keys + lo + lane) >> 32) < target;
+            return lo + __popc(__ballot_sync(0xffffffffu, pred));
+        }
+        auto probe = [&](unsigned k) { return lo + (unsigned)(((unsigned long long)(k + 1) * len) / 33u); };
+        const bool pred = (unsigned)(__ldg(keys + probe(lane)) >> 32) < target;
+        const unsigned cnt = __popc(__ballot_sync(0xffffffffu, pred));      // keys are sorted: a prefix of lanes
+        const unsigned nlo = cnt ? probe(cnt - 1) + 1 : lo;
+        const unsigned nhi = cnt < 32 ? probe(cnt) : hi;
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(RANGE_THREADS)
+tile_ranges_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ counters,
+                   long long n_cap, uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
+                   unsigned* __restrict__ bucket_list, int tiles) {
+    __shared__ unsigned s_len[RANGE_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * (RANGE_THREADS / 32) + warp;
+    const unsigned n = (unsigned)min((long long)counters[CNT_NUM_RENDERED], n_cap);
+    unsigned c = 0;
+    if (t < tiles) {                                     // warp-uniform
+        const unsigned lo = warp_lower_bound(keys, n, (unsigned)t, lane);
+        const unsigned hi = warp_lower_bound(keys, n, (unsigned)t + 1u, lane);
+        c = hi - lo;
+        if (lane == 0) ranges[t] = c ? make_uint2(lo, hi) : make_uint2(0u, 0u);
+    }
+    if (lane == 0) s_len[warp] = c;
     __syncthreads();
-    // ---- ranges: thread t owns the contiguous tiles [t*per, (t+1)*per) ----
-    const int per = (tiles + ORDER_THREADS - 1) / ORDER_THREADS;
-    const int t0 = tid * per, t1 = min(t0 + per, tiles);
-    unsigned sum = 0;
-    for (int t = t0; t < t1; t++) sum += tile_count[t];
-    unsigned incl = sum;
+    if (warp != 0) return;
+    const int tt = blockIdx.x * (RANGE_THREADS / 32) + lane;
+    const bool ok = tt < tiles;
+    const unsigned bk = ok ? (unsigned)(32 - __clz(s_len[lane])) % LEN_BUCKETS : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, bk);
+    const int leader = __ffs(peers) - 1;
+    unsigned slot = 0;
+    if (ok && lane == leader) slot = atomicAdd(&bucket_count[bk], (unsigned)__popc(peers));
+    slot = __shfl_sync(0xffffffffu, slot, leader);
+    if (ok) bucket_list[(size_t)bk * tiles + slot + __popc(peers & lanemask_lt())] = (unsigned)tt;
+}
+
+// The i-th tile in longest-bucket-first order (whole warp calls it with the same i).
+__device__ __forceinline__ unsigned tile_of_rank(const unsigned* __restrict__ bucket_count,
+                                                 const unsigned* __restrict__ bucket_list, int tiles,
+                                                 unsigned i) {
+    const int lane = threadIdx.x & 31;
+    const unsigned cnt = __ldg(bucket_count + (LEN_BUCKETS - 1 - lane));    // lane 0 = longest bucket
+    unsigned incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         unsigned x = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += x;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned v = s_warp[lane], inc2 = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned x = __shfl_up_sync(0xffffffffu, inc2, d);
-            if (lane >= d) inc2 += x;
-        }
-        s_warp[lane] = inc2 - v;
-    }
-    __syncthreads();
-    unsigned run = s_warp[warp] + incl - sum;
-    for (int t = t0; t < t1; t++) {
-        const unsigned c = tile_count[t];
-        ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
-        run += c;
-    }
-    // ---- bucket sizes (warp-aggregated: most tiles are empty and share one bucket) ----
-    for (int base = 0; base < tiles; base += ORDER_THREADS) {
-        const int t = base + tid;
-        const bool ok = t < tiles;
-        const unsigned c = ok ? tile_count[t] : 0u;
-        const unsigned bk = ok ? ORDER_BUCKETS - 1 - min(c >> 4, (unsigned)ORDER_BUCKETS - 1) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, bk);
-        if (ok && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bk], (unsigned)__popc(peers));
-    }
-    __syncthreads();
-    // ---- exclusive scan of the 256 bucket counts (warps 0..7) ----
-    unsigned v = 0, binc = 0;
-    if (tid < ORDER_BUCKETS) {
-        v = s_cnt[tid];
-        binc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned x = __shfl_up_sync(0xffffffffu, binc, d);
-            if (lane >= d) binc += x;
-        }
-        if (lane == 31) s_warp[warp] = binc;
-    }
-    __syncthreads();
-    if (tid < ORDER_BUCKETS) {
-        unsigned off = 0;
-        for (int w = 0; w < warp; w++) off += s_warp[w];
-        s_cnt[tid] = off + binc - v;
-    }
-    __syncthreads();
-    for (int base = 0; base < tiles; base += ORDER_THREADS) {
-        const int t = base + tid;
-        const bool ok = t < tiles;
-        const unsigned c = ok ? tile_count[t] : 0u;
-        const unsigned bk = ok ? ORDER_BUCKETS - 1 - min(c >> 4, (unsigned)ORDER_BUCKETS - 1) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, bk);
-        const int leader = __ffs(peers) - 1;
-        unsigned slot = 0;
-        if (ok && lane == leader) slot = atomicAdd(&s_cnt[bk], (unsigned)__popc(peers));
-        slot = __shfl_sync(0xffffffffu, slot, leader);
-        if (ok) order[slot + __popc(peers & lanemask_lt())] = (unsigned)t;
-    }
+    const unsigned before = __ballot_sync(0xffffffffu, incl <= i);          // buckets entirely before i
+    const int b = __popc(before);                                           // lane holding the bucket of i
+    const unsigned excl = __shfl_sync(0xffffffffu, incl - cnt, b & 31);
+    return __ldg(bucket_list + (size_t)(LEN_BUCKETS - 1 - b) * tiles + (i - excl));
 }
 
 static inline const unsigned long long* sorted_keys(const RasterLayout& lay, const char* bin) {
@@ -122,11 +110,12 @@ static inline const unsigned* sorted_vals(const RasterLayout& lay, const char* b
     return reinterpret_cast<const unsigned*>(bin + ((lay.passes & 1) ? lay.vals1_off : lay.vals0_off));
 }
 
-int launch_tile_ranges(const RasterLayout& lay, char* bin, cudaStream_t stream) {
-    tile_order_kernel<<<1, ORDER_THREADS, 0, stream>>>(
-        reinterpret_cast<const unsigned*>(bin + lay.tilecnt_off),
+int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
+    tile_ranges_kernel<<<(lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32), RANGE_THREADS, 0, stream>>>(
+        sorted_keys(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
         reinterpret_cast<uint2*>(bin + lay.ranges_off),
-        reinterpret_cast<unsigned*>(bin + lay.order_off), lay.tiles);
+        reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
+        reinterpret_cast<unsigned*>(bin + lay.bktlist_off), lay.tiles);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -186,7 +175,8 @@ struct FwdBatch {
 };
 
 __global__ void __launch_bounds__(TILE_PIX, 2)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ order,
+blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
+                 const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
@@ -197,7 +187,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     __shared__ float4 s_q2[TILE_PIX / 32][RING_SLOTS];     // g, b, depth, list position + 1
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = order[blockIdx.x];
+    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -316,7 +306,8 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
                      float* out_depth, cudaStream_t stream) {
     blend_fwd_kernel<<<lay.tiles, TILE_PIX, 0, stream>>>(
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
-        reinterpret_cast<const unsigned*>(bin + lay.order_off), sorted_vals(lay, bin),
+        reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
+        reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
         reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth);
@@ -354,7 +345,8 @@ struct BwdWarpSmem {
 };
 
 __global__ void __launch_bounds__(TILE_PIX, 2)
-blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ order,
+blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
+                 const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
@@ -362,7 +354,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     extern __shared__ __align__(16) char s_bwd_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[warp];
-    const unsigned tile = order[blockIdx.x];
+    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -533,7 +525,8 @@ int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, co
     SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     blend_bwd_kernel<<<lay.tiles, TILE_PIX, smem, stream>>>(
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
-        reinterpret_cast<const unsigned*>(bin + lay.order_off), sorted_vals(lay, bin),
+        reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
+        reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
         reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc);

@@ -53,10 +53,10 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.hist_off = o;     o += align_up((size_t)MAX_PASSES * RADIX * 4, 256);
     l.scan_off = o;     o += align_up((size_t)l.scan_blocks * 8, 256);
     l.sortstat_off = o; o += align_up((size_t)l.passes * l.sort_blocks * RADIX * 4, 256);
-    l.tilecnt_off = o;  o += align_up((size_t)l.tiles * 4, 256);
+    l.bktcnt_off = o;   o += align_up(32 * 4, 256);
     l.zero_bytes = o;
     l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
-    l.order_off = o;    o += align_up((size_t)l.tiles * 4, 256);
+    l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 4, 256);
     size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
     l.keys0_off = o;    o += align_up(cap * 8, 256);
     l.keys1_off = o;    o += align_up(cap * 8, 256);
@@ -76,7 +76,6 @@ struct GeoOut {
     float* rec;
     int* counters;
     unsigned* hist;
-    unsigned* tile_count;
     unsigned long long* scan_status;
     unsigned long long* keys;
     unsigned* vals;
@@ -288,6 +287,18 @@ geometry_kernel(GeomArgs a, GeoOut o) {
 
     // ---- emit (tile|depth) keys and Gaussian ids: [upstream] duplicateWithKeys ----
     const unsigned long long prefix = s_prefix;
+    // the four depth digits are the same for all pairs of a Gaussian: one weighted shared
+    // atomic per digit and Gaussian (weight = pairs actually emitted, i.e. clipped at L_cap)
+    if (tiles > 0) {
+        const unsigned long long start = prefix + (incl - tiles);
+        const unsigned long long room = start < (unsigned long long)o.L_cap ? (unsigned long long)o.L_cap - start : 0ull;
+        const unsigned emitted = room < tiles ? (unsigned)room : tiles;
+        const unsigned dbits = __float_as_uint(depth);
+        if (emitted) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * RADIX + ((dbits >> (p * RADIX_BITS)) & (RADIX - 1))], emitted);
+        }
+    }
     for (unsigned e = tid; e < block_total; e += GEO_THREADS) {
         int lo = 0, hi = GEO_THREADS - 1;          // first g with s_incl[g] > e
         while (lo < hi) {
@@ -305,8 +316,7 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         if (pos < (unsigned long long)o.L_cap) {
             o.keys[pos] = key;
             o.vals[pos] = (unsigned)(base + g);
-            atomicAdd(&o.tile_count[tile_id], 1u);          // RED: per-tile list lengths
-            for (int p = 0; p < o.passes; p++)
+            for (int p = 4; p < o.passes; p++)          // tile-id digits differ per pair
                 atomicAdd(&s_hist[p * RADIX + (unsigned)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
         }
     }
@@ -335,7 +345,7 @@ static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec
 
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
                     char* geom, char* bin, cudaStream_t stream) {
-    // one memset clears counters, histograms, scan + sort look-back status and tile counts
+    // one memset clears counters, histograms, scan + sort look-back status and the tile-length bucket counts
     SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
     if (a.P <= 0) return 0;
     GeoOut o;
@@ -343,7 +353,6 @@ int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap,
     o.rec = reinterpret_cast<float*>(geom + lay.rec_off);
     o.counters = reinterpret_cast<int*>(bin + lay.cnt_off);
     o.hist = reinterpret_cast<unsigned*>(bin + lay.hist_off);
-    o.tile_count = reinterpret_cast<unsigned*>(bin + lay.tilecnt_off);
     o.scan_status = reinterpret_cast<unsigned long long*>(bin + lay.scan_off);
     o.keys = reinterpret_cast<unsigned long long*>(bin + lay.keys0_off);
     o.vals = reinterpret_cast<unsigned*>(bin + lay.vals0_off);

@@ -258,6 +258,13 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
         }
     }
 
+    if (live && b.stat_accum) {
+        // densification statistics of this view, fused (sings_hybrid.py:1013-1015,
+        // gs_trainer.py:487-490): norm of the screen-space gradient, count, max radius
+        b.stat_accum[idx] += sqrtf(g2x * g2x + g2y * g2y);
+        b.stat_denom[idx] += 1.0f;
+        b.stat_max_radii[idx] = fmaxf(b.stat_max_radii[idx], (float)b.radii[idx]);
+    }
     if (in_range) {
         b.dL_dmeans3D[3 * idx] = dmean[0]; b.dL_dmeans3D[3 * idx + 1] = dmean[1]; b.dL_dmeans3D[3 * idx + 2] = dmean[2];
         b.dL_dmeans2D[3 * idx] = g2x; b.dL_dmeans2D[3 * idx + 1] = g2y; b.dL_dmeans2D[3 * idx + 2] = 0.0f;

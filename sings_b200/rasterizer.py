@@ -238,8 +238,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _lib.ptr(shc), _lib.ptr(radii), _lib.ptr(g), ctx.L_cap, _lib.ptr(geom),
                 _lib.ptr(binning), _lib.ptr(img), _lib.ptr(acc), _lib.ptr(d_means3D),
                 _lib.ptr(d_means2D), _lib.ptr(d_colors), _lib.ptr(d_opac), _lib.ptr(d_cov),
-                _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), stream.cuda_stream,
-                int(bool(rs.debug)), None)
+                _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), None, None, None,
+                stream.cuda_stream, int(bool(rs.debug)), None)
             _lib.check(rc, "sgs_raster_backward")
         except Exception:
             if rs.debug:

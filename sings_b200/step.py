@@ -86,8 +86,9 @@ class AvatarStep:
         self.n_param_grads = int(offs[5])
         self.max_radii2D = torch.zeros(N, device=dev, dtype=torch.float32)
         # small per-frame gradients
-        self.d_A = torch.zeros(1, J, 4, 4, device=dev)
-        self.d_transl = torch.zeros(1, 3, device=dev)
+        self.small_grads = torch.zeros(J * 16 + 4, device=dev)
+        self.d_A = self.small_grads[:J * 16].view(1, J, 4, 4)
+        self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
         self.timing = None
         if timing:
@@ -139,11 +140,11 @@ class AvatarStep:
             float(fr.tanfovy), p(self.shs), p(self.radii), p(dL_dimage), self.L_cap, p(self.geom),
             p(self.binning), p(self.img), p(self.acc), p(self.g_means3D), p(self.g_means2D),
             p(self.g_colors), p(self.d_opacity), p(self.g_cov), p(self.d_shs), p(self.g_scales_r),
-            p(self.g_rots), st, 0, tm), "sgs_raster_backward")
+            p(self.g_rots), p(self.grad_accum) if stats else None, p(self.denom) if stats else None,
+            p(self.max_radii2D) if stats else None, st, 0, tm), "sgs_raster_backward")
         if tm:
             L_.sgs_timing_record(tm, 10, st)
-        self.d_A.zero_()
-        self.d_transl.zero_()
+        self.small_grads.zero_()           # d_A and d_transl live in one buffer: one fill
         pose = fr.pose.reshape(1, self.J, 3)
         _lib.check(L_.sgs_lbs_bwd(1, self.N, self.J, p(self.A), p(self.xyz_canon), p(self.W_lbs),
                                   p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
@@ -154,12 +155,31 @@ class AvatarStep:
         _lib.check(L_.sgs_pose_to_A_bwd(p(pose), p(self.rest), p(self.parents), p(self.inv_A),
                                         p(self.G), p(self.d_A), 1, self.J, p(self.d_pose), st),
                    "sgs_pose_to_A_bwd")
-        if stats:
-            _lib.check(L_.sgs_densify_stats(self.N, p(self.g_means2D), p(self.radii),
-                                            p(self.grad_accum), p(self.denom), p(self.max_radii2D), st),
-                       "sgs_densify_stats")
         if tm:
             L_.sgs_timing_record(tm, 11, st)
+
+    def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None):
+        """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
+        graph and return replay().  The launch sequence is static -- capacity-sized pair list,
+        device-side counts, no host round trip -- so the whole frame becomes one graph launch.
+        `fr`'s tensors and `dL_dimage` are captured by address: refresh their contents in
+        place before each replay.  Stage events keep working (external event-record nodes)."""
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # warm-up outside the capture (lazy initialisation)
+            self.forward(fr)
+            self.backward(dL_dimage)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            img = self.forward(fr)
+            if loss_weight is not None:
+                self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
+            self.backward(dL_dimage)
+        self.graph = g
+        return g.replay
 
     def reset_stats(self):
         self.grad_accum.zero_()
@@ -182,7 +202,7 @@ class AvatarStep:
             raise _lib.SgsError("AvatarStep(timing=True) required")
         out = {}
         ms = C.c_float()
-        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("ranges", 1, 12), ("sort", 12, 2),
+        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("sort", 1, 2), ("ranges", 2, 3),
                            ("blend_fwd", 3, 4), ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7),
                            ("lbs_bwd", 10, 11), ("total", 8, 11)]:
             _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
