@@ -156,6 +156,8 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     tick(timing, 2, stream);
     rc = launch_tile_ranges(lay, L_cap, b, stream);    // ranges + tiles bucketed by list length
     if (rc) return rc;
+    rc = launch_pair_masks(lay, L_cap, g, b, stream);  // per-pair reach mask over the 8 pixel blocks of a tile
+    if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);

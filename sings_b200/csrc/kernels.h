@@ -31,7 +31,7 @@ struct RasterLayout {
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
     size_t cnt_off, hist_off, scan_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
-    size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
+    size_t keys0_off, keys1_off, vals0_off, vals1_off, masks_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
     int scan_blocks, sort_blocks, tiles, gx, gy, end_bit, passes;
@@ -68,6 +68,9 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
 size_t sort_scratch_bytes(long long n);
 
 int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
+
+int launch_pair_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                      cudaStream_t stream);
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,

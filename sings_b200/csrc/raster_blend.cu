@@ -155,6 +155,45 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
     return r;
 }
 
+// Reach mask of every sorted (tile, Gaussian) pair: bit w says whether the Gaussian's
+// alpha >= 1/255 footprint can touch 8x4 pixel block w of the tile (w = blend warp index).
+// One thread per pair, computed ONCE per frame; the forward and the backward blend then
+// stream one byte per pair and gather the 64-byte record only for the ~10 % of
+// (warp, pair) combinations that can contribute, instead of every warp re-reading and
+// re-testing every record of its tile.
+__global__ void __launch_bounds__(256)
+pair_mask_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ point_list,
+                 const int* __restrict__ counters, long long n_cap, const float4* __restrict__ rec,
+                 int gx_tiles, unsigned char* __restrict__ masks) {
+    const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned tile = (unsigned)(__ldg(keys + i) >> 32);
+    const unsigned id = __ldg(point_list + i);
+    const float4* p = rec + 4 * (size_t)id;
+    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q3 = __ldg(p + 3);
+    const float tx = (float)((tile % (unsigned)gx_tiles) * TILE), ty = (float)((tile / (unsigned)gx_tiles) * TILE);
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PIX / 32; w++) {
+        const float bx0 = tx + (float)((w & 1) << 3), by0 = ty + (float)((w >> 1) << 2);
+        if (reaches_block(q0, q1, q3, bx0, bx0 + 7.0f, by0, by0 + 3.0f)) m |= 1u << w;
+    }
+    masks[i] = (unsigned char)m;
+}
+
+int launch_pair_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                      cudaStream_t stream) {
+    long long blocks = (L_cap + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    pair_mask_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+        sorted_keys(lay, bin), sorted_vals(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
+        reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx,
+        reinterpret_cast<unsigned char*>(bin + lay.masks_off));
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // forward.  Warp-autonomous: every warp streams the tile's depth-sorted list by itself, 32
 // pairs at a time (one per lane, prefetched one chunk ahead), keeps the pairs that can reach
@@ -177,7 +216,8 @@ struct FwdBatch {
 __global__ void __launch_bounds__(TILE_PIX, 2)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
-                 const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
+                 const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
+                 const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
@@ -257,12 +297,21 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     rq1[lane] = rq1[lane + 32] = make_float4(0, 0, 0, 0);
     rq2[lane] = rq2[lane + 32] = make_float4(0, 0, 0, 0);
 
+    // Staging pipeline, per chunk of 32 list entries (one per lane): reach-mask bytes run four
+    // chunks ahead, Gaussian ids of the relevant entries two chunks ahead, their records one
+    // chunk ahead -- the dependent mask -> id -> record gather never sits on the critical path,
+    // and a chunk without relevant entries costs a ballot.
+    const unsigned char* mk = masks + range.x;
+    const unsigned* pl = point_list + range.x;
+    auto mask_at = [&](int at) { return at + lane < len ? (unsigned)__ldg(mk + at + lane) : 0u; };
+    unsigned m0 = mask_at(0), m1 = mask_at(32), m2 = mask_at(64), m3 = mask_at(96);
     Rec p;
     p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
-    if (lane < len) p = load_rec(rec, __ldg(point_list + range.x + lane));
+    if ((m0 >> warp) & 1u) p = load_rec(rec, __ldg(pl + lane));
+    unsigned nid = ((m1 >> warp) & 1u) ? __ldg(pl + 32 + lane) : 0u;
     for (int pos = 0; pos < len; pos += 32) {
         if (__all_sync(0xffffffffu, done)) break;
-        const bool rel = (pos + lane < len) && reaches_block(p.q0, p.q1, p.q3, bx0, bx1, by0, by1);
+        const bool rel = (m0 >> warp) & 1u;
         const unsigned bits = __ballot_sync(0xffffffffu, rel);
         __syncwarp();                  // earlier ring reads are complete before slots are reused
         if (rel) {
@@ -273,7 +322,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
         tail += __popc(bits);
         __syncwarp();
-        if (pos + 32 + lane < len) p = load_rec(rec, __ldg(point_list + range.x + pos + 32 + lane));
+        if ((m1 >> warp) & 1u) p = load_rec(rec, nid);
+        if ((m2 >> warp) & 1u) nid = __ldg(pl + pos + 64 + lane);
+        m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(pos + 128);
         while (tail - head >= FWD_U) {
             FwdBatch nxt;
             eval(nxt, head, tail);
@@ -308,6 +359,7 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
+        reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
         reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth);
@@ -347,7 +399,8 @@ struct BwdWarpSmem {
 __global__ void __launch_bounds__(TILE_PIX, 2)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
-                 const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
+                 const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
+                 const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, float* __restrict__ acc) {
@@ -465,19 +518,26 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         __syncwarp();
     };
 
+    // Same staging pipeline as the forward (masks four chunks ahead, ids two, records one),
+    // walking the list back to front: chunk c covers list positions top-lane, top =
+    // wlast-1-32c, so lane order is back-to-front order.
+    const unsigned char* mk = masks + range.x;
+    const unsigned* pl = point_list + range.x;
+    auto mask_at = [&](int top) { return top - lane >= 0 ? (unsigned)__ldg(mk + top - lane) : 0u; };
+    unsigned m0 = mask_at(wlast - 1), m1 = mask_at(wlast - 33), m2 = mask_at(wlast - 65), m3 = mask_at(wlast - 97);
     Rec p;
     unsigned pid = 0;
     p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
-    if (lane < wlast) {
-        pid = __ldg(point_list + range.x + (wlast - 1 - lane));
+    if ((m0 >> warp) & 1u) {
+        pid = __ldg(pl + (wlast - 1 - lane));
         p = load_rec(rec, pid);
     }
+    unsigned nid = ((m1 >> warp) & 1u) ? __ldg(pl + (wlast - 33 - lane)) : 0u;
     // `cur` starts as an empty batch at consumption index -BWD_U: its SEQ writes zeros into
     // rows that real pairs overwrite before any reduction reads them.
     unsigned pend = 0u - BWD_U;
-    // chunk c covers list positions top-lane, top = wlast-1-32c: lane order = back-to-front order
     for (int top = wlast - 1; top >= 0; top -= 32) {
-        const bool rel = (top - lane >= 0) && reaches_block(p.q0, p.q1, p.q3, bx0, bx1, by0, by1);
+        const bool rel = (m0 >> warp) & 1u;
         const unsigned bits = __ballot_sync(0xffffffffu, rel);
         __syncwarp();
         if (rel) {
@@ -488,10 +548,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
         tail += __popc(bits);
         __syncwarp();
-        if (top - 32 - lane >= 0) {
-            pid = __ldg(point_list + range.x + (top - 32 - lane));
+        if ((m1 >> warp) & 1u) {
+            pid = nid;
             p = load_rec(rec, pid);
         }
+        if ((m2 >> warp) & 1u) nid = __ldg(pl + (top - 64 - lane));
+        m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(top - 128);
         while (tail - head >= BWD_U) {
             BwdBatch nxt;
             eval(nxt, head, tail);
@@ -527,6 +589,7 @@ int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, co
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
+        reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
         reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc);

@@ -62,6 +62,7 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.keys1_off = o;    o += align_up(cap * 8, 256);
     l.vals0_off = o;    o += align_up(cap * 4, 256);
     l.vals1_off = o;    o += align_up(cap * 4, 256);
+    l.masks_off = o;    o += align_up(cap, 256);
     l.bin_bytes = o;
     // image state
     size_t pix = (size_t)W * H;
