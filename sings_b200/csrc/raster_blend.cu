@@ -155,12 +155,44 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
     return r;
 }
 
-// Reach mask of every sorted (tile, Gaussian) pair: bit w says whether the Gaussian's
-// alpha >= 1/255 footprint can touch 8x4 pixel block w of the tile (w = blend warp index).
-// One thread per pair, computed ONCE per frame; the forward and the backward blend then
-// stream one byte per pair and gather the 64-byte record only for the ~10 % of
-// (warp, pair) combinations that can contribute, instead of every warp re-reading and
-// re-testing every record of its tile.
+// Reach mask of a (tile, Gaussian) pair: bit w says whether the Gaussian's alpha >= 1/255
+// footprint can touch 8x4 pixel block w of the tile (w = blend warp index): reaches_block for
+// the 2 x 4 blocks, sharing the per-column / per-row terms.  Computed ONCE per frame and pair;
+// the forward and the backward blend then stream one byte per pair and gather the 64-byte
+// record only for the ~10 % of (warp, pair) combinations that can contribute.
+__device__ __forceinline__ unsigned reach_mask(const float4 q0, const float4 q1, const float4 q3,
+                                               float tx, float ty) {
+    const float a = -2.0f * q0.z, b2 = -2.0f * q0.w, c = -2.0f * q1.x;
+    float X0[2], X1[2], cx[2], acx2[2], bcx[2], ycx[2];
+    float Y0[4], Y1[4], cy[4], ccy2[4], bcy[4], xcy[4];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        X0[k] = tx + (float)(8 * k) - q0.x; X1[k] = X0[k] + 7.0f;
+        cx[k] = fminf(fmaxf(0.0f, X0[k]), X1[k]);
+        acx2[k] = a * cx[k] * cx[k]; bcx[k] = b2 * cx[k]; ycx[k] = q3.y * cx[k];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        Y0[r] = ty + (float)(4 * r) - q0.y; Y1[r] = Y0[r] + 3.0f;
+        cy[r] = fminf(fmaxf(0.0f, Y0[r]), Y1[r]);
+        ccy2[r] = c * cy[r] * cy[r]; bcy[r] = b2 * cy[r]; xcy[r] = q3.z * cy[r];
+    }
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PIX / 32; w++) {
+        const int k = w & 1, r = w >> 1;
+        const float dy1 = fminf(fmaxf(ycx[k], Y0[r]), Y1[r]);       // minimiser on the edge x = cx
+        const float dx2 = fminf(fmaxf(xcy[r], X0[k]), X1[k]);       // minimiser on the edge y = cy
+        const float qa = fmaf(dy1, fmaf(c, dy1, bcx[k]), acx2[k]);
+        const float qb = fmaf(dx2, fmaf(a, dx2, bcy[r]), ccy2[r]);
+        if (fminf(qa, qb) <= q3.x) m |= 1u << w;
+    }
+    return m;
+}
+
+// One thread per sorted pair.  (A per-tile shared-memory bitonic sort of the depth bits that
+// also produced these masks was tried in place of the four depth passes of the onesweep sort:
+// n log^2 n compare-exchanges cost as many instructions as the four radix passes; rejected.)
 __global__ void __launch_bounds__(256)
 pair_mask_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ point_list,
                  const int* __restrict__ counters, long long n_cap, const float4* __restrict__ rec,
@@ -173,13 +205,7 @@ pair_mask_kernel(const unsigned long long* __restrict__ keys, const unsigned* __
     const float4* p = rec + 4 * (size_t)id;
     const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q3 = __ldg(p + 3);
     const float tx = (float)((tile % (unsigned)gx_tiles) * TILE), ty = (float)((tile / (unsigned)gx_tiles) * TILE);
-    unsigned m = 0;
-#pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; w++) {
-        const float bx0 = tx + (float)((w & 1) << 3), by0 = ty + (float)((w >> 1) << 2);
-        if (reaches_block(q0, q1, q3, bx0, bx0 + 7.0f, by0, by0 + 3.0f)) m |= 1u << w;
-    }
-    masks[i] = (unsigned char)m;
+    masks[i] = (unsigned char)reach_mask(q0, q1, q3, tx, ty);
 }
 
 int launch_pair_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
@@ -247,10 +273,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     unsigned last = 0;
     unsigned head = 0, tail = 0;       // ring: consumed / produced pair counts (warp-uniform)
 
-    FwdBatch cur;                      // the batch waiting to be composited (starts empty)
+    FwdBatch bat_a, bat_b;             // one waits to be composited (starts empty), one is being evaluated
+    bool cur_is_b = false;             // which of the two is waiting (warp-uniform)
 #pragma unroll
     for (int u = 0; u < FWD_U; u++) {
-        cur.al[u] = 0.0f; cur.om[u] = 1.0f; cur.r[u] = cur.g[u] = cur.b[u] = cur.z[u] = 0.0f; cur.pos[u] = 0;
+        bat_a.al[u] = 0.0f; bat_a.om[u] = 1.0f; bat_a.r[u] = bat_a.g[u] = bat_a.b[u] = bat_a.z[u] = 0.0f; bat_a.pos[u] = 0;
     }
 
     // alphas of ring entries [base, base + FWD_U); entries at or beyond `limit` are empty
@@ -325,20 +352,17 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         if ((m1 >> warp) & 1u) p = load_rec(rec, nid);
         if ((m2 >> warp) & 1u) nid = __ldg(pl + pos + 64 + lane);
         m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(pos + 128);
+        // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= FWD_U) {
-            FwdBatch nxt;
-            eval(nxt, head, tail);
-            composite(cur);
-            cur = nxt;
+            if (!cur_is_b) { eval(bat_b, head, tail); composite(bat_a); }
+            else           { eval(bat_a, head, tail); composite(bat_b); }
+            cur_is_b = !cur_is_b;
             head += FWD_U;
         }
     }
-    {   // drain: the waiting batch, then the (partial) remainder of the ring
-        FwdBatch nxt;
-        eval(nxt, head, tail);
-        composite(cur);
-        composite(nxt);
-    }
+    // drain: the waiting batch, then the (partial) remainder of the ring
+    if (!cur_is_b) { eval(bat_b, head, tail); composite(bat_a); composite(bat_b); }
+    else           { eval(bat_a, head, tail); composite(bat_b); composite(bat_a); }
     if (inside) {
         const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
         const float Tr = done ? T_fin : T;       // a saturated pixel reports the T it stopped at
@@ -440,11 +464,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     unsigned head = 0, tail = 0;               // ring: consumed / produced pair counts
     unsigned row0 = 0;                         // first pair (consumption index) of the open [pair][pixel] tile; multiple of 32
 
-    BwdBatch cur;
+    BwdBatch bat_a, bat_b;             // one waits for SEQ (starts empty), one is being evaluated
+    bool cur_is_b = false;
 #pragma unroll
     for (int u = 0; u < BWD_U; u++) {
-        cur.al[u] = 0.0f; cur.G[u] = 0.0f; cur.om[u] = 1.0f; cur.inv[u] = 1.0f;
-        cur.r[u] = cur.g[u] = cur.b[u] = 0.0f;
+        bat_a.al[u] = 0.0f; bat_a.G[u] = 0.0f; bat_a.om[u] = 1.0f; bat_a.inv[u] = 1.0f;
+        bat_a.r[u] = bat_a.g[u] = bat_a.b[u] = 0.0f;
     }
 
     auto eval = [&](BwdBatch& e, unsigned base, unsigned limit) {
@@ -554,30 +579,30 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
         if ((m2 >> warp) & 1u) nid = __ldg(pl + (top - 64 - lane));
         m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(top - 128);
+        // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= BWD_U) {
-            BwdBatch nxt;
-            eval(nxt, head, tail);
-            seq(cur, pend);
+            if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
+            else           { eval(bat_a, head, tail); seq(bat_b, pend); }
+            cur_is_b = !cur_is_b;
             if (pend + BWD_U - row0 == 32) {       // the open tile is full (32 % BWD_U == 0)
                 reduce_rows(32);
                 row0 += 32;
             }
-            cur = nxt;
             pend = head;
             head += BWD_U;
         }
     }
-    {   // drain: the waiting batch, the partial remainder of the ring, the partial tile
-        BwdBatch nxt;
-        eval(nxt, head, tail);
-        seq(cur, pend);
-        if (pend + BWD_U - row0 == 32) {
-            reduce_rows(32);
-            row0 += 32;
-        }
-        if (tail > head) seq(nxt, head);
-        if (tail > row0) reduce_rows(tail - row0);
+    // drain: the waiting batch, the partial remainder of the ring, the partial tile
+    if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
+    else           { eval(bat_a, head, tail); seq(bat_b, pend); }
+    if (pend + BWD_U - row0 == 32) {
+        reduce_rows(32);
+        row0 += 32;
     }
+    if (tail > head) {
+        if (!cur_is_b) seq(bat_b, head); else seq(bat_a, head);
+    }
+    if (tail > row0) reduce_rows(tail - row0);
 }
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
