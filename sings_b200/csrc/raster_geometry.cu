@@ -182,9 +182,63 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         }
     }
 
-    // ---- colour: SH -> RGB (or precomputed) and the blend record ----
+    // ---- block scan of tiles touched (before the colour work, so that warp 0's chained-scan
+    //      look-back overlaps the SH evaluation of the other warps) ----
+    unsigned incl = tiles;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    s_rect[tid] = make_int4(x0, y0, x1 - x0, __float_as_int(depth));
     if constexpr (HAS_SH) cp_async_wait_all();
     __syncthreads();
+    unsigned warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < GEO_THREADS / 32; w++) {
+        unsigned v = s_warp[w];
+        if (w < warp) warp_off += v;
+        block_total += v;
+    }
+    incl += warp_off;
+    s_incl[tid] = incl;
+
+    // ---- chained scan across CTAs (decoupled look-back, one warp) ----
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (lane == 0)
+            st_relaxed_u64(&o.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
+        if (chunk > 0) {
+            int look = chunk - 1;
+            while (true) {
+                int j = look - lane;
+                unsigned long long s = j >= 0 ? ld_relaxed_u64(&o.scan_status[j]) : FLAG_INCL;
+                while (__any_sync(0xffffffffu, (s & FLAG_MASK) == 0)) {
+                    if ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&o.scan_status[j]);
+                }
+                unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
+                unsigned long long val = s & ~FLAG_MASK;
+                int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                unsigned long long v = lane <= first ? val : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&o.scan_status[chunk], FLAG_INCL | (excl + block_total));
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            unsigned long long total = excl + block_total;
+            if (chunk == (int)gridDim.x - 1)
+                o.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+            if (total > (unsigned long long)o.L_cap) o.counters[CNT_OVERFLOW] = 1;
+        }
+    }
+
+    // ---- colour: SH -> RGB (or precomputed) and the blend record ----
     if (tiles > 0) {
         float rgb[3];
         unsigned flags = 0;
@@ -230,61 +284,7 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         rec[3] = make_float4(t_m, nb_c, nb_a, __uint_as_float(flags));
     }
     if (in_range) o.radii[idx] = rad;
-
-    // ---- block scan of tiles touched ----
-    unsigned incl = tiles;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    s_rect[tid] = make_int4(x0, y0, x1 - x0, __float_as_int(depth));
-    __syncthreads();
-    unsigned warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < GEO_THREADS / 32; w++) {
-        unsigned v = s_warp[w];
-        if (w < warp) warp_off += v;
-        block_total += v;
-    }
-    incl += warp_off;
-    s_incl[tid] = incl;
-
-    // ---- chained scan across CTAs (decoupled look-back, one warp) ----
-    if (warp == 0) {
-        unsigned long long excl = 0;
-        if (lane == 0)
-            st_relaxed_u64(&o.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
-        if (chunk > 0) {
-            int look = chunk - 1;
-            while (true) {
-                int j = look - lane;
-                unsigned long long s = j >= 0 ? ld_relaxed_u64(&o.scan_status[j]) : FLAG_INCL;
-                while (__any_sync(0xffffffffu, (s & FLAG_MASK) == 0)) {
-                    if ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&o.scan_status[j]);
-                }
-                unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
-                unsigned long long val = s & ~FLAG_MASK;
-                int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-                unsigned long long v = lane <= first ? val : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(&o.scan_status[chunk], FLAG_INCL | (excl + block_total));
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            unsigned long long total = excl + block_total;
-            if (chunk == (int)gridDim.x - 1)
-                o.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-            if (total > (unsigned long long)o.L_cap) o.counters[CNT_OVERFLOW] = 1;
-        }
-    }
-    __syncthreads();
+    __syncthreads();          // s_prefix (chained scan) and the records are complete
 
     // ---- emit (tile|depth) keys and Gaussian ids: [upstream] duplicateWithKeys ----
     const unsigned long long prefix = s_prefix;
