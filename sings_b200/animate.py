@@ -1,0 +1,53 @@
+"""Forward-only rendering of a pose sequence (the reference's animation path), frames sharded
+over ranks.
+
+Mirrors /root/reference/sings/rec/trainer/gs_trainer.py:664-728 (`animate_chunk`: per frame
+`human_gs.forward` under `torch.no_grad()` then `render_human_scene`) for the part that is on
+the hot path: pose -> A -> LBS -> rasterize.  Frames are independent given the replicated
+canonical Gaussians, so rank r of R renders the contiguous range `dp.shard_frames(F, r, R)`
+with no collective (BASELINE.json configs[3]).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import dp
+from .step import AvatarStep, FrameInputs
+
+
+def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0, world: int = 1,
+                  out: Optional[torch.Tensor] = None, clamp: bool = True) -> Tuple[int, int, torch.Tensor]:
+    """Render this rank's share of `frames`; returns (lo, hi, images (hi-lo, 3, H, W)).
+
+    `out` (optional, (>= hi-lo, 3, H, W) on the device) receives the images; `clamp` applies
+    the reference's `torch.clamp(rendered_image, 0, 1)` (gs_renderer_single.py:96).  The
+    launch sequence per frame has no host synchronisation; the pair-list capacity is checked
+    once at the end (and the affected frames re-rendered if it had to grow)."""
+    lo, hi = dp.shard_frames(len(frames), rank, world)
+    n = hi - lo
+    if out is None:
+        out = torch.empty(max(n, 0), 3, step.H, step.Wd, device=step.dev, dtype=torch.float32)
+    from ._lib import SgsError
+    first = lo
+    while first < hi:
+        overflow_at = None
+        for f in range(first, hi):
+            img = step.forward(frames[f])
+            out[f - lo].copy_(img)
+            # the counters of frame f are only valid until the next forward overwrites them, so
+            # examine them lazily: one event-free read after a stream sync every 32 frames
+            if (f - first) % 32 == 31 or f == hi - 1:
+                torch.cuda.current_stream(step.dev).synchronize()
+                try:
+                    step.check_capacity()
+                except SgsError:
+                    overflow_at = max(first, f - 31)
+                    break
+        if overflow_at is None:
+            break
+        first = overflow_at            # capacity has been raised: redo the last block
+    if clamp:
+        out[:n].clamp_(0.0, 1.0)
+    return lo, hi, out[:n]

@@ -168,7 +168,9 @@ class AvatarStep:
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):          # warm-up outside the capture (lazy initialisation)
-            self.forward(fr)
+            img = self.forward(fr)
+            if loss_weight is not None:
+                self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
             self.backward(dL_dimage)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)

@@ -264,3 +264,21 @@ def test_stress_shape_2048_sort_key_width():
     st = run_oracle(sc, bg, 1)
     leaves, out = run_cuda(sc, bg, 1)
     check_forward(sc, st, out)
+
+
+def test_config_c5_full_size_1m_gaussians_2048():
+    """BASELINE.json configs[4] at full size (1M Gaussians, 2048^2, fwd+bwd): forward against
+    the oracle bit for bit (the OpenMP oracle needs ~10 s), structure properties of the binning
+    state, and the gradients against the oracle's backward."""
+    sc = make_scene(N=1_000_000, H=2048, W=2048, seed=5, scale_range=(0.002, 0.008))
+    bg = np.zeros(3, np.float32)
+    st = run_oracle(sc, bg, 3)
+    leaves, out = run_cuda(sc, bg, 3)
+    ins = check_forward(sc, st, out)
+    L = ins["num_rendered"]
+    assert L > 2_000_000
+    k = ins["keys"]
+    assert np.all(k[1:] >= k[:-1])
+    r = ins["ranges"].astype(np.int64)
+    assert int((r[:, 1] - r[:, 0]).sum()) == L
+    check_backward(sc, st, leaves, out[0])
