@@ -155,6 +155,17 @@ int sgs_lbs_fwd(int B, int N, int J, const float* A, const float* xyz_canon, con
                 const float* ext_scale, float* xyz_out, float* rotq_out, float* scales_out,
                 float* T_out, sgs_stream_t stream);
 
+/* sgs_pose_to_A immediately followed by sgs_lbs_fwd on A_out (the per-frame deform segment,
+ * sings_hybrid.py:398-428, in one call).  Same results as the two calls; because the library
+ * knows the kernel that precedes the LBS kernel, the LBS kernel fetches its canonical-parameter
+ * tiles while pose -> A is still running (programmatic dependent launch).  The canonical
+ * arrays must not be written by work enqueued on `stream` after the call preceding this one. */
+int sgs_pose_lbs_fwd(const float* pose, const float* rest, const int* parents,
+                     const float* inv_A_t2cano, int B, int N, int J, float* A_out, float* G_out,
+                     const float* xyz_canon, const float* W, const float* rot_canon,
+                     const float* scales, const float* smpl_scale, const float* transl,
+                     float* xyz_out, float* rotq_out, float* scales_out, sgs_stream_t stream);
+
 /* Backward of sgs_lbs_fwd for upstream gradients g_xyz, g_rotq, g_scales and (optional,
  * null if T was not used) g_T (B,N,16).  Written:
  * d_xyz_canon (N,3), d_rot_canon (N,9) or null, d_scales (N,3).  Accumulated into

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "sgs_pose_to_A_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "sgs_lbs_fwd": (_i, [_i, _i, _i] + [_vp] * 15),
     "sgs_lbs_bwd": (_i, [_i, _i, _i] + [_vp] * 21),
+    "sgs_pose_lbs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i] + [_vp] * 12),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -4,7 +4,15 @@
 #include "kernels.h"
 #include "kernels_lbs.h"
 
+#include <stdlib.h>
+
 using namespace sgs;
+
+bool sgs::pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("SGS_NO_PDL") ? 0 : 1;
+    return v != 0;
+}
 
 struct Timing {
     int n;
@@ -90,8 +98,8 @@ int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info
     info[0] = (long long)l.cnt_off;
     info[1] = (long long)l.keys0_off;
     info[2] = (long long)l.vals0_off;
-    info[3] = (long long)((l.passes & 1) ? l.keys1_off : l.keys0_off);
-    info[4] = (long long)((l.passes & 1) ? l.vals1_off : l.vals0_off);
+    info[3] = (long long)(l.sorted_in_1() ? l.keys1_off : l.keys0_off);
+    info[4] = (long long)(l.sorted_in_1() ? l.vals1_off : l.vals0_off);
     info[5] = (long long)l.ranges_off;
     info[6] = (long long)l.finalT_off;
     info[7] = (long long)l.ncontrib_off;
@@ -150,13 +158,16 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
     if (P > 0) {
-        rc = launch_radix_sort(lay, L_cap, b, stream, debug);
+        rc = launch_depth_sort(P, lay, b, stream, debug);     // Gaussians by depth (N items)
+        if (rc) return rc;
+        rc = launch_emit_pairs(P, lay, L_cap, b, stream);     // scan + (tile|depth, id) pairs in depth order
+        if (rc) return rc;
+        rc = launch_tile_sort(lay, L_cap, b, stream, debug);  // stable passes over the tile-id digits (L items)
         if (rc) return rc;
     }
     tick(timing, 2, stream);
-    rc = launch_tile_ranges(lay, L_cap, b, stream);    // ranges + tiles bucketed by list length
-    if (rc) return rc;
-    rc = launch_pair_masks(lay, L_cap, g, b, stream);  // per-pair reach mask over the 8 pixel blocks of a tile
+    // ranges + tiles bucketed by list length; per-pair reach mask over the 8 pixel blocks of a tile
+    rc = launch_ranges_masks(lay, L_cap, g, b, stream);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
@@ -276,6 +287,23 @@ int sgs_lbs_fwd(int B, int N, int J, const float* A, const float* xyz_canon, con
     if (rc) return rc;
     if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
     LbsOut o{xyz_out, rotq_out, scales_out, T_out};
+    return launch_lbs_fwd(a, o, (cudaStream_t)stream);
+}
+
+int sgs_pose_lbs_fwd(const float* pose, const float* rest, const int* parents,
+                     const float* inv_A_t2cano, int B, int N, int J, float* A_out, float* G_out,
+                     const float* xyz_canon, const float* W, const float* rot_canon,
+                     const float* scales, const float* smpl_scale, const float* transl,
+                     float* xyz_out, float* rotq_out, float* scales_out, sgs_stream_t stream) {
+    if (B < 0 || (B > 0 && (!pose || !rest || !parents || !A_out))) return SGS_ERR_BAD_ARG;
+    LbsArgs a;
+    int rc = fill_lbs(a, B, N, J, A_out, xyz_canon, W, rot_canon, scales, smpl_scale, transl, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
+    rc = launch_pose_to_A(pose, rest, parents, inv_A_t2cano, B, J, A_out, G_out, (cudaStream_t)stream);
+    if (rc) return rc;
+    a.early_params = 1;      // the preceding kernel is pose_to_A, which never writes them
+    LbsOut o{xyz_out, rotq_out, scales_out, nullptr};
     return launch_lbs_fwd(a, o, (cudaStream_t)stream);
 }
 

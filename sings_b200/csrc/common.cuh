@@ -47,9 +47,47 @@ enum : int {
     CNT_SCAN_TICKET = 2,    // block ticket of the geometry kernel
     CNT_VISIBLE = 3,        // number of Gaussians with radii > 0 (statistics)
     CNT_RANGES_DONE = 4,    // CTAs of the tile-range kernel that have finished
+    CNT_VARBITS = 5,        // [5] = OR of the visible depth keys, [6] = OR of their complements
     CNT_SORT_TICKET0 = 8,   // + pass: block ticket of each radix pass (8 slots)
     CNT_SLOTS = 32,
 };
+
+// ---- programmatic dependent launch (PDL, sm_90+) ----
+// Every kernel of the frame is launched with the programmatic-stream-serialization attribute
+// and begins (after set-up that touches no global memory) with pdl_wait() followed by
+// pdl_launch_dependents(): the next kernel's launch, CTA scheduling and prologue overlap this
+// kernel's execution, and pdl_wait() returns only when the whole preceding grid has completed
+// and its writes are visible.  EVERY kernel waits BEFORE it releases its dependents, so when
+// kernel n+1 starts, kernel n-1 is complete: completion is transitive along the chain, and a
+// kernel may read, ahead of its own wait, data that is at least two of OUR kernels old.
+// The frame is ~20 kernels of 5-150 us: launch latency is a measurable share of it.
+// SGS_NO_PDL=1 in the environment launches them the ordinary way (A/B, debugging).
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {       // the default kernel prologue
+    pdl_wait();
+    pdl_launch_dependents();
+}
+
+bool pdl_enabled();      // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -143,6 +181,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Depth-sort pass skipping.  varbits[0] & varbits[1] = the key bits that differ among the
+// visible Gaussians; a pass whose 8-bit digit has none of them is the identity on the visible
+// items and is not run.  Which of the two ping-pong buffers holds the items before pass
+// `pass` (= after all passes when pass == DEPTH_PASSES) follows from the same two words.
+__device__ __forceinline__ bool depth_pass_runs(unsigned diff, int pass) {
+    return ((diff >> (8 * pass)) & 0xffu) != 0u;
+}
+__device__ __forceinline__ int depth_sort_parity(const unsigned* __restrict__ varbits, int pass) {
+    const unsigned diff = varbits[0] & varbits[1];
+    int par = 0;
+    for (int q = 0; q < pass; q++) par ^= (int)depth_pass_runs(diff, q);
+    return par;
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {

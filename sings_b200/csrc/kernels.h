@@ -19,22 +19,28 @@ constexpr int ACC_FLOATS = 12;
 // accumulator layout: [0]=dL/dmean2D.x, [1]=.y, [2]=dL/dconic.a, [3]=dL/dconic.b (un-doubled),
 // [4]=dL/dconic.c, [5]=dL/dopacity, [6..8]=dL/dcolor rgb, [9..11] unused
 
-constexpr int SORT_ITEMS = 8;              // keys per thread in one radix tile
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_TILE = SORT_ITEMS * SORT_THREADS;
+constexpr int SORT_ITEMS_N = 8;            // keys per thread in one radix tile: per-Gaussian depth items
+constexpr int SORT_ITEMS_L = 16;           // ... and (tile|depth, id) pairs (fewer, larger tiles: shorter look-back)
+constexpr int SORT_TILE_N = SORT_ITEMS_N * SORT_THREADS;
+constexpr int SORT_TILE_L = SORT_ITEMS_L * SORT_THREADS;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
+constexpr int DEPTH_PASSES = 4;            // radix passes over the 32 depth bits, run once per Gaussian
 
 struct RasterLayout {
     // geometry state (per Gaussian)
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
-    size_t cnt_off, hist_off, scan_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
+    size_t cnt_off, hist_off, scan_off, nstat_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
+    size_t nkeys0_off, nkeys1_off, nvals0_off, nvals1_off, rects_off;   // per-Gaussian depth-sort items
     size_t keys0_off, keys1_off, vals0_off, vals1_off, masks_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
-    int scan_blocks, sort_blocks, tiles, gx, gy, end_bit, passes;
+    int scan_blocks, sort_blocks, nsort_blocks, tiles, gx, gy, end_bit, passes;
+    // the sorted pair list is in keys1/vals1 when the number of tile-id passes is odd
+    bool sorted_in_1() const { return ((passes - DEPTH_PASSES) & 1) != 0; }
 };
 
 RasterLayout raster_layout(int P, int W, int H, long long L_cap);
@@ -59,18 +65,22 @@ struct GeomArgs {
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
                     char* geom, char* bin, cudaStream_t stream);
 
-int launch_radix_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
-                      int debug);
+// depth passes over the P per-Gaussian items (passes whose digit is constant are skipped)
+int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t stream, int debug);
+// chained scan of tiles touched + (tile|depth, id) emission in depth order
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
+// stable passes over the tile-id digits of the emitted pairs
+int launch_tile_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
+                     int debug);
 // stand-alone sort (A/B against CUB): sorts n pairs on key bits [0,end_bit)
 int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned long long* keys_tmp,
                           unsigned* vals_tmp, char* scratch, size_t scratch_bytes, long long n,
                           int end_bit, int* result_in_tmp, cudaStream_t stream);
 size_t sort_scratch_bytes(long long n);
 
-int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
-
-int launch_pair_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
-                      cudaStream_t stream);
+// tile ranges (+ tiles bucketed by list length) and per-pair reach masks, one launch
+int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                        cudaStream_t stream);
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,

@@ -17,6 +17,10 @@ struct LbsArgs {
     const float* ext_trans;   // (B,3) |
     const float* ext_rot;     // (B,9) | all three set or all null
     const float* ext_scale;   // (B)   |
+    // 1: the canonical arrays (xyz, W, rot, scales) were final before the PREVIOUS kernel of
+    // the stream started (that kernel being one of ours, e.g. pose_to_A), so their tiles may
+    // be fetched ahead of the programmatic-dependency wait (common.cuh, PDL)
+    int early_params = 0;
 };
 
 struct LbsOut {

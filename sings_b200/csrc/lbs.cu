@@ -60,6 +60,7 @@ __global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __
     extern __shared__ float s_local[];     // J x 12 local transforms
     __shared__ int s_par[64];
     const int b = blockIdx.x, j = threadIdx.x;
+    pdl_sync();
     if (j < J) {
         float R[9];
         const float* p = pose + ((size_t)b * J + j) * 3;
@@ -121,7 +122,7 @@ int launch_pose_to_A(const float* pose, const float* rest, const int* parents, c
                      int B, int J, float* A_out, float* G_out, cudaStream_t stream) {
     if (B <= 0) return 0;
     if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
-    pose_to_A_kernel<<<B, 64, (size_t)J * 12 * 4, stream>>>(pose, rest, parents, inv_A, J, A_out, G_out);
+    launch_pdl(pose_to_A_kernel, B, 64, (size_t)J * 12 * 4, stream, pose, rest, parents, inv_A, J, A_out, G_out);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -142,6 +143,7 @@ __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float
     __shared__ int s_par[64], s_depth[64], s_maxd;
     const int b = blockIdx.x, j = threadIdx.x;
     float R[9];
+    pdl_sync();
     if (j == 0) s_maxd = 0;
     if (j < J) {
         const float* p = pose + ((size_t)b * J + j) * 3;
@@ -275,7 +277,7 @@ int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parent
                          float* d_pose, cudaStream_t stream) {
     if (B <= 0) return 0;
     if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
-    pose_to_A_bwd_kernel<<<B, 64, (size_t)J * 36 * 4, stream>>>(pose, rest, parents, inv_A, G, dA, J, d_pose);
+    launch_pdl(pose_to_A_bwd_kernel, B, 64, (size_t)J * 36 * 4, stream, pose, rest, parents, inv_A, G, dA, J, d_pose);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -535,6 +537,7 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut 
         mbar_fence_init();
     }
     __syncthreads();
+    if (!a.early_params) pdl_sync();
     BlockLoads ld{s.bar, 0};
     {
         const float* src[4] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
@@ -543,6 +546,7 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut 
         const unsigned n[4] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)rows * 9};
         ld.load(src, dst, n, 4);
     }
+    if (a.early_params) pdl_sync();
     stage_frames(a, s);
     ld.wait();
     const int n = base + tid;
@@ -622,7 +626,7 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
     const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lbs_fwd_kernel<<<(a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream>>>(a, o);
+    launch_pdl(lbs_fwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, o);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -643,6 +647,7 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(LbsArgs a, LbsGrad
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_sync();
     BlockLoads ld{s.bar, 0};
     {
         const float* src[7] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
@@ -832,7 +837,7 @@ int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
     const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, true);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lbs_bwd_kernel<<<(a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream>>>(a, g);
+    launch_pdl(lbs_bwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, g);
     SGS_LAUNCH_OK();
     return 0;
 }

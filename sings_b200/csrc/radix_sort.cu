@@ -5,8 +5,13 @@
 // [0, 32+getHigherMsb(tiles)); SURVEY.md A.1/A.3, K6 of section 2.4).  A stable LSD radix sort
 // has a unique answer, so the sorted arrays are bit-identical to CUB's.
 //
+// In the rasterizer the 64-bit sort is split (raster_geometry.cu): the four depth digits are
+// sorted once per GAUSSIAN (32-bit keys, launch_depth_sort; a pass whose digit is the same for
+// every visible Gaussian is skipped), pairs are emitted in that order, and only the tile-id
+// digits are sorted per PAIR (launch_tile_sort).  The stand-alone entry point sorts all digits.
+//
 // One kernel per 8-bit digit ("onesweep"): the digit histograms of ALL passes are produced
-// up front (fused into the key-emitting geometry kernel, or by histogram_kernel for the
+// up front (fused into the geometry / emission kernels, or by histogram_kernel for the
 // stand-alone entry point); each pass ranks its tile stably (warp match_any + per-warp
 // counters), obtains the tile's global digit offsets by decoupled look-back over the
 // preceding tiles, and scatters through shared memory so global stores are digit-run
@@ -14,6 +19,7 @@
 // The item count is read from device memory, so the launch needs no host round trip.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace sgs {
 
@@ -21,20 +27,25 @@ constexpr unsigned ST_AGG = 1u << 30;
 constexpr unsigned ST_INCL = 2u << 30;
 constexpr unsigned ST_FLAG = 3u << 30;
 constexpr unsigned ST_VAL = ~ST_FLAG;
-constexpr int LOOKBACK_BATCH = 8;
 
+
+// One pass.  K = unsigned (per-Gaussian depth items) or unsigned long long (pairs).
+// The items come from buffer `par` of the ping-pong pair and go to the other one; with
+// `varbits` set (depth sort) the pass first decides from the varying key bits whether it runs
+// at all and which buffer is current (see depth_sort_parity, common.cuh).
+template <typename K>
 struct SortPass {
-    const unsigned long long* keys_in;
-    const unsigned* vals_in;
-    unsigned long long* keys_out;
-    unsigned* vals_out;
-    const unsigned* hist;   // 256 bins of this pass
-    unsigned* status;       // [tiles][256] look-back words of this pass (zeroed)
-    int* ticket;            // zeroed
-    const int* n_ptr;       // item count on the device (may be null -> n_cap)
+    K* keys[2];
+    unsigned* vals[2];
+    const unsigned* hist;     // 256 bins of this pass
+    unsigned* status;         // [tiles][256] look-back words of this pass (zeroed)
+    int* ticket;              // zeroed
+    const int* n_ptr;         // item count on the device (may be null -> n_cap)
+    const unsigned* varbits;  // null: always run, source = buffer `par`
     long long n_cap;
     int shift;
-    unsigned mask;          // (1 << bits of this digit) - 1; < 255 only in a partial last pass
+    unsigned mask;            // (1 << bits of this digit) - 1; < 255 only in a partial last pass
+    int par;                  // source buffer (without varbits) / pass index (with varbits)
 };
 
 // exclusive scan of one value per thread over a 256-thread block
@@ -55,37 +66,50 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_tmp,
     return off + incl - v;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass a) {
+template <typename K, int SORT_ITEMS, int LOOKBACK_BATCH>
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K> a) {
+    constexpr int SORT_TILE = SORT_ITEMS * SORT_THREADS;
     __shared__ unsigned s_cnt[SORT_THREADS / 32][RADIX];
     __shared__ unsigned s_bexcl[RADIX];
     __shared__ unsigned s_gbase[RADIX];
-    __shared__ unsigned long long s_keys[SORT_TILE];
-    __shared__ unsigned s_vals[SORT_TILE];
+    extern __shared__ __align__(16) unsigned char s_dyn[];     // SORT_TILE keys, then SORT_TILE values
+    K* const s_keys = reinterpret_cast<K*>(s_dyn);
+    unsigned* const s_vals = reinterpret_cast<unsigned*>(s_dyn + (size_t)SORT_TILE * sizeof(K));
     __shared__ unsigned s_tmp[SORT_THREADS / 32];
     __shared__ int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long n = a.n_ptr ? (long long)*a.n_ptr : a.n_cap;
-    if (n > a.n_cap) n = a.n_cap;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1);
 #pragma unroll
     for (int w = 0; w < SORT_THREADS / 32; w++) s_cnt[w][tid] = 0;
+    pdl_sync();
+    int src = a.par;
+    if (a.varbits) {
+        if (!depth_pass_runs(a.varbits[0] & a.varbits[1], a.par)) return;      // grid-uniform
+        src = depth_sort_parity(a.varbits, a.par);
+    }
+    const K* __restrict__ keys_in = src ? a.keys[1] : a.keys[0];
+    const unsigned* __restrict__ vals_in = src ? a.vals[1] : a.vals[0];
+    K* __restrict__ keys_out = src ? a.keys[0] : a.keys[1];
+    unsigned* __restrict__ vals_out = src ? a.vals[0] : a.vals[1];
+    long long n = a.n_ptr ? (long long)*a.n_ptr : a.n_cap;
+    if (n > a.n_cap) n = a.n_cap;
+    if (a.ticket && tid == 0) s_tile = atomicAdd(a.ticket, 1);
     __syncthreads();
-    const int tile = s_tile;
+    const int tile = a.ticket ? s_tile : (int)blockIdx.x;
     const long long start = (long long)tile * SORT_TILE;
     if (start >= n) return;
     const int n_valid = (int)min((long long)SORT_TILE, n - start);
 
     // ---- load, warp-striped: warp w owns items [w*256, w*256+256), item i of lane l = i*32+l ----
-    unsigned long long key[SORT_ITEMS];
+    K key[SORT_ITEMS];
     unsigned val[SORT_ITEMS];
     unsigned rank[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         int local = warp * (32 * SORT_ITEMS) + i * 32 + lane;
         bool ok = local < n_valid;
-        key[i] = ok ? a.keys_in[start + local] : ~0ull;
-        val[i] = ok ? a.vals_in[start + local] : 0u;
+        key[i] = ok ? keys_in[start + local] : (K)~(K)0;
+        val[i] = ok ? vals_in[start + local] : 0u;
     }
     // ---- stable rank inside the warp's segment ----
 #pragma unroll
@@ -156,11 +180,11 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass a)
     for (int k = 0; k < SORT_ITEMS; k++) {
         int p = tid + k * SORT_THREADS;
         if (p < n_valid) {
-            unsigned long long kk = s_keys[p];
+            K kk = s_keys[p];
             unsigned d = (unsigned)(kk >> a.shift) & a.mask;
             size_t dst = (size_t)s_gbase[d] + (unsigned)(p - (int)s_bexcl[d]);
-            a.keys_out[dst] = kk;
-            a.vals_out[dst] = s_vals[p];
+            keys_out[dst] = kk;
+            vals_out[dst] = s_vals[p];
         }
     }
 }
@@ -184,31 +208,83 @@ __global__ void __launch_bounds__(256) histogram_kernel(const unsigned long long
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
+// Tiles may be taken in blockIdx order instead of ticket order (one contended atomic and one
+// L2 round trip less per CTA) when every CTA of the pass is resident at once: a CTA spinning
+// on a predecessor's look-back word can then never keep that predecessor from running.
+template <typename Kern>
+static bool all_resident(Kern k, int blocks, size_t smem) {
+    static const void* c_k[4];           // tiny cache: the occupancy query costs microseconds
+    static size_t c_smem[4];
+    static long long c_cap[4];
+    static int c_n = 0;
+    for (int i = 0; i < c_n; i++)
+        if (c_k[i] == (const void*)k && c_smem[i] == smem) return (long long)blocks <= c_cap[i];
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SORT_THREADS, smem) != cudaSuccess) return false;
+    const long long cap = (long long)sms * per_sm;
+    if (c_n < 4) { c_k[c_n] = (const void*)k; c_smem[c_n] = smem; c_cap[c_n] = cap; c_n++; }
+    return (long long)blocks <= cap;
+}
+
+// passes [p0, p1) of the 64-bit pair sort; pass p sorts key bits [8p, 8p+8) below end_bit
 static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* k1, unsigned* v1,
                       const unsigned* hist, unsigned* status, int* tickets, const int* n_ptr,
-                      long long n_cap, int passes, int end_bit, int blocks, cudaStream_t stream,
+                      long long n_cap, int p0, int p1, int end_bit, int blocks, cudaStream_t stream,
                       int debug) {
-    for (int p = 0; p < passes; p++) {
-        SortPass a;
-        a.keys_in = (p & 1) ? k1 : k0;
-        a.vals_in = (p & 1) ? v1 : v0;
-        a.keys_out = (p & 1) ? k0 : k1;
-        a.vals_out = (p & 1) ? v0 : v1;
+    for (int p = p0; p < p1; p++) {
+        SortPass<unsigned long long> a;
+        a.keys[0] = k0; a.keys[1] = k1;
+        a.vals[0] = v0; a.vals[1] = v1;
         a.hist = hist + (size_t)p * RADIX;
-        a.status = status + (size_t)p * blocks * RADIX;
+        a.status = status + (size_t)(p - p0) * blocks * RADIX;
         a.ticket = tickets + p;
         a.n_ptr = n_ptr;
+        a.varbits = nullptr;
         a.n_cap = n_cap;
         a.shift = p * RADIX_BITS;
         a.mask = (1u << min(RADIX_BITS, end_bit - p * RADIX_BITS)) - 1u;
-        onesweep_pass_kernel<<<blocks, SORT_THREADS, 0, stream>>>(a);
+        a.par = (p - p0) & 1;
+        auto k = onesweep_pass_kernel<unsigned long long, SORT_ITEMS_L, 8>;
+        const size_t smem = (size_t)SORT_TILE_L * 12;
+        SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (all_resident(k, blocks, smem)) a.ticket = nullptr;
+        SGS_CUDA_OK(launch_pdl(k, blocks, SORT_THREADS, smem, stream, a));
         SGS_STAGE_OK(debug, stream);
     }
     return 0;
 }
 
-int launch_radix_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
-                      int debug) {
+int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t stream, int debug) {
+    if (P <= 0) return 0;
+    int* counters = reinterpret_cast<int*>(bin + lay.cnt_off);
+    for (int p = 0; p < DEPTH_PASSES; p++) {
+        SortPass<unsigned> a;
+        a.keys[0] = reinterpret_cast<unsigned*>(bin + lay.nkeys0_off);
+        a.keys[1] = reinterpret_cast<unsigned*>(bin + lay.nkeys1_off);
+        a.vals[0] = reinterpret_cast<unsigned*>(bin + lay.nvals0_off);
+        a.vals[1] = reinterpret_cast<unsigned*>(bin + lay.nvals1_off);
+        a.hist = reinterpret_cast<const unsigned*>(bin + lay.hist_off) + (size_t)p * RADIX;
+        a.status = reinterpret_cast<unsigned*>(bin + lay.nstat_off) + (size_t)p * lay.nsort_blocks * RADIX;
+        a.ticket = counters + CNT_SORT_TICKET0 + p;
+        a.n_ptr = nullptr;
+        a.varbits = reinterpret_cast<const unsigned*>(counters + CNT_VARBITS);
+        a.n_cap = P;
+        a.shift = p * RADIX_BITS;
+        a.mask = RADIX - 1;
+        a.par = p;
+        auto k = onesweep_pass_kernel<unsigned, SORT_ITEMS_N, 8>;
+        const size_t smem = (size_t)SORT_TILE_N * 8;
+        if (all_resident(k, lay.nsort_blocks, smem)) a.ticket = nullptr;
+        SGS_CUDA_OK(launch_pdl(k, lay.nsort_blocks, SORT_THREADS, smem, stream, a));
+        SGS_STAGE_OK(debug, stream);
+    }
+    return 0;
+}
+
+int launch_tile_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
+                     int debug) {
     if (L_cap >= (1ll << 30)) return SGS_ERR_CAPACITY;
     int* counters = reinterpret_cast<int*>(bin + lay.cnt_off);
     return run_passes(reinterpret_cast<unsigned long long*>(bin + lay.keys0_off),
@@ -217,12 +293,12 @@ int launch_radix_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaS
                       reinterpret_cast<unsigned*>(bin + lay.vals1_off),
                       reinterpret_cast<const unsigned*>(bin + lay.hist_off),
                       reinterpret_cast<unsigned*>(bin + lay.sortstat_off),
-                      counters + CNT_SORT_TICKET0, counters + CNT_NUM_RENDERED, L_cap, lay.passes,
-                      lay.end_bit, lay.sort_blocks, stream, debug);
+                      counters + CNT_SORT_TICKET0, counters + CNT_NUM_RENDERED, L_cap, DEPTH_PASSES,
+                      lay.passes, lay.end_bit, lay.sort_blocks, stream, debug);
 }
 
 size_t sort_scratch_bytes(long long n) {
-    size_t blocks = (size_t)((n + SORT_TILE - 1) / SORT_TILE);
+    size_t blocks = (size_t)((n + SORT_TILE_L - 1) / SORT_TILE_L);
     if (blocks < 1) blocks = 1;
     return align_up(CNT_SLOTS * 4, 256) + align_up((size_t)MAX_PASSES * RADIX * 4, 256) +
            align_up((size_t)MAX_PASSES * blocks * RADIX * 4, 256);
@@ -234,7 +310,7 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
     if (n < 0 || end_bit < 1 || end_bit > 64 || n >= (1ll << 30)) return SGS_ERR_BAD_ARG;
     if (scratch_bytes < sort_scratch_bytes(n)) return SGS_ERR_CAPACITY;
     const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
-    const int blocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    const int blocks = (int)((n + SORT_TILE_L - 1) / SORT_TILE_L);
     if (result_in_tmp) *result_in_tmp = passes & 1;
     if (n == 0) return 0;
     SGS_CUDA_OK(cudaMemsetAsync(scratch, 0, sort_scratch_bytes(n), stream));
@@ -245,7 +321,7 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
     int hb = (int)min((long long)148 * 8, (n + 255) / 256);
     histogram_kernel<<<hb, 256, 0, stream>>>(keys, n, passes, end_bit, hist);
     SGS_LAUNCH_OK();
-    return run_passes(keys, vals, keys_tmp, vals_tmp, hist, status, tickets, nullptr, n, passes,
+    return run_passes(keys, vals, keys_tmp, vals_tmp, hist, status, tickets, nullptr, n, 0, passes,
                       end_bit, blocks, stream, 0);
 }
 

@@ -30,11 +30,11 @@ constexpr int FWD_U = 4;      // pairs evaluated together per pixel in the forwa
 // tile without pairs.  One WARP per tile: a 33-ary search (32 probes per step, ballot) for the
 // lower bounds of tile and tile + 1 over the sorted keys -- 4 dependent L2 round trips at a
 // million pairs instead of the 21 of a binary search; no pass over the list, no atomics on
-// the ranges, no memset.  The CTA (32 tiles) then files its tiles in buckets by list length
+// the ranges, no memset.  The CTA (8 tiles) then files its tiles in buckets by list length
 // (bucket = bit length of the count, 0 = empty) so the blend kernels can take tiles
 // longest-first: the few tiles with thousands of pairs must not form the tail.
 constexpr int LEN_BUCKETS = 32;
-constexpr int RANGE_THREADS = 1024;
+constexpr int RANGE_THREADS = 256;
 
 // first index in [0, n) whose key's tile id is >= target (warp-cooperative)
 __device__ __forceinline__ unsigned warp_lower_bound(const unsigned long long* __restrict__ keys,
@@ -56,13 +56,13 @@ __device__ __forceinline__ unsigned warp_lower_bound(const unsigned long long* _
     return lo;
 }
 
-__global__ void __launch_bounds__(RANGE_THREADS)
-tile_ranges_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ counters,
-                   long long n_cap, uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
-                   unsigned* __restrict__ bucket_list, int tiles) {
+__device__ __forceinline__ void tile_ranges_block(int block, const unsigned long long* __restrict__ keys,
+                                                  const int* __restrict__ counters, long long n_cap,
+                                                  uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
+                                                  unsigned* __restrict__ bucket_list, int tiles) {
     __shared__ unsigned s_len[RANGE_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.x * (RANGE_THREADS / 32) + warp;
+    const int t = block * (RANGE_THREADS / 32) + warp;
     const unsigned n = (unsigned)min((long long)counters[CNT_NUM_RENDERED], n_cap);
     unsigned c = 0;
     if (t < tiles) {                                     // warp-uniform
@@ -74,8 +74,8 @@ tile_ranges_kernel(const unsigned long long* __restrict__ keys, const int* __res
     if (lane == 0) s_len[warp] = c;
     __syncthreads();
     if (warp != 0) return;
-    const int tt = blockIdx.x * (RANGE_THREADS / 32) + lane;
-    const bool ok = tt < tiles;
+    const int tt = block * (RANGE_THREADS / 32) + lane;
+    const bool ok = lane < RANGE_THREADS / 32 && tt < tiles;
     const unsigned bk = ok ? (unsigned)(32 - __clz(s_len[lane])) % LEN_BUCKETS : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, bk);
     const int leader = __ffs(peers) - 1;
@@ -104,20 +104,10 @@ __device__ __forceinline__ unsigned tile_of_rank(const unsigned* __restrict__ bu
 }
 
 static inline const unsigned long long* sorted_keys(const RasterLayout& lay, const char* bin) {
-    return reinterpret_cast<const unsigned long long*>(bin + ((lay.passes & 1) ? lay.keys1_off : lay.keys0_off));
+    return reinterpret_cast<const unsigned long long*>(bin + (lay.sorted_in_1() ? lay.keys1_off : lay.keys0_off));
 }
 static inline const unsigned* sorted_vals(const RasterLayout& lay, const char* bin) {
-    return reinterpret_cast<const unsigned*>(bin + ((lay.passes & 1) ? lay.vals1_off : lay.vals0_off));
-}
-
-int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
-    tile_ranges_kernel<<<(lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32), RANGE_THREADS, 0, stream>>>(
-        sorted_keys(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
-        reinterpret_cast<uint2*>(bin + lay.ranges_off),
-        reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
-        reinterpret_cast<unsigned*>(bin + lay.bktlist_off), lay.tiles);
-    SGS_LAUNCH_OK();
-    return 0;
+    return reinterpret_cast<const unsigned*>(bin + (lay.sorted_in_1() ? lay.vals1_off : lay.vals0_off));
 }
 
 __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
@@ -190,15 +180,24 @@ __device__ __forceinline__ unsigned reach_mask(const float4 q0, const float4 q1,
     return m;
 }
 
-// One thread per sorted pair.  (A per-tile shared-memory bitonic sort of the depth bits that
-// also produced these masks was tried in place of the four depth passes of the onesweep sort:
-// n log^2 n compare-exchanges cost as many instructions as the four radix passes; rejected.)
-__global__ void __launch_bounds__(256)
-pair_mask_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ point_list,
-                 const int* __restrict__ counters, long long n_cap, const float4* __restrict__ rec,
-                 int gx_tiles, unsigned char* __restrict__ masks) {
+// Tile ranges and reach masks in ONE launch (both only read the sorted list): the first
+// `range_blocks` CTAs search the ranges of 8 tiles each (a chain of dependent probes, so they
+// start first), the others compute one reach mask per thread.  (A per-tile shared-memory
+// bitonic sort of the depth bits that also produced these masks was tried in place of the depth
+// passes of the radix sort: n log^2 n compare-exchanges cost as many instructions; rejected.)
+__global__ void __launch_bounds__(RANGE_THREADS)
+ranges_masks_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ point_list,
+                    const int* __restrict__ counters, long long n_cap, const float4* __restrict__ rec,
+                    int gx_tiles, int tiles, int range_blocks, uint2* __restrict__ ranges,
+                    unsigned* __restrict__ bucket_count, unsigned* __restrict__ bucket_list,
+                    unsigned char* __restrict__ masks) {
+    pdl_sync();
+    if ((int)blockIdx.x < range_blocks) {
+        tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
+        return;
+    }
     const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)(blockIdx.x - range_blocks) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned tile = (unsigned)(__ldg(keys + i) >> 32);
     const unsigned id = __ldg(point_list + i);
@@ -208,13 +207,17 @@ pair_mask_kernel(const unsigned long long* __restrict__ keys, const unsigned* __
     masks[i] = (unsigned char)reach_mask(q0, q1, q3, tx, ty);
 }
 
-int launch_pair_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
-                      cudaStream_t stream) {
-    long long blocks = (L_cap + 255) / 256;
+int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                        cudaStream_t stream) {
+    const int range_blocks = (lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32);
+    long long blocks = (L_cap + RANGE_THREADS - 1) / RANGE_THREADS;
     if (blocks < 1) blocks = 1;
-    pair_mask_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+    launch_pdl(ranges_masks_kernel, (unsigned)(range_blocks + blocks), RANGE_THREADS, 0, stream,
         sorted_keys(lay, bin), sorted_vals(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
-        reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx,
+        reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx, lay.tiles, range_blocks,
+        reinterpret_cast<uint2*>(bin + lay.ranges_off),
+        reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
+        reinterpret_cast<unsigned*>(bin + lay.bktlist_off),
         reinterpret_cast<unsigned char*>(bin + lay.masks_off));
     SGS_LAUNCH_OK();
     return 0;
@@ -253,6 +256,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     __shared__ float4 s_q2[TILE_PIX / 32][RING_SLOTS];     // g, b, depth, list position + 1
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_sync();
     const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
@@ -379,7 +383,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
                      float* out_depth, cudaStream_t stream) {
-    blend_fwd_kernel<<<lay.tiles, TILE_PIX, 0, stream>>>(
+    launch_pdl(blend_fwd_kernel, lay.tiles, TILE_PIX, 0, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
@@ -431,6 +435,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     extern __shared__ __align__(16) char s_bwd_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[warp];
+    pdl_sync();
     const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
@@ -610,7 +615,7 @@ int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, co
                      cudaStream_t stream) {
     const size_t smem = sizeof(BwdWarpSmem) * (TILE_PIX / 32);
     SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    blend_bwd_kernel<<<lay.tiles, TILE_PIX, smem, stream>>>(
+    launch_pdl(blend_bwd_kernel, lay.tiles, TILE_PIX, smem, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),

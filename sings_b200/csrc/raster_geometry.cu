@@ -1,18 +1,28 @@
-// raster_geometry.cu -- fused forward "geometry" stage of the rasterizer:
-//   preprocess (cull, 3D cov, EWA 2D cov, conic, radius, tile rect, SH->RGB)
-//   + tiles-touched prefix sum (single-pass chained scan, decoupled look-back)
-//   + (tile|depth) key / Gaussian-id emission for every touched tile
-//   + the digit histograms of all radix passes,
-// in ONE pass over HBM.  Replaces, with identical results, the reference's
+// raster_geometry.cu -- forward "geometry" stage of the rasterizer, two kernels:
+//   geometry_kernel: preprocess (cull, 3D cov, EWA 2D cov, conic, radius, tile rect, SH->RGB)
+//     + one (depth, Gaussian id) sort item and one packed tile rectangle per Gaussian
+//     + the digit histograms of the four depth passes -- ONE pass over HBM;
+//   emit_pairs_kernel (after the Gaussians have been sorted by depth, radix_sort.cu):
+//     tiles-touched prefix sum (single-pass chained scan, decoupled look-back)
+//     + (tile|depth) key / Gaussian-id emission for every touched tile, in depth order,
+//     + the digit histograms of the tile-id passes.
+// Together with the radix passes they replace, with identical results, the reference's
 //   [upstream] forward.cu preprocessCUDA, cub::DeviceScan::InclusiveSum,
-//   rasterizer_impl.cu duplicateWithKeys (K3+K4+K5 of section 2.4),
+//   rasterizer_impl.cu duplicateWithKeys + cub::DeviceRadixSort::SortPairs
+//   (K3..K6 of section 2.4),
 // reached from /root/reference/sings/rec/renderer/gs_renderer_single.py:87-95.
 //
-// Layout: one CTA = 256 consecutive Gaussians, taken in ticket order so the chained scan can
-// never wait on a CTA that has not started.  SH rows (192 B each at M=16) are staged with
+// Why the order of work differs from upstream: all pairs of a Gaussian share its depth, so the
+// four depth digits of the 64-bit (tile|depth) key are sorted ONCE PER GAUSSIAN (N items)
+// instead of once per pair (L ~ 5.5 N items); pairs emitted in depth order then need only the
+// stable passes over the tile-id digits.  A stable LSD sort has a unique answer: the sorted
+// key/value lists are bit-identical to sorting the pairs on all 45 bits.
+//
+// Layout: one CTA = 256 consecutive Gaussians.  SH rows (192 B each at M=16) are staged with
 // 16-byte cp.async into padded shared rows; the other attributes are read directly.
-// Emission is load-balanced over the CTA (binary search of the block-local offsets), so key
-// and value stores are fully coalesced.
+// Emission CTAs are taken in ticket order so the chained scan can never wait on a CTA that
+// has not started, and emission is load-balanced over the CTA (binary search of the
+// block-local offsets), so key and value stores are fully coalesced.
 #include "geom_math.cuh"
 #include "kernels.h"
 
@@ -42,8 +52,10 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.passes = (l.end_bit + RADIX_BITS - 1) / RADIX_BITS;
     l.scan_blocks = (P + GEO_THREADS - 1) / GEO_THREADS;
     if (l.scan_blocks < 1) l.scan_blocks = 1;
-    l.sort_blocks = (int)((L_cap + SORT_TILE - 1) / SORT_TILE);
+    l.sort_blocks = (int)((L_cap + SORT_TILE_L - 1) / SORT_TILE_L);
     if (l.sort_blocks < 1) l.sort_blocks = 1;
+    l.nsort_blocks = (P + SORT_TILE_N - 1) / SORT_TILE_N;
+    if (l.nsort_blocks < 1) l.nsort_blocks = 1;
     // geometry state
     l.rec_off = 0;
     l.geom_bytes = align_up((size_t)(P > 0 ? P : 1) * REC_FLOATS * 4, 256);
@@ -52,9 +64,16 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.cnt_off = o;      o += align_up(CNT_SLOTS * 4, 256);
     l.hist_off = o;     o += align_up((size_t)MAX_PASSES * RADIX * 4, 256);
     l.scan_off = o;     o += align_up((size_t)l.scan_blocks * 8, 256);
-    l.sortstat_off = o; o += align_up((size_t)l.passes * l.sort_blocks * RADIX * 4, 256);
+    l.nstat_off = o;    o += align_up((size_t)DEPTH_PASSES * l.nsort_blocks * RADIX * 4, 256);
+    l.sortstat_off = o; o += align_up((size_t)(l.passes - DEPTH_PASSES) * l.sort_blocks * RADIX * 4, 256);
     l.bktcnt_off = o;   o += align_up(32 * 4, 256);
     l.zero_bytes = o;
+    size_t np = (size_t)(P > 0 ? P : 1);
+    l.nkeys0_off = o;   o += align_up(np * 4, 256);
+    l.nkeys1_off = o;   o += align_up(np * 4, 256);
+    l.nvals0_off = o;   o += align_up(np * 4, 256);
+    l.nvals1_off = o;   o += align_up(np * 4, 256);
+    l.rects_off = o;    o += align_up(np * 8, 256);
     l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
     l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 4, 256);
     size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
@@ -75,13 +94,11 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
 struct GeoOut {
     int* radii;
     float* rec;
-    int* counters;
-    unsigned* hist;
-    unsigned long long* scan_status;
-    unsigned long long* keys;
-    unsigned* vals;
-    long long L_cap;
-    int passes;
+    unsigned* hist;          // digit histograms, [pass][256]; this kernel fills the depth passes
+    unsigned* varbits;       // [0] = OR of the visible depth keys, [1] = OR of their complements
+    unsigned* nkeys;         // (P) depth bits (0 for a Gaussian that touches no tile)
+    unsigned* nvals;         // (P) Gaussian id
+    uint2* rects;            // (P) x0 | y0 << 16, width | height << 16 (tiles)
     int gx, gy;
     float fx, fy;
 };
@@ -96,22 +113,18 @@ geometry_kernel(GeomArgs a, GeoOut o) {
     constexpr int S4 = HAS_SH ? sh_stride4(NVEC) : 0;
     extern __shared__ float4 s_sh[];                 // GEO_THREADS * S4 float4
     __shared__ float s_cam[36];
-    __shared__ unsigned s_incl[GEO_THREADS];         // block-local inclusive tile offsets
-    __shared__ int4 s_rect[GEO_THREADS];             // x0, y0, width, depth bits
-    __shared__ unsigned s_warp[GEO_THREADS / 32];
-    __shared__ unsigned s_hist[MAX_PASSES * RADIX];
-    __shared__ int s_ticket;
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_hist[DEPTH_PASSES * RADIX];
+    __shared__ unsigned s_var[2];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_ticket = atomicAdd(&o.counters[CNT_SCAN_TICKET], 1);
+    const int tid = threadIdx.x;
+    pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
-    for (int i = tid; i < o.passes * RADIX; i += GEO_THREADS) s_hist[i] = 0;
+    else if (tid < 37) s_var[tid - 35] = 0;
+    for (int i = tid; i < DEPTH_PASSES * RADIX; i += GEO_THREADS) s_hist[i] = 0;
     __syncthreads();
-    const int chunk = s_ticket;
-    const int base = chunk * GEO_THREADS;
+    const int base = blockIdx.x * GEO_THREADS;
     const int idx = base + tid;
     const bool in_range = idx < a.P;
     const float* V = s_cam;
@@ -182,61 +195,31 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         }
     }
 
-    // ---- block scan of tiles touched (before the colour work, so that warp 0's chained-scan
-    //      look-back overlaps the SH evaluation of the other warps) ----
-    unsigned incl = tiles;
+    // ---- the Gaussian's sort item: depth bits (all its pairs share them), id, tile rectangle.
+    //      A Gaussian without tiles sorts with key 0 and emits nothing.  The bits that differ
+    //      among the VISIBLE keys are tracked so that a radix pass whose digit is the same for
+    //      all of them (sign/exponent bytes of an avatar a few metres deep) can be skipped. ----
+    const unsigned dkey = tiles ? __float_as_uint(depth) : 0u;
+    if (in_range) {
+        o.nkeys[idx] = dkey;
+        o.nvals[idx] = (unsigned)idx;
+        o.rects[idx] = make_uint2((unsigned)x0 | ((unsigned)y0 << 16),
+                                  (unsigned)(x1 - x0) | ((unsigned)(y1 - y0) << 16));
+        o.radii[idx] = rad;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
+        for (int p = 0; p < DEPTH_PASSES; p++)
+            atomicAdd(&s_hist[p * RADIX + ((dkey >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
     }
-    if (lane == 31) s_warp[warp] = incl;
-    s_rect[tid] = make_int4(x0, y0, x1 - x0, __float_as_int(depth));
+    {
+        const unsigned w_or = __reduce_or_sync(0xffffffffu, tiles ? dkey : 0u);
+        const unsigned w_nor = __reduce_or_sync(0xffffffffu, tiles ? ~dkey : 0u);
+        if ((tid & 31) == 0) {
+            if (w_or) atomicOr(&s_var[0], w_or);
+            if (w_nor) atomicOr(&s_var[1], w_nor);
+        }
+    }
     if constexpr (HAS_SH) cp_async_wait_all();
     __syncthreads();
-    unsigned warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < GEO_THREADS / 32; w++) {
-        unsigned v = s_warp[w];
-        if (w < warp) warp_off += v;
-        block_total += v;
-    }
-    incl += warp_off;
-    s_incl[tid] = incl;
-
-    // ---- chained scan across CTAs (decoupled look-back, one warp) ----
-    if (warp == 0) {
-        unsigned long long excl = 0;
-        if (lane == 0)
-            st_relaxed_u64(&o.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
-        if (chunk > 0) {
-            int look = chunk - 1;
-            while (true) {
-                int j = look - lane;
-                unsigned long long s = j >= 0 ? ld_relaxed_u64(&o.scan_status[j]) : FLAG_INCL;
-                while (__any_sync(0xffffffffu, (s & FLAG_MASK) == 0)) {
-                    if ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&o.scan_status[j]);
-                }
-                unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
-                unsigned long long val = s & ~FLAG_MASK;
-                int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-                unsigned long long v = lane <= first ? val : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(&o.scan_status[chunk], FLAG_INCL | (excl + block_total));
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            unsigned long long total = excl + block_total;
-            if (chunk == (int)gridDim.x - 1)
-                o.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-            if (total > (unsigned long long)o.L_cap) o.counters[CNT_OVERFLOW] = 1;
-        }
-    }
 
     // ---- colour: SH -> RGB (or precomputed) and the blend record ----
     if (tiles > 0) {
@@ -283,23 +266,117 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         rec[2] = make_float4(rgb[1], rgb[2], depth, 0.0f);
         rec[3] = make_float4(t_m, nb_c, nb_a, __uint_as_float(flags));
     }
-    if (in_range) o.radii[idx] = rad;
-    __syncthreads();          // s_prefix (chained scan) and the records are complete
+    for (int i = tid; i < DEPTH_PASSES * RADIX; i += GEO_THREADS) {
+        unsigned c = s_hist[i];
+        if (c) atomicAdd(&o.hist[i], c);
+    }
+    if (tid < 2 && s_var[tid]) atomicOr(&o.varbits[tid], s_var[tid]);
+}
 
-    // ---- emit (tile|depth) keys and Gaussian ids: [upstream] duplicateWithKeys ----
-    const unsigned long long prefix = s_prefix;
-    // the four depth digits are the same for all pairs of a Gaussian: one weighted shared
-    // atomic per digit and Gaussian (weight = pairs actually emitted, i.e. clipped at L_cap)
-    if (tiles > 0) {
-        const unsigned long long start = prefix + (incl - tiles);
-        const unsigned long long room = start < (unsigned long long)o.L_cap ? (unsigned long long)o.L_cap - start : 0ull;
-        const unsigned emitted = room < tiles ? (unsigned)room : tiles;
-        const unsigned dbits = __float_as_uint(depth);
-        if (emitted) {
+// ------------------------------------------------------------------------------------------
+// Pair emission in depth order: [upstream] InclusiveSum + duplicateWithKeys.  Thread i of
+// chunk c takes the Gaussian at position c*256+i of the depth-sorted list.
+// ------------------------------------------------------------------------------------------
+struct EmitArgs {
+    int P;
+    const unsigned* nkeys[2];   // depth-sorted keys are in buffer depth_sort_parity(varbits)
+    const unsigned* nvals[2];
+    const unsigned* varbits;
+    const uint2* rects;
+    int* counters;
+    unsigned* hist;             // [pass][256]; this kernel fills passes >= DEPTH_PASSES
+    unsigned long long* scan_status;
+    unsigned long long* keys;
+    unsigned* vals;
+    long long L_cap;
+    int passes;
+    int gx;
+};
+
+__global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
+    __shared__ unsigned s_incl[GEO_THREADS];         // block-local inclusive tile offsets
+    __shared__ int4 s_rect[GEO_THREADS];             // x0, y0, width, depth bits
+    __shared__ unsigned s_gid[GEO_THREADS];
+    __shared__ unsigned s_warp[GEO_THREADS / 32];
+    __shared__ unsigned s_hist[(MAX_PASSES - DEPTH_PASSES) * RADIX];
+    __shared__ int s_ticket;
+    __shared__ unsigned long long s_prefix;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_passes = a.passes - DEPTH_PASSES;
+    pdl_sync();
+    if (tid == 0) s_ticket = atomicAdd(&a.counters[CNT_SCAN_TICKET], 1);
+    for (int i = tid; i < tile_passes * RADIX; i += GEO_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const int chunk = s_ticket;
+    const int base = chunk * GEO_THREADS;
+    const int pos_sorted = base + tid;
+    const int par = depth_sort_parity(a.varbits, DEPTH_PASSES);
+    unsigned tiles = 0;
+    if (pos_sorted < a.P) {
+        const unsigned dkey = (par ? a.nkeys[1] : a.nkeys[0])[pos_sorted];
+        const unsigned gid = (par ? a.nvals[1] : a.nvals[0])[pos_sorted];
+        const uint2 r = __ldg(a.rects + gid);
+        const int w = (int)(r.y & 0xffffu), h = (int)(r.y >> 16);
+        tiles = (unsigned)(w * h);
+        s_rect[tid] = make_int4((int)(r.x & 0xffffu), (int)(r.x >> 16), w, (int)dkey);
+        s_gid[tid] = gid;
+    }
+    unsigned incl = tiles;
 #pragma unroll
-            for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * RADIX + ((dbits >> (p * RADIX_BITS)) & (RADIX - 1))], emitted);
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < GEO_THREADS / 32; w++) {
+        unsigned v = s_warp[w];
+        if (w < warp) warp_off += v;
+        block_total += v;
+    }
+    incl += warp_off;
+    s_incl[tid] = incl;
+
+    // ---- chained scan across CTAs (decoupled look-back, one warp) ----
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (lane == 0)
+            st_relaxed_u64(&a.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
+        if (chunk > 0) {
+            int look = chunk - 1;
+            while (true) {
+                int j = look - lane;
+                unsigned long long s = j >= 0 ? ld_relaxed_u64(&a.scan_status[j]) : FLAG_INCL;
+                while (__any_sync(0xffffffffu, (s & FLAG_MASK) == 0)) {
+                    if ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&a.scan_status[j]);
+                }
+                unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
+                unsigned long long val = s & ~FLAG_MASK;
+                int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                unsigned long long v = lane <= first ? val : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&a.scan_status[chunk], FLAG_INCL | (excl + block_total));
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            unsigned long long total = excl + block_total;
+            if (chunk == (int)gridDim.x - 1)
+                a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+            if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
         }
     }
+    __syncthreads();          // s_prefix, s_incl, s_rect
+
+    // ---- emit (tile|depth) keys and Gaussian ids ----
+    const unsigned long long prefix = s_prefix;
     for (unsigned e = tid; e < block_total; e += GEO_THREADS) {
         int lo = 0, hi = GEO_THREADS - 1;          // first g with s_incl[g] > e
         while (lo < hi) {
@@ -311,21 +388,44 @@ geometry_kernel(GeomArgs a, GeoOut o) {
         const unsigned first = g ? s_incl[g - 1] : 0u;
         const unsigned k = e - first;
         const unsigned ty = k / (unsigned)r.z, tx = k - ty * (unsigned)r.z;
-        const unsigned tile_id = (unsigned)(r.y + (int)ty) * (unsigned)o.gx + (unsigned)(r.x + (int)tx);
+        const unsigned tile_id = (unsigned)(r.y + (int)ty) * (unsigned)a.gx + (unsigned)(r.x + (int)tx);
         const unsigned long long key = ((unsigned long long)tile_id << 32) | (unsigned)r.w;
         const unsigned long long pos = prefix + e;
-        if (pos < (unsigned long long)o.L_cap) {
-            o.keys[pos] = key;
-            o.vals[pos] = (unsigned)(base + g);
-            for (int p = 4; p < o.passes; p++)          // tile-id digits differ per pair
-                atomicAdd(&s_hist[p * RADIX + (unsigned)((key >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        if (pos < (unsigned long long)a.L_cap) {
+            a.keys[pos] = key;
+            a.vals[pos] = s_gid[g];
+            for (int p = 0; p < tile_passes; p++)
+                atomicAdd(&s_hist[p * RADIX + ((tile_id >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
         }
     }
     __syncthreads();
-    for (int i = tid; i < o.passes * RADIX; i += GEO_THREADS) {
+    for (int i = tid; i < tile_passes * RADIX; i += GEO_THREADS) {
         unsigned c = s_hist[i];
-        if (c) atomicAdd(&o.hist[i], c);
+        if (c) atomicAdd(&a.hist[DEPTH_PASSES * RADIX + i], c);
     }
+}
+
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    EmitArgs a;
+    a.P = P;
+    a.nkeys[0] = reinterpret_cast<const unsigned*>(bin + lay.nkeys0_off);
+    a.nkeys[1] = reinterpret_cast<const unsigned*>(bin + lay.nkeys1_off);
+    a.nvals[0] = reinterpret_cast<const unsigned*>(bin + lay.nvals0_off);
+    a.nvals[1] = reinterpret_cast<const unsigned*>(bin + lay.nvals1_off);
+    a.counters = reinterpret_cast<int*>(bin + lay.cnt_off);
+    a.varbits = reinterpret_cast<const unsigned*>(a.counters + CNT_VARBITS);
+    a.rects = reinterpret_cast<const uint2*>(bin + lay.rects_off);
+    a.hist = reinterpret_cast<unsigned*>(bin + lay.hist_off);
+    a.scan_status = reinterpret_cast<unsigned long long*>(bin + lay.scan_off);
+    a.keys = reinterpret_cast<unsigned long long*>(bin + lay.keys0_off);
+    a.vals = reinterpret_cast<unsigned*>(bin + lay.vals0_off);
+    a.L_cap = L_cap;
+    a.passes = lay.passes;
+    a.gx = lay.gx;
+    launch_pdl(emit_pairs_kernel, lay.scan_blocks, GEO_THREADS, 0, stream, a);
+    SGS_LAUNCH_OK();
+    return 0;
 }
 
 template <int D, bool HAS_SH>
@@ -334,11 +434,11 @@ static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec
     if (vec16) {
         auto k = geometry_kernel<D, HAS_SH, true>;
         if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, GEO_THREADS, smem, st>>>(a, o);
+        launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
     } else {
         auto k = geometry_kernel<D, HAS_SH, false>;
         if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, GEO_THREADS, smem, st>>>(a, o);
+        launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
     }
     SGS_LAUNCH_OK();
     return 0;
@@ -349,16 +449,15 @@ int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap,
     // one memset clears counters, histograms, scan + sort look-back status and the tile-length bucket counts
     SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
     if (a.P <= 0) return 0;
+    if (lay.gx > 0xffff || lay.gy > 0xffff) return SGS_ERR_CAPACITY;
     GeoOut o;
     o.radii = radii;
     o.rec = reinterpret_cast<float*>(geom + lay.rec_off);
-    o.counters = reinterpret_cast<int*>(bin + lay.cnt_off);
     o.hist = reinterpret_cast<unsigned*>(bin + lay.hist_off);
-    o.scan_status = reinterpret_cast<unsigned long long*>(bin + lay.scan_off);
-    o.keys = reinterpret_cast<unsigned long long*>(bin + lay.keys0_off);
-    o.vals = reinterpret_cast<unsigned*>(bin + lay.vals0_off);
-    o.L_cap = L_cap;
-    o.passes = lay.passes;
+    o.varbits = reinterpret_cast<unsigned*>(reinterpret_cast<int*>(bin + lay.cnt_off) + CNT_VARBITS);
+    o.nkeys = reinterpret_cast<unsigned*>(bin + lay.nkeys0_off);
+    o.nvals = reinterpret_cast<unsigned*>(bin + lay.nvals0_off);
+    o.rects = reinterpret_cast<uint2*>(bin + lay.rects_off);
     o.gx = lay.gx; o.gy = lay.gy;
     o.fx = (float)a.W / (2.0f * a.tanfovx);
     o.fy = (float)a.H / (2.0f * a.tanfovy);

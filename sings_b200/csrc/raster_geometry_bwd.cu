@@ -30,6 +30,7 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
     const int base = blockIdx.x * GB_THREADS;
     const int idx = base + tid;
     const bool in_range = idx < a.P;
+    pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
@@ -288,11 +289,11 @@ static int launch_gb_t(const GeomBwdArgs& b, const float4* rec, int blocks, bool
     if (vec16) {
         auto k = geometry_bwd_kernel<D, HAS_SH, true>;
         if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, GB_THREADS, smem, st>>>(b, rec);
+        launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
     } else {
         auto k = geometry_bwd_kernel<D, HAS_SH, false>;
         if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<blocks, GB_THREADS, smem, st>>>(b, rec);
+        launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
     }
     SGS_LAUNCH_OK();
     return 0;

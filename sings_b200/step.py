@@ -111,12 +111,10 @@ class AvatarStep:
         tm = self.timing
         if tm:
             L_.sgs_timing_record(tm, 8, st)
-        _lib.check(L_.sgs_pose_to_A(p(pose), p(self.rest), p(self.parents), p(self.inv_A), 1, self.J,
-                                    p(self.A), p(self.G), st), "sgs_pose_to_A")
-        _lib.check(L_.sgs_lbs_fwd(1, self.N, self.J, p(self.A), p(self.xyz_canon), p(self.W_lbs),
-                                  p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
-                                  None, None, None, p(self.xyz), p(self.rotq), p(self.sc), None, st),
-                   "sgs_lbs_fwd")
+        _lib.check(L_.sgs_pose_lbs_fwd(p(pose), p(self.rest), p(self.parents), p(self.inv_A), 1, self.N,
+                                       self.J, p(self.A), p(self.G), p(self.xyz_canon), p(self.W_lbs),
+                                       p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
+                                       p(self.xyz), p(self.rotq), p(self.sc), st), "sgs_pose_lbs_fwd")
         if tm:
             L_.sgs_timing_record(tm, 9, st)
         _lib.check(L_.sgs_raster_forward(
