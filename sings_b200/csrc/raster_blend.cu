@@ -23,8 +23,27 @@
 
 namespace sgs {
 
-constexpr int BWD_U = 4;      // pairs per software-pipeline stage in the backward blend
-constexpr int FWD_U = 4;      // pairs evaluated together per pixel in the forward blend
+// A/B knobs (tools/sweep.sh builds variants with -DSGS_...): pipeline depth vs. resident CTAs
+#ifndef SGS_BWD_U
+#define SGS_BWD_U 4
+#endif
+#ifndef SGS_FWD_U
+#define SGS_FWD_U 4
+#endif
+#ifndef SGS_FWD_MINB
+#define SGS_FWD_MINB 2
+#endif
+#ifndef SGS_BWD_MINB
+#define SGS_BWD_MINB 2
+#endif
+#ifndef SGS_BWD_ROWS
+#define SGS_BWD_ROWS 32
+#endif
+#ifndef SGS_BWD_P2ROW            // phase 2 of the backward: 1 = one pixel row per loop trip, 0 = flat unrolled
+#define SGS_BWD_P2ROW 1
+#endif
+constexpr int BWD_U = SGS_BWD_U;      // pairs per software-pipeline stage in the backward blend
+constexpr int FWD_U = SGS_FWD_U;      // pairs evaluated together per pixel in the forward blend
 
 // [upstream] identifyTileRanges: ranges[tile] = [start, end) in the sorted list, (0, 0) for a
 // tile without pairs.  One WARP per tile: a 33-ary search (32 probes per step, ballot) for the
@@ -242,7 +261,7 @@ struct FwdBatch {
     unsigned pos[FWD_U];
 };
 
-__global__ void __launch_bounds__(TILE_PIX, 2)
+__global__ void __launch_bounds__(TILE_PIX, SGS_FWD_MINB)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
@@ -409,22 +428,26 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
 //    the nine gradients and issues 2 vector + 1 scalar reduction for its Gaussian.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_ROW = 33;        // padded row of the [pair][pixel] tiles: conflict-free both ways
+constexpr int BWD_ROWS = SGS_BWD_ROWS;          // pair rows per [pair][pixel] tile: 32, or 16 (half the shared memory)
+constexpr int BWD_HALVES = 32 / BWD_ROWS;       // phase-2 lanes per pair row; each walks 32 / BWD_HALVES pixels
+static_assert(BWD_ROWS == 32 || BWD_ROWS == 16, "BWD_ROWS must be 16 or 32");
+static_assert(BWD_ROWS % BWD_U == 0, "a [pair][pixel] tile must hold whole batches");
 
 struct BwdBatch {
-    float al[BWD_U], G[BWD_U], om[BWD_U], inv[BWD_U], r[BWD_U], g[BWD_U], b[BWD_U];
+    float al[BWD_U], G[BWD_U], inv[BWD_U], r[BWD_U], g[BWD_U], b[BWD_U];
 };
 
 struct BwdWarpSmem {
     float4 q0[RING_SLOTS];          // x, y, -a/2, -b
     float4 q1[RING_SLOTS];          // -c/2, opacity, list position (bits), r
     float4 q2[RING_SLOTS];          // g, b, -, Gaussian id (bits)
-    float w[32 * BWD_ROW];          // G * dL/dalpha   [pair][pixel]
-    float d[32 * BWD_ROW];          // alpha * T       [pair][pixel]
+    float w[BWD_ROWS * BWD_ROW];    // G * dL/dalpha   [pair][pixel]
+    float d[BWD_ROWS * BWD_ROW];    // alpha * T       [pair][pixel]
     float dp[3][32];                // dL/dpixel rgb of the warp's 32 pixels
-    unsigned id[2][32];             // Gaussian of each pair row (double-buffered by tile parity)
+    unsigned id[2][BWD_ROWS];       // Gaussian of each pair row (double-buffered by tile parity)
 };
 
-__global__ void __launch_bounds__(TILE_PIX, 2)
+__global__ void __launch_bounds__(TILE_PIX, SGS_BWD_MINB)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
@@ -467,13 +490,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     float T = T_final;
     float B0 = 0.0f, B1 = 0.0f, B2 = 0.0f;     // colour accumulated behind the current pair
     unsigned head = 0, tail = 0;               // ring: consumed / produced pair counts
-    unsigned row0 = 0;                         // first pair (consumption index) of the open [pair][pixel] tile; multiple of 32
+    unsigned row0 = 0;                         // first pair (consumption index) of the open [pair][pixel] tile; multiple of BWD_ROWS
 
     BwdBatch bat_a, bat_b;             // one waits for SEQ (starts empty), one is being evaluated
     bool cur_is_b = false;
 #pragma unroll
     for (int u = 0; u < BWD_U; u++) {
-        bat_a.al[u] = 0.0f; bat_a.G[u] = 0.0f; bat_a.om[u] = 1.0f; bat_a.inv[u] = 1.0f;
+        bat_a.al[u] = 0.0f; bat_a.G[u] = 0.0f; bat_a.inv[u] = 1.0f;
         bat_a.r[u] = bat_a.g[u] = bat_a.b[u] = 0.0f;
     }
 
@@ -493,10 +516,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                             !(al < 1.0f / 255.0f);
             e.al[u] = ok ? al : 0.0f;
             e.G[u] = ok ? G : 0.0f;
-            e.om[u] = 1.0f - e.al[u];
-            e.inv[u] = __fdividef(1.0f, e.om[u]);
+            e.inv[u] = __fdividef(1.0f, 1.0f - e.al[u]);
             e.r[u] = q1.w; e.g[u] = q2.x; e.b[u] = q2.y;
-            if (lane == u) sm.id[((base + u) >> 5) & 1][(base + u) & 31] = __float_as_uint(q2.w);
+            if (lane == u) sm.id[((base + u) / BWD_ROWS) & 1][(base + u) % BWD_ROWS] = __float_as_uint(q2.w);
         }
     };
     // advance the pixel state over a batch whose first pair has consumption index `base`
@@ -505,45 +527,85 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         for (int u = 0; u < BWD_U; u++) {
             T = T * e.inv[u];
             const float dch = e.al[u] * T;
-            const float dot = (e.r[u] - B0) * dp0 + (e.g[u] - B1) * dp1 + (e.b[u] - B2) * dp2;
-            const float dLda = T * dot + nTf_bg * e.inv[u];
-            const unsigned row = (base + u) & 31;
+            const float t0 = e.r[u] - B0, t1 = e.g[u] - B1, t2 = e.b[u] - B2;
+            const float dot = fmaf(t2, dp2, fmaf(t1, dp1, t0 * dp0));
+            const float dLda = fmaf(T, dot, nTf_bg * e.inv[u]);
+            const unsigned row = (base + u) % BWD_ROWS;
             sm.w[row * BWD_ROW + lane] = e.G[u] * dLda;
             sm.d[row * BWD_ROW + lane] = dch;
-            B0 = e.al[u] * e.r[u] + e.om[u] * B0;
-            B1 = e.al[u] * e.g[u] + e.om[u] * B1;
-            B2 = e.al[u] * e.b[u] + e.om[u] * B2;
+            B0 = fmaf(e.al[u], t0, B0);       // = al * c + (1 - al) * B
+            B1 = fmaf(e.al[u], t1, B1);
+            B2 = fmaf(e.al[u], t2, B2);
         }
     };
-    // phase 2 over the `cnt` (<= 32) pair rows of the open tile
+    // phase 2 over the `cnt` (<= BWD_ROWS) pair rows of the open tile.  Lane = (pair row r,
+    // pixel half h); it walks its 32 / BWD_HALVES pixels accumulating RAW moments of w about the
+    // block origin -- the pixel offsets kx, ky are compile-time constants of the unrolled loop,
+    // so a moment costs one FMA with an immediate -- and re-centres them on the Gaussian after
+    // the loop:  sum w dx = ax S0 - Mx,  sum w dx^2 = ax (ax S0 - 2 Mx) + Mxx, ... (dx = ax - kx).
     auto reduce_rows = [&](unsigned cnt) {
         __syncwarp();
-        if (lane < cnt) {
-            const unsigned id = sm.id[(row0 >> 5) & 1][lane];
-            const float4 q0 = __ldg(rec + 4 * (size_t)id);
-            const float4 q1 = __ldg(rec + 4 * (size_t)id + 1);
-            float S0 = 0, Sx = 0, Sy = 0, Sxx = 0, Sxy = 0, Syy = 0, Sr = 0, Sg = 0, Sb = 0;
-            const float* wr = sm.w + lane * BWD_ROW;
-            const float* dr = sm.d + lane * BWD_ROW;
+        const unsigned r = lane % BWD_ROWS, h = lane / BWD_ROWS;
+        const bool valid = r < cnt;
+        const unsigned id = valid ? sm.id[(row0 / BWD_ROWS) & 1][r] : 0u;
+        const float4 q0 = __ldg(rec + 4 * (size_t)id);
+        const float4 q1 = __ldg(rec + 4 * (size_t)id + 1);
+        float S0 = 0, Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, Sr = 0, Sg = 0, Sb = 0;
+        const float* wr = sm.w + r * BWD_ROW + h * BWD_ROWS;
+        const float* dr = sm.d + r * BWD_ROW + h * BWD_ROWS;
+        const float* dpp = &sm.dp[0][h * BWD_ROWS];
+#if SGS_BWD_P2ROW
+#pragma unroll 1
+        for (int yy = 0; yy < BWD_ROWS / 8; yy++) {           // one pixel row of the 8x4 block per trip
+            const float ky = (float)yy;
+            float R0 = 0, Rx = 0, Rxx = 0;                    // this row's moments in x
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
+            for (int kx = 0; kx < 8; kx++) {
+                const int k = yy * 8 + kx;
                 const float w = wr[k], d = dr[k];
-                const float dx = __fsub_rn(q0.x, bx0 + (float)(k & 7));
-                const float dy = __fsub_rn(q0.y, by0 + (float)(k >> 3));
-                const float wdx = w * dx, wdy = w * dy;
-                S0 += w;
-                Sx += wdx; Sy += wdy;
-                Sxx = fmaf(wdx, dx, Sxx); Sxy = fmaf(wdx, dy, Sxy); Syy = fmaf(wdy, dy, Syy);
-                Sr = fmaf(d, sm.dp[0][k], Sr); Sg = fmaf(d, sm.dp[1][k], Sg); Sb = fmaf(d, sm.dp[2][k], Sb);
+                R0 += w;
+                if (kx != 0) { Rx = fmaf(w, (float)kx, Rx); Rxx = fmaf(w, (float)(kx * kx), Rxx); }
+                Sr = fmaf(d, dpp[k], Sr); Sg = fmaf(d, dpp[32 + k], Sg); Sb = fmaf(d, dpp[64 + k], Sb);
             }
+            S0 += R0; Mx += Rx; Mxx += Rxx;
+            My = fmaf(R0, ky, My); Myy = fmaf(R0, ky * ky, Myy); Mxy = fmaf(Rx, ky, Mxy);
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < BWD_ROWS; k++) {
+            const float w = wr[k], d = dr[k];
+            const float kx = (float)(k & 7), ky = (float)(k >> 3);
+            S0 += w;
+            if ((k & 7) != 0) { Mx = fmaf(w, kx, Mx); Mxx = fmaf(w, kx * kx, Mxx); }
+            if ((k >> 3) != 0) { My = fmaf(w, ky, My); Myy = fmaf(w, ky * ky, Myy); }
+            if ((k & 7) != 0 && (k >> 3) != 0) Mxy = fmaf(w, kx * ky, Mxy);
+            Sr = fmaf(d, dpp[k], Sr); Sg = fmaf(d, dpp[32 + k], Sg); Sb = fmaf(d, dpp[64 + k], Sb);
+        }
+#endif
+        const float ax = q0.x - bx0, ay = q0.y - (by0 + (float)(h * (BWD_ROWS / 8)));
+        float Sx = fmaf(ax, S0, -Mx), Sy = fmaf(ay, S0, -My);
+        float Sxx = fmaf(ax, fmaf(ax, S0, -2.0f * Mx), Mxx);
+        float Syy = fmaf(ay, fmaf(ay, S0, -2.0f * My), Myy);
+        float Sxy = fmaf(ax, fmaf(ay, S0, -My), fmaf(-ay, Mx, Mxy));
+        if (BWD_HALVES == 2) {
+            S0 += __shfl_xor_sync(0xffffffffu, S0, 16); Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
+            Sy += __shfl_xor_sync(0xffffffffu, Sy, 16); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
+            Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16); Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
+            Sr += __shfl_xor_sync(0xffffffffu, Sr, 16); Sg += __shfl_xor_sync(0xffffffffu, Sg, 16);
+            Sb += __shfl_xor_sync(0xffffffffu, Sb, 16);
+        }
+        if (valid) {
             // conic entries: a = -2*q0.z, b = -q0.w, c = -2*q1.x
             const float ca = -2.0f * q0.z, cb = -q0.w, cc = -2.0f * q1.x, o = q1.y;
             float* dst = acc + (size_t)id * ACC_FLOATS;
             // accumulator slots 0..8: mean2D.x, .y, conic a, b, c, opacity, r, g, b
-            red_add_f4(dst, -o * ddelx_dx * (ca * Sx + cb * Sy), -o * ddely_dy * (cc * Sy + cb * Sx),
-                       -0.5f * o * Sxx, -0.5f * o * Sxy);
-            red_add_f4(dst + 4, -0.5f * o * Syy, S0, Sr, Sg);
-            atomicAdd(dst + 8, Sb);
+            if (BWD_HALVES == 1 || h == 0)
+                red_add_f4(dst, -o * ddelx_dx * (ca * Sx + cb * Sy), -o * ddely_dy * (cc * Sy + cb * Sx),
+                           -0.5f * o * Sxx, -0.5f * o * Sxy);
+            if (BWD_HALVES == 1 || h == 1) {
+                red_add_f4(dst + 4, -0.5f * o * Syy, S0, Sr, Sg);
+                atomicAdd(dst + 8, Sb);
+            }
         }
         __syncwarp();
     };
@@ -589,9 +651,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
             if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
             else           { eval(bat_a, head, tail); seq(bat_b, pend); }
             cur_is_b = !cur_is_b;
-            if (pend + BWD_U - row0 == 32) {       // the open tile is full (32 % BWD_U == 0)
-                reduce_rows(32);
-                row0 += 32;
+            if (pend + BWD_U - row0 == BWD_ROWS) {       // the open tile is full
+                reduce_rows(BWD_ROWS);
+                row0 += BWD_ROWS;
             }
             pend = head;
             head += BWD_U;
@@ -600,9 +662,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     // drain: the waiting batch, the partial remainder of the ring, the partial tile
     if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
     else           { eval(bat_a, head, tail); seq(bat_b, pend); }
-    if (pend + BWD_U - row0 == 32) {
-        reduce_rows(32);
-        row0 += 32;
+    if (pend + BWD_U - row0 == BWD_ROWS) {
+        reduce_rows(BWD_ROWS);
+        row0 += BWD_ROWS;
     }
     if (tail > head) {
         if (!cur_is_b) seq(bat_b, head); else seq(bat_a, head);
