@@ -330,8 +330,11 @@ def gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         s = sets[0]
         frames = [(s["av"], s["pose"], s["transl"], s["view"], s["G_np"], s["bg"])]
-        n_cpu = 2
-        fps, ms, cores = run_cpu(n_cpu, 1, frames)
+        # bounded sample of the same workload: ~15 s of host work (probe one frame, then size the run)
+        t0 = time.perf_counter()
+        cpu_frame(*frames[0])
+        n_cpu = max(2, min(200, int(15.0 / max(time.perf_counter() - t0, 1e-3))))
+        fps, ms, cores = run_cpu(n_cpu, 0, frames)
         cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                     "sample": f"{n_cpu} full frames of the same workload on the host (torch restatement of the "
                               f"reference LBS + OpenMP C rasterizer oracle, fwd+bwd)"}

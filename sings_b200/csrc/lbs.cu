@@ -22,7 +22,14 @@
 
 namespace sgs {
 
-constexpr int LBS_THREADS = 256;
+// Gaussians per CTA (A/B knob, tools/sweep.sh)
+#ifndef SGS_LBS_THREADS
+#define SGS_LBS_THREADS 256
+#endif
+constexpr int LBS_THREADS = SGS_LBS_THREADS;
+#ifndef SGS_LBS_BWD_MINB          // resident CTAs per SM the backward is compiled for (register cap)
+#define SGS_LBS_BWD_MINB 2
+#endif
 
 // ------------------------------------------------------------------------------------------
 // pose -> A
@@ -127,11 +134,17 @@ int launch_pose_to_A(const float* pose, const float* rest, const int* parents, c
     return 0;
 }
 
-// backward of pose_to_A_kernel: dL/dA (B,J,16) -> dL/dpose (B,J,3).  One CTA per frame, one
-// thread per joint.  Thread j seeds dL/dG_j; the kinematic tree is then walked leaves-to-root
-// one depth level at a time (a parent gathers dG_k L_k^T from its children, whose dG are
-// final after the previous level), each thread converts dL/dG_j to dL/dL_j with its parent's
-// G, and differentiates its Rodrigues formula.  Everything the walk touches is in shared memory.
+// backward of pose_to_A_kernel: dL/dA (B,J,16) -> dL/dpose (B,J,3).  One CTA per frame.
+// The kernel is one short dependent chain (it sits alone at the end of the frame), so the chain
+// is cut two ways: (1) everything that does not depend on dL/dA -- Rodrigues, the local
+// transforms, the forward's G, the children lists, tree depths -- is done by one thread per
+// joint BEFORE the grid-dependency wait, i.e. while the LBS backward is still running (all of
+// it is at least two kernels old, common.cuh); (2) after the wait the 3x4 matrices are handled
+// one ELEMENT per thread (12 threads per joint): seed dL/dG_j, then walk the kinematic tree
+// leaves-to-root one depth level at a time (a parent gathers dG_k L_k^T from its children, whose
+// dG are final after the previous level), then dL/dR_j = G_parent^T dL/dG_j.  The last step,
+// the derivative of the Rodrigues formula, is per joint again.  All sums keep the order of the
+// per-joint formulation (children highest index first), so results do not depend on the mapping.
 __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float* __restrict__ rest,
                                      const int* __restrict__ parents, const float* __restrict__ inv_A,
                                      const float* __restrict__ G_all, const float* __restrict__ dA,
@@ -140,14 +153,23 @@ __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float
     float* s_L = s_mem;              // J x 12 local transforms
     float* s_dG = s_mem + 12 * J;    // J x 12 dL/dG
     float* s_G = s_mem + 24 * J;     // J x 12 global transforms (forward's G_out)
+    float* s_dO = s_mem + 36 * J;    // J x 12 dL/dA rows 0..2, later dL/dArel
+    float* s_E = s_mem + 48 * J;     // J x 9  dL/dR
+    float* s_B = s_mem + 57 * J;     // J x 12 inv_A rows 0..2
     __shared__ int s_par[64], s_depth[64], s_maxd;
-    const int b = blockIdx.x, j = threadIdx.x;
-    float R[9];
-    pdl_sync();
-    if (j == 0) s_maxd = 0;
+    __shared__ unsigned char s_nchild[64], s_child[64][64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int j = t;                 // joint role: threads 0..J-1
+    const int ej = t / 12, ee = t - ej * 12, er = ee >> 2, ec = ee & 3;   // element role
+    const bool elem = ej < J;
+    // ---------------- before the wait: nothing here depends on dL/dA ----------------
+    if (t == 0) s_maxd = 0;
+    float rx = 0, ry = 0, rz = 0;
     if (j < J) {
         const float* p = pose + ((size_t)b * J + j) * 3;
-        rodrigues(p[0], p[1], p[2], R);
+        rx = p[0]; ry = p[1]; rz = p[2];
+        float R[9];
+        rodrigues(rx, ry, rz, R);
         const int par = parents[j];
         s_par[j] = par;
         float* L = s_L + 12 * j;
@@ -156,36 +178,10 @@ __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float
             L[4 * r] = R[3 * r]; L[4 * r + 1] = R[3 * r + 1]; L[4 * r + 2] = R[3 * r + 2];
             L[4 * r + 3] = rest[3 * j + r] - (par >= 0 ? rest[3 * par + r] : 0.0f);
         }
-#pragma unroll
-        for (int k = 0; k < 12; k++) s_G[12 * j + k] = G_all[((size_t)b * J + j) * 12 + k];
-        // dOut -> dArel (through @ inv_A) -> dG
-        float dO[12];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) dO[4 * r + c] = dA[((size_t)b * J + j) * 16 + 4 * r + c];
-        float dAr[12];
-        if (inv_A) {
-            const float* Bm = inv_A + (size_t)j * 16;
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    dAr[4 * r + c] = dO[4 * r] * Bm[4 * c] + dO[4 * r + 1] * Bm[4 * c + 1] +
-                                     dO[4 * r + 2] * Bm[4 * c + 2] + dO[4 * r + 3] * Bm[4 * c + 3];
-                dAr[4 * r + 3] = dO[4 * r + 3];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 12; k++) dAr[k] = dO[k];
-        }
-        float* dG = s_dG + 12 * j;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) dG[4 * r + c] = dAr[4 * r + c] - dAr[4 * r + 3] * rest[3 * j + c];
-            dG[4 * r + 3] = dAr[4 * r + 3];
-        }
+    }
+    if (elem) {
+        s_G[12 * ej + ee] = G_all[((size_t)b * J + ej) * 12 + ee];
+        if (inv_A) s_B[12 * ej + ee] = inv_A[(size_t)ej * 16 + ee];
     }
     __syncthreads();
     int depth = 0;
@@ -193,54 +189,75 @@ __global__ void pose_to_A_bwd_kernel(const float* __restrict__ pose, const float
         for (int k = s_par[j]; k >= 0 && depth < 64; k = s_par[k]) depth++;
         s_depth[j] = depth;
         atomicMax(&s_maxd, depth);
+        int nc = 0;
+        for (int k = J - 1; k > j; k--)             // children, highest index first
+            if (s_par[k] == j) s_child[j][nc++] = (unsigned char)k;
+        s_nchild[j] = (unsigned char)nc;
     }
+    pdl_sync();
+    // ---------------- after the wait ----------------
+    if (elem) s_dO[12 * ej + ee] = dA[((size_t)b * J + ej) * 16 + ee];
     __syncthreads();
     const int maxd = s_maxd;
+    const float rest_c = (elem && ec < 3) ? rest[3 * ej + ec] : 0.0f;
+    float dAr = 0.0f;
+    if (elem) {
+        // dOut -> dArel (through @ inv_A)
+        const float* dO = s_dO + 12 * ej + 4 * er;
+        if (inv_A && ec < 3) {
+            const float* Bm = s_B + 12 * ej + 4 * ec;      // row ec of inv_A
+            dAr = dO[0] * Bm[0] + dO[1] * Bm[1] + dO[2] * Bm[2] + dO[3] * Bm[3];
+        } else {
+            dAr = dO[ec];
+        }
+    }
+    __syncthreads();
+    if (elem) s_dO[12 * ej + ee] = dAr;
+    __syncthreads();
+    if (elem) {
+        // dArel -> dG:  Arel[:, 3] = G[:, 3] - G[:, :3] rest_j
+        const float d3 = s_dO[12 * ej + 4 * er + 3];
+        s_dG[12 * ej + ee] = ec < 3 ? dAr - d3 * rest_c : d3;
+    }
+    __syncthreads();
+    const int edepth = elem ? s_depth[ej] : -1;
     for (int d = maxd - 1; d >= 0; d--) {
-        if (j < J && depth == d) {
-            float acc[12];
-#pragma unroll
-            for (int q = 0; q < 12; q++) acc[q] = s_dG[12 * j + q];
-            for (int k = J - 1; k > j; k--) {           // children, highest index first
-                if (s_par[k] != j) continue;
-                const float* dG = s_dG + 12 * k;
-                const float* L = s_L + 12 * k;
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        acc[4 * r + c] += dG[4 * r] * L[4 * c] + dG[4 * r + 1] * L[4 * c + 1] +
-                                          dG[4 * r + 2] * L[4 * c + 2] + dG[4 * r + 3] * L[4 * c + 3];
-                    acc[4 * r + 3] += dG[4 * r + 3];
+        if (edepth == d) {
+            float acc = s_dG[12 * ej + ee];
+            const int nc = s_nchild[ej];
+            for (int q = 0; q < nc; q++) {
+                const int k = s_child[ej][q];
+                const float* dG = s_dG + 12 * k + 4 * er;
+                if (ec < 3) {
+                    const float* L = s_L + 12 * k + 4 * ec;
+                    acc += dG[0] * L[0] + dG[1] * L[1] + dG[2] * L[2] + dG[3] * L[3];
+                } else {
+                    acc += dG[3];
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 12; q++) s_dG[12 * j + q] = acc[q];
+            s_dG[12 * ej + ee] = acc;      // no other thread reads this joint's dG at this level
         }
         __syncthreads();
     }
-    if (j >= J) return;
     // E = dL/dR_j: rotation part of dL/dL_j = G_parent^T dL/dG_j (the root's L is G itself)
-    float E[9];
-    {
-        const float* dG = s_dG + 12 * j;
-        const int par = s_par[j];
+    if (elem && ee < 9) {
+        const int r = ee / 3, c = ee - 3 * r;
+        const float* dG = s_dG + 12 * ej;
+        const int par = s_par[ej];
+        float v;
         if (par >= 0) {
             const float* Gp = s_G + 12 * par;
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    E[3 * r + c] = Gp[r] * dG[c] + Gp[4 + r] * dG[4 + c] + Gp[8 + r] * dG[8 + c];
+            v = Gp[r] * dG[c] + Gp[4 + r] * dG[4 + c] + Gp[8 + r] * dG[8 + c];
         } else {
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) E[3 * r + c] = dG[4 * r + c];
+            v = dG[4 * r + c];
         }
+        s_E[9 * ej + ee] = v;
     }
-    const float* p = pose + ((size_t)b * J + j) * 3;
-    const float rx = p[0], ry = p[1], rz = p[2];
+    __syncthreads();
+    if (j >= J) return;
+    float E[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) E[k] = s_E[9 * j + k];
     const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
     const float th = sqrtf(ax * ax + ay * ay + az * az);
     const float x = rx / th, y = ry / th, z = rz / th;
@@ -277,7 +294,7 @@ int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parent
                          float* d_pose, cudaStream_t stream) {
     if (B <= 0) return 0;
     if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
-    launch_pdl(pose_to_A_bwd_kernel, B, 64, (size_t)J * 36 * 4, stream, pose, rest, parents, inv_A, G, dA, J, d_pose);
+    launch_pdl(pose_to_A_bwd_kernel, B, (J * 12 + 31) / 32 * 32, (size_t)J * 69 * 4, stream, pose, rest, parents, inv_A, G, dA, J, d_pose);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -634,7 +651,7 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(LbsArgs a, LbsGrads g) {
+__global__ void __launch_bounds__(LBS_THREADS, SGS_LBS_BWD_MINB) lbs_bwd_kernel(LbsArgs a, LbsGrads g) {
     extern __shared__ __align__(16) char s_raw[];
     const bool iso = a.rot == nullptr;
     LbsTile s;

@@ -48,26 +48,44 @@ struct SortPass {
     int par;                  // source buffer (without varbits) / pass index (with varbits)
 };
 
-// exclusive scan of one value per thread over a 256-thread block
-__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_tmp, int lane, int warp) {
-    unsigned incl = v;
+// exclusive scan of two values per thread over a 256-thread block (one barrier)
+__device__ __forceinline__ uint2 block_excl_scan2(uint2 v, uint2* s_tmp, int lane, int warp) {
+    uint2 incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
+        unsigned nx = __shfl_up_sync(0xffffffffu, incl.x, d);
+        unsigned ny = __shfl_up_sync(0xffffffffu, incl.y, d);
+        if (lane >= d) { incl.x += nx; incl.y += ny; }
     }
     if (lane == 31) s_tmp[warp] = incl;
     __syncthreads();
-    unsigned off = 0;
+    uint2 off = make_uint2(0u, 0u);
 #pragma unroll
     for (int w = 0; w < SORT_THREADS / 32; w++)
-        if (w < warp) off += s_tmp[w];
-    __syncthreads();
-    return off + incl - v;
+        if (w < warp) { off.x += s_tmp[w].x; off.y += s_tmp[w].y; }
+    return make_uint2(off.x + incl.x - v.x, off.y + incl.y - v.y);
 }
 
+// look-back batch: predecessor words in flight per thread (A/B knob, tools/sweep.sh)
+#ifndef SGS_SORT_EARLY_REORDER    // shared-memory reorder before (1) or after (0) the look-back
+#define SGS_SORT_EARLY_REORDER 1
+#endif
+#ifndef SGS_LOOKBACK_N
+#define SGS_LOOKBACK_N 4
+#endif
+#ifndef SGS_LOOKBACK_L
+#define SGS_LOOKBACK_L 4
+#endif
+
+// resident CTAs per SM the pair-sort kernel is compiled for (register cap).  Measured (sweep
+// v6b): 3 per SM -- a whole pass of 391 CTAs resident at once, no tickets -- is 9 us SLOWER per
+// frame than 2 per SM with a second wave in ticket order.
+#ifndef SGS_SORT_MINB_L
+#define SGS_SORT_MINB_L 2
+#endif
+
 template <typename K, int SORT_ITEMS, int LOOKBACK_BATCH>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K> a) {
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 8 ? SGS_SORT_MINB_L : 4) onesweep_pass_kernel(SortPass<K> a) {
     constexpr int SORT_TILE = SORT_ITEMS * SORT_THREADS;
     __shared__ unsigned s_cnt[SORT_THREADS / 32][RADIX];
     __shared__ unsigned s_bexcl[RADIX];
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K>
     extern __shared__ __align__(16) unsigned char s_dyn[];     // SORT_TILE keys, then SORT_TILE values
     K* const s_keys = reinterpret_cast<K*>(s_dyn);
     unsigned* const s_vals = reinterpret_cast<unsigned*>(s_dyn + (size_t)SORT_TILE * sizeof(K));
-    __shared__ unsigned s_tmp[SORT_THREADS / 32];
+    __shared__ uint2 s_tmp2[SORT_THREADS / 32];
     __shared__ int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,13 +153,30 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K>
         s_cnt[w][tid] = count;
         count += t;
     }
-    // ---- decoupled look-back over preceding tiles, one digit per thread ----
+    // The tile's digit counts are published first; everything that needs only tile-local
+    // information (the shared-memory reorder) is done while the other tiles publish theirs.
     unsigned* row = a.status + (size_t)tile * RADIX;
     st_relaxed_u32(&row[tid], (tile == 0 ? ST_INCL : ST_AGG) | count);
+    // ---- digit bases: global (from the up-front histogram) and inside the tile ----
+    const uint2 ex = block_excl_scan2(make_uint2(a.hist[tid], count), s_tmp2, lane, warp);
+    s_bexcl[tid] = ex.y;
+    __syncthreads();
+#if SGS_SORT_EARLY_REORDER
+    // ---- reorder through shared memory into tile-sorted order (keys/values leave registers) ----
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        unsigned d = (unsigned)(key[i] >> a.shift) & a.mask;
+        unsigned pos = s_bexcl[d] + s_cnt[warp][d] + rank[i];
+        s_keys[pos] = key[i];
+        s_vals[pos] = val[i];
+    }
+#endif
+    // ---- decoupled look-back over preceding tiles, one digit per thread ----
     // The predecessors' words are fetched LOOKBACK_BATCH at a time (independent loads in
     // flight together) and consumed in order: when every tile of a pass starts at once, tile
-    // k finds k-1 .. 1 still at AGGREGATE, and a walk of one dependent L2 round trip per
-    // predecessor would be the whole pass time.
+    // k finds its predecessors still at AGGREGATE, and a walk of one dependent L2 round trip
+    // per predecessor would be the whole pass time.  With batches of B the INCLUSIVE front
+    // moves B tiles per round trip while the walk comes B tiles per round trip towards it.
     unsigned prev = 0;
     if (tile > 0) {
         bool found = false;
@@ -161,13 +196,9 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K>
         }
         st_relaxed_u32(&row[tid], ST_INCL | (prev + count));
     }
-    // ---- digit bases: global (from the up-front histogram) and inside the tile ----
-    unsigned gexcl = block_excl_scan(a.hist[tid], s_tmp, lane, warp);
-    unsigned bexcl = block_excl_scan(count, s_tmp, lane, warp);
-    s_gbase[tid] = gexcl + prev;
-    s_bexcl[tid] = bexcl;
-    __syncthreads();
-    // ---- reorder through shared memory into tile-sorted order ----
+    s_gbase[tid] = ex.x + prev;
+#if !SGS_SORT_EARLY_REORDER
+    // ---- reorder through shared memory into tile-sorted order (keys/values leave registers) ----
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         unsigned d = (unsigned)(key[i] >> a.shift) & a.mask;
@@ -175,6 +206,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(SortPass<K>
         s_keys[pos] = key[i];
         s_vals[pos] = val[i];
     }
+#endif
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; k++) {
@@ -246,7 +278,7 @@ static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* 
         a.shift = p * RADIX_BITS;
         a.mask = (1u << min(RADIX_BITS, end_bit - p * RADIX_BITS)) - 1u;
         a.par = (p - p0) & 1;
-        auto k = onesweep_pass_kernel<unsigned long long, SORT_ITEMS_L, 8>;
+        auto k = onesweep_pass_kernel<unsigned long long, SORT_ITEMS_L, SGS_LOOKBACK_L>;
         const size_t smem = (size_t)SORT_TILE_L * 12;
         SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (all_resident(k, blocks, smem)) a.ticket = nullptr;
@@ -274,7 +306,7 @@ int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t st
         a.shift = p * RADIX_BITS;
         a.mask = RADIX - 1;
         a.par = p;
-        auto k = onesweep_pass_kernel<unsigned, SORT_ITEMS_N, 8>;
+        auto k = onesweep_pass_kernel<unsigned, SORT_ITEMS_N, SGS_LOOKBACK_N>;
         const size_t smem = (size_t)SORT_TILE_N * 8;
         if (all_resident(k, lay.nsort_blocks, smem)) a.ticket = nullptr;
         SGS_CUDA_OK(launch_pdl(k, lay.nsort_blocks, SORT_THREADS, smem, stream, a));

@@ -29,6 +29,13 @@
 namespace sgs {
 
 constexpr int GEO_THREADS = 256;
+// A/B knobs (tools/sweep.sh)
+#ifndef SGS_EMIT_WIDE             // emission scan: look-back by the whole CTA (1) or one warp (0)
+#define SGS_EMIT_WIDE 0
+#endif
+#ifndef SGS_EMIT_MATCH            // tile-digit histogram: one shared atomic per group of equal digits
+#define SGS_EMIT_MATCH 0
+#endif
 constexpr unsigned long long FLAG_AGG = 1ull << 62;
 constexpr unsigned long long FLAG_INCL = 2ull << 62;
 constexpr unsigned long long FLAG_MASK = 3ull << 62;
@@ -300,6 +307,8 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     __shared__ unsigned s_warp[GEO_THREADS / 32];
     __shared__ unsigned s_hist[(MAX_PASSES - DEPTH_PASSES) * RADIX];
     __shared__ int s_ticket;
+    __shared__ unsigned long long s_wsum[GEO_THREADS / 32];
+    __shared__ int s_wincl[GEO_THREADS / 32];
     __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -340,6 +349,52 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     incl += warp_off;
     s_incl[tid] = incl;
 
+#if SGS_EMIT_WIDE
+    // ---- chained scan across CTAs: decoupled look-back by the WHOLE CTA, 256 predecessors
+    // per round trip.  All emission CTAs are normally resident and publish their aggregates
+    // at the same time, so a walk of 32 predecessors per round trip (one warp) would make
+    // chunk k wait ~k/64 dependent L2 round trips; here it is ~k/512 + 1.
+    if (tid == 0)
+        st_relaxed_u64(&a.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
+    unsigned long long excl = 0;                     // CTA-uniform
+    if (chunk > 0) {
+        for (int look = chunk - 1;; look -= GEO_THREADS) {
+            const int j = look - tid;
+            unsigned long long s = j >= 0 ? ld_relaxed_u64(&a.scan_status[j]) : FLAG_INCL;
+            while ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&a.scan_status[j]);
+            const unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
+            const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+            unsigned long long v = lane <= first ? (s & ~FLAG_MASK) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) {
+                s_wsum[warp] = v;
+                s_wincl[warp] = inc_mask != 0;
+            }
+            __syncthreads();
+            bool done = false;                       // warp 0 holds the nearest predecessors
+#pragma unroll
+            for (int w = 0; w < GEO_THREADS / 32; w++) {
+                if (!done) {
+                    excl += s_wsum[w];
+                    done = s_wincl[w] != 0;
+                }
+            }
+            __syncthreads();                         // before the next round overwrites s_wsum
+            if (done) break;
+        }
+        if (tid == 0) st_relaxed_u64(&a.scan_status[chunk], FLAG_INCL | (excl + block_total));
+    }
+    if (tid == 0) {
+        unsigned long long total = excl + block_total;
+        if (chunk == (int)gridDim.x - 1)
+            a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+        if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
+    }
+    __syncthreads();          // s_incl, s_rect
+
+    const unsigned long long prefix = excl;
+#else
     // ---- chained scan across CTAs (decoupled look-back, one warp) ----
     if (warp == 0) {
         unsigned long long excl = 0;
@@ -375,8 +430,9 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     }
     __syncthreads();          // s_prefix, s_incl, s_rect
 
-    // ---- emit (tile|depth) keys and Gaussian ids ----
     const unsigned long long prefix = s_prefix;
+#endif
+    // ---- emit (tile|depth) keys and Gaussian ids ----
     for (unsigned e = tid; e < block_total; e += GEO_THREADS) {
         int lo = 0, hi = GEO_THREADS - 1;          // first g with s_incl[g] > e
         while (lo < hi) {
@@ -394,8 +450,19 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
         if (pos < (unsigned long long)a.L_cap) {
             a.keys[pos] = key;
             a.vals[pos] = s_gid[g];
+#if SGS_EMIT_MATCH
+            // neighbouring pairs are neighbouring tiles: the upper digits are shared by most
+            // of the warp, so equal digits are counted once (one shared atomic per group)
+            const unsigned act = __activemask();
+            for (int p = 0; p < tile_passes; p++) {
+                const unsigned d = (tile_id >> (p * RADIX_BITS)) & (RADIX - 1);
+                const unsigned peers = __match_any_sync(act, d);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * RADIX + d], (unsigned)__popc(peers));
+            }
+#else
             for (int p = 0; p < tile_passes; p++)
                 atomicAdd(&s_hist[p * RADIX + ((tile_id >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+#endif
         }
     }
     __syncthreads();
