@@ -156,16 +156,21 @@ class AvatarStep:
         if tm:
             L_.sgs_timing_record(tm, 11, st)
 
-    def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None):
+    def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None,
+                prologue=None):
         """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
         graph and return replay().  The launch sequence is static -- capacity-sized pair list,
         device-side counts, no host round trip -- so the whole frame becomes one graph launch.
         `fr`'s tensors and `dL_dimage` are captured by address: refresh their contents in
-        place before each replay.  Stage events keep working (external event-record nodes)."""
+        place before each replay.  Stage events keep working (external event-record nodes).
+        `prologue()` (optional) runs first inside the graph -- e.g. the caller's decoding of an
+        uploaded target image into `dL_dimage` / `loss_weight`."""
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):          # warm-up outside the capture (lazy initialisation)
+            if prologue is not None:
+                prologue()
             img = self.forward(fr)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
@@ -174,6 +179,8 @@ class AvatarStep:
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
+            if prologue is not None:
+                prologue()
             img = self.forward(fr)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
