@@ -178,6 +178,35 @@ int sgs_lbs_bwd(int B, int N, int J, const float* A, const float* xyz_canon, con
                 float* d_scales, float* d_A, float* d_smpl_scale, float* d_transl,
                 sgs_stream_t stream);
 
+/* The same two calls with the canonical rotation given in the 6D representation the model
+ * stores (rot6d_canon (N,6); sings_hybrid.py:354-356: rotation_6d_to_matrix of
+ * sings/rec/utils/geometry/rotations.py:545-566, Gram-Schmidt with rows b1, b2, b3) -- the
+ * (N,3,3) matrix is never materialised.  d_rot6d_canon is (N,6). */
+int sgs_lbs_fwd_rot6d(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                      const float* rot6d_canon, const float* scales, const float* smpl_scale,
+                      const float* transl, const float* ext_trans, const float* ext_rot,
+                      const float* ext_scale, float* xyz_out, float* rotq_out, float* scales_out,
+                      float* T_out, sgs_stream_t stream);
+int sgs_lbs_bwd_rot6d(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                      const float* rot6d_canon, const float* scales, const float* smpl_scale,
+                      const float* transl, const float* ext_trans, const float* ext_rot,
+                      const float* ext_scale, const float* g_xyz, const float* g_rotq,
+                      const float* g_scales, const float* g_T, float* d_xyz_canon,
+                      float* d_rot6d_canon, float* d_scales, float* d_A, float* d_smpl_scale,
+                      float* d_transl, sgs_stream_t stream);
+
+/* 6D rotation conversions of sings/rec/utils/geometry/rotations.py, n rotations each:
+ * rotation_6d_to_matrix (:545-566) d6 (n,6) -> R (n,9) row-major, and
+ * rotation_6d_to_axis_angle (:601-603 = matrix_to_quaternion :98-149 + quaternion_to_axis_angle
+ * :514-542) d6 (n,6) -> aa (n,3): the per-frame conversion of the stored global_orient /
+ * body_pose parameters (sings_hybrid.py:370-376).  The _bwd calls write dL/dd6 (n,6). */
+int sgs_rot6d_to_matrix(const float* d6, int n, float* R_out, sgs_stream_t stream);
+int sgs_rot6d_to_matrix_bwd(const float* d6, const float* dL_dR, int n, float* dL_dd6,
+                            sgs_stream_t stream);
+int sgs_rot6d_to_axis_angle(const float* d6, int n, float* aa_out, sgs_stream_t stream);
+int sgs_rot6d_to_axis_angle_bwd(const float* d6, const float* dL_daa, int n, float* dL_dd6,
+                                sgs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,9 @@ Parity status: PINNED.  tests/golden/lbs_golden_*.npz hold inputs and outputs (v
 autograd gradients) produced by importing the reference's OWN code in the build container
 (tests/golden/make_lbs_golden.py: lbs_extra from /root/reference/sings/rec/utils/body_model/
 lbs.py:16-74, matrix_to_quaternion / quaternion_multiply from .../geometry/rotations.py:98-149,
-393-407, batch_rodrigues / batch_rigid_transform from .../body_model/smpl.py:415-513);
+393-407, batch_rodrigues / batch_rigid_transform from .../body_model/smpl.py:415-513;
+tests/golden/make_rot6d_golden.py: rotation_6d_to_matrix / rotation_6d_to_axis_angle from
+.../geometry/rotations.py:545-566, 601-603 -> tests/golden/rot6d_golden_*.npz);
 tests/test_oracle_lbs.py checks every function below against those vectors.
 
 Every function works on torch tensors of any float dtype and is autograd-differentiable,
@@ -109,8 +111,37 @@ def quaternion_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.where(q[..., 0:1] < 0, -q, q)
 
 
+def rotation_6d_to_matrix(d6: torch.Tensor) -> torch.Tensor:
+    """(...,6) -> (...,3,3), rows b1, b2, b3 (rotations.py:545-566): Gram-Schmidt with
+    F.normalize semantics (divide by max(norm, 1e-12))."""
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = a1 / a1.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+    u = a2 - (b1 * a2).sum(-1, keepdim=True) * b1
+    b2 = u / u.norm(dim=-1, keepdim=True).clamp(min=1e-12)
+    b3 = torch.linalg.cross(b1, b2, dim=-1)
+    return torch.stack((b1, b2, b3), dim=-2)
+
+
+def quaternion_to_axis_angle(q: torch.Tensor) -> torch.Tensor:
+    """(...,4) real first -> (...,3) (rotations.py:514-542): half = atan2(|v|, w), angle = 2 half,
+    v / (sin(half)/angle), with the series 0.5 - angle^2/48 where |angle| < 1e-6."""
+    norms = q[..., 1:].norm(dim=-1, keepdim=True)
+    half = torch.atan2(norms, q[..., :1])
+    angle = 2 * half
+    small = angle.abs() < 1e-6
+    safe = torch.where(small, torch.ones_like(angle), angle)
+    s = torch.where(small, 0.5 - (angle * angle) / 48, torch.sin(torch.where(small, torch.ones_like(half), half)) / safe)
+    return q[..., 1:] / s
+
+
+def rotation_6d_to_axis_angle(d6: torch.Tensor) -> torch.Tensor:
+    """rotations.py:601-603: 6D -> matrix -> quaternion (:98-149) -> axis-angle; the per-frame
+    conversion of the stored pose parameters (sings_hybrid.py:370-376)."""
+    return quaternion_to_axis_angle(matrix_to_quaternion(rotation_6d_to_matrix(d6)))
+
+
 def deform(A_cano2pose, xyz_canon, lbs_weights, scales, rotmat_canon=None, smpl_scale=None,
-           transl=None, ext_tfs=None):
+           transl=None, ext_tfs=None, rot6d_canon=None):
     """The deform segment of SinGS.forward / forward_chunk (sings_hybrid.py:398-428, :525-552;
     SURVEY.md Appendix B steps 2-6), batched over B frames.
 
@@ -122,6 +153,8 @@ def deform(A_cano2pose, xyz_canon, lbs_weights, scales, rotmat_canon=None, smpl_
     """
     B = A_cano2pose.shape[0]
     N = xyz_canon.shape[0]
+    if rot6d_canon is not None:      # sings_hybrid.py:354-356
+        rotmat_canon = rotation_6d_to_matrix(rot6d_canon)
     xyz, T = lbs_extra(A_cano2pose, xyz_canon[None].expand(B, -1, -1), lbs_weights)
     sc = scales[None].expand(B, -1, -1)
     if smpl_scale is not None:

@@ -41,6 +41,12 @@ _SIGNATURES = {
     "sgs_lbs_fwd": (_i, [_i, _i, _i] + [_vp] * 15),
     "sgs_lbs_bwd": (_i, [_i, _i, _i] + [_vp] * 21),
     "sgs_pose_lbs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i] + [_vp] * 12),
+    "sgs_lbs_fwd_rot6d": (_i, [_i, _i, _i] + [_vp] * 15),
+    "sgs_lbs_bwd_rot6d": (_i, [_i, _i, _i] + [_vp] * 21),
+    "sgs_rot6d_to_matrix": (_i, [_vp, _i, _vp, _vp]),
+    "sgs_rot6d_to_matrix_bwd": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "sgs_rot6d_to_axis_angle": (_i, [_vp, _i, _vp, _vp]),
+    "sgs_rot6d_to_axis_angle_bwd": (_i, [_vp, _vp, _i, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

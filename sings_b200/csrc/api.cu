@@ -8,6 +8,19 @@
 
 using namespace sgs;
 
+// sgs_pose_lbs_fwd: pose -> A inside the LBS kernel's prologue (1) or as its own kernel in front
+// (0); fused only up to this many frames per call -- beyond it every CTA would repeat too much
+// serial work (A/B knobs, tools/sweep.sh).  Measured (profiles/README.md, v7): fused 25.0 us vs
+// 24.7 us for the deform stage -- the separate kernel is already hidden behind the LBS kernel's
+// early tile prefetch, while the fused prologue puts the joint chain on every CTA's critical
+// path -- so the default stays 0.
+#ifndef SGS_FUSE_POSE
+#define SGS_FUSE_POSE 0
+#endif
+#ifndef SGS_FUSE_POSE_MAX_B
+#define SGS_FUSE_POSE_MAX_B 4
+#endif
+
 bool sgs::pdl_enabled() {
     static int v = -1;
     if (v < 0) v = getenv("SGS_NO_PDL") ? 0 : 1;
@@ -300,10 +313,17 @@ int sgs_pose_lbs_fwd(const float* pose, const float* rest, const int* parents,
     int rc = fill_lbs(a, B, N, J, A_out, xyz_canon, W, rot_canon, scales, smpl_scale, transl, nullptr, nullptr, nullptr);
     if (rc) return rc;
     if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
+    LbsOut o{xyz_out, rotq_out, scales_out, nullptr};
+    if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
+    if (SGS_FUSE_POSE && B <= SGS_FUSE_POSE_MAX_B && N > 0) {
+        // one kernel: every LBS CTA derives the joint transforms in its prologue (lbs.cu)
+        a.pose = pose; a.rest = rest; a.parents = parents; a.inv_A = inv_A_t2cano;
+        a.A_out = A_out; a.G_out = G_out;
+        return launch_lbs_fwd(a, o, (cudaStream_t)stream);
+    }
     rc = launch_pose_to_A(pose, rest, parents, inv_A_t2cano, B, J, A_out, G_out, (cudaStream_t)stream);
     if (rc) return rc;
     a.early_params = 1;      // the preceding kernel is pose_to_A, which never writes them
-    LbsOut o{xyz_out, rotq_out, scales_out, nullptr};
     return launch_lbs_fwd(a, o, (cudaStream_t)stream);
 }
 
@@ -320,6 +340,55 @@ int sgs_lbs_bwd(int B, int N, int J, const float* A, const float* xyz_canon, con
     if (B > 0 && N > 0 && (!g_xyz || !g_rotq || !g_scales || !d_xyz_canon || !d_scales || !d_A)) return SGS_ERR_BAD_ARG;
     LbsGrads g{g_xyz, g_rotq, g_scales, g_T, d_xyz_canon, d_rot_canon, d_scales, d_A, d_smpl_scale, d_transl};
     return launch_lbs_bwd(a, g, (cudaStream_t)stream);
+}
+
+int sgs_lbs_fwd_rot6d(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                      const float* rot6d_canon, const float* scales, const float* smpl_scale,
+                      const float* transl, const float* ext_trans, const float* ext_rot,
+                      const float* ext_scale, float* xyz_out, float* rotq_out, float* scales_out,
+                      float* T_out, sgs_stream_t stream) {
+    if (B > 0 && N > 0 && !rot6d_canon) return SGS_ERR_BAD_ARG;
+    LbsArgs a;
+    int rc = fill_lbs(a, B, N, J, A, xyz_canon, W, rot6d_canon, scales, smpl_scale, transl, ext_trans, ext_rot, ext_scale);
+    if (rc) return rc;
+    if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
+    a.rot6d = 1;
+    LbsOut o{xyz_out, rotq_out, scales_out, T_out};
+    return launch_lbs_fwd(a, o, (cudaStream_t)stream);
+}
+
+int sgs_lbs_bwd_rot6d(int B, int N, int J, const float* A, const float* xyz_canon, const float* W,
+                      const float* rot6d_canon, const float* scales, const float* smpl_scale,
+                      const float* transl, const float* ext_trans, const float* ext_rot,
+                      const float* ext_scale, const float* g_xyz, const float* g_rotq,
+                      const float* g_scales, const float* g_T, float* d_xyz_canon,
+                      float* d_rot6d_canon, float* d_scales, float* d_A, float* d_smpl_scale,
+                      float* d_transl, sgs_stream_t stream) {
+    if (B > 0 && N > 0 && !rot6d_canon) return SGS_ERR_BAD_ARG;
+    LbsArgs a;
+    int rc = fill_lbs(a, B, N, J, A, xyz_canon, W, rot6d_canon, scales, smpl_scale, transl, ext_trans, ext_rot, ext_scale);
+    if (rc) return rc;
+    if (B > 0 && N > 0 && (!g_xyz || !g_rotq || !g_scales || !d_xyz_canon || !d_scales || !d_A)) return SGS_ERR_BAD_ARG;
+    a.rot6d = 1;
+    LbsGrads g{g_xyz, g_rotq, g_scales, g_T, d_xyz_canon, d_rot6d_canon, d_scales, d_A, d_smpl_scale, d_transl};
+    return launch_lbs_bwd(a, g, (cudaStream_t)stream);
+}
+
+int sgs_rot6d_to_matrix(const float* d6, int n, float* R_out, sgs_stream_t stream) {
+    if (n < 0 || (n > 0 && (!d6 || !R_out))) return SGS_ERR_BAD_ARG;
+    return launch_rot6d_convert(d6, n, 0, R_out, (cudaStream_t)stream);
+}
+int sgs_rot6d_to_matrix_bwd(const float* d6, const float* dL_dR, int n, float* dL_dd6, sgs_stream_t stream) {
+    if (n < 0 || (n > 0 && (!d6 || !dL_dR || !dL_dd6))) return SGS_ERR_BAD_ARG;
+    return launch_rot6d_convert_bwd(d6, dL_dR, n, 0, dL_dd6, (cudaStream_t)stream);
+}
+int sgs_rot6d_to_axis_angle(const float* d6, int n, float* aa_out, sgs_stream_t stream) {
+    if (n < 0 || (n > 0 && (!d6 || !aa_out))) return SGS_ERR_BAD_ARG;
+    return launch_rot6d_convert(d6, n, 1, aa_out, (cudaStream_t)stream);
+}
+int sgs_rot6d_to_axis_angle_bwd(const float* d6, const float* dL_daa, int n, float* dL_dd6, sgs_stream_t stream) {
+    if (n < 0 || (n > 0 && (!d6 || !dL_daa || !dL_dd6))) return SGS_ERR_BAD_ARG;
+    return launch_rot6d_convert_bwd(d6, dL_daa, n, 1, dL_dd6, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -10,7 +10,7 @@ struct LbsArgs {
     const float* A;           // (B,J,16) cano->pose joint transforms, row-major 4x4
     const float* xyz;         // (N,3) canonical means
     const float* W;           // (N,J) skinning weights
-    const float* rot;         // (N,9) canonical rotation matrices, or null (= identity)
+    const float* rot;         // (N,9) canonical rotation matrices -- (N,6) 6D rotations when rot6d -- or null (= identity)
     const float* scales;      // (N,3)
     const float* smpl_scale;  // (B) or null
     const float* transl;      // (B,3) or null
@@ -21,6 +21,16 @@ struct LbsArgs {
     // the stream started (that kernel being one of ours, e.g. pose_to_A), so their tiles may
     // be fetched ahead of the programmatic-dependency wait (common.cuh, PDL)
     int early_params = 0;
+    int rot6d = 0;            // rot holds 6D rotations; d_rot is (N,6)
+    // fused pose -> A (forward only): when `pose` is set, A is not read -- every CTA computes the
+    // joint transforms from pose (B,J,3), rest (J,3), parents (J), inv_A (J,16)|null in its
+    // prologue, and CTA 0 writes them to A_out (B,J,16) / G_out (B,J,12)|null
+    const float* pose = nullptr;
+    const float* rest = nullptr;
+    const int* parents = nullptr;
+    const float* inv_A = nullptr;
+    float* A_out = nullptr;
+    float* G_out = nullptr;
 };
 
 struct LbsOut {
@@ -36,7 +46,7 @@ struct LbsGrads {
     const float* g_scales;  // (B,N,3)
     const float* g_T;       // (B,N,16) gradient w.r.t. the optional T output, or null
     float* d_xyz;           // (N,3)   written
-    float* d_rot;           // (N,9)   written, or null
+    float* d_rot;           // (N,9) -- (N,6) when rot6d -- written, or null
     float* d_scales;        // (N,3)   written
     float* d_A;             // (B,J,16) accumulated (caller zeroes)
     float* d_smpl_scale;    // (B) accumulated (caller zeroes) or null
@@ -48,6 +58,9 @@ int launch_pose_to_A(const float* pose, const float* rest, const int* parents, c
 int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parents,
                          const float* inv_A, const float* G, const float* dA, int B, int J,
                          float* d_pose, cudaStream_t stream);
+int launch_rot6d_convert(const float* d6, int n, int mode, float* out, cudaStream_t stream);
+int launch_rot6d_convert_bwd(const float* d6, const float* g_out, int n, int mode, float* g_d6,
+                             cudaStream_t stream);
 int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream);
 int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream);
 

@@ -59,36 +59,34 @@ __device__ __forceinline__ void affine_mul(const float* a, const float* b, float
     }
 }
 
-// one CTA per frame, one thread per joint; each thread multiplies its own ancestor chain
-// from the root down (same association as the reference's sequential loop, smpl.py:495-501)
-__global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __restrict__ rest,
-                                 const int* __restrict__ parents, const float* __restrict__ inv_A,
-                                 int J, float* __restrict__ A_out, float* __restrict__ G_out) {
-    extern __shared__ float s_local[];     // J x 12 local transforms
-    __shared__ int s_par[64];
-    const int b = blockIdx.x, j = threadIdx.x;
-    pdl_sync();
-    if (j < J) {
-        float R[9];
-        const float* p = pose + ((size_t)b * J + j) * 3;
-        rodrigues(p[0], p[1], p[2], R);
-        const int par = parents[j];
-        s_par[j] = par;
-        float t[3];
+// pose -> A in two steps with a block barrier between them (used by pose_to_A_kernel and by the
+// fused prologue of lbs_fwd_kernel; identical arithmetic, so identical results):
+//   pose_local: joint j's local transform [R(pose_j) | rest_j - rest_parent] into s_local
+//   pose_chain: each thread multiplies its own ancestor chain from the root down (same
+//     association as the reference's sequential loop, smpl.py:495-501), then
+//     A = G - pad(G [rest_j; 0]) (smpl.py:510-511) and A @ inv_A_t2cano (sings_hybrid.py:399)
+__device__ __forceinline__ void pose_local(const float* __restrict__ pose_bj, const float* __restrict__ rest,
+                                           const int* __restrict__ parents, int j, float* s_local, int* s_par) {
+    float R[9];
+    rodrigues(pose_bj[0], pose_bj[1], pose_bj[2], R);
+    const int par = parents[j];
+    s_par[j] = par;
+    float t[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) t[k] = rest[3 * j + k] - (par >= 0 ? rest[3 * par + k] : 0.0f);
-        float* L = s_local + 12 * j;
+    for (int k = 0; k < 3; k++) t[k] = rest[3 * j + k] - (par >= 0 ? rest[3 * par + k] : 0.0f);
+    float* L = s_local + 12 * j;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            L[4 * r] = R[3 * r]; L[4 * r + 1] = R[3 * r + 1]; L[4 * r + 2] = R[3 * r + 2]; L[4 * r + 3] = t[r];
-        }
+    for (int r = 0; r < 3; r++) {
+        L[4 * r] = R[3 * r]; L[4 * r + 1] = R[3 * r + 1]; L[4 * r + 2] = R[3 * r + 2]; L[4 * r + 3] = t[r];
     }
-    __syncthreads();
-    if (j >= J) return;
+}
+
+__device__ __forceinline__ void pose_chain(const float* __restrict__ rest, const float* __restrict__ inv_A, int j,
+                                           const float* s_local, const int* s_par, float* G, float* out) {
     int chain[64];
     int depth = 0;
     for (int k = j; k >= 0 && depth < 64; k = s_par[k]) chain[depth++] = k;
-    float G[12], tmp[12];
+    float tmp[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) G[k] = s_local[12 * chain[depth - 1] + k];
     for (int d = depth - 2; d >= 0; d--) {
@@ -96,18 +94,12 @@ __global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __
 #pragma unroll
         for (int k = 0; k < 12; k++) G[k] = tmp[k];
     }
-    if (G_out) {
-#pragma unroll
-        for (int k = 0; k < 12; k++) G_out[((size_t)b * J + j) * 12 + k] = G[k];
-    }
-    // A = G - pad(G [rest_j; 0])  (smpl.py:510-511)
     float Arel[12];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         Arel[4 * r] = G[4 * r]; Arel[4 * r + 1] = G[4 * r + 1]; Arel[4 * r + 2] = G[4 * r + 2];
         Arel[4 * r + 3] = G[4 * r + 3] - (G[4 * r] * rest[3 * j] + G[4 * r + 1] * rest[3 * j + 1] + G[4 * r + 2] * rest[3 * j + 2]);
     }
-    float out[12];
     if (inv_A) {
         float Bm[12];
 #pragma unroll
@@ -119,10 +111,34 @@ __global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __
 #pragma unroll
         for (int k = 0; k < 12; k++) out[k] = Arel[k];
     }
-    float* dst = A_out + ((size_t)b * J + j) * 16;
+}
+
+__device__ __forceinline__ void pose_store(float* __restrict__ A_out, float* __restrict__ G_out, size_t bj,
+                                           const float* G, const float* out) {
+    if (G_out) {
+#pragma unroll
+        for (int k = 0; k < 12; k++) G_out[bj * 12 + k] = G[k];
+    }
+    float* dst = A_out + bj * 16;
 #pragma unroll
     for (int k = 0; k < 12; k++) dst[k] = out[k];
     dst[12] = 0.0f; dst[13] = 0.0f; dst[14] = 0.0f; dst[15] = 1.0f;
+}
+
+// one CTA per frame, one thread per joint
+__global__ void pose_to_A_kernel(const float* __restrict__ pose, const float* __restrict__ rest,
+                                 const int* __restrict__ parents, const float* __restrict__ inv_A,
+                                 int J, float* __restrict__ A_out, float* __restrict__ G_out) {
+    extern __shared__ float s_local[];     // J x 12 local transforms
+    __shared__ int s_par[64];
+    const int b = blockIdx.x, j = threadIdx.x;
+    pdl_sync();
+    if (j < J) pose_local(pose + ((size_t)b * J + j) * 3, rest, parents, j, s_local, s_par);
+    __syncthreads();
+    if (j >= J) return;
+    float G[12], out[12];
+    pose_chain(rest, inv_A, j, s_local, s_par, G, out);
+    pose_store(A_out, G_out, (size_t)b * J + j, G, out);
 }
 
 int launch_pose_to_A(const float* pose, const float* rest, const int* parents, const float* inv_A,
@@ -380,6 +396,99 @@ __device__ __forceinline__ void quat_mul(const float* a, const float* b, float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// 6D rotation (Zhou et al.) -> matrix by Gram-Schmidt, rows b1, b2, b3 (rotations.py:545-566:
+// F.normalize(a1); a2 - (b1.a2) b1; F.normalize; cross; stack on dim -2) and its backward.
+// F.normalize divides by max(||v||, 1e-12).
+// ------------------------------------------------------------------------------------------
+constexpr float NORMALIZE_EPS = 1e-12f;
+
+__device__ __forceinline__ void rot6d_to_mat(const float* d6, float* R) {
+    const float n1 = sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]);
+    const float i1 = 1.0f / fmaxf(n1, NORMALIZE_EPS);
+    const float b1[3] = {d6[0] * i1, d6[1] * i1, d6[2] * i1};
+    const float d = b1[0] * d6[3] + b1[1] * d6[4] + b1[2] * d6[5];
+    const float u[3] = {d6[3] - d * b1[0], d6[4] - d * b1[1], d6[5] - d * b1[2]};
+    const float n2 = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    const float i2 = 1.0f / fmaxf(n2, NORMALIZE_EPS);
+    const float b2[3] = {u[0] * i2, u[1] * i2, u[2] * i2};
+    R[0] = b1[0]; R[1] = b1[1]; R[2] = b1[2];
+    R[3] = b2[0]; R[4] = b2[1]; R[5] = b2[2];
+    R[6] = b1[1] * b2[2] - b1[2] * b2[1];
+    R[7] = b1[2] * b2[0] - b1[0] * b2[2];
+    R[8] = b1[0] * b2[1] - b1[1] * b2[0];
+}
+
+// v / max(||v||, eps) backward: g_v = (g - b (b.g)) / n above the floor, g / eps below it
+__device__ __forceinline__ void normalize_bwd(const float* b, float n, const float* g, float* gv) {
+    if (n > NORMALIZE_EPS) {
+        const float bg = b[0] * g[0] + b[1] * g[1] + b[2] * g[2];
+        const float inv = 1.0f / n;
+#pragma unroll
+        for (int k = 0; k < 3; k++) gv[k] = (g[k] - b[k] * bg) * inv;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) gv[k] = g[k] * (1.0f / NORMALIZE_EPS);
+    }
+}
+
+// dL/dR (row-major 9) -> dL/dd6 (6)
+__device__ __forceinline__ void rot6d_to_mat_bwd(const float* d6, const float* gR, float* g6) {
+    const float n1 = sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]);
+    const float i1 = 1.0f / fmaxf(n1, NORMALIZE_EPS);
+    const float b1[3] = {d6[0] * i1, d6[1] * i1, d6[2] * i1};
+    const float a2[3] = {d6[3], d6[4], d6[5]};
+    const float d = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+    const float u[3] = {a2[0] - d * b1[0], a2[1] - d * b1[1], a2[2] - d * b1[2]};
+    const float n2 = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    const float i2 = 1.0f / fmaxf(n2, NORMALIZE_EPS);
+    const float b2[3] = {u[0] * i2, u[1] * i2, u[2] * i2};
+    const float* g3 = gR + 6;
+    // b3 = b1 x b2:  dL/db1 += b2 x g3,  dL/db2 += g3 x b1
+    float gb1[3] = {gR[0] + (b2[1] * g3[2] - b2[2] * g3[1]), gR[1] + (b2[2] * g3[0] - b2[0] * g3[2]),
+                    gR[2] + (b2[0] * g3[1] - b2[1] * g3[0])};
+    const float gb2[3] = {gR[3] + (g3[1] * b1[2] - g3[2] * b1[1]), gR[4] + (g3[2] * b1[0] - g3[0] * b1[2]),
+                          gR[5] + (g3[0] * b1[1] - g3[1] * b1[0])};
+    float gu[3];
+    normalize_bwd(b2, n2, gb2, gu);
+    // u = a2 - (b1.a2) b1
+    const float gub1 = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        g6[3 + k] = gu[k] - gub1 * b1[k];
+        gb1[k] += -gub1 * a2[k] - d * gu[k];
+    }
+    normalize_bwd(b1, n1, gb1, g6);
+}
+
+// quaternion (real first) -> axis-angle (rotations.py:514-542): half = atan2(||v||, w),
+// angle = 2 half, v / (sin(half)/angle), series 0.5 - angle^2/48 below 1e-6
+__device__ __forceinline__ void quat_to_axis_angle(const float* q, float* aa) {
+    const float n = sqrtf(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float half = atan2f(n, q[0]);
+    const float angle = 2.0f * half;
+    const float s = fabsf(angle) < 1e-6f ? 0.5f - (angle * angle) / 48.0f : sinf(half) / angle;
+    aa[0] = q[1] / s; aa[1] = q[2] / s; aa[2] = q[3] / s;
+}
+
+__device__ __forceinline__ void quat_to_axis_angle_bwd(const float* q, const float* g, float* gq) {
+    const float n = sqrtf(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float half = atan2f(n, q[0]);
+    const float angle = 2.0f * half;
+    const bool small = fabsf(angle) < 1e-6f;
+    const float s = small ? 0.5f - (angle * angle) / 48.0f : sinf(half) / angle;
+    // d s / d half: series -angle/24 per unit angle (x2); else (cos(half) angle - 2 sin(half)) / angle^2
+    const float ds_dhalf = small ? -angle / 12.0f : (cosf(half) * angle - 2.0f * sinf(half)) / (angle * angle);
+    const float gs = -(g[0] * q[1] + g[1] * q[2] + g[2] * q[3]) / (s * s);
+    const float gh = gs * ds_dhalf;
+    const float r2 = n * n + q[0] * q[0];
+    const float gn = r2 > 0.0f ? gh * q[0] / r2 : 0.0f;
+    gq[0] = r2 > 0.0f ? -gh * n / r2 : 0.0f;
+    const float gn_over_n = n > 0.0f ? gn / n : 0.0f;      // torch.norm has a zero sub-gradient at 0
+#pragma unroll
+    for (int k = 0; k < 3; k++) gq[1 + k] = g[k] / s + gn_over_n * q[1 + k];
+}
+
+// ------------------------------------------------------------------------------------------
 // shared-memory tile of one CTA (256 consecutive Gaussians).  Every per-Gaussian array is a
 // contiguous block in global memory, so it is moved as a block: one TMA bulk copy
 // (cp.async.bulk + mbarrier) when the block is 16-byte aligned and a multiple of 16 bytes,
@@ -399,11 +508,13 @@ struct LbsTile {
     float* f_scl;     // [256][3]
     float* dT;        // backward: [256][12]
     float* part;      // backward: [8][J][12] per-warp partial dA
+    float* poseL;     // fused pose -> A prologue: [LBS_THREADS/64][J][12] local transforms
+    int* posePar;     // [64] parents
     unsigned long long* bar;
 };
 
 __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bwd, LbsTile* t = nullptr,
-                                                 char* raw = nullptr) {
+                                                 char* raw = nullptr, bool fused_pose = false) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 16); return at; };
     const size_t oA = take((size_t)B * J * 3 * 16), oF = take((size_t)B * 16 * 4);
@@ -413,6 +524,7 @@ __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bw
     const size_t oFX = take(LBS_THREADS * 12), oFQ = take(LBS_THREADS * 16), oFS = take(LBS_THREADS * 12);
     const size_t oT = take(bwd ? LBS_THREADS * 48 : 0);
     const size_t oP = take(bwd ? (size_t)(LBS_THREADS / 32) * J * 48 : 0);
+    const size_t oPL = take(fused_pose ? (size_t)(LBS_THREADS / 64) * J * 48 : 0), oPP = take(fused_pose ? 64 * 4 : 0);
     const size_t oB = take(16);
     if (t) {
         t->A = reinterpret_cast<float4*>(raw + oA);  t->frame = reinterpret_cast<float*>(raw + oF);
@@ -421,6 +533,7 @@ __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bw
         t->f_xyz = reinterpret_cast<float*>(raw + oFX); t->f_q = reinterpret_cast<float*>(raw + oFQ);
         t->f_scl = reinterpret_cast<float*>(raw + oFS); t->dT = reinterpret_cast<float*>(raw + oT);
         t->part = reinterpret_cast<float*>(raw + oP);
+        t->poseL = reinterpret_cast<float*>(raw + oPL); t->posePar = reinterpret_cast<int*>(raw + oPP);
         t->bar = reinterpret_cast<unsigned long long*>(raw + oB);
     }
     return o;
@@ -478,9 +591,11 @@ __device__ __forceinline__ void block_store(float* dst, const float* src, unsign
 
 __device__ __forceinline__ void stage_frames(const LbsArgs& a, LbsTile& s) {
     const int tid = threadIdx.x;
-    for (int f = tid; f < a.B * a.J * 3; f += LBS_THREADS) {
-        int bj = f / 3, r = f - bj * 3;
-        s.A[f] = reinterpret_cast<const float4*>(a.A)[(size_t)bj * 4 + r];
+    if (!a.pose) {
+        for (int f = tid; f < a.B * a.J * 3; f += LBS_THREADS) {
+            int bj = f / 3, r = f - bj * 3;
+            s.A[f] = reinterpret_cast<const float4*>(a.A)[(size_t)bj * 4 + r];
+        }
     }
     for (int b = tid; b < a.B; b += LBS_THREADS) {
         float* fr = s.frame + 16 * b;
@@ -544,8 +659,9 @@ __device__ __forceinline__ void compose_rot(const float* T, const float* Rc, boo
 __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut o) {
     extern __shared__ __align__(16) char s_raw[];
     const bool iso = a.rot == nullptr;
+    const int rw = a.rot6d ? 6 : 9;      // floats per canonical rotation: 6D (Gram-Schmidt here) or matrix
     LbsTile s;
-    lbs_tile_bytes(a.B, a.J, iso, false, &s, s_raw);
+    lbs_tile_bytes(a.B, a.J, iso, false, &s, s_raw, a.pose != nullptr);
     const int tid = threadIdx.x;
     const int base = blockIdx.x * LBS_THREADS;
     const int rows = min(LBS_THREADS, a.N - base);
@@ -558,24 +674,55 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut 
     BlockLoads ld{s.bar, 0};
     {
         const float* src[4] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
-                               iso ? nullptr : a.rot + (size_t)base * 9};
+                               iso ? nullptr : a.rot + (size_t)base * rw};
         float* dst[4] = {s.W, s.xyz, s.scl, s.rot};
-        const unsigned n[4] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)rows * 9};
+        const unsigned n[4] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)(rows * rw)};
         ld.load(src, dst, n, 4);
     }
     if (a.early_params) pdl_sync();
     stage_frames(a, s);
+    if (a.pose) {
+        // Fused pose -> A (sgs_pose_lbs_fwd): every CTA derives the B x J joint transforms itself
+        // while its weight tile is in flight -- 64 threads per frame, LBS_THREADS/64 frames at a
+        // time -- instead of waiting for a one-CTA kernel in front of the whole grid.  CTA 0
+        // also writes A and G out for the backward.  Same device functions as pose_to_A_kernel.
+        const int grp = tid >> 6, j = tid & 63;
+        float* L = s.poseL + (size_t)grp * a.J * 12;
+        for (int b0 = 0; b0 < a.B; b0 += LBS_THREADS / 64) {
+            const int b = b0 + grp;
+            const bool on = b < a.B && j < a.J;
+            if (on) pose_local(a.pose + ((size_t)b * a.J + j) * 3, a.rest, a.parents, j, L, s.posePar);
+            __syncthreads();
+            if (on) {
+                float G[12], out[12];
+                pose_chain(a.rest, a.inv_A, j, L, s.posePar, G, out);
+                float4* dst = s.A + ((size_t)b * a.J + j) * 3;
+                dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+                dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+                dst[2] = make_float4(out[8], out[9], out[10], out[11]);
+                if (blockIdx.x == 0) pose_store(a.A_out, a.G_out, (size_t)b * a.J + j, G, out);
+            }
+            if (b0 + LBS_THREADS / 64 < a.B) __syncthreads();
+        }
+    }
     ld.wait();
     const int n = base + tid;
     const bool live = n < a.N;
     float x = 0, y = 0, z = 0, s0 = 0, s1 = 0, s2 = 0;
     float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float d6[6] = {1, 0, 0, 0, 1, 0};
     if (live) {
         x = s.xyz[3 * tid]; y = s.xyz[3 * tid + 1]; z = s.xyz[3 * tid + 2];
         s0 = s.scl[3 * tid]; s1 = s.scl[3 * tid + 1]; s2 = s.scl[3 * tid + 2];
         if (!iso) {
+            if (a.rot6d) {      // rotation_6d_to_matrix (sings_hybrid.py:354-356)
 #pragma unroll
-            for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
+                for (int k = 0; k < 6; k++) d6[k] = s.rot[6 * tid + k];
+                rot6d_to_mat(d6, Rc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
+            }
         }
     }
     for (int b = 0; b < a.B; b++) {
@@ -640,7 +787,8 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
     if (a.N <= 0 || a.B <= 0) return 0;
     if (a.J < 1 || a.J > 64) return SGS_ERR_BAD_JOINTS;
     if (((uintptr_t)a.A & 15) || (o.T && ((uintptr_t)o.T & 15))) return SGS_ERR_MISALIGNED;
-    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false);
+    if (a.pose && (!a.rest || !a.parents || !a.A_out)) return SGS_ERR_BAD_ARG;
+    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false, nullptr, nullptr, a.pose != nullptr);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(lbs_fwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, o);
@@ -654,6 +802,7 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
 __global__ void __launch_bounds__(LBS_THREADS, SGS_LBS_BWD_MINB) lbs_bwd_kernel(LbsArgs a, LbsGrads g) {
     extern __shared__ __align__(16) char s_raw[];
     const bool iso = a.rot == nullptr;
+    const int rw = a.rot6d ? 6 : 9;      // floats per canonical rotation: 6D (Gram-Schmidt here) or matrix
     LbsTile s;
     lbs_tile_bytes(a.B, a.J, iso, true, &s, s_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -668,10 +817,10 @@ __global__ void __launch_bounds__(LBS_THREADS, SGS_LBS_BWD_MINB) lbs_bwd_kernel(
     BlockLoads ld{s.bar, 0};
     {
         const float* src[7] = {a.W + (size_t)base * a.J, a.xyz + (size_t)base * 3, a.scales + (size_t)base * 3,
-                               iso ? nullptr : a.rot + (size_t)base * 9, g.g_xyz + (size_t)base * 3,
+                               iso ? nullptr : a.rot + (size_t)base * rw, g.g_xyz + (size_t)base * 3,
                                g.g_rotq + (size_t)base * 4, g.g_scales + (size_t)base * 3};
         float* dst[7] = {s.W, s.xyz, s.scl, s.rot, s.f_xyz, s.f_q, s.f_scl};
-        const unsigned n[7] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)rows * 9,
+        const unsigned n[7] = {(unsigned)(rows * a.J), (unsigned)rows * 3, (unsigned)rows * 3, iso ? 0u : (unsigned)(rows * rw),
                                (unsigned)rows * 3, (unsigned)rows * 4, (unsigned)rows * 3};
         ld.load(src, dst, n, 7);
     }
@@ -681,12 +830,19 @@ __global__ void __launch_bounds__(LBS_THREADS, SGS_LBS_BWD_MINB) lbs_bwd_kernel(
     const bool live = n < a.N;
     float x = 0, y = 0, z = 0, s0 = 0, s1 = 0, s2 = 0;
     float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float d6[6] = {1, 0, 0, 0, 1, 0};
     if (live) {
         x = s.xyz[3 * tid]; y = s.xyz[3 * tid + 1]; z = s.xyz[3 * tid + 2];
         s0 = s.scl[3 * tid]; s1 = s.scl[3 * tid + 1]; s2 = s.scl[3 * tid + 2];
         if (!iso) {
+            if (a.rot6d) {      // rotation_6d_to_matrix (sings_hybrid.py:354-356)
 #pragma unroll
-            for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
+                for (int k = 0; k < 6; k++) d6[k] = s.rot[6 * tid + k];
+                rot6d_to_mat(d6, Rc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) Rc[k] = s.rot[9 * tid + k];
+            }
         }
     }
     float dx = 0, dy = 0, dz = 0, ds0 = 0, ds1 = 0, ds2 = 0;
@@ -832,15 +988,24 @@ __global__ void __launch_bounds__(LBS_THREADS, SGS_LBS_BWD_MINB) lbs_bwd_kernel(
         s.xyz[3 * tid] = dx; s.xyz[3 * tid + 1] = dy; s.xyz[3 * tid + 2] = dz;
         s.scl[3 * tid] = ds0; s.scl[3 * tid + 1] = ds1; s.scl[3 * tid + 2] = ds2;
         if (g.d_rot && !iso) {
+            if (a.rot6d) {
+                float in6[6], g6[6];      // re-read: keeps the 6 inputs out of the frame loop's registers
 #pragma unroll
-            for (int k = 0; k < 9; k++) s.rot[9 * tid + k] = dRc[k];
+                for (int k = 0; k < 6; k++) in6[k] = s.rot[6 * tid + k];
+                rot6d_to_mat_bwd(in6, dRc, g6);
+#pragma unroll
+                for (int k = 0; k < 6; k++) s.rot[6 * tid + k] = g6[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) s.rot[9 * tid + k] = dRc[k];
+            }
         }
     }
     fence_proxy_async();
     __syncthreads();
     block_store(g.d_xyz + (size_t)base * 3, s.xyz, (unsigned)rows * 3);
     block_store(g.d_scales + (size_t)base * 3, s.scl, (unsigned)rows * 3);
-    if (g.d_rot && !iso) block_store(g.d_rot + (size_t)base * 9, s.rot, (unsigned)rows * 9);
+    if (g.d_rot && !iso) block_store(g.d_rot + (size_t)base * rw, s.rot, (unsigned)(rows * rw));
     if (tid == 0) {
         bulk_commit();
         bulk_wait_read();
@@ -855,6 +1020,71 @@ int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(lbs_bwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, g);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone 6D-rotation conversions (one thread per rotation): the pose parameters are stored
+// as 6D rotations and turned into axis-angle every frame (sings_hybrid.py:370-376:
+// rotation_6d_to_axis_angle = 6D -> matrix -> quaternion -> axis-angle, rotations.py:601-603).
+// mode 0: matrix out (n,9); mode 1: axis-angle out (n,3).
+// ------------------------------------------------------------------------------------------
+__global__ void rot6d_convert_kernel(const float* __restrict__ d6_all, int n, int mode, float* __restrict__ out) {
+    pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d6[6], R[9];
+#pragma unroll
+    for (int k = 0; k < 6; k++) d6[k] = d6_all[(size_t)i * 6 + k];
+    rot6d_to_mat(d6, R);
+    if (mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) out[(size_t)i * 9 + k] = R[k];
+    } else {
+        float q[4], aa[3];
+        mat_to_quat(R, q);
+        quat_to_axis_angle(q, aa);
+#pragma unroll
+        for (int k = 0; k < 3; k++) out[(size_t)i * 3 + k] = aa[k];
+    }
+}
+
+__global__ void rot6d_convert_bwd_kernel(const float* __restrict__ d6_all, const float* __restrict__ g_out, int n,
+                                         int mode, float* __restrict__ g_d6) {
+    pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d6[6], R[9], gR[9], g6[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) d6[k] = d6_all[(size_t)i * 6 + k];
+    if (mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) gR[k] = g_out[(size_t)i * 9 + k];
+    } else {
+        rot6d_to_mat(d6, R);
+        float q[4], gq[4];
+        mat_to_quat(R, q);
+        const float g[3] = {g_out[(size_t)i * 3], g_out[(size_t)i * 3 + 1], g_out[(size_t)i * 3 + 2]};
+        quat_to_axis_angle_bwd(q, g, gq);
+        mat_to_quat_bwd(R, gq, gR);
+    }
+    rot6d_to_mat_bwd(d6, gR, g6);
+#pragma unroll
+    for (int k = 0; k < 6; k++) g_d6[(size_t)i * 6 + k] = g6[k];
+}
+
+int launch_rot6d_convert(const float* d6, int n, int mode, float* out, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    launch_pdl(rot6d_convert_kernel, (n + 127) / 128, 128, 0, stream, d6, n, mode, out);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+int launch_rot6d_convert_bwd(const float* d6, const float* g_out, int n, int mode, float* g_d6,
+                             cudaStream_t stream) {
+    if (n <= 0) return 0;
+    launch_pdl(rot6d_convert_bwd_kernel, (n + 127) / 128, 128, 0, stream, d6, g_out, n, mode, g_d6);
     SGS_LAUNCH_OK();
     return 0;
 }

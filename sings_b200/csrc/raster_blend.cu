@@ -42,6 +42,15 @@ namespace sgs {
 #ifndef SGS_BWD_P2ROW            // phase 2 of the backward: 1 = one pixel row per loop trip, 0 = flat unrolled
 #define SGS_BWD_P2ROW 1
 #endif
+#ifndef SGS_FWD_WPC              // warps per CTA of the blend kernels: the 8 warps of a tile are autonomous,
+#define SGS_FWD_WPC 8            // so a tile may be spread over 8 / WPC smaller CTAs (finer scheduling grain)
+#endif
+#ifndef SGS_BWD_WPC
+#define SGS_BWD_WPC 8
+#endif
+constexpr int FWD_WPC = SGS_FWD_WPC, BWD_WPC = SGS_BWD_WPC;
+constexpr int TILE_WARPS = TILE_PIX / 32;
+static_assert(TILE_WARPS % FWD_WPC == 0 && TILE_WARPS % BWD_WPC == 0, "warps per CTA must divide 8");
 constexpr int BWD_U = SGS_BWD_U;      // pairs per software-pipeline stage in the backward blend
 constexpr int FWD_U = SGS_FWD_U;      // pairs evaluated together per pixel in the forward blend
 
@@ -129,8 +138,7 @@ static inline const unsigned* sorted_vals(const RasterLayout& lay, const char* b
     return reinterpret_cast<const unsigned*>(bin + (lay.sorted_in_1() ? lay.vals1_off : lay.vals0_off));
 }
 
-__device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
-    const int warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ void pixel_of_thread(int warp, int lane, int& lx, int& ly) {
     lx = ((warp & 1) << 3) + (lane & 7);
     ly = ((warp >> 1) << 2) + (lane >> 3);
 }
@@ -261,7 +269,7 @@ struct FwdBatch {
     unsigned pos[FWD_U];
 };
 
-__global__ void __launch_bounds__(TILE_PIX, SGS_FWD_MINB)
+__global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_MINB * (TILE_WARPS / FWD_WPC))
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
@@ -270,16 +278,18 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
                  float* __restrict__ out_depth) {
-    __shared__ float4 s_q0[TILE_PIX / 32][RING_SLOTS];     // x, y, -a/2, -b
-    __shared__ float4 s_q1[TILE_PIX / 32][RING_SLOTS];     // -c/2, opacity, pmin, r
-    __shared__ float4 s_q2[TILE_PIX / 32][RING_SLOTS];     // g, b, depth, list position + 1
+    __shared__ float4 s_q0[FWD_WPC][RING_SLOTS];     // x, y, -a/2, -b
+    __shared__ float4 s_q1[FWD_WPC][RING_SLOTS];     // -c/2, opacity, pmin, r
+    __shared__ float4 s_q2[FWD_WPC][RING_SLOTS];     // g, b, depth, list position + 1
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PARTS = TILE_WARPS / FWD_WPC;      // CTAs per tile
+    const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
+    const int warp = (int)(blockIdx.x % PARTS) * FWD_WPC + cwarp;      // pixel block of the tile
     pdl_sync();
-    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
+    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x / PARTS);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
-    pixel_of_thread(tid, lx, ly);
+    pixel_of_thread(warp, lane, lx, ly);
     const int px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
@@ -287,9 +297,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2)), by1 = by0 + 3.0f;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
-    float4* const rq0 = s_q0[warp];
-    float4* const rq1 = s_q1[warp];
-    float4* const rq2 = s_q2[warp];
+    float4* const rq0 = s_q0[cwarp];
+    float4* const rq1 = s_q1[cwarp];
+    float4* const rq2 = s_q2[cwarp];
 
     bool done = !inside;
     float T = 1.0f, T_fin = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dacc = 0.0f;
@@ -402,7 +412,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
                      float* out_depth, cudaStream_t stream) {
-    launch_pdl(blend_fwd_kernel, lay.tiles, TILE_PIX, 0, stream,
+    launch_pdl(blend_fwd_kernel, lay.tiles * (TILE_WARPS / FWD_WPC), FWD_WPC * 32, 0, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
@@ -447,7 +457,7 @@ struct BwdWarpSmem {
     unsigned id[2][BWD_ROWS];       // Gaussian of each pair row (double-buffered by tile parity)
 };
 
-__global__ void __launch_bounds__(TILE_PIX, SGS_BWD_MINB)
+__global__ void __launch_bounds__(BWD_WPC * 32, SGS_BWD_MINB * (TILE_WARPS / BWD_WPC))
 blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
@@ -456,13 +466,15 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, float* __restrict__ acc) {
     extern __shared__ __align__(16) char s_bwd_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[warp];
+    constexpr int PARTS = TILE_WARPS / BWD_WPC;      // CTAs per tile
+    const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
+    const int warp = (int)(blockIdx.x % PARTS) * BWD_WPC + cwarp;      // pixel block of the tile
+    BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[cwarp];
     pdl_sync();
-    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x);
+    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x / PARTS);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
-    pixel_of_thread(tid, lx, ly);
+    pixel_of_thread(warp, lane, lx, ly);
     const int px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
@@ -675,9 +687,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      const char* img, const float* bg, const float* dL_dpix, float* acc,
                      cudaStream_t stream) {
-    const size_t smem = sizeof(BwdWarpSmem) * (TILE_PIX / 32);
+    const size_t smem = sizeof(BwdWarpSmem) * BWD_WPC;
     SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(blend_bwd_kernel, lay.tiles, TILE_PIX, smem, stream,
+    launch_pdl(blend_bwd_kernel, lay.tiles * (TILE_WARPS / BWD_WPC), BWD_WPC * 32, smem, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),

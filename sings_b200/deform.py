@@ -78,10 +78,51 @@ def pose_to_A(pose: torch.Tensor, rest_joints: torch.Tensor, parents: torch.Tens
     return A[0] if squeeze else A
 
 
+class _Rot6dConvert(torch.autograd.Function):
+    """mode 0: (…,6) -> (…,3,3); mode 1: (…,6) -> (…,3) axis-angle."""
+
+    @staticmethod
+    def forward(ctx, d6, mode):
+        _need_cuda(d6, "rotation_6d conversion")
+        d6_c = _c(d6).reshape(-1, 6)
+        n = d6_c.shape[0]
+        out = torch.empty((n, 9) if mode == 0 else (n, 3), device=d6.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(d6.device).cuda_stream
+        fn = _lib.lib().sgs_rot6d_to_matrix if mode == 0 else _lib.lib().sgs_rot6d_to_axis_angle
+        _lib.check(fn(d6_c.data_ptr(), n, out.data_ptr(), st), "sgs_rot6d_to_*")
+        ctx.save_for_backward(d6_c)
+        ctx.mode, ctx.in_shape = mode, d6.shape
+        return out.reshape(d6.shape[:-1] + ((3, 3) if mode == 0 else (3,)))
+
+    @staticmethod
+    def backward(ctx, g):
+        (d6_c,) = ctx.saved_tensors
+        n = d6_c.shape[0]
+        g_c = _c(g).reshape(n, -1)
+        g6 = torch.empty(n, 6, device=d6_c.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(d6_c.device).cuda_stream
+        fn = _lib.lib().sgs_rot6d_to_matrix_bwd if ctx.mode == 0 else _lib.lib().sgs_rot6d_to_axis_angle_bwd
+        _lib.check(fn(d6_c.data_ptr(), g_c.data_ptr(), n, g6.data_ptr(), st), "sgs_rot6d_to_*_bwd")
+        return g6.reshape(ctx.in_shape), None
+
+
+def rotation_6d_to_matrix(d6: torch.Tensor) -> torch.Tensor:
+    """(…,6) -> (…,3,3), rows b1, b2, b3 of the Gram-Schmidt basis; same name and meaning as
+    /root/reference/sings/rec/utils/geometry/rotations.py:545-566.  One kernel each way."""
+    return _Rot6dConvert.apply(d6, 0)
+
+
+def rotation_6d_to_axis_angle(d6: torch.Tensor) -> torch.Tensor:
+    """(…,6) -> (…,3) axis-angle: rotations.py:601-603 (6D -> matrix -> quaternion ->
+    axis-angle), the per-frame conversion of the stored pose parameters
+    (sings_hybrid.py:370-376).  One kernel each way instead of ~40 eager ops."""
+    return _Rot6dConvert.apply(d6, 1)
+
+
 class _DeformGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, xyz, W, rot, scales, smpl_scale, transl, ext_trans, ext_rot, ext_scale,
-                want_T):
+                want_T, rot6d=False):
         _need_cuda(xyz, "deform_gaussians")
         A_c, xyz_c, W_c, rot_c, sc_c = _c(A), _c(xyz), _c(W), _c(rot), _c(scales)
         ss_c, tr_c = _c(smpl_scale), _c(transl)
@@ -94,12 +135,14 @@ class _DeformGaussians(torch.autograd.Function):
         sc_o = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         T_o = torch.empty(B, N, 4, 4, device=dev, dtype=torch.float32) if want_T else None
         st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib().sgs_lbs_fwd(
+        fwd = _lib.lib().sgs_lbs_fwd_rot6d if rot6d else _lib.lib().sgs_lbs_fwd
+        _lib.check(fwd(
             B, N, J, A_c.data_ptr(), xyz_c.data_ptr(), W_c.data_ptr(), _lib.ptr(rot_c),
             sc_c.data_ptr(), _lib.ptr(ss_c), _lib.ptr(tr_c), _lib.ptr(et_c), _lib.ptr(er_c),
             _lib.ptr(es_c), xyz_o.data_ptr(), rotq_o.data_ptr(), sc_o.data_ptr(), _lib.ptr(T_o), st),
             "sgs_lbs_fwd")
         ctx.save_for_backward(A_c, xyz_c, W_c, rot_c, sc_c, ss_c, tr_c, et_c, er_c, es_c)
+        ctx.rot6d = bool(rot6d)
         ctx.shapes = (A.shape, smpl_scale.shape if smpl_scale is not None else None,
                       transl.shape if transl is not None else None)
         if want_T:
@@ -118,13 +161,16 @@ class _DeformGaussians(torch.autograd.Function):
         g_scales = _c(g_scales) if g_scales is not None else z(B, N, 3)
         g_T = _c(g_T)
         d_xyz = torch.empty(N, 3, device=dev, dtype=torch.float32)
-        d_rot = torch.empty(N, 3, 3, device=dev, dtype=torch.float32) if rot_c is not None else None
+        d_rot = None
+        if rot_c is not None:
+            d_rot = torch.empty((N, 6) if ctx.rot6d else (N, 3, 3), device=dev, dtype=torch.float32)
         d_sc = torch.empty(N, 3, device=dev, dtype=torch.float32)
         d_A = z(B, J, 4, 4)
         d_ss = z(B) if ss_c is not None else None
         d_tr = z(B, 3) if tr_c is not None else None
         st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib().sgs_lbs_bwd(
+        bwd = _lib.lib().sgs_lbs_bwd_rot6d if ctx.rot6d else _lib.lib().sgs_lbs_bwd
+        _lib.check(bwd(
             B, N, J, A_c.data_ptr(), xyz_c.data_ptr(), W_c.data_ptr(), _lib.ptr(rot_c),
             sc_c.data_ptr(), _lib.ptr(ss_c), _lib.ptr(tr_c), _lib.ptr(et_c), _lib.ptr(er_c),
             _lib.ptr(es_c), g_xyz.data_ptr(), g_rotq.data_ptr(), g_scales.data_ptr(),
@@ -133,7 +179,7 @@ class _DeformGaussians(torch.autograd.Function):
         A_shape, ss_shape, tr_shape = ctx.shapes
         return (d_A.reshape(A_shape), d_xyz, None, d_rot, d_sc,
                 d_ss.reshape(ss_shape) if d_ss is not None else None,
-                d_tr.reshape(tr_shape) if d_tr is not None else None, None, None, None, None)
+                d_tr.reshape(tr_shape) if d_tr is not None else None, None, None, None, None, None)
 
 
 def deform_gaussians(A_cano2pose: torch.Tensor, xyz_canon: torch.Tensor,
@@ -141,11 +187,13 @@ def deform_gaussians(A_cano2pose: torch.Tensor, xyz_canon: torch.Tensor,
                      scales: torch.Tensor, smpl_scale: Optional[torch.Tensor] = None,
                      transl: Optional[torch.Tensor] = None,
                      ext_tfs: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
-                     return_T: bool = False):
+                     return_T: bool = False, rot6d_canon: Optional[torch.Tensor] = None):
     """Fused deform of every Gaussian.
 
     A_cano2pose (J,4,4) or (B,J,4,4); xyz_canon (N,3); lbs_weights (N,J);
-    rotmat_canon (N,3,3) or None (identity = the isotropic case, sings_hybrid.py:360);
+    rotmat_canon (N,3,3) or None (identity = the isotropic case, sings_hybrid.py:360) -- or
+    pass rot6d_canon (N,6), the stored parameter, and the kernel does rotation_6d_to_matrix
+    (sings_hybrid.py:354-356) itself, forward and backward, without the (N,3,3) round trip;
     scales (N,3); smpl_scale (1,) / (B,1) / (B,); transl (3,) / (B,3);
     ext_tfs = (trans (B,3)|(1,3), rotmat (B,3,3)|(1,3,3), scale (B,1)|(1,1)).
     Returns (xyz, rotq, scales[, T]) with a leading B dimension iff A had one."""
@@ -160,8 +208,13 @@ def deform_gaussians(A_cano2pose: torch.Tensor, xyz_canon: torch.Tensor,
         et = trans.reshape(-1, 3).expand(B, 3)
         er = rotmat.reshape(-1, 3, 3).expand(B, 3, 3)
         es = scale.reshape(-1).expand(B)
-    out = _DeformGaussians.apply(A, xyz_canon, lbs_weights, rotmat_canon, scales, ss, tr, et, er,
-                                 es, return_T)
+    if rot6d_canon is not None and rotmat_canon is not None:
+        raise ValueError("pass rotmat_canon or rot6d_canon, not both")
+    if rot6d_canon is not None and rot6d_canon.shape[-1] != 6:
+        raise ValueError("rot6d_canon must have shape (N, 6)")
+    out = _DeformGaussians.apply(A, xyz_canon, lbs_weights,
+                                 rot6d_canon if rot6d_canon is not None else rotmat_canon, scales,
+                                 ss, tr, et, er, es, return_T, rot6d_canon is not None)
     if single:
         out = tuple(o[0] for o in out)
     return out

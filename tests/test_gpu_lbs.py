@@ -100,3 +100,76 @@ def test_pose_to_A_identity_and_batch():
     A = deform.pose_to_A(torch.zeros(3, 24, 3, device="cuda"), torch.tensor(rest, dtype=torch.float32, device="cuda"),
                          torch.from_numpy(parents), None)
     assert (A.cpu() - torch.eye(4).expand(3, 24, 4, 4)).abs().max() < 1e-6
+
+
+def test_rot6d_conversions_against_reference_golden():
+    """rotation_6d_to_matrix / rotation_6d_to_axis_angle kernels (rotations.py:545-566, 601-603)
+    against vectors made by the reference's own functions; gradients against its float64 autograd."""
+    base = os.path.join(os.path.dirname(__file__), "golden", "rot6d_golden_")
+    g = {k: torch.from_numpy(v) for k, v in np.load(base + "f32.npz").items()}
+    g64 = {k: torch.from_numpy(v) for k, v in np.load(base + "f64.npz").items()}
+    d6 = g["d6"].cuda().requires_grad_(True)
+    R = deform.rotation_6d_to_matrix(d6)
+    aa = deform.rotation_6d_to_axis_angle(d6)
+    assert R.shape == (d6.shape[0], 3, 3) and aa.shape == (d6.shape[0], 3)
+    assert (R.detach().cpu() - g["R"]).abs().max() < VAL_TOL
+    # near pi the axis-angle is ill-conditioned in float32: compare with the float32 reference run
+    assert (aa.detach().cpu() - g["aa"]).abs().max() < 2e-4
+    well = (g64["aa"].norm(dim=-1) < 2.8)
+    assert (aa.detach().cpu()[well] - g64["aa"][well].float()).abs().max() < 2e-5
+    (dR,) = torch.autograd.grad((R * g["gR"].cuda()).sum(), d6, retain_graph=True)
+    (daa,) = torch.autograd.grad((aa * g["gaa"].cuda()).sum(), d6)
+    assert rel_err(dR.cpu().numpy(), g64["d_d6_from_R"].numpy()) < GRAD_TOL
+    assert rel_err(daa.cpu().numpy()[well], g64["d_d6_from_aa"].numpy()[well]) < GRAD_TOL
+    # batched leading dimensions, as the model stores them: (frames, 23, 6)
+    d = torch.randn(4, 23, 6, device="cuda")
+    assert deform.rotation_6d_to_axis_angle(d).shape == (4, 23, 3)
+    assert torch.equal(deform.rotation_6d_to_matrix(d).reshape(-1, 3, 3), deform.rotation_6d_to_matrix(d.reshape(-1, 6)))
+
+
+@pytest.mark.parametrize("N,J,B,ext", [(301, 24, 3, True), (5003, 52, 2, False), (200_000, 24, 1, False)])
+def test_deform_from_rot6d_vs_oracle(N, J, B, ext):
+    """The stored 6D canonical rotation goes straight into the LBS kernels (sings_hybrid.py:354-356
+    fused away): values equal the matrix path bit for bit, gradients w.r.t. the 6D parameter
+    match float64 autograd of the oracle."""
+    av = syn.make_avatar(N, J, seed=7)
+    gen = torch.Generator().manual_seed(N)
+    t = torch.from_numpy
+    d6 = torch.randn(N, 6, generator=gen)
+    pose = torch.stack([t(syn.random_pose(J, seed=b)) for b in range(B)])
+    A = lo.pose_to_A(pose, t(av.rest), av.parents, t(av.inv_A_t2cano))
+    transl = torch.randn(B, 3, generator=gen)
+    ss = 1.0 + 0.1 * torch.rand(B, 1, generator=gen)
+    ext_tfs = None
+    if ext:
+        ext_tfs = (torch.randn(B, 3, generator=gen), lo.batch_rodrigues(torch.randn(B, 3, generator=gen)),
+                   0.5 + torch.rand(B, 1, generator=gen))
+    gx, gq, gs = (torch.randn(B, N, k, generator=gen) for k in (3, 4, 3))
+    # float64 oracle
+    dd = lambda a: a.double()
+    d6o, xo_c, so_c = dd(d6).requires_grad_(True), dd(t(av.xyz_canon)).requires_grad_(True), dd(t(av.scales)).requires_grad_(True)
+    xo, qo, sco, _ = lo.deform(dd(A), xo_c, dd(t(av.lbs_weights)), so_c, None, dd(ss), dd(transl),
+                               tuple(dd(e) for e in ext_tfs) if ext else None, rot6d_canon=d6o)
+    ((xo * gx).sum() + (qo * gq).sum() + (sco * gs).sum()).backward()
+    # CUDA, 6D in
+    c = lambda a: a.cuda()
+    d6c, x_c, s_c = c(d6).requires_grad_(True), c(t(av.xyz_canon)).requires_grad_(True), c(t(av.scales)).requires_grad_(True)
+    ext_c = tuple(c(e) for e in ext_tfs) if ext else None
+    x, q, s = deform.deform_gaussians(c(A), x_c, c(t(av.lbs_weights)), None, s_c, c(ss), c(transl), ext_c,
+                                      rot6d_canon=d6c)
+    ((x * c(gx)).sum() + (q * c(gq)).sum() + (s * c(gs)).sum()).backward()
+    # CUDA, matrix in (the kernel pair, composed)
+    with torch.no_grad():
+        Rm = deform.rotation_6d_to_matrix(c(d6))
+        x2, q2, s2 = deform.deform_gaussians(c(A), c(t(av.xyz_canon)), c(t(av.lbs_weights)), Rm, c(t(av.scales)),
+                                             c(ss), c(transl), ext_c)
+    assert torch.equal(x.detach(), x2) and torch.equal(q.detach(), q2) and torch.equal(s.detach(), s2)
+    assert (x.detach().cpu() - xo.detach().float()).abs().max() < 2e-5
+    from oracle.raster_ref64 import quat_to_R
+    assert (quat_to_R(q.detach().cpu().reshape(-1, 4).double()) - quat_to_R(qo.detach().reshape(-1, 4))).abs().max() < 1e-4
+    assert d6c.grad.shape == (N, 6)
+    for name, got, ref in (("d_rot6d", d6c.grad, d6o.grad), ("d_xyz", x_c.grad, xo_c.grad), ("d_scales", s_c.grad, so_c.grad)):
+        e = rel_err(got.cpu().numpy(), ref.numpy())
+        assert e < GRAD_TOL, f"{name}: {e}"
+    with pytest.raises(ValueError):
+        deform.deform_gaussians(c(A), x_c, c(t(av.lbs_weights)), Rm, s_c, rot6d_canon=d6c)

@@ -55,3 +55,38 @@ def test_quaternion_not_normalised_and_identity_pose():
     xyz, q, sc, _ = lo.deform(A, g["xyz_canon"], g["lbs_weights"], g["scales"])
     assert (xyz[0] - g["xyz_canon"]).abs().max() < 1e-5
     assert (q[0] - torch.tensor([1.0, 0, 0, 0], dtype=q.dtype)).abs().max() < 1e-5
+
+
+ROT6D = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "rot6d_golden_*.npz")))
+
+
+@pytest.mark.parametrize("path", ROT6D, ids=[os.path.basename(p)[13:-4] for p in ROT6D])
+def test_rot6d_oracle_matches_reference_golden(path):
+    """rotation_6d_to_matrix / rotation_6d_to_axis_angle (rotations.py:545-566, 601-603) and their
+    autograd gradients, incl. far-from-unit inputs, small angles, the identity and angles near pi."""
+    g = load(path)
+    f64 = path.endswith("f64.npz")
+    tol = 1e-12 if f64 else 2e-6
+    d6 = g["d6"].requires_grad_(True)
+    R = lo.rotation_6d_to_matrix(d6)
+    aa = lo.rotation_6d_to_axis_angle(d6)
+    assert (R - g["R"]).abs().max() <= tol
+    assert (aa - g["aa"]).abs().max() <= tol * 10
+    d_R = torch.autograd.grad((R * g["gR"]).sum(), d6, retain_graph=True)[0]
+    d_aa = torch.autograd.grad((aa * g["gaa"]).sum(), d6)[0]
+    for got, name in ((d_R, "d_d6_from_R"), (d_aa, "d_d6_from_aa")):
+        ref = g[name]
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max() <= (1e-9 if f64 else 2e-3) * (ref.abs().max() + 1e-12), name
+
+
+def test_deform_rot6d_equals_matrix_path():
+    """deform(rot6d_canon=d6) == deform(rotmat_canon=rotation_6d_to_matrix(d6)) (sings_hybrid.py:354-356)."""
+    g = load([p for p in GOLD if "j24_aniso_ext_f64" in p][0])
+    N = g["xyz_canon"].shape[0]
+    d6 = torch.randn(N, 6, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    A = g["A_cano2pose"]
+    a = lo.deform(A, g["xyz_canon"], g["lbs_weights"], g["scales"], rot6d_canon=d6)
+    b = lo.deform(A, g["xyz_canon"], g["lbs_weights"], g["scales"], rotmat_canon=lo.rotation_6d_to_matrix(d6))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
