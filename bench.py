@@ -219,22 +219,22 @@ def gpu_arm(args):
                          projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(bg),
                          tanfovx=view.tanfovx, tanfovy=view.tanfovy)
         sets.append(dict(step=step, fr=fr, G=t(G), av=av, pose=pose, transl=transl, view=view, G_np=G, bg=bg))
-    exch = dp.GradExchange(N_GAUSS, sets[0]["step"].n_param_grads, dev) if world > 1 else None
+    exch = dp.GradExchange(N_GAUSS, sets[0]["step"].n_param_grads, dev,
+                           defer_max=not os.environ.get("SGS_DP_MAX_EVERY_STEP")) if world > 1 else None
 
     def one_step(i, pending):
         s = sets[i % RING]
         st = s["step"]
         if exch is not None and pending[i % RING] is not None:
-            pending[i % RING]()            # finish the all-reduce that last used this bucket
+            pending[i % RING]()            # finish the all-reduce that last used this bucket (folds + clears the step statistics)
             pending[i % RING] = None
-            st.grad_accum.zero_(); st.denom.zero_(); st.max_radii2D.zero_()
         if "replay" in s:
             s["replay"]()                  # the whole frame as one CUDA-graph launch
         else:
             st.forward(s["fr"])
             st.backward(s["G"])
         if exch is not None:
-            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True)
+            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)
 
     def barrier():
         if world > 1:
@@ -280,6 +280,8 @@ def gpu_arm(args):
         if pending[i] is not None:
             pending[i]()
             pending[i] = None
+    if exch is not None:
+        exch.sync_max()                    # the deferred all-reduce(MAX) of max_radii2D, inside the timed region
     e1.record()
     barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -454,9 +456,8 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         if i + 1 < n_total:
             prefetch(i + 1)
         if exch is not None and pending[i % RING] is not None:
-            pending[i % RING]()            # finish the all-reduce that last used this bucket
+            pending[i % RING]()            # finish the all-reduce that last used this bucket (folds + clears the step statistics)
             pending[i % RING] = None
-            st.grad_accum.zero_(); st.denom.zero_(); st.max_radii2D.zero_()
         cur.wait_event(sb["ready"])
         if replays[i % RING] is not None:
             replays[i % RING]()            # forward + loss + backward as one CUDA-graph launch
@@ -466,7 +467,7 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
             loss = torch.dot(img.view(-1), sb["G"].view(-1))      # L = sum(image * G); dL/dimage = G
             st.backward(sb["G"])
         if exch is not None:
-            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True)
+            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)
         finish_step(i, loss, sb)
 
     # ---- drop-in autograd path ----

@@ -117,6 +117,13 @@ int sgs_densify_stats(int P, const float* grad_means2D, const int* radii,
                       float* xyz_gradient_accum, float* denom, float* max_radii2D,
                       sgs_stream_t stream);
 
+/* Data-parallel step epilogue (views sharded over ranks): after the all-reduce of
+ * one step's statistics -- SUM for the xyz_gradient_accum / denom increments
+ * (sings_hybrid.py:1013-1015), MAX for the radii (gs_trainer.py:487-490) -- fold them into the
+ * persistent accumulators and zero the step buffers, in one launch. */
+int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii,
+                   float* xyz_gradient_accum, float* denom, float* max_radii2D, sgs_stream_t stream);
+
 /* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
  * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]
  * rasterizer_impl.cu).  The result is in (keys,vals) when *result_in_tmp (host) == 0, else

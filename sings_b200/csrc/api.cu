@@ -101,7 +101,7 @@ int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
     if (geom_bytes) *geom_bytes = l.geom_bytes;
     if (binning_bytes) *binning_bytes = l.bin_bytes;
     if (img_bytes) *img_bytes = l.img_bytes;
-    if (acc_bytes) *acc_bytes = align_up((size_t)(P > 0 ? P : 1) * ACC_FLOATS * 4, 256);
+    if (acc_bytes) *acc_bytes = acc_total_bytes(P);
     return 0;
 }
 
@@ -220,9 +220,9 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     if (P == 0) return 0;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     tick(timing, 5, stream);
-    SGS_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P * ACC_FLOATS * 4, stream));
+    SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), stream));
     rc = launch_blend_bwd(lay, W, H, (const char*)geom, (const char*)binning, (const char*)img, bg,
-                          dL_dout_color, (float*)acc, stream);
+                          dL_dout_color, (float*)acc, reinterpret_cast<int*>((char*)acc + acc_rows_bytes(P)), stream);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 6, stream);
@@ -250,6 +250,14 @@ int sgs_densify_stats(int P, const float* grad_means2D, const int* radii, float*
         return SGS_ERR_BAD_ARG;
     return launch_densify_stats(P, grad_means2D, radii, xyz_gradient_accum, denom, max_radii2D,
                                 (cudaStream_t)stream);
+}
+
+int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii,
+                   float* xyz_gradient_accum, float* denom, float* max_radii2D, sgs_stream_t stream) {
+    if (P < 0 || (P > 0 && (!step_accum || !step_denom || !step_max_radii || !xyz_gradient_accum || !denom || !max_radii2D)))
+        return SGS_ERR_BAD_ARG;
+    return launch_fold_stats(P, step_accum, step_denom, step_max_radii, xyz_gradient_accum, denom, max_radii2D,
+                             (cudaStream_t)stream);
 }
 
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }

@@ -49,6 +49,7 @@ enum : int {
     CNT_RANGES_DONE = 4,    // CTAs of the tile-range kernel that have finished
     CNT_VARBITS = 5,        // [5] = OR of the visible depth keys, [6] = OR of their complements
     CNT_SORT_TICKET0 = 8,   // + pass: block ticket of each radix pass (8 slots)
+    CNT_BLEND_TICKET = 16,  // item ticket of the forward blend (persistent warps)
     CNT_SLOTS = 32,
 };
 

@@ -34,4 +34,28 @@ int launch_densify_stats(int P, const float* grad2d, const int* radii, float* ac
     return 0;
 }
 
+// Data-parallel step epilogue: after the all-reduce, fold this step's statistics
+// (SUM-reduced accum / denom increments, MAX-reduced radii) into the persistent accumulators and
+// clear the step buffers for the next view -- one launch instead of three adds and three fills.
+__global__ void fold_stats_kernel(int P, float* __restrict__ step_accum, float* __restrict__ step_denom,
+                                  float* __restrict__ step_max_radii, float* __restrict__ accum,
+                                  float* __restrict__ denom, float* __restrict__ max_radii) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    accum[i] += step_accum[i];
+    denom[i] += step_denom[i];
+    max_radii[i] = fmaxf(max_radii[i], step_max_radii[i]);
+    step_accum[i] = 0.0f;
+    step_denom[i] = 0.0f;
+    step_max_radii[i] = 0.0f;
+}
+
+int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
+                      float* denom, float* max_radii, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    fold_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, step_accum, step_denom, step_max_radii, accum, denom, max_radii);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace sgs

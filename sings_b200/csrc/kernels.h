@@ -16,6 +16,10 @@ constexpr int REC_FLOATS = 16;
 
 // floats per Gaussian in the blend-backward accumulator
 constexpr int ACC_FLOATS = 12;
+// backward accumulator buffer: P rows of ACC_FLOATS, then one 256-byte line of counters (the item
+// ticket of the backward blend) -- zeroed together by one memset per backward
+inline size_t acc_rows_bytes(int P) { return ((size_t)(P > 0 ? P : 1) * ACC_FLOATS * 4 + 255) / 256 * 256; }
+inline size_t acc_total_bytes(int P) { return acc_rows_bytes(P) + 256; }
 // accumulator layout: [0]=dL/dmean2D.x, [1]=.y, [2]=dL/dconic.a, [3]=dL/dconic.b (un-doubled),
 // [4]=dL/dconic.c, [5]=dL/dopacity, [6..8]=dL/dcolor rgb, [9..11] unused
 
@@ -87,7 +91,7 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
                      float* out_depth, cudaStream_t stream);
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
-                     const char* img, const float* bg, const float* dL_dpix, float* acc,
+                     const char* img, const float* bg, const float* dL_dpix, float* acc, int* ticket,
                      cudaStream_t stream);
 
 struct GeomBwdArgs {
@@ -111,6 +115,8 @@ int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t str
 int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
                         cudaStream_t stream);
 
+int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
+                      float* denom, float* max_radii, cudaStream_t stream);
 int launch_densify_stats(int P, const float* grad2d, const int* radii, float* accum, float* denom,
                          float* max_radii, cudaStream_t stream);
 

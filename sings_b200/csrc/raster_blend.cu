@@ -43,10 +43,13 @@ namespace sgs {
 #define SGS_BWD_P2ROW 1
 #endif
 #ifndef SGS_FWD_WPC              // warps per CTA of the blend kernels: the 8 warps of a tile are autonomous,
-#define SGS_FWD_WPC 8            // so a tile may be spread over 8 / WPC smaller CTAs (finer scheduling grain)
+#define SGS_FWD_WPC 4            // so a tile may be spread over 8 / WPC smaller CTAs (finer scheduling grain)
 #endif
 #ifndef SGS_BWD_WPC
-#define SGS_BWD_WPC 8
+#define SGS_BWD_WPC 4
+#endif
+#ifndef SGS_BLEND_PERSIST        // 1: persistent warps take (tile, pixel block) items from a device-side ticket
+#define SGS_BLEND_PERSIST 0      // counter, longest lists first; 0: one CTA per WPC pixel blocks of a tile
 #endif
 constexpr int FWD_WPC = SGS_FWD_WPC, BWD_WPC = SGS_BWD_WPC;
 constexpr int TILE_WARPS = TILE_PIX / 32;
@@ -113,22 +116,102 @@ __device__ __forceinline__ void tile_ranges_block(int block, const unsigned long
     if (ok) bucket_list[(size_t)bk * tiles + slot + __popc(peers & lanemask_lt())] = (unsigned)tt;
 }
 
-// The i-th tile in longest-bucket-first order (whole warp calls it with the same i).
-__device__ __forceinline__ unsigned tile_of_rank(const unsigned* __restrict__ bucket_count,
-                                                 const unsigned* __restrict__ bucket_list, int tiles,
-                                                 unsigned i) {
+// The i-th tile in longest-bucket-first order (whole warp calls it with the same i).  The bucket
+// prefix sums depend only on the frame, so a persistent warp builds them once (BucketScan: lane l
+// holds bucket LEN_BUCKETS-1-l, lane 0 = longest) and a rank costs one load afterwards.
+struct BucketScan {
+    unsigned cnt, incl;
+};
+__device__ __forceinline__ BucketScan bucket_scan(const unsigned* __restrict__ bucket_count) {
     const int lane = threadIdx.x & 31;
-    const unsigned cnt = __ldg(bucket_count + (LEN_BUCKETS - 1 - lane));    // lane 0 = longest bucket
-    unsigned incl = cnt;
+    BucketScan b;
+    b.cnt = __ldg(bucket_count + (LEN_BUCKETS - 1 - lane));
+    b.incl = b.cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned x = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += x;
+        unsigned x = __shfl_up_sync(0xffffffffu, b.incl, d);
+        if (lane >= d) b.incl += x;
     }
-    const unsigned before = __ballot_sync(0xffffffffu, incl <= i);          // buckets entirely before i
+    return b;
+}
+__device__ __forceinline__ unsigned tile_of_rank(const BucketScan& bs, const unsigned* __restrict__ bucket_list,
+                                                 int tiles, unsigned i) {
+    const unsigned before = __ballot_sync(0xffffffffu, bs.incl <= i);       // buckets entirely before i
     const int b = __popc(before);                                           // lane holding the bucket of i
-    const unsigned excl = __shfl_sync(0xffffffffu, incl - cnt, b & 31);
+    const unsigned excl = __shfl_sync(0xffffffffu, bs.incl - bs.cnt, b & 31);
     return __ldg(bucket_list + (size_t)(LEN_BUCKETS - 1 - b) * tiles + (i - excl));
+}
+
+// Work distribution of the two blend kernels.  An item is (tile rank, pixel block): the 8 warps
+// of a tile are autonomous, so items are handed out one per WARP, in rank order (longest lists
+// first), from a device-side ticket counter: no CTA waits for its slowest warp, the ~3/4 of the
+// tiles that are empty cost a loop trip instead of a CTA launch, and the tail is one warp deep.
+// The next ticket is requested before the current item is processed (its latency is hidden).
+// for_each_item(fn): fn(tile, warp) with warp = pixel block 0..7 of the tile.
+template <int WPC, typename Fn>
+__device__ __forceinline__ void for_each_item(const unsigned* __restrict__ bucket_count,
+                                              const unsigned* __restrict__ bucket_list, int tiles,
+                                              int* __restrict__ ticket, Fn fn) {
+    const int lane = threadIdx.x & 31;
+    const BucketScan bs = bucket_scan(bucket_count);
+#if SGS_BLEND_PERSIST == 2
+    // CTA-level tickets: an item is (tile rank, group of WPC pixel blocks); the CTA's warps work on
+    // the same tile at the same time, so its list, masks and records are shared through L1
+    constexpr int PARTS = TILE_WARPS / WPC;
+    __shared__ unsigned s_item;
+    const unsigned n_items = (unsigned)tiles * PARTS;
+    unsigned next = 0;
+    if (threadIdx.x == 0) s_item = (unsigned)atomicAdd(ticket, 1);
+    __syncthreads();
+    for (;;) {
+        const unsigned item = s_item;
+        if (item >= n_items) break;
+        if (threadIdx.x == 0) next = (unsigned)atomicAdd(ticket, 1);     // consumed after the item
+        fn(tile_of_rank(bs, bucket_list, tiles, item / PARTS), (int)(item % PARTS) * WPC + (int)(threadIdx.x >> 5));
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = next;
+        __syncthreads();
+    }
+#elif SGS_BLEND_PERSIST
+    const unsigned n_items = (unsigned)tiles * TILE_WARPS;
+    unsigned next = lane == 0 ? (unsigned)atomicAdd(ticket, 1) : 0u;
+    for (;;) {
+        const unsigned item = __shfl_sync(0xffffffffu, next, 0);
+        if (item >= n_items) break;
+        if (lane == 0) next = (unsigned)atomicAdd(ticket, 1);
+        fn(tile_of_rank(bs, bucket_list, tiles, item / TILE_WARPS), (int)(item % TILE_WARPS));
+        __syncwarp();
+    }
+#else
+    constexpr int PARTS = TILE_WARPS / WPC;      // CTAs per tile
+#ifdef SGS_DEBUG_TOPK            // timing experiment only: process just the K longest tiles (wrong results)
+    if ((int)(blockIdx.x / PARTS) >= SGS_DEBUG_TOPK) return;
+#endif
+    fn(tile_of_rank(bs, bucket_list, tiles, blockIdx.x / PARTS),
+       (int)(blockIdx.x % PARTS) * WPC + (int)(threadIdx.x >> 5));
+#endif
+}
+
+// persistent grid: every SM filled with as many CTAs as fit (cached occupancy query)
+template <typename Kern>
+static int persistent_blocks(Kern k, int threads, size_t smem, long long max_blocks) {
+    static const void* c_k[4];
+    static size_t c_smem[4];
+    static int c_blocks[4];
+    static int c_n = 0;
+    int blocks = 0;
+    for (int i = 0; i < c_n; i++)
+        if (c_k[i] == (const void*)k && c_smem[i] == smem) blocks = c_blocks[i];
+    if (!blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess || per_sm < 1)
+            return 0;
+        blocks = sms * per_sm;
+        if (c_n < 4) { c_k[c_n] = (const void*)k; c_smem[c_n] = smem; c_blocks[c_n] = blocks; c_n++; }
+    }
+    return (int)(blocks < max_blocks ? blocks : max_blocks);
 }
 
 static inline const unsigned long long* sorted_keys(const RasterLayout& lay, const char* bin) {
@@ -277,16 +360,21 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
-                 float* __restrict__ out_depth) {
+                 float* __restrict__ out_depth, int* __restrict__ ticket) {
     __shared__ float4 s_q0[FWD_WPC][RING_SLOTS];     // x, y, -a/2, -b
     __shared__ float4 s_q1[FWD_WPC][RING_SLOTS];     // -c/2, opacity, pmin, r
     __shared__ float4 s_q2[FWD_WPC][RING_SLOTS];     // g, b, depth, list position + 1
 
-    constexpr int PARTS = TILE_WARPS / FWD_WPC;      // CTAs per tile
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
-    const int warp = (int)(blockIdx.x % PARTS) * FWD_WPC + cwarp;      // pixel block of the tile
+    float4* const rq0 = s_q0[cwarp];
+    float4* const rq1 = s_q1[cwarp];
+    float4* const rq2 = s_q2[cwarp];
+    // ring slots always hold finite records (an empty slot contributes colour * 0)
+    rq0[lane] = rq0[lane + 32] = make_float4(0, 0, 0, 0);
+    rq1[lane] = rq1[lane + 32] = make_float4(0, 0, 0, 0);
+    rq2[lane] = rq2[lane + 32] = make_float4(0, 0, 0, 0);
     pdl_sync();
-    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x / PARTS);
+  for_each_item<FWD_WPC>(bucket_count, bucket_list, tiles, ticket, [&](const unsigned tile, const int warp) {
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
@@ -297,9 +385,6 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2)), by1 = by0 + 3.0f;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
-    float4* const rq0 = s_q0[cwarp];
-    float4* const rq1 = s_q1[cwarp];
-    float4* const rq2 = s_q2[cwarp];
 
     bool done = !inside;
     float T = 1.0f, T_fin = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dacc = 0.0f;
@@ -352,11 +437,6 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
     };
 
-    // ring slots always hold finite records (an empty slot contributes colour * 0)
-    rq0[lane] = rq0[lane + 32] = make_float4(0, 0, 0, 0);
-    rq1[lane] = rq1[lane + 32] = make_float4(0, 0, 0, 0);
-    rq2[lane] = rq2[lane + 32] = make_float4(0, 0, 0, 0);
-
     // Staging pipeline, per chunk of 32 list entries (one per lane): reach-mask bytes run four
     // chunks ahead, Gaussian ids of the relevant entries two chunks ahead, their records one
     // chunk ahead -- the dependent mask -> id -> record gather never sits on the critical path,
@@ -407,19 +487,26 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         if (out_alpha) out_alpha[pix] = __fsub_rn(1.0f, Tr);
         if (out_depth) out_depth[pix] = Dacc;
     }
+  });
 }
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
                      float* out_depth, cudaStream_t stream) {
-    launch_pdl(blend_fwd_kernel, lay.tiles * (TILE_WARPS / FWD_WPC), FWD_WPC * 32, 0, stream,
+    long long blocks = (long long)lay.tiles * (TILE_WARPS / FWD_WPC);
+#if SGS_BLEND_PERSIST
+    blocks = persistent_blocks(blend_fwd_kernel, FWD_WPC * 32, 0, blocks);
+    if (blocks < 1) return SGS_ERR_BAD_ARG;
+#endif
+    launch_pdl(blend_fwd_kernel, (unsigned)blocks, FWD_WPC * 32, 0, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
-        reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth);
+        reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth,
+        reinterpret_cast<int*>(const_cast<char*>(bin) + lay.cnt_off) + CNT_BLEND_TICKET);
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -464,14 +551,16 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
-                 const float* __restrict__ dL_dpix, float* __restrict__ acc) {
+                 const float* __restrict__ dL_dpix, float* __restrict__ acc, int* __restrict__ ticket) {
     extern __shared__ __align__(16) char s_bwd_raw[];
-    constexpr int PARTS = TILE_WARPS / BWD_WPC;      // CTAs per tile
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
-    const int warp = (int)(blockIdx.x % PARTS) * BWD_WPC + cwarp;      // pixel block of the tile
     BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[cwarp];
+    // ring slots always hold finite records
+    sm.q0[lane] = sm.q0[lane + 32] = make_float4(0, 0, 0, 0);
+    sm.q1[lane] = sm.q1[lane + 32] = make_float4(0, 0, 0, 0);
+    sm.q2[lane] = sm.q2[lane + 32] = make_float4(0, 0, 0, 0);
     pdl_sync();
-    const unsigned tile = tile_of_rank(bucket_count, bucket_list, tiles, blockIdx.x / PARTS);
+  for_each_item<BWD_WPC>(bucket_count, bucket_list, tiles, ticket, [&](const unsigned tile, const int warp) {
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
@@ -494,10 +583,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     sm.dp[0][lane] = dp0; sm.dp[1][lane] = dp1; sm.dp[2][lane] = dp2;
     const float nTf_bg = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
-    // ring slots always hold finite records
-    sm.q0[lane] = sm.q0[lane + 32] = make_float4(0, 0, 0, 0);
-    sm.q1[lane] = sm.q1[lane + 32] = make_float4(0, 0, 0, 0);
-    sm.q2[lane] = sm.q2[lane + 32] = make_float4(0, 0, 0, 0);
 
     float T = T_final;
     float B0 = 0.0f, B1 = 0.0f, B2 = 0.0f;     // colour accumulated behind the current pair
@@ -682,21 +767,27 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         if (!cur_is_b) seq(bat_b, head); else seq(bat_a, head);
     }
     if (tail > row0) reduce_rows(tail - row0);
+  });
 }
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
-                     const char* img, const float* bg, const float* dL_dpix, float* acc,
+                     const char* img, const float* bg, const float* dL_dpix, float* acc, int* ticket,
                      cudaStream_t stream) {
     const size_t smem = sizeof(BwdWarpSmem) * BWD_WPC;
     SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(blend_bwd_kernel, lay.tiles * (TILE_WARPS / BWD_WPC), BWD_WPC * 32, smem, stream,
+    long long blocks = (long long)lay.tiles * (TILE_WARPS / BWD_WPC);
+#if SGS_BLEND_PERSIST
+    blocks = persistent_blocks(blend_bwd_kernel, BWD_WPC * 32, smem, blocks);
+    if (blocks < 1) return SGS_ERR_BAD_ARG;
+#endif
+    launch_pdl(blend_bwd_kernel, (unsigned)blocks, BWD_WPC * 32, smem, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
-        reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc);
+        reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc, ticket);
     SGS_LAUNCH_OK();
     return 0;
 }

@@ -42,7 +42,11 @@ class GradExchange:
     """
 
     def __init__(self, n_gaussians: int, n_param_grads: int, device, group=None,
-                 average_grads: bool = False):
+                 average_grads: bool = False, defer_max: bool = False):
+        # defer_max: max is idempotent and commutes with the running maximum over steps, so the
+        # cross-rank MAX of max_radii2D can be taken once when the statistics are consumed
+        # (sync_max(), at densification time) instead of every step: one collective per step.
+        self.defer_max = defer_max
         self.N = n_gaussians
         self.n_param_grads = n_param_grads
         self.group = group
@@ -54,27 +58,48 @@ class GradExchange:
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def exchange(self, bucket: torch.Tensor, max_radii: torch.Tensor, async_op: bool = False):
+    def exchange(self, bucket: torch.Tensor, max_radii: torch.Tensor, async_op: bool = False,
+                 reset_step: bool = False):
         """All-reduce one step's bucket (SUM) and radii (MAX) in place and fold the statistics
         into the persistent accumulators.  With async_op=True returns a finish() callable so
-        the exchange overlaps whatever the caller launches next."""
+        the exchange overlaps whatever the caller launches next.  reset_step=True also clears
+        the step's statistics (the bucket's accum / denom slices and max_radii) for the next
+        view; on CUDA the fold and the clearing are one kernel (sgs_fold_stats)."""
         handles = []
         if self.world > 1:
             handles.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-            handles.append(dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
+            if not self.defer_max:
+                handles.append(dist.all_reduce(max_radii, op=dist.ReduceOp.MAX, group=self.group, async_op=True))
 
         def finish():
             for h in handles:
                 h.wait()
-            n = self.n_param_grads
+            n, N = self.n_param_grads, self.N
             if self.average and self.world > 1:
                 bucket[:n].div_(self.world)
-            self.xyz_gradient_accum += bucket[n:n + self.N]
-            self.denom += bucket[n + self.N:n + 2 * self.N]
-            torch.maximum(self.max_radii2D, max_radii, out=self.max_radii2D)
+            s_acc, s_den = bucket[n:n + N], bucket[n + N:n + 2 * N]
+            if bucket.is_cuda and reset_step:
+                from . import _lib
+                _lib.check(_lib.lib().sgs_fold_stats(
+                    N, s_acc.data_ptr(), s_den.data_ptr(), max_radii.data_ptr(),
+                    self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(), self.max_radii2D.data_ptr(),
+                    torch.cuda.current_stream(bucket.device).cuda_stream), "sgs_fold_stats")
+            else:
+                self.xyz_gradient_accum += s_acc
+                self.denom += s_den
+                torch.maximum(self.max_radii2D, max_radii, out=self.max_radii2D)
+                if reset_step:
+                    s_acc.zero_(); s_den.zero_(); max_radii.zero_()
             return bucket[:n]
 
         return finish if async_op else finish()
+
+    def sync_max(self):
+        """With defer_max: the one all-reduce(MAX) that makes max_radii2D global; call before the
+        statistics are read (gs_trainer.py:487-490 consumes them at densification time)."""
+        if self.defer_max and self.world > 1:
+            dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=self.group)
+        return self.max_radii2D
 
     def reset(self):
         self.xyz_gradient_accum.zero_()
@@ -94,6 +119,12 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     when WORLD_SIZE > 1 (backend nccl on CUDA, gloo otherwise)."""
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The exchange overlaps the next frame (it has RING-1 frames of slack), so it should be thin
+    # rather than fast: a cap on NCCL's CTAs keeps it from taking SMs and HBM bandwidth from the
+    # memory-bound head of the next frame.  Measured (profiles/README.md, v7), frames/s at 2 GPUs:
+    # NCCL's default 3708; capped at 32 CTAs 3831, 16 4006, 8 3967, 6 3875, 4 2770 (the exchange
+    # becomes the bottleneck); at 8 GPUs: 32 CTAs 13548, 16 13752, 8 14334.
+    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("SGS_NCCL_MAX_CTAS", "8"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():

@@ -63,6 +63,25 @@ def _worker(rank, world, port, q):
         mx = torch.maximum(mx, exp_max)
         assert torch.allclose(ex.xyz_gradient_accum, accum, atol=1e-5)
         assert torch.allclose(ex.denom, den) and torch.equal(ex.max_radii2D, mx)
+    # deferred MAX + reset_step: one collective per step; the radii become global at sync_max()
+    ex2 = dp.GradExchange(N, n_param, "cpu", defer_max=True)
+    local_mx = torch.zeros(N)
+    all_mx = torch.zeros(N)
+    for step in range(2):
+        bucket = torch.full((n_param + 2 * N,), float(rank + 1))
+        radii = torch.full((N,), float(10 * step + rank))
+        radii[rank] = 99.0 + rank                       # an entry only this rank makes large
+        local_mx = torch.maximum(local_mx, radii)
+        for rr in range(world):
+            rd = torch.full((N,), float(10 * step + rr))
+            rd[rr] = 99.0 + rr
+            all_mx = torch.maximum(all_mx, rd)
+        grads = ex2.exchange(bucket, radii, async_op=True, reset_step=True)()
+        assert torch.equal(grads, torch.full((n_param,), float(sum(range(1, world + 1)))))
+        assert torch.equal(ex2.max_radii2D, local_mx)                  # still local
+        assert float(bucket[n_param:].abs().max()) == 0.0 and float(radii.abs().max()) == 0.0   # step buffers cleared
+    assert torch.equal(ex2.sync_max(), all_mx)
+    assert torch.equal(ex2.denom, torch.full((N,), 2.0 * sum(range(1, world + 1))))
     t = torch.full((4,), float(rank))
     dp.broadcast_parameters([t], src=1)
     assert torch.equal(t, torch.ones(4))
