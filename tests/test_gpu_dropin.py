@@ -239,3 +239,74 @@ def test_config_c1_neutral_pose_sh0_512():
                     shs=av.shs, scales=step.sc[0].cpu().numpy(), rotations=step.rotq[0].cpu().numpy(), sh_degree=0)
     assert np.array_equal(step.radii.cpu().numpy(), st.radii)
     assert np.array_equal(img.cpu().numpy(), st.color)
+
+
+def test_config_c3_turnaround_views_gradient_accumulation():
+    """BASELINE.json configs[2]: human_complex-style step, 300k Gaussians, a batch of 8 synthetic
+    turn-around views at 1024^2.  One GPU plays the 8 ranks in turn (the multi-rank exchange is
+    covered by tests/test_dp_gloo.py): per view AvatarStep forward+backward, the per-view
+    buckets summed and the statistics folded by GradExchange exactly as bench.py does under
+    torchrun.  Checked against the oracle chain (C rasterizer forward/backward + float64 autograd
+    of the LBS restatement): every image bit for bit, the batch gradient of every canonical
+    parameter within 1e-3, the densification statistics of the batch."""
+    from oracle import lbs_oracle as lo
+    from sings_b200 import dp
+    from sings_b200 import synthetic as syn
+    N, H, W, V = 300_000, 1024, 1024, 8
+    sc = make_scene(N=N, H=H, W=W, seed=21, scale_range=(0.002, 0.010))
+    av = sc["avatar"]
+    step = _avatar_step(sc, H, W, 3)
+    ex = dp.GradExchange(N, step.n_param_grads, "cuda", defer_max=True)
+    bg = np.ones(3, np.float32)
+    tz = float(sc["transl"][2])
+    views = [syn.make_view(H, W, yaw=2.0 * math.pi * k / V, centre=(0.0, 0.0, tz)) for k in range(V)]
+    rng = np.random.default_rng(33)
+    total = torch.zeros(step.n_param_grads, device="cuda")
+    d_pose = []
+    # oracle accumulators
+    t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double()
+    xyz_c, rot_c, scl_c = t64(av.xyz_canon).requires_grad_(True), t64(av.rotmat_canon).requires_grad_(True), t64(av.scales).requires_grad_(True)
+    A64 = t64(sc["A"])[None]
+    xyz64, q64, s64, _ = lo.deform(A64, xyz_c, t64(av.lbs_weights), scl_c, rot_c, None, t64(sc["transl"])[None])
+    o_sh, o_op = np.zeros_like(av.shs, dtype=np.float64), np.zeros_like(av.opacity, dtype=np.float64)
+    o_accum, o_denom, o_maxr = np.zeros(N), np.zeros(N), np.zeros(N)
+    g_xyz, g_q, g_s = np.zeros((N, 3)), np.zeros((N, 4)), np.zeros((N, 3))
+    for k, view in enumerate(views):
+        G = rng.normal(size=(3, H, W)).astype(np.float32)
+        sck = dict(sc, view=view)
+        img = step.forward(_frame(sck)).clone()
+        step.backward(torch.from_numpy(G).cuda())
+        total += step.bucket[:step.n_param_grads]
+        d_pose.append(step.d_pose.clone())
+        ex.exchange(step.bucket, step.max_radii2D, async_op=True, reset_step=True)()
+        torch.cuda.synchronize()
+        assert step.check_capacity() > 0
+        # the oracle rasterizes what the CUDA deformer produced (LBS parity is tolerance-based,
+        # tests/test_gpu_lbs.py), so the images can be compared bit for bit
+        npy = lambda x: np.ascontiguousarray(x[0].cpu().numpy())
+        st = ro.forward(oracle_camera(view), npy(step.xyz), sc["opacity"], bg, sh_degree=3, shs=sc["shs"],
+                        scales=npy(step.sc), rotations=npy(step.rotq))
+        assert np.array_equal(img.cpu().numpy(), st.color), f"view {k}: image must be bit-exact"
+        assert np.array_equal(step.radii.cpu().numpy(), st.radii)
+        gr = ro.backward(st, G)
+        g_xyz += gr["means3D"]; g_q += gr["rotations"]; g_s += gr["scales"]
+        o_sh += gr["sh"]; o_op += gr["opacities"]
+        vis = st.radii > 0
+        o_accum[vis] += np.linalg.norm(gr["means2D"][vis, :2].astype(np.float64), axis=1)
+        o_denom[vis] += 1.0
+        o_maxr = np.maximum(o_maxr, np.where(vis, st.radii, 0).astype(np.float64))
+    ((xyz64[0] * t64(g_xyz)).sum() + (q64[0] * t64(g_q)).sum() + (s64[0] * t64(g_s)).sum()).backward()
+    n3, n9, M = 3 * N, 9 * N, av.shs.shape[1]
+    got = total.cpu().numpy().astype(np.float64)
+    parts = [("xyz_canon", got[:n3], xyz_c.grad.numpy().ravel()),
+             ("scales", got[n3:2 * n3], scl_c.grad.numpy().ravel()),
+             ("rot_canon", got[2 * n3:2 * n3 + n9], rot_c.grad.numpy().ravel()),
+             ("opacity", got[2 * n3 + n9:2 * n3 + n9 + N], o_op.ravel()),
+             ("shs", got[2 * n3 + n9 + N:2 * n3 + n9 + N + 3 * M * N], o_sh.ravel())]
+    for name, a, b in parts:
+        assert rel_err(a, b) < 1e-3, f"batch gradient {name}: {rel_err(a, b)}"
+    assert np.array_equal(ex.denom.cpu().numpy(), o_denom.astype(np.float32))
+    assert np.array_equal(ex.sync_max().cpu().numpy(), o_maxr.astype(np.float32))
+    assert rel_err(ex.xyz_gradient_accum.cpu().numpy(), o_accum) < 1e-3
+    assert float(step.bucket[step.n_param_grads:].abs().max()) == 0.0 and float(step.max_radii2D.abs().max()) == 0.0
+    assert all(torch.isfinite(p).all() for p in d_pose)
