@@ -175,7 +175,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
         if (rc) return rc;
         rc = launch_emit_pairs(P, lay, L_cap, b, stream);     // scan + (tile|depth, id) pairs in depth order
         if (rc) return rc;
-        rc = launch_tile_sort(lay, L_cap, b, stream, debug);  // stable passes over the tile-id digits (L items)
+        rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
         if (rc) return rc;
     }
     tick(timing, 2, stream);

@@ -92,6 +92,51 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Where the per-pair reach masks are computed (A/B knob): 1 = by the last tile-id pass of the
+// pair sort, for every pair it scatters (the pair's tile and Gaussian id are in registers
+// there); 0 = by a pass of its own over the sorted list (ranges_masks_kernel).  Measured (v7):
+// in the sort the stage pair sort + ranges goes 74.8 + 20.5 -> 86.0 + 10.2 us, i.e. nothing is
+// gained -- the record gather delays the pass's scatter as much as the separate pass costs.
+#ifndef SGS_MASKS_IN_SORT
+#define SGS_MASKS_IN_SORT 0
+#endif
+
+// Reach mask of a (tile, Gaussian) pair: bit w says whether the Gaussian's alpha >= 1/255
+// footprint can touch 8x4 pixel block w of the tile (w = blend warp index): reaches_block for
+// the 2 x 4 blocks, sharing the per-column / per-row terms.  Computed ONCE per frame and pair;
+// the forward and the backward blend then stream one byte per pair and gather the 64-byte
+// record only for the ~10 % of (warp, pair) combinations that can contribute.
+__device__ __forceinline__ unsigned reach_mask(const float4 q0, const float4 q1, const float4 q3,
+                                               float tx, float ty) {
+    const float a = -2.0f * q0.z, b2 = -2.0f * q0.w, c = -2.0f * q1.x;
+    float X0[2], X1[2], cx[2], acx2[2], bcx[2], ycx[2];
+    float Y0[4], Y1[4], cy[4], ccy2[4], bcy[4], xcy[4];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        X0[k] = tx + (float)(8 * k) - q0.x; X1[k] = X0[k] + 7.0f;
+        cx[k] = fminf(fmaxf(0.0f, X0[k]), X1[k]);
+        acx2[k] = a * cx[k] * cx[k]; bcx[k] = b2 * cx[k]; ycx[k] = q3.y * cx[k];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        Y0[r] = ty + (float)(4 * r) - q0.y; Y1[r] = Y0[r] + 3.0f;
+        cy[r] = fminf(fmaxf(0.0f, Y0[r]), Y1[r]);
+        ccy2[r] = c * cy[r] * cy[r]; bcy[r] = b2 * cy[r]; xcy[r] = q3.z * cy[r];
+    }
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PIX / 32; w++) {
+        const int k = w & 1, r = w >> 1;
+        const float dy1 = fminf(fmaxf(ycx[k], Y0[r]), Y1[r]);       // minimiser on the edge x = cx
+        const float dx2 = fminf(fmaxf(xcy[r], X0[k]), X1[k]);       // minimiser on the edge y = cy
+        const float qa = fmaf(dy1, fmaf(c, dy1, bcx[k]), acx2[k]);
+        const float qb = fmaf(dx2, fmaf(a, dx2, bcy[r]), ccy2[r]);
+        if (fminf(qa, qb) <= q3.x) m |= 1u << w;
+    }
+    return m;
+}
+
+
 // ---- scoped loads/stores for the decoupled look-back status words ----
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;

@@ -74,7 +74,7 @@ int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t st
 // chained scan of tiles touched + (tile|depth, id) emission in depth order
 int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
 // stable passes over the tile-id digits of the emitted pairs
-int launch_tile_sort(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream,
+int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom, char* bin, cudaStream_t stream,
                      int debug);
 // stand-alone sort (A/B against CUB): sorts n pairs on key bits [0,end_bit)
 int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned long long* keys_tmp,

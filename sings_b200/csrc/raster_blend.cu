@@ -255,41 +255,6 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
     return r;
 }
 
-// Reach mask of a (tile, Gaussian) pair: bit w says whether the Gaussian's alpha >= 1/255
-// footprint can touch 8x4 pixel block w of the tile (w = blend warp index): reaches_block for
-// the 2 x 4 blocks, sharing the per-column / per-row terms.  Computed ONCE per frame and pair;
-// the forward and the backward blend then stream one byte per pair and gather the 64-byte
-// record only for the ~10 % of (warp, pair) combinations that can contribute.
-__device__ __forceinline__ unsigned reach_mask(const float4 q0, const float4 q1, const float4 q3,
-                                               float tx, float ty) {
-    const float a = -2.0f * q0.z, b2 = -2.0f * q0.w, c = -2.0f * q1.x;
-    float X0[2], X1[2], cx[2], acx2[2], bcx[2], ycx[2];
-    float Y0[4], Y1[4], cy[4], ccy2[4], bcy[4], xcy[4];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        X0[k] = tx + (float)(8 * k) - q0.x; X1[k] = X0[k] + 7.0f;
-        cx[k] = fminf(fmaxf(0.0f, X0[k]), X1[k]);
-        acx2[k] = a * cx[k] * cx[k]; bcx[k] = b2 * cx[k]; ycx[k] = q3.y * cx[k];
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        Y0[r] = ty + (float)(4 * r) - q0.y; Y1[r] = Y0[r] + 3.0f;
-        cy[r] = fminf(fmaxf(0.0f, Y0[r]), Y1[r]);
-        ccy2[r] = c * cy[r] * cy[r]; bcy[r] = b2 * cy[r]; xcy[r] = q3.z * cy[r];
-    }
-    unsigned m = 0;
-#pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; w++) {
-        const int k = w & 1, r = w >> 1;
-        const float dy1 = fminf(fmaxf(ycx[k], Y0[r]), Y1[r]);       // minimiser on the edge x = cx
-        const float dx2 = fminf(fmaxf(xcy[r], X0[k]), X1[k]);       // minimiser on the edge y = cy
-        const float qa = fmaf(dy1, fmaf(c, dy1, bcx[k]), acx2[k]);
-        const float qb = fmaf(dx2, fmaf(a, dx2, bcy[r]), ccy2[r]);
-        if (fminf(qa, qb) <= q3.x) m |= 1u << w;
-    }
-    return m;
-}
-
 // Tile ranges and reach masks in ONE launch (both only read the sorted list): the first
 // `range_blocks` CTAs search the ranges of 8 tiles each (a chain of dependent probes, so they
 // start first), the others compute one reach mask per thread.  (A per-tile shared-memory
@@ -306,6 +271,7 @@ ranges_masks_kernel(const unsigned long long* __restrict__ keys, const unsigned*
         tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
         return;
     }
+    if (!masks) return;              // the masks came out of the last sort pass (radix_sort.cu)
     const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
     const long long i = (long long)(blockIdx.x - range_blocks) * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -322,13 +288,14 @@ int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* ge
     const int range_blocks = (lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32);
     long long blocks = (L_cap + RANGE_THREADS - 1) / RANGE_THREADS;
     if (blocks < 1) blocks = 1;
+    if (SGS_MASKS_IN_SORT) blocks = 0;       // only the tile-range CTAs
     launch_pdl(ranges_masks_kernel, (unsigned)(range_blocks + blocks), RANGE_THREADS, 0, stream,
         sorted_keys(lay, bin), sorted_vals(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
         reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx, lay.tiles, range_blocks,
         reinterpret_cast<uint2*>(bin + lay.ranges_off),
         reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<unsigned*>(bin + lay.bktlist_off),
-        reinterpret_cast<unsigned char*>(bin + lay.masks_off));
+        SGS_MASKS_IN_SORT ? nullptr : reinterpret_cast<unsigned char*>(bin + lay.masks_off));
     SGS_LAUNCH_OK();
     return 0;
 }
