@@ -33,6 +33,12 @@ typedef void* sgs_stream_t; /* cudaStream_t */
 #define SGS_ERR_MISALIGNED -4
 #define SGS_ERR_CAPACITY -5
 
+/* bits of the `debug` argument of sgs_raster_forward / sgs_raster_backward */
+#define SGS_FLAG_SYNC_CHECK 1   /* synchronise and check after every stage (the reference's debug=True) */
+#define SGS_FLAG_PRECLEARED 2   /* the caller ran sgs_raster_clear on (binning, acc) for this frame: the
+                                   entry points skip their own memsets -- a memset between two kernels
+                                   costs their overlapped launch, so a per-frame caller clears once, up front */
+
 int sgs_version(void);
 const char* sgs_error_string(int code);
 
@@ -68,13 +74,21 @@ int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
  * [11]=record floats per Gaussian (geom). */
 int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info);
 
+/* Zero what one frame needs zeroed: the counters / histograms / look-back words at the head of
+ * `binning` (for the forward) and `acc` (for the backward; null to skip).  Optional: without
+ * SGS_FLAG_PRECLEARED the forward and the backward do this themselves. */
+int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, sgs_stream_t stream);
+
 /* Forward: replaces _C.rasterize_gaussians ([upstream] rasterize_points.cu
  * RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward).  Exactly one of
  * shs (P,M,3) / colors_precomp (P,3) and one of (scales (P,3) + rotations (P,4)) /
  * cov3D_precomp (P,6) is non-null.  out_color (3,H,W) and radii (P) are fully written.
  * out_alpha / out_depth (H,W) are optional (null to skip).  host_counters (host, pinned,
- * 2 ints, optional) receives {num_rendered, overflow} by an async copy on `stream`; if
- * overflow != 0 the pair list did not fit L_cap: grow the binning buffer and call again. */
+ * 2 ints, optional) receives {num_rendered, overflow} in stream order -- written by the emission
+ * kernel itself when the memory is mapped into the device's address space (cudaHostAlloc /
+ * torch pin_memory under unified addressing), else by an async copy on `stream`; read it after
+ * synchronising.  If overflow != 0 the pair list did not fit L_cap: grow the binning buffer and
+ * call again.  `debug`: SGS_FLAG_* bits. */
 int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
                        const float* colors_precomp, const float* opacities, const float* scales,
                        float scale_modifier, const float* rotations, const float* cov3D_precomp,

@@ -105,6 +105,14 @@ int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
     return 0;
 }
 
+int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, sgs_stream_t stream) {
+    if (P < 0 || W <= 0 || H <= 0 || L_cap < 1 || !binning) return SGS_ERR_BAD_ARG;
+    RasterLayout l = raster_layout(P, W, H, L_cap);
+    SGS_CUDA_OK(cudaMemsetAsync(binning, 0, l.zero_bytes, (cudaStream_t)stream));
+    if (acc) SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), (cudaStream_t)stream));
+    return 0;
+}
+
 int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info) {
     if (!info || P < 0 || W <= 0 || H <= 0 || L_cap < 0) return SGS_ERR_BAD_ARG;
     RasterLayout l = raster_layout(P, W, H, L_cap);
@@ -165,15 +173,23 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (((uintptr_t)geom & 15) || ((uintptr_t)binning & 15) || ((uintptr_t)img & 15)) return SGS_ERR_MISALIGNED;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     char* g = (char*)geom; char* b = (char*)binning; char* im = (char*)img;
+    const bool precleared = (debug & SGS_FLAG_PRECLEARED) != 0;
+    debug &= SGS_FLAG_SYNC_CHECK;
+    // {num_rendered, overflow} for the host: by the emission kernel when the memory is mapped
+    int* host_dev = nullptr;
+    if (host_counters && P > 0 && cudaHostGetDevicePointer((void**)&host_dev, host_counters, 0) != cudaSuccess) {
+        host_dev = nullptr;
+        (void)cudaGetLastError();
+    }
     tick(timing, 0, stream);
-    rc = launch_geometry(a, lay, L_cap, radii, g, b, stream);
+    rc = launch_geometry(a, lay, L_cap, radii, g, b, stream, !precleared);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
     if (P > 0) {
         rc = launch_depth_sort(P, lay, b, stream, debug);     // Gaussians by depth (N items)
         if (rc) return rc;
-        rc = launch_emit_pairs(P, lay, L_cap, b, stream);     // scan + (tile|depth, id) pairs in depth order
+        rc = launch_emit_pairs(P, lay, L_cap, b, host_dev, stream);     // scan + (tile|depth, id) pairs in depth order
         if (rc) return rc;
         rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
         if (rc) return rc;
@@ -188,7 +204,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (rc) return rc;
     tick(timing, 4, stream);
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
-    if (host_counters)
+    if (host_counters && !host_dev)
         SGS_CUDA_OK(cudaMemcpyAsync(host_counters, b + lay.cnt_off, 2 * sizeof(int),
                                     cudaMemcpyDeviceToHost, stream));
     return 0;
@@ -219,8 +235,10 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     if (n_stat != 0 && n_stat != 3) return SGS_ERR_BAD_ARG;
     if (P == 0) return 0;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
+    const bool precleared = (debug & SGS_FLAG_PRECLEARED) != 0;
+    debug &= SGS_FLAG_SYNC_CHECK;
     tick(timing, 5, stream);
-    SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), stream));
+    if (!precleared) SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), stream));
     rc = launch_blend_bwd(lay, W, H, (const char*)geom, (const char*)binning, (const char*)img, bg,
                           dL_dout_color, (float*)acc, reinterpret_cast<int*>((char*)acc + acc_rows_bytes(P)), stream);
     if (rc) return rc;

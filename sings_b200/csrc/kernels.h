@@ -67,12 +67,13 @@ struct GeomArgs {
 };
 
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
-                    char* geom, char* bin, cudaStream_t stream);
+                    char* geom, char* bin, cudaStream_t stream, bool clear = true);
 
 // depth passes over the P per-Gaussian items (passes whose digit is constant are skipped)
 int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t stream, int debug);
 // chained scan of tiles touched + (tile|depth, id) emission in depth order
-int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
+                      cudaStream_t stream);
 // stable passes over the tile-id digits of the emitted pairs
 int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom, char* bin, cudaStream_t stream,
                      int debug);

@@ -298,6 +298,7 @@ struct EmitArgs {
     long long L_cap;
     int passes;
     int gx;
+    int* host_counters;         // mapped host memory for {num_rendered, overflow}, or null
 };
 
 __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
@@ -387,8 +388,14 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     }
     if (tid == 0) {
         unsigned long long total = excl + block_total;
-        if (chunk == (int)gridDim.x - 1)
+        if (chunk == (int)gridDim.x - 1) {
             a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+            if (a.host_counters) {     // the grand total decides the overflow: the last chunk knows both
+                a.host_counters[0] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+                a.host_counters[1] = total > (unsigned long long)a.L_cap ? 1 : 0;
+                __threadfence_system();
+            }
+        }
         if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
     }
     __syncthreads();          // s_incl, s_rect
@@ -423,8 +430,14 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
         if (lane == 0) {
             s_prefix = excl;
             unsigned long long total = excl + block_total;
-            if (chunk == (int)gridDim.x - 1)
+            if (chunk == (int)gridDim.x - 1) {
                 a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+                if (a.host_counters) {     // the grand total decides the overflow: the last chunk knows both
+                    a.host_counters[0] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
+                    a.host_counters[1] = total > (unsigned long long)a.L_cap ? 1 : 0;
+                    __threadfence_system();
+                }
+            }
             if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
         }
     }
@@ -472,7 +485,8 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     }
 }
 
-int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
+                      cudaStream_t stream) {
     if (P <= 0) return 0;
     EmitArgs a;
     a.P = P;
@@ -490,6 +504,7 @@ int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin
     a.L_cap = L_cap;
     a.passes = lay.passes;
     a.gx = lay.gx;
+    a.host_counters = host_counters;
     launch_pdl(emit_pairs_kernel, lay.scan_blocks, GEO_THREADS, 0, stream, a);
     SGS_LAUNCH_OK();
     return 0;
@@ -512,9 +527,9 @@ static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec
 }
 
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
-                    char* geom, char* bin, cudaStream_t stream) {
+                    char* geom, char* bin, cudaStream_t stream, bool clear) {
     // one memset clears counters, histograms, scan + sort look-back status and the tile-length bucket counts
-    SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
+    if (clear) SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
     if (a.P <= 0) return 0;
     if (lay.gx > 0xffff || lay.gy > 0xffff) return SGS_ERR_CAPACITY;
     GeoOut o;

@@ -90,7 +90,13 @@ class AvatarStep:
         self.d_A = self.small_grads[:J * 16].view(1, J, 4, 4)
         self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
+        self._bwd_clean = False
         self.timing = None
+        # stage events are recorded only while this is set.  Inside a captured frame every
+        # record is a graph node between two kernels, which turns their programmatic
+        # (overlapped) launch edge into a full dependency: ~4 us per event, ~45 us per frame at
+        # 200k Gaussians / 1024^2 (tools/probe_events.py) -- so capture(stages=False) for speed.
+        self.record_stages = True
         if timing:
             h = C.c_void_p()
             _lib.check(self.L.sgs_timing_create(16, C.byref(h)), "sgs_timing_create")
@@ -108,7 +114,13 @@ class AvatarStep:
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         self._fr = fr
         pose = fr.pose.reshape(1, self.J, 3)
-        tm = self.timing
+        tm = self.timing if self.record_stages else None
+        # everything the frame needs zeroed is cleared here, up front: a memset between two
+        # kernels would cost them their overlapped (programmatic dependent) launch
+        _lib.check(L_.sgs_raster_clear(self.N, self.Wd, self.H, self.L_cap, p(self.binning), p(self.acc), st),
+                   "sgs_raster_clear")
+        self.small_grads.zero_()           # d_A and d_transl live in one buffer: one fill
+        self._bwd_clean = True             # one backward may rely on the up-front clearing
         if tm:
             L_.sgs_timing_record(tm, 8, st)
         _lib.check(L_.sgs_pose_lbs_fwd(p(pose), p(self.rest), p(self.parents), p(self.inv_A), 1, self.N,
@@ -122,7 +134,7 @@ class AvatarStep:
             p(self.sc), 1.0, p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos),
             float(fr.tanfovx), float(fr.tanfovy), p(self.shs), 0, self.L_cap, p(self.geom),
             p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-            self.counters.data_ptr(), st, 0, tm), "sgs_raster_forward")
+            self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED, tm), "sgs_raster_forward")
         return self.color
 
     def backward(self, dL_dimage: torch.Tensor, stream=None, stats: bool = True):
@@ -131,7 +143,11 @@ class AvatarStep:
         L_, p = self.L, _lib.ptr
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         fr = self._fr
-        tm = self.timing
+        tm = self.timing if self.record_stages else None
+        flags = _lib.FLAG_PRECLEARED if self._bwd_clean else 0
+        if not self._bwd_clean:            # a second backward of the same forward: clear again
+            self.small_grads.zero_()
+        self._bwd_clean = False
         _lib.check(L_.sgs_raster_backward(
             self.N, self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.xyz), None, p(self.sc), 1.0,
             p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos), float(fr.tanfovx),
@@ -139,10 +155,9 @@ class AvatarStep:
             p(self.binning), p(self.img), p(self.acc), p(self.g_means3D), p(self.g_means2D),
             p(self.g_colors), p(self.d_opacity), p(self.g_cov), p(self.d_shs), p(self.g_scales_r),
             p(self.g_rots), p(self.grad_accum) if stats else None, p(self.denom) if stats else None,
-            p(self.max_radii2D) if stats else None, st, 0, tm), "sgs_raster_backward")
+            p(self.max_radii2D) if stats else None, st, flags, tm), "sgs_raster_backward")
         if tm:
             L_.sgs_timing_record(tm, 10, st)
-        self.small_grads.zero_()           # d_A and d_transl live in one buffer: one fill
         pose = fr.pose.reshape(1, self.J, 3)
         _lib.check(L_.sgs_lbs_bwd(1, self.N, self.J, p(self.A), p(self.xyz_canon), p(self.W_lbs),
                                   p(self.rot_canon), p(self.scales), p(fr.smpl_scale), p(fr.transl),
@@ -157,14 +172,22 @@ class AvatarStep:
             L_.sgs_timing_record(tm, 11, st)
 
     def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None,
-                prologue=None):
+                prologue=None, stages: bool = True):
         """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
         graph and return replay().  The launch sequence is static -- capacity-sized pair list,
         device-side counts, no host round trip -- so the whole frame becomes one graph launch.
         `fr`'s tensors and `dL_dimage` are captured by address: refresh their contents in
         place before each replay.  Stage events keep working (external event-record nodes).
         `prologue()` (optional) runs first inside the graph -- e.g. the caller's decoding of an
-        uploaded target image into `dL_dimage` / `loss_weight`."""
+        uploaded target image into `dL_dimage` / `loss_weight`.  stages=False leaves the stage
+        event records out of the graph (see record_stages)."""
+        keep, self.record_stages = self.record_stages, bool(stages)
+        try:
+            return self._capture(fr, dL_dimage, loss_weight, prologue)
+        finally:
+            self.record_stages = keep
+
+    def _capture(self, fr, dL_dimage, loss_weight, prologue):
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)

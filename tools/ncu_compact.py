@@ -23,7 +23,8 @@ want=[('gpu__time_duration.sum','us'),('dram__bytes_read.sum','rdMB'),('dram__by
 ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','smem_wf')]
 seen=set()
 for r in rows[2:]:
-    name=r[idx['Kernel Name']].split('(')[0].replace('sgs::','')[:28]
+    name=r[idx['Kernel Name']].split('(')[0].replace('sgs::','').replace('void ','')
+    name=name.replace('unsigned long long','u64').replace('unsigned int','u32')[:40]   # keep the template arguments: the u32 and u64 sort passes are different kernels
     if name in seen: continue
     seen.add(name)
     def fmt(v):
