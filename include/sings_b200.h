@@ -74,10 +74,13 @@ int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
  * [11]=record floats per Gaussian (geom). */
 int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info);
 
-/* Zero what one frame needs zeroed: the counters / histograms / look-back words at the head of
- * `binning` (for the forward) and `acc` (for the backward; null to skip).  Optional: without
- * SGS_FLAG_PRECLEARED the forward and the backward do this themselves. */
-int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, sgs_stream_t stream);
+/* Zero what one frame needs zeroed, in ONE kernel launch: the counters / histograms / look-back
+ * words at the head of `binning` (for the forward), `acc` (for the backward; null to skip) and
+ * an optional caller buffer `extra` of extra_bytes (e.g. the d_A / d_transl accumulators of
+ * sgs_lbs_bwd; null to skip); all 16-byte aligned.  Optional: without SGS_FLAG_PRECLEARED the
+ * forward and the backward clear their own state. */
+int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, void* extra,
+                     size_t extra_bytes, sgs_stream_t stream);
 
 /* Forward: replaces _C.rasterize_gaussians ([upstream] rasterize_points.cu
  * RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward).  Exactly one of

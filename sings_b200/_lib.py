@@ -26,7 +26,7 @@ _SIGNATURES = {
     "sgs_timing_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_f)]),
     "sgs_raster_sizes": (_i, [_i, _i, _i, _ll, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "sgs_raster_layout_info": (_i, [_i, _i, _i, _ll, C.POINTER(_ll)]),
-    "sgs_raster_clear": (_i, [_i, _i, _i, _ll, _vp, _vp, _vp]),
+    "sgs_raster_clear": (_i, [_i, _i, _i, _ll, _vp, _vp, _vp, _sz, _vp]),
     "sgs_raster_forward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                                 _vp, _f, _f, _vp, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _i, _vp]),

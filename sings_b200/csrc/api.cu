@@ -105,12 +105,13 @@ int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
     return 0;
 }
 
-int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, sgs_stream_t stream) {
+int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* acc, void* extra,
+                     size_t extra_bytes, sgs_stream_t stream) {
     if (P < 0 || W <= 0 || H <= 0 || L_cap < 1 || !binning) return SGS_ERR_BAD_ARG;
+    if (((uintptr_t)binning & 15) || ((uintptr_t)acc & 15) || ((uintptr_t)extra & 15)) return SGS_ERR_MISALIGNED;
     RasterLayout l = raster_layout(P, W, H, L_cap);
-    SGS_CUDA_OK(cudaMemsetAsync(binning, 0, l.zero_bytes, (cudaStream_t)stream));
-    if (acc) SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), (cudaStream_t)stream));
-    return 0;
+    return launch_clear3(binning, l.zero_bytes, acc, acc ? acc_total_bytes(P) : 0, extra, extra ? extra_bytes : 0,
+                         (cudaStream_t)stream);
 }
 
 int sgs_raster_layout_info(int P, int W, int H, long long L_cap, long long* info) {

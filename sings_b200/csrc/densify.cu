@@ -34,6 +34,36 @@ int launch_densify_stats(int P, const float* grad2d, const int* radii, float* ac
     return 0;
 }
 
+// Up-front clearing of a frame's state (sgs_raster_clear): up to three regions zeroed by ONE
+// kernel -- one graph node with an overlapped launch instead of three serialised memset nodes.
+// Regions are 16-byte aligned; sizes are rounded up to 16 bytes inside their allocations'
+// 256-byte granularity (the caller guarantees it) except the last words, handled bytewise.
+__global__ void __launch_bounds__(256) clear3_kernel(char* a, size_t na, char* b, size_t nb, char* c, size_t nc) {
+    pdl_sync();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    char* const ptr[3] = {a, b, c};
+    const size_t len[3] = {na, nb, nc};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const size_t n16 = len[r] / 16;
+        uint4* p = reinterpret_cast<uint4*>(ptr[r]);
+        for (size_t i = tid; i < n16; i += stride) p[i] = z;
+        for (size_t i = n16 * 16 + tid; i < len[r]; i += stride) ptr[r][i] = 0;
+    }
+}
+
+int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream) {
+    const size_t total = na + nb + nc;
+    if (total == 0) return 0;
+    long long blocks = (long long)((total / 16 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_pdl(clear3_kernel, (unsigned)blocks, 256, 0, stream, (char*)a, na, (char*)b, nb, (char*)c, nc);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
 // Data-parallel step epilogue: after the all-reduce, fold this step's statistics
 // (SUM-reduced accum / denom increments, MAX-reduced radii) into the persistent accumulators and
 // clear the step buffers for the next view -- one launch instead of three adds and three fills.

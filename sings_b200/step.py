@@ -117,9 +117,9 @@ class AvatarStep:
         tm = self.timing if self.record_stages else None
         # everything the frame needs zeroed is cleared here, up front: a memset between two
         # kernels would cost them their overlapped (programmatic dependent) launch
-        _lib.check(L_.sgs_raster_clear(self.N, self.Wd, self.H, self.L_cap, p(self.binning), p(self.acc), st),
+        _lib.check(L_.sgs_raster_clear(self.N, self.Wd, self.H, self.L_cap, p(self.binning), p(self.acc),
+                                       p(self.small_grads), self.small_grads.numel() * 4, st),   # d_A and d_transl
                    "sgs_raster_clear")
-        self.small_grads.zero_()           # d_A and d_transl live in one buffer: one fill
         self._bwd_clean = True             # one backward may rely on the up-front clearing
         if tm:
             L_.sgs_timing_record(tm, 8, st)
