@@ -53,6 +53,16 @@ int sgs_timing_destroy(void* handle);
 int sgs_timing_record(void* handle, int i, sgs_stream_t stream);
 int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms);
 
+/* Record-and-replay of a launch sequence (CUDA graph).  Everything enqueued on `stream` between
+ * sgs_graph_begin and sgs_graph_end -- calls of this library; `stream` must not be the legacy
+ * default stream -- becomes one executable graph; sgs_graph_launch replays it on any stream.
+ * The entry points of this library are capture-safe: no allocation, no host synchronisation,
+ * device-side counts.  Buffers are bound by address. */
+int sgs_graph_begin(sgs_stream_t stream);
+int sgs_graph_end(sgs_stream_t stream, void** graph_exec);
+int sgs_graph_launch(void* graph_exec, sgs_stream_t stream);
+int sgs_graph_destroy(void* graph_exec);
+
 /* ---------------------------------------------------------------------------------------
  * Rasterizer.  Replaces the pybind extension `diff_gaussian_rasterization._C`
  * (rasterize_gaussians / rasterize_gaussians_backward / mark_visible) that

@@ -24,6 +24,10 @@ _SIGNATURES = {
     "sgs_timing_destroy": (_i, [_vp]),
     "sgs_timing_record": (_i, [_vp, _i, _vp]),
     "sgs_timing_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_f)]),
+    "sgs_graph_begin": (_i, [_vp]),
+    "sgs_graph_end": (_i, [_vp, C.POINTER(_vp)]),
+    "sgs_graph_launch": (_i, [_vp, _vp]),
+    "sgs_graph_destroy": (_i, [_vp]),
     "sgs_raster_sizes": (_i, [_i, _i, _i, _ll, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "sgs_raster_layout_info": (_i, [_i, _i, _i, _ll, C.POINTER(_ll)]),
     "sgs_raster_clear": (_i, [_i, _i, _i, _ll, _vp, _vp, _vp, _sz, _vp]),

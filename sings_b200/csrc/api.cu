@@ -80,6 +80,36 @@ int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms) {
     return 0;
 }
 
+// A frame recorded once and replayed as one launch.  Plain CUDA graph capture of whatever the
+// caller enqueues on `stream` between begin and end (library calls only -- nothing here knows
+// about torch's allocator); used by AvatarStep.capture for the pure C-ABI frame, whose replay
+// then costs a single cudaGraphLaunch (torch.cuda.CUDAGraph.replay adds two RNG-state fill
+// kernels in front of every launch).
+int sgs_graph_begin(sgs_stream_t stream) {
+    SGS_CUDA_OK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+    return 0;
+}
+int sgs_graph_end(sgs_stream_t stream, void** graph_exec) {
+    if (!graph_exec) return SGS_ERR_BAD_ARG;
+    cudaGraph_t g = nullptr;
+    SGS_CUDA_OK(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t e = nullptr;
+    cudaError_t err = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) return (int)err;
+    *graph_exec = e;
+    return 0;
+}
+int sgs_graph_launch(void* graph_exec, sgs_stream_t stream) {
+    if (!graph_exec) return SGS_ERR_BAD_ARG;
+    SGS_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return 0;
+}
+int sgs_graph_destroy(void* graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+    return 0;
+}
+
 const char* sgs_error_string(int code) {
     switch (code) {
         case 0: return "ok";

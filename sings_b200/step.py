@@ -17,6 +17,7 @@ of `max_radii2D` (sings_b200/dp.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -91,6 +92,7 @@ class AvatarStep:
         self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
         self._bwd_clean = False
+        self._graphs = []
         self.timing = None
         # stage events are recorded only while this is set.  Inside a captured frame every
         # record is a graph node between two kernels, which turns their programmatic
@@ -200,6 +202,20 @@ class AvatarStep:
             self.backward(dL_dimage)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
+        if prologue is None and loss_weight is None and not os.environ.get("SGS_TORCH_GRAPH"):
+            # the pure C-ABI frame: recorded through the library (no torch op inside), replayed
+            # with a single cudaGraphLaunch on the current stream
+            h = C.c_void_p()
+            _lib.check(self.L.sgs_graph_begin(side.cuda_stream), "sgs_graph_begin")
+            try:
+                self.forward(fr, stream=side)
+                self.backward(dL_dimage, stream=side)
+            finally:
+                rc = self.L.sgs_graph_end(side.cuda_stream, C.byref(h))
+            _lib.check(rc, "sgs_graph_end")
+            self._graphs.append(h)
+            launch, dev = self.L.sgs_graph_launch, self.dev
+            return lambda: _lib.check(launch(h, torch.cuda.current_stream(dev).cuda_stream), "sgs_graph_launch")
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if prologue is not None:
@@ -240,6 +256,11 @@ class AvatarStep:
         return out
 
     def __del__(self):
+        try:
+            for h in self._graphs:
+                self.L.sgs_graph_destroy(h)
+        except Exception:
+            pass
         try:
             if self.timing:
                 self.L.sgs_timing_destroy(self.timing)
