@@ -38,6 +38,11 @@ typedef void* sgs_stream_t; /* cudaStream_t */
 #define SGS_FLAG_PRECLEARED 2   /* the caller ran sgs_raster_clear on (binning, acc) for this frame: the
                                    entry points skip their own memsets -- a memset between two kernels
                                    costs their overlapped launch, so a per-frame caller clears once, up front */
+#define SGS_FLAG_EARLY_PARAMS 4 /* the caller vouches that `shs` was last written before the kernel that
+                                   precedes this call on the stream started, and that that kernel is one of
+                                   this library's (e.g. sgs_lbs_fwd before the forward, the forward's own
+                                   kernels before the backward): the SH rows are then fetched ahead of the
+                                   programmatic-dependency wait, while the preceding kernel drains */
 
 int sgs_version(void);
 const char* sgs_error_string(int code);

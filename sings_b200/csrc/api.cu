@@ -8,19 +8,6 @@
 
 using namespace sgs;
 
-// sgs_pose_lbs_fwd: pose -> A inside the LBS kernel's prologue (1) or as its own kernel in front
-// (0); fused only up to this many frames per call -- beyond it every CTA would repeat too much
-// serial work (A/B knobs, tools/sweep.sh).  Measured (profiles/README.md, v7): fused 25.0 us vs
-// 24.7 us for the deform stage -- the separate kernel is already hidden behind the LBS kernel's
-// early tile prefetch, while the fused prologue puts the joint chain on every CTA's critical
-// path -- so the default stays 0.
-#ifndef SGS_FUSE_POSE
-#define SGS_FUSE_POSE 0
-#endif
-#ifndef SGS_FUSE_POSE_MAX_B
-#define SGS_FUSE_POSE_MAX_B 4
-#endif
-
 bool sgs::pdl_enabled() {
     static int v = -1;
     if (v < 0) v = getenv("SGS_NO_PDL") ? 0 : 1;
@@ -205,6 +192,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     char* g = (char*)geom; char* b = (char*)binning; char* im = (char*)img;
     const bool precleared = (debug & SGS_FLAG_PRECLEARED) != 0;
+    a.early_params = (debug & SGS_FLAG_EARLY_PARAMS) != 0;
     debug &= SGS_FLAG_SYNC_CHECK;
     // {num_rendered, overflow} for the host: by the emission kernel when the memory is mapped
     int* host_dev = nullptr;
@@ -267,6 +255,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     if (P == 0) return 0;
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     const bool precleared = (debug & SGS_FLAG_PRECLEARED) != 0;
+    b.fwd.early_params = (debug & SGS_FLAG_EARLY_PARAMS) != 0;
     debug &= SGS_FLAG_SYNC_CHECK;
     tick(timing, 5, stream);
     if (!precleared) SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), stream));
@@ -371,13 +360,10 @@ int sgs_pose_lbs_fwd(const float* pose, const float* rest, const int* parents,
     if (rc) return rc;
     if (B > 0 && N > 0 && (!xyz_out || !rotq_out || !scales_out)) return SGS_ERR_BAD_ARG;
     LbsOut o{xyz_out, rotq_out, scales_out, nullptr};
-    if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
-    if (SGS_FUSE_POSE && B <= SGS_FUSE_POSE_MAX_B && N > 0) {
-        // one kernel: every LBS CTA derives the joint transforms in its prologue (lbs.cu)
-        a.pose = pose; a.rest = rest; a.parents = parents; a.inv_A = inv_A_t2cano;
-        a.A_out = A_out; a.G_out = G_out;
-        return launch_lbs_fwd(a, o, (cudaStream_t)stream);
-    }
+    // (pose -> A recomputed by every LBS CTA in its prologue, i.e. one kernel instead of two, was
+    // measured at 25.0 us against 24.7 us for this pair: the small kernel is already hidden behind
+    // the LBS kernel's early tile prefetch, and the extra code cost the LBS kernel instruction-cache
+    // misses; removed)
     rc = launch_pose_to_A(pose, rest, parents, inv_A_t2cano, B, J, A_out, G_out, (cudaStream_t)stream);
     if (rc) return rc;
     a.early_params = 1;      // the preceding kernel is pose_to_A, which never writes them

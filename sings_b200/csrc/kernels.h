@@ -64,6 +64,10 @@ struct GeomArgs {
     const float* proj;
     const float* campos;
     int prefiltered;
+    // 1: shs (forward, backward) were final before the kernel that precedes this one on the
+    // stream started, that kernel being one of ours: they may be fetched ahead of the
+    // programmatic-dependency wait (common.cuh).  Set through SGS_FLAG_EARLY_PARAMS.
+    int early_params = 0;
 };
 
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,

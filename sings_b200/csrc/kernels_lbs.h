@@ -22,15 +22,6 @@ struct LbsArgs {
     // be fetched ahead of the programmatic-dependency wait (common.cuh, PDL)
     int early_params = 0;
     int rot6d = 0;            // rot holds 6D rotations; d_rot is (N,6)
-    // fused pose -> A (forward only): when `pose` is set, A is not read -- every CTA computes the
-    // joint transforms from pose (B,J,3), rest (J,3), parents (J), inv_A (J,16)|null in its
-    // prologue, and CTA 0 writes them to A_out (B,J,16) / G_out (B,J,12)|null
-    const float* pose = nullptr;
-    const float* rest = nullptr;
-    const int* parents = nullptr;
-    const float* inv_A = nullptr;
-    float* A_out = nullptr;
-    float* G_out = nullptr;
 };
 
 struct LbsOut {

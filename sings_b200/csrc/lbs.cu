@@ -59,8 +59,7 @@ __device__ __forceinline__ void affine_mul(const float* a, const float* b, float
     }
 }
 
-// pose -> A in two steps with a block barrier between them (used by pose_to_A_kernel and by the
-// fused prologue of lbs_fwd_kernel; identical arithmetic, so identical results):
+// pose -> A in two steps with a block barrier between them:
 //   pose_local: joint j's local transform [R(pose_j) | rest_j - rest_parent] into s_local
 //   pose_chain: each thread multiplies its own ancestor chain from the root down (same
 //     association as the reference's sequential loop, smpl.py:495-501), then
@@ -508,13 +507,11 @@ struct LbsTile {
     float* f_scl;     // [256][3]
     float* dT;        // backward: [256][12]
     float* part;      // backward: [8][J][12] per-warp partial dA
-    float* poseL;     // fused pose -> A prologue: [LBS_THREADS/64][J][12] local transforms
-    int* posePar;     // [64] parents
     unsigned long long* bar;
 };
 
 __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bwd, LbsTile* t = nullptr,
-                                                 char* raw = nullptr, bool fused_pose = false) {
+                                                 char* raw = nullptr) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 16); return at; };
     const size_t oA = take((size_t)B * J * 3 * 16), oF = take((size_t)B * 16 * 4);
@@ -524,7 +521,6 @@ __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bw
     const size_t oFX = take(LBS_THREADS * 12), oFQ = take(LBS_THREADS * 16), oFS = take(LBS_THREADS * 12);
     const size_t oT = take(bwd ? LBS_THREADS * 48 : 0);
     const size_t oP = take(bwd ? (size_t)(LBS_THREADS / 32) * J * 48 : 0);
-    const size_t oPL = take(fused_pose ? (size_t)(LBS_THREADS / 64) * J * 48 : 0), oPP = take(fused_pose ? 64 * 4 : 0);
     const size_t oB = take(16);
     if (t) {
         t->A = reinterpret_cast<float4*>(raw + oA);  t->frame = reinterpret_cast<float*>(raw + oF);
@@ -533,7 +529,6 @@ __host__ __device__ inline size_t lbs_tile_bytes(int B, int J, bool iso, bool bw
         t->f_xyz = reinterpret_cast<float*>(raw + oFX); t->f_q = reinterpret_cast<float*>(raw + oFQ);
         t->f_scl = reinterpret_cast<float*>(raw + oFS); t->dT = reinterpret_cast<float*>(raw + oT);
         t->part = reinterpret_cast<float*>(raw + oP);
-        t->poseL = reinterpret_cast<float*>(raw + oPL); t->posePar = reinterpret_cast<int*>(raw + oPP);
         t->bar = reinterpret_cast<unsigned long long*>(raw + oB);
     }
     return o;
@@ -591,11 +586,9 @@ __device__ __forceinline__ void block_store(float* dst, const float* src, unsign
 
 __device__ __forceinline__ void stage_frames(const LbsArgs& a, LbsTile& s) {
     const int tid = threadIdx.x;
-    if (!a.pose) {
-        for (int f = tid; f < a.B * a.J * 3; f += LBS_THREADS) {
-            int bj = f / 3, r = f - bj * 3;
-            s.A[f] = reinterpret_cast<const float4*>(a.A)[(size_t)bj * 4 + r];
-        }
+    for (int f = tid; f < a.B * a.J * 3; f += LBS_THREADS) {
+        int bj = f / 3, r = f - bj * 3;
+        s.A[f] = reinterpret_cast<const float4*>(a.A)[(size_t)bj * 4 + r];
     }
     for (int b = tid; b < a.B; b += LBS_THREADS) {
         float* fr = s.frame + 16 * b;
@@ -661,7 +654,7 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut 
     const bool iso = a.rot == nullptr;
     const int rw = a.rot6d ? 6 : 9;      // floats per canonical rotation: 6D (Gram-Schmidt here) or matrix
     LbsTile s;
-    lbs_tile_bytes(a.B, a.J, iso, false, &s, s_raw, a.pose != nullptr);
+    lbs_tile_bytes(a.B, a.J, iso, false, &s, s_raw);
     const int tid = threadIdx.x;
     const int base = blockIdx.x * LBS_THREADS;
     const int rows = min(LBS_THREADS, a.N - base);
@@ -681,30 +674,6 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(LbsArgs a, LbsOut 
     }
     if (a.early_params) pdl_sync();
     stage_frames(a, s);
-    if (a.pose) {
-        // Fused pose -> A (sgs_pose_lbs_fwd): every CTA derives the B x J joint transforms itself
-        // while its weight tile is in flight -- 64 threads per frame, LBS_THREADS/64 frames at a
-        // time -- instead of waiting for a one-CTA kernel in front of the whole grid.  CTA 0
-        // also writes A and G out for the backward.  Same device functions as pose_to_A_kernel.
-        const int grp = tid >> 6, j = tid & 63;
-        float* L = s.poseL + (size_t)grp * a.J * 12;
-        for (int b0 = 0; b0 < a.B; b0 += LBS_THREADS / 64) {
-            const int b = b0 + grp;
-            const bool on = b < a.B && j < a.J;
-            if (on) pose_local(a.pose + ((size_t)b * a.J + j) * 3, a.rest, a.parents, j, L, s.posePar);
-            __syncthreads();
-            if (on) {
-                float G[12], out[12];
-                pose_chain(a.rest, a.inv_A, j, L, s.posePar, G, out);
-                float4* dst = s.A + ((size_t)b * a.J + j) * 3;
-                dst[0] = make_float4(out[0], out[1], out[2], out[3]);
-                dst[1] = make_float4(out[4], out[5], out[6], out[7]);
-                dst[2] = make_float4(out[8], out[9], out[10], out[11]);
-                if (blockIdx.x == 0) pose_store(a.A_out, a.G_out, (size_t)b * a.J + j, G, out);
-            }
-            if (b0 + LBS_THREADS / 64 < a.B) __syncthreads();
-        }
-    }
     ld.wait();
     const int n = base + tid;
     const bool live = n < a.N;
@@ -787,8 +756,7 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
     if (a.N <= 0 || a.B <= 0) return 0;
     if (a.J < 1 || a.J > 64) return SGS_ERR_BAD_JOINTS;
     if (((uintptr_t)a.A & 15) || (o.T && ((uintptr_t)o.T & 15))) return SGS_ERR_MISALIGNED;
-    if (a.pose && (!a.rest || !a.parents || !a.A_out)) return SGS_ERR_BAD_ARG;
-    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false, nullptr, nullptr, a.pose != nullptr);
+    const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(lbs_fwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, o);

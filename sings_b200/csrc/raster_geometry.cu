@@ -124,6 +124,33 @@ geometry_kernel(GeomArgs a, GeoOut o) {
     __shared__ unsigned s_var[2];
 
     const int tid = threadIdx.x;
+    const int base = blockIdx.x * GEO_THREADS;
+    // ---- stage this CTA's SH rows (asynchronously; consumed after the geometry math).  With
+    // early_params (the caller vouches that shs was final two library kernels ago, common.cuh)
+    // the copies are issued AHEAD of the dependency wait: the largest operand of the kernel is
+    // in flight while the preceding kernel (the LBS forward) drains.
+    auto stage_sh = [&]() {
+        if constexpr (HAS_SH) {
+            const int rows = min(GEO_THREADS, a.P - base);
+            const size_t row_floats = (size_t)a.M * 3;
+            if (VEC16) {
+                const int total = rows * NVEC;
+                for (int f = tid; f < total; f += GEO_THREADS) {
+                    int row = f / NVEC, col = f - row * NVEC;
+                    cp_async16(&s_sh[row * S4 + col], a.shs + (size_t)(base + row) * row_floats + col * 4);
+                }
+            } else {
+                float* s_f = reinterpret_cast<float*>(s_sh);
+                const int total = rows * NB * 3;
+                for (int f = tid; f < total; f += GEO_THREADS) {
+                    int row = f / (NB * 3), col = f - row * (NB * 3);
+                    cp_async4(&s_f[row * S4 * 4 + col], a.shs + (size_t)(base + row) * row_floats + col);
+                }
+            }
+            cp_async_commit();
+        }
+    };
+    if (a.early_params) stage_sh();
     pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
@@ -131,32 +158,11 @@ geometry_kernel(GeomArgs a, GeoOut o) {
     else if (tid < 37) s_var[tid - 35] = 0;
     for (int i = tid; i < DEPTH_PASSES * RADIX; i += GEO_THREADS) s_hist[i] = 0;
     __syncthreads();
-    const int base = blockIdx.x * GEO_THREADS;
     const int idx = base + tid;
     const bool in_range = idx < a.P;
     const float* V = s_cam;
     const float* Mx = s_cam + 16;
-
-    // ---- stage this CTA's SH rows (asynchronously; consumed after the geometry math) ----
-    if constexpr (HAS_SH) {
-        const int rows = min(GEO_THREADS, a.P - base);
-        const size_t row_floats = (size_t)a.M * 3;
-        if (VEC16) {
-            const int total = rows * NVEC;
-            for (int f = tid; f < total; f += GEO_THREADS) {
-                int row = f / NVEC, col = f - row * NVEC;
-                cp_async16(&s_sh[row * S4 + col], a.shs + (size_t)(base + row) * row_floats + col * 4);
-            }
-        } else {
-            float* s_f = reinterpret_cast<float*>(s_sh);
-            const int total = rows * NB * 3;
-            for (int f = tid; f < total; f += GEO_THREADS) {
-                int row = f / (NB * 3), col = f - row * (NB * 3);
-                cp_async4(&s_f[row * S4 * 4 + col], a.shs + (size_t)(base + row) * row_floats + col);
-            }
-        }
-        cp_async_commit();
-    }
+    if (!a.early_params) stage_sh();
 
     // ---- per-Gaussian geometry ----
     unsigned tiles = 0;

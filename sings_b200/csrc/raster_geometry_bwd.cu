@@ -30,29 +30,35 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
     const int base = blockIdx.x * GB_THREADS;
     const int idx = base + tid;
     const bool in_range = idx < a.P;
+    const int rows = min(GB_THREADS, a.P - base);
+    const size_t row_floats = (size_t)a.M * 3;
+    // SH rows: staged ahead of the dependency wait when the caller vouches for early_params (the
+    // preceding kernel, the blend backward, only produces `acc`)
+    auto stage_sh = [&]() {
+        if constexpr (HAS_SH) {
+            if (VEC16) {
+                const int total = rows * NVEC;
+                for (int f = tid; f < total; f += GB_THREADS) {
+                    int row = f / NVEC, col = f - row * NVEC;
+                    cp_async16(&s_sh[row * S4 + col], a.shs + (size_t)(base + row) * row_floats + col * 4);
+                }
+            } else {
+                float* s_f = reinterpret_cast<float*>(s_sh);
+                const int total = rows * NB * 3;
+                for (int f = tid; f < total; f += GB_THREADS) {
+                    int row = f / (NB * 3), col = f - row * (NB * 3);
+                    cp_async4(&s_f[row * S4 * 4 + col], a.shs + (size_t)(base + row) * row_floats + col);
+                }
+            }
+            cp_async_commit();
+        }
+    };
+    if (a.early_params) stage_sh();
     pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
-    const int rows = min(GB_THREADS, a.P - base);
-    const size_t row_floats = (size_t)a.M * 3;
-    if constexpr (HAS_SH) {
-        if (VEC16) {
-            const int total = rows * NVEC;
-            for (int f = tid; f < total; f += GB_THREADS) {
-                int row = f / NVEC, col = f - row * NVEC;
-                cp_async16(&s_sh[row * S4 + col], a.shs + (size_t)(base + row) * row_floats + col * 4);
-            }
-        } else {
-            float* s_f = reinterpret_cast<float*>(s_sh);
-            const int total = rows * NB * 3;
-            for (int f = tid; f < total; f += GB_THREADS) {
-                int row = f / (NB * 3), col = f - row * (NB * 3);
-                cp_async4(&s_f[row * S4 * 4 + col], a.shs + (size_t)(base + row) * row_floats + col);
-            }
-        }
-        cp_async_commit();
-    }
+    if (!a.early_params) stage_sh();
     __syncthreads();
     const float* V = s_cam;
     const float* Mx = s_cam + 16;

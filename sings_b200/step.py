@@ -92,6 +92,10 @@ class AvatarStep:
         self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
         self._bwd_clean = False
+        # shs is a model parameter: the kernels in front of the geometry kernels (LBS forward,
+        # blend backward) are this library's and never write it, so its rows may be prefetched
+        # ahead of the dependency wait (SGS_FLAG_EARLY_PARAMS)
+        self._early = 0 if os.environ.get("SGS_NO_EARLY_PARAMS") else _lib.FLAG_EARLY_PARAMS
         self._graphs = []
         self.timing = None
         # stage events are recorded only while this is set.  Inside a captured frame every
@@ -136,7 +140,7 @@ class AvatarStep:
             p(self.sc), 1.0, p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos),
             float(fr.tanfovx), float(fr.tanfovy), p(self.shs), 0, self.L_cap, p(self.geom),
             p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-            self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED, tm), "sgs_raster_forward")
+            self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_raster_forward")
         return self.color
 
     def backward(self, dL_dimage: torch.Tensor, stream=None, stats: bool = True):
@@ -146,7 +150,7 @@ class AvatarStep:
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         fr = self._fr
         tm = self.timing if self.record_stages else None
-        flags = _lib.FLAG_PRECLEARED if self._bwd_clean else 0
+        flags = (_lib.FLAG_PRECLEARED if self._bwd_clean else 0) | self._early
         if not self._bwd_clean:            # a second backward of the same forward: clear again
             self.small_grads.zero_()
         self._bwd_clean = False
