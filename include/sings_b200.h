@@ -56,6 +56,10 @@ const char* sgs_error_string(int code);
 int sgs_timing_create(int n_events, void** handle);
 int sgs_timing_destroy(void* handle);
 int sgs_timing_record(void* handle, int i, sgs_stream_t stream);
+/* Only the events whose bit is set are recorded from now on (default: all).  Every record between
+ * two kernels costs their overlapped launch (~4 us), so a coarse measurement -- e.g. one interval
+ * spanning several stages -- should enable only its two end points. */
+int sgs_timing_set_mask(void* handle, unsigned mask);
 int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms);
 
 /* Record-and-replay of a launch sequence (CUDA graph).  Everything enqueued on `stream` between

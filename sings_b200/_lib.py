@@ -23,6 +23,7 @@ _SIGNATURES = {
     "sgs_timing_create": (_i, [_i, C.POINTER(_vp)]),
     "sgs_timing_destroy": (_i, [_vp]),
     "sgs_timing_record": (_i, [_vp, _i, _vp]),
+    "sgs_timing_set_mask": (_i, [_vp, C.c_uint]),
     "sgs_timing_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_f)]),
     "sgs_graph_begin": (_i, [_vp]),
     "sgs_graph_end": (_i, [_vp, C.POINTER(_vp)]),

@@ -17,6 +17,7 @@ bool sgs::pdl_enabled() {
 struct Timing {
     int n;
     cudaEvent_t* ev;
+    unsigned mask;        // events that are recorded (bit i = event i); the others are skipped
 };
 // Inside a stream capture the record becomes an "external" event-record node, so the stage
 // events keep working (cudaEventElapsedTime) when the frame is replayed as a CUDA graph.
@@ -29,7 +30,7 @@ static inline cudaError_t record_event(cudaEvent_t ev, cudaStream_t s) {
 static inline void tick(void* timing, int i, cudaStream_t s) {
     if (!timing) return;
     Timing* t = (Timing*)timing;
-    if (i < t->n) record_event(t->ev[i], s);
+    if (i < t->n && ((t->mask >> i) & 1u)) record_event(t->ev[i], s);
 }
 
 extern "C" {
@@ -40,6 +41,7 @@ int sgs_timing_create(int n_events, void** handle) {
     if (n_events < 1 || !handle) return SGS_ERR_BAD_ARG;
     Timing* t = new Timing;
     t->n = n_events;
+    t->mask = 0xffffffffu;
     t->ev = new cudaEvent_t[n_events];
     for (int i = 0; i < n_events; i++) SGS_CUDA_OK(cudaEventCreate(&t->ev[i]));
     *handle = t;
@@ -55,7 +57,13 @@ int sgs_timing_destroy(void* handle) {
 }
 int sgs_timing_record(void* handle, int i, sgs_stream_t stream) {
     if (!handle || i < 0 || i >= ((Timing*)handle)->n) return SGS_ERR_BAD_ARG;
+    if (!((((Timing*)handle)->mask >> i) & 1u)) return 0;
     SGS_CUDA_OK(record_event(((Timing*)handle)->ev[i], (cudaStream_t)stream));
+    return 0;
+}
+int sgs_timing_set_mask(void* handle, unsigned mask) {
+    if (!handle) return SGS_ERR_BAD_ARG;
+    ((Timing*)handle)->mask = mask;
     return 0;
 }
 int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms) {

@@ -178,7 +178,7 @@ class AvatarStep:
             L_.sgs_timing_record(tm, 11, st)
 
     def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None,
-                prologue=None, stages: bool = True):
+                prologue=None, stages: bool = True, stage_mask: Optional[int] = None):
         """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
         graph and return replay().  The launch sequence is static -- capacity-sized pair list,
         device-side counts, no host round trip -- so the whole frame becomes one graph launch.
@@ -188,10 +188,14 @@ class AvatarStep:
         uploaded target image into `dL_dimage` / `loss_weight`.  stages=False leaves the stage
         event records out of the graph (see record_stages)."""
         keep, self.record_stages = self.record_stages, bool(stages)
+        if self.timing and stage_mask is not None:     # record only these stage events in this graph
+            self.L.sgs_timing_set_mask(self.timing, int(stage_mask) & 0xffffffff)
         try:
             return self._capture(fr, dL_dimage, loss_weight, prologue)
         finally:
             self.record_stages = keep
+            if self.timing and stage_mask is not None:
+                self.L.sgs_timing_set_mask(self.timing, 0xffffffff)
 
     def _capture(self, fr, dL_dimage, loss_weight, prologue):
         cur = torch.cuda.current_stream(self.dev)
@@ -245,6 +249,12 @@ class AvatarStep:
             self._alloc_scratch()
             raise _lib.SgsError(f"pair list overflowed (needed {L}); capacity raised to {self.L_cap}, re-render")
         return L
+
+    def interval_ms(self, i: int, j: int) -> float:
+        """Device time between stage events i and j of the last frame that recorded both."""
+        ms = C.c_float()
+        _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
+        return float(ms.value)
 
     def stage_ms(self) -> dict:
         """Per-stage device times of the last forward+backward (needs timing=True)."""
