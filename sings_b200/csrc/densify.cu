@@ -40,16 +40,17 @@ int launch_densify_stats(int P, const float* grad2d, const int* radii, float* ac
 // 256-byte granularity (the caller guarantees it) except the last words, handled bytewise.
 __global__ void __launch_bounds__(256) clear3_kernel(char* a, size_t na, char* b, size_t nb, char* c, size_t nc) {
     pdl_sync();
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     char* const ptr[3] = {a, b, c};
     const size_t len[3] = {na, nb, nc};
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const size_t n16 = len[r] / 16;
-        uint4* p = reinterpret_cast<uint4*>(ptr[r]);
-        for (size_t i = tid; i < n16; i += stride) p[i] = z;
-        for (size_t i = n16 * 16 + tid; i < len[r]; i += stride) ptr[r][i] = 0;
+        const unsigned n16 = (unsigned)(len[r] / 16);           // regions are far below 64 GB
+        uint4* __restrict__ p = reinterpret_cast<uint4*>(ptr[r]);
+#pragma unroll 4
+        for (unsigned i = tid; i < n16; i += stride) p[i] = z;
+        for (size_t i = (size_t)n16 * 16 + tid; i < len[r]; i += stride) ptr[r][i] = 0;
     }
 }
 
