@@ -216,10 +216,15 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (P > 0) {
         rc = launch_depth_sort(P, lay, b, stream, debug);     // Gaussians by depth (N items)
         if (rc) return rc;
-        rc = launch_emit_pairs(P, lay, L_cap, b, host_dev, stream);     // scan + (tile|depth, id) pairs in depth order
-        if (rc) return rc;
-        rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
-        if (rc) return rc;
+        if (bin_css_supported(lay)) {
+            rc = launch_bin_css(P, lay, L_cap, b, host_dev, stream, debug);   // count / scan / scatter: the sorted pair list
+            if (rc) return rc;
+        } else {
+            rc = launch_emit_pairs(P, lay, L_cap, b, host_dev, stream);     // scan + (tile|depth, id) pairs in depth order
+            if (rc) return rc;
+            rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
+            if (rc) return rc;
+        }
     }
     tick(timing, 2, stream);
     // ranges + tiles bucketed by list length; per-pair reach mask over the 8 pixel blocks of a tile

@@ -40,6 +40,10 @@ struct RasterLayout {
     size_t cnt_off, hist_off, scan_off, nstat_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
     size_t nkeys0_off, nkeys1_off, nvals0_off, nvals1_off, rects_off;   // per-Gaussian depth-sort items
     size_t keys0_off, keys1_off, vals0_off, vals1_off, masks_off, bin_bytes;
+    // count / scan / scatter binning (raster_geometry.cu): per-(chunk, tile) pair counts (u16),
+    // their exclusive prefix over the chunks (u32), per-tile totals (u32); bin_ctas chunks
+    size_t bcount_off, bbase_off, btotal_off;
+    int bin_ctas;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
     int scan_blocks, sort_blocks, nsort_blocks, tiles, gx, gy, end_bit, passes;
@@ -78,6 +82,11 @@ int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t st
 // chained scan of tiles touched + (tile|depth, id) emission in depth order
 int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
                       cudaStream_t stream);
+// the pair list by count / scan / scatter instead of emit_pairs + tile-id passes; writes the SORTED
+// list directly.  bin_css_supported: tile count within the shared-memory budget of the kernels.
+bool bin_css_supported(const RasterLayout& lay);
+int launch_bin_css(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
+                   cudaStream_t stream, int debug);
 // stable passes over the tile-id digits of the emitted pairs
 int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom, char* bin, cudaStream_t stream,
                      int debug);
