@@ -62,7 +62,10 @@ int sgs_timing_record(void* handle, int i, sgs_stream_t stream);
 int sgs_timing_set_mask(void* handle, unsigned mask);
 int sgs_timing_elapsed_ms(void* handle, int i, int j, float* ms);
 
-/* Record-and-replay of a launch sequence (CUDA graph).  Everything enqueued on `stream` between
+/* Record-and-replay of a launch sequence (CUDA graph).  No reference counterpart: the reference
+ * launches ~100 eager kernels per frame with host round trips in between
+ * (gs_renderer_single.py:87-95 blocks on a device-to-host copy inside the rasterizer; the
+ * matrix -> quaternion code of rotations.py:98-149 synchronises on boolean masks).  Everything enqueued on `stream` between
  * sgs_graph_begin and sgs_graph_end -- calls of this library; `stream` must not be the legacy
  * default stream -- becomes one executable graph; sgs_graph_launch replays it on any stream.
  * The entry points of this library are capture-safe: no allocation, no host synchronisation,
