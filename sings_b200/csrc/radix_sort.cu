@@ -89,6 +89,27 @@ __device__ __forceinline__ uint2 block_excl_scan2(uint2 v, uint2* s_tmp, int lan
 #define SGS_SORT_MINB_L 2
 #endif
 
+// Lanes of the warp holding the same 8-bit digit.  match.any's latency grows with the number of
+// distinct values in the warp, and a warp of radix digits holds ~28 of them: eight ballots (one
+// per bit, independent of each other) give the same mask in a few dozen cycles.
+#ifndef SGS_SORT_MATCH_BALLOT
+#define SGS_SORT_MATCH_BALLOT 1
+#endif
+__device__ __forceinline__ unsigned match_digit(unsigned d) {
+#if SGS_SORT_MATCH_BALLOT
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+#else
+    return __match_any_sync(0xffffffffu, d);
+#endif
+}
+
 template <typename K, int SORT_ITEMS, int LOOKBACK_BATCH>
 __global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 8 ? SGS_SORT_MINB_L : 4) onesweep_pass_kernel(SortPass<K> a) {
     constexpr int SORT_TILE = SORT_ITEMS * SORT_THREADS;
@@ -138,7 +159,7 @@ __global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 8 ? SGS_SORT_MINB_L
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         unsigned d = (unsigned)(key[i] >> a.shift) & a.mask;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned peers = match_digit(d);
         int leader = __ffs(peers) - 1;
         unsigned old = 0;
         if (lane == leader) {
