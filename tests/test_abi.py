@@ -72,3 +72,14 @@ def test_settings_tuple_is_the_classic_12_field_api():
     GaussianRasterizationSettings(image_height=1, image_width=1, tanfovx=1.0, tanfovy=1.0, bg=None,
                                   scale_modifier=1.0, viewmatrix=None, projmatrix=None, sh_degree=0,
                                   campos=None, prefiltered=False, debug=False)
+
+
+def test_flag_constants_match_header():
+    """The bits of the rasterizer entry points' `debug` argument are the same in the header and in
+    the Python binding."""
+    import re
+    from sings_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "sings_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SGS_FLAG_(\w+)\s+(\d+)", hdr)}
+    assert flags == {"SYNC_CHECK": _lib.FLAG_SYNC_CHECK, "PRECLEARED": _lib.FLAG_PRECLEARED,
+                     "EARLY_PARAMS": _lib.FLAG_EARLY_PARAMS}
