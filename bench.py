@@ -185,9 +185,10 @@ def algorithmic_bytes(N, J, M, L, W, H, n_vis, passes=6):
     return {
         "lbs_fwd": N * (100 + 4 * J),
         "lbs_bwd": N * (148 + 4 * J),
-        "geometry": N * (236 + 75) + 8 * N + 20 * N + 12 * L,      # preprocess + scan + duplicateWithKeys
-        "sort": (8 + 24 * passes) * L,
-        "ranges": 8 * L + 8 * tiles,
+        "geometry": N * (236 + 75),                                 # preprocessCUDA
+        # InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges: one stage
+        # here, because the count / scan / scatter binning produces list and ranges together
+        "binning": 8 * N + 20 * N + 12 * L + (8 + 24 * passes) * L + 8 * L + 8 * tiles,
         "blend_fwd": 40 * L + 20 * pix + 8 * tiles,
         "blend_bwd": 40 * L + 20 * pix + 36 * n_vis,
         "geometry_bwd": (300 + 256) * n_vis,
@@ -331,6 +332,7 @@ def gpu_arm(args):
         barrier()
         hot_coarse = float(np.mean([s["step"].interval_ms(8, 3) for s in sets]))
     stage = {k: float(np.mean(v)) for k, v in stage.items()}
+    stage["binning"] = stage.pop("sort") + stage.pop("ranges")
     Lm = float(np.mean([s["L"] for s in sets]))
     n_vis = float(np.mean([int((s["step"].radii > 0).sum().item()) for s in sets]))
     ab = algorithmic_bytes(N_GAUSS, N_JOINTS, 16, Lm, W_IMG, H_IMG, n_vis)
@@ -342,7 +344,7 @@ def gpu_arm(args):
             stages_out[k] = {"ms": round(ms, 4), "alg_mb": round(b / 1e6, 2), "gbs": round(gbs, 1),
                              "frac": round(gbs / hbm_peak, 4)}
     dom = max((k for k in stages_out), key=lambda k: stages_out[k]["ms"])
-    hot = ["lbs_fwd", "geometry", "sort", "ranges"]
+    hot = ["lbs_fwd", "geometry", "binning"]
     hot_b = sum(ab[k] for k in hot)
     hot_ms = sum(stage[k] for k in hot)
     hot_one = hot_coarse if hot_coarse else hot_ms
@@ -352,7 +354,7 @@ def gpu_arm(args):
         with open(tp) as f:
             tj = json.load(f)
         kern = {"lbs_fwd": "lbs_fwd_kernel", "lbs_bwd": "lbs_bwd_kernel", "geometry": "geometry_kernel",
-                "sort": "onesweep_pass_kernel", "ranges": "ranges_masks_kernel", "blend_fwd": "blend_fwd_kernel",
+                "binning": "bin_scatter_kernel", "blend_fwd": "blend_fwd_kernel",
                 "blend_bwd": "blend_bwd_kernel", "geometry_bwd": "geometry_bwd_kernel"}[dom]
         if kern in tj.get("kernels", {}):
             traffic, traffic_src = tj["kernels"][kern]["dram_bytes"], f"profiles/{tj.get('source')} ({kern})"

@@ -69,8 +69,9 @@ int ro_max_threads(void) {
  * coefficients), fixed op order.  Returns 0 below -80 (alpha would be < 1e-34). */
 static inline float expneg(float x) {
     x = fmaxf(x, -80.0f);
-    const float t = x * 1.44269504088896341f;
-    const float r = t + 12582912.0f;            /* 1.5 * 2^23: rounds t to the nearest integer */
+    /* one fused multiply-add: x log2(e) rounded to the nearest integer by the 1.5 * 2^23 magic
+     * addend (the packed f32x2 form of the CUDA kernels contracts a mul + add here anyway) */
+    const float r = fmaf(x, 1.44269504088896341f, 12582912.0f);
     const float n = r + -12582912.0f;
     float g = fmaf(n, -0.693359375f, x);
     g = fmaf(n, 2.12194440e-4f, g);

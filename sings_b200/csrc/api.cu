@@ -8,10 +8,53 @@
 
 using namespace sgs;
 
+#include <mutex>
+#include <vector>
+
 bool sgs::pdl_enabled() {
-    static int v = -1;
-    if (v < 0) v = getenv("SGS_NO_PDL") ? 0 : 1;
-    return v != 0;
+    static const bool v = getenv("SGS_NO_PDL") == nullptr;      // C++11: initialised once, thread-safe
+    return v;
+}
+
+// Per-(kernel, device) launch attributes are process state of the CUDA runtime, not of this
+// library; what we cache about them is guarded by one mutex so that concurrent host threads
+// (each on its own stream) may call every entry point.
+namespace {
+struct FuncState { const void* f; int dev; size_t smem; int threads; size_t occ_smem; long long resident; };
+std::mutex g_mu;
+std::vector<FuncState> g_funcs;
+FuncState& func_state(const void* f, int dev) {
+    for (auto& s : g_funcs)
+        if (s.f == f && s.dev == dev) return s;
+    g_funcs.push_back(FuncState{f, dev, 48 * 1024, 0, 0, -1});
+    return g_funcs.back();
+}
+}  // namespace
+
+cudaError_t sgs::ensure_max_smem(const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    FuncState& s = func_state(func, dev);
+    if (bytes <= s.smem) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) s.smem = bytes;
+    return e;
+}
+
+long long sgs::resident_ctas(const void* func, int threads, size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    FuncState& s = func_state(func, dev);
+    if (s.resident >= 0 && s.threads == threads && s.occ_smem == smem) return s.resident;
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem) != cudaSuccess) return 0;
+    s.threads = threads; s.occ_smem = smem; s.resident = (long long)sms * per_sm;
+    return s.resident;
 }
 
 struct Timing {
@@ -213,11 +256,15 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
+    // the binning by count / scan / scatter needs Gaussians to bin; an empty frame takes the
+    // search-based range kernel, which files every tile as empty
+    const bool css = P > 0 && bin_css_supported(lay) && !getenv("SGS_RADIX_BINNING");
     if (P > 0) {
         rc = launch_depth_sort(P, lay, b, stream, debug);     // Gaussians by depth (N items)
         if (rc) return rc;
-        if (bin_css_supported(lay)) {
-            rc = launch_bin_css(P, lay, L_cap, b, host_dev, stream, debug);   // count / scan / scatter: the sorted pair list
+        if (css) {
+            // count / scan / scatter: sorted pair list, tile ranges, length buckets, reach masks
+            rc = launch_bin_css(P, lay, L_cap, g, b, host_dev, stream, debug);
             if (rc) return rc;
         } else {
             rc = launch_emit_pairs(P, lay, L_cap, b, host_dev, stream);     // scan + (tile|depth, id) pairs in depth order
@@ -227,9 +274,11 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
         }
     }
     tick(timing, 2, stream);
-    // ranges + tiles bucketed by list length; per-pair reach mask over the 8 pixel blocks of a tile
-    rc = launch_ranges_masks(lay, L_cap, g, b, stream);
-    if (rc) return rc;
+    if (!css) {
+        // ranges + tiles bucketed by list length; per-pair reach mask over the 8 pixel blocks of a tile
+        rc = launch_ranges_masks(lay, L_cap, g, b, stream);
+        if (rc) return rc;
+    }
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
@@ -273,7 +322,7 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     tick(timing, 5, stream);
     if (!precleared) SGS_CUDA_OK(cudaMemsetAsync(acc, 0, acc_total_bytes(P), stream));
     rc = launch_blend_bwd(lay, W, H, (const char*)geom, (const char*)binning, (const char*)img, bg,
-                          dL_dout_color, (float*)acc, reinterpret_cast<int*>((char*)acc + acc_rows_bytes(P)), stream);
+                          dL_dout_color, (float*)acc, stream);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 6, stream);

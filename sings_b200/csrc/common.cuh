@@ -73,6 +73,13 @@ __device__ __forceinline__ void pdl_sync() {       // the default kernel prologu
 }
 
 bool pdl_enabled();      // api.cu
+// cudaFuncAttributeMaxDynamicSharedMemorySize, raised once per (kernel, device) under a mutex
+// instead of on every launch (api.cu)
+cudaError_t ensure_max_smem(const void* func, size_t bytes);
+template <typename Kern>
+inline cudaError_t set_max_smem(Kern k, size_t bytes) { return ensure_max_smem((const void*)k, bytes); }
+// resident CTAs of a kernel on the current device (SMs x occupancy), cached under the same mutex
+long long resident_ctas(const void* func, int threads, size_t smem);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
@@ -256,8 +263,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 // clamped (the result, 1.8e-35, is far below every threshold that consumes it).
 __device__ __forceinline__ float expneg(float x) {
     x = fmaxf(x, -80.0f);
-    const float t = __fmul_rn(x, 1.44269504088896341f);
-    const float r = __fadd_rn(t, 12582912.0f);
+    const float r = __fmaf_rn(x, 1.44269504088896341f, 12582912.0f);
     const float n = __fadd_rn(r, -12582912.0f);
     float g = __fmaf_rn(n, -0.693359375f, x);
     g = __fmaf_rn(n, 2.12194440e-4f, g);
@@ -267,6 +273,52 @@ __device__ __forceinline__ float expneg(float x) {
     const float c = __fmaf_rn(8.2901455462e-03f, g, 4.1898854077e-02f);
     const float p = __fmaf_rn(__fmaf_rn(c, g2, b), g2, a);
     return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+// ---- packed binary32 pairs (sm_100: FFMA2 / FMUL2 / FADD2, one issue slot for two IEEE rn
+// operations).  The blend kernels evaluate two list entries per instruction with them; the
+// results are those of the scalar sequence, lane by lane.  NOTE: ptxas contracts a
+// mul.rn.f32x2 whose only consumer is an add.rn.f32x2 into one FFMA2 even under -fmad=false
+// (the scalar _rn forms are never contracted), so bit-exact code must not spell that
+// pattern: every multiply here feeds a multiply, an fma multiplicand, or an fma ADDEND. ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmov.b64 rc, {%6,%7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0,%1}, rd;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\n"
+        "mul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\n"
+        "add.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// expneg of two arguments at once (each lane of the pair: exactly the scalar sequence above).
+// r2 is returned too: the caller splices the exponents in with integer adds.
+__device__ __forceinline__ float2 expneg2(float2 x) {
+    x.x = fmaxf(x.x, -80.0f); x.y = fmaxf(x.y, -80.0f);
+    const float2 r = ffma2(x, splat2(1.44269504088896341f), splat2(12582912.0f));
+    const float2 n = fadd2(r, splat2(-12582912.0f));
+    float2 g = ffma2(n, splat2(-0.693359375f), x);
+    g = ffma2(n, splat2(2.12194440e-4f), g);
+    const float2 g2 = fmul2(g, g);
+    const float2 a = ffma2(splat2(9.9999970198e-01f), g, splat2(1.0f));
+    const float2 b = ffma2(splat2(1.6667643189e-01f), g, splat2(4.9999141693e-01f));
+    const float2 c = ffma2(splat2(8.2901455462e-03f), g, splat2(4.1898854077e-02f));
+    const float2 p = ffma2(ffma2(c, g2, b), g2, a);
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
 }
 
 // column-major 4x4 times (x,y,z,1), row r  ([upstream] auxiliary.h transformPoint4x3/4x4)

@@ -758,7 +758,7 @@ int launch_lbs_fwd(const LbsArgs& a, const LbsOut& o, cudaStream_t stream) {
     if (((uintptr_t)a.A & 15) || (o.T && ((uintptr_t)o.T & 15))) return SGS_ERR_MISALIGNED;
     const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, false);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
-    SGS_CUDA_OK(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGS_CUDA_OK(set_max_smem(lbs_fwd_kernel, smem));
     launch_pdl(lbs_fwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, o);
     SGS_LAUNCH_OK();
     return 0;
@@ -986,7 +986,7 @@ int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
     if (((uintptr_t)a.A & 15) || (g.g_T && ((uintptr_t)g.g_T & 15))) return SGS_ERR_MISALIGNED;
     const size_t smem = lbs_tile_bytes(a.B, a.J, a.rot == nullptr, true);
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
-    SGS_CUDA_OK(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGS_CUDA_OK(set_max_smem(lbs_bwd_kernel, smem));
     launch_pdl(lbs_bwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, g);
     SGS_LAUNCH_OK();
     return 0;

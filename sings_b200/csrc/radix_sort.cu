@@ -282,19 +282,7 @@ __global__ void __launch_bounds__(256) histogram_kernel(const unsigned long long
 // on a predecessor's look-back word can then never keep that predecessor from running.
 template <typename Kern>
 static bool all_resident(Kern k, int blocks, size_t smem) {
-    static const void* c_k[4];           // tiny cache: the occupancy query costs microseconds
-    static size_t c_smem[4];
-    static long long c_cap[4];
-    static int c_n = 0;
-    for (int i = 0; i < c_n; i++)
-        if (c_k[i] == (const void*)k && c_smem[i] == smem) return (long long)blocks <= c_cap[i];
-    int dev = 0, sms = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SORT_THREADS, smem) != cudaSuccess) return false;
-    const long long cap = (long long)sms * per_sm;
-    if (c_n < 4) { c_k[c_n] = (const void*)k; c_smem[c_n] = smem; c_cap[c_n] = cap; c_n++; }
-    return (long long)blocks <= cap;
+    return (long long)blocks <= resident_ctas((const void*)k, SORT_THREADS, smem);
 }
 
 // passes [p0, p1) of the 64-bit pair sort; pass p sorts key bits [8p, 8p+8) below end_bit
@@ -321,7 +309,7 @@ static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* 
         a.gx_tiles = gx_tiles;
         auto k = onesweep_pass_kernel<unsigned long long, SORT_ITEMS_L, SGS_LOOKBACK_L>;
         const size_t smem = (size_t)SORT_TILE_L * 12;
-        SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGS_CUDA_OK(set_max_smem(k, smem));
         if (all_resident(k, blocks, smem)) a.ticket = nullptr;
         SGS_CUDA_OK(launch_pdl(k, blocks, SORT_THREADS, smem, stream, a));
         SGS_STAGE_OK(debug, stream);
@@ -370,7 +358,7 @@ int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom,
                       counters + CNT_SORT_TICKET0, counters + CNT_NUM_RENDERED, L_cap, DEPTH_PASSES,
                       lay.passes, lay.end_bit, lay.sort_blocks, stream, debug,
                       reinterpret_cast<const float4*>(geom + lay.rec_off),
-                      SGS_MASKS_IN_SORT ? reinterpret_cast<unsigned char*>(bin + lay.masks_off) : nullptr, lay.gx);
+                      nullptr, lay.gx);
 }
 
 size_t sort_scratch_bytes(long long n) {

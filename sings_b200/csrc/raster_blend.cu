@@ -20,6 +20,7 @@
 //    per warp and Gaussian (lanes 0..8 -> nine consecutive floats).
 #include "common.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace sgs {
 
@@ -36,20 +37,11 @@ namespace sgs {
 #ifndef SGS_BWD_MINB
 #define SGS_BWD_MINB 2
 #endif
-#ifndef SGS_BWD_ROWS
-#define SGS_BWD_ROWS 32
-#endif
-#ifndef SGS_BWD_P2ROW            // phase 2 of the backward: 1 = one pixel row per loop trip, 0 = flat unrolled
-#define SGS_BWD_P2ROW 1
-#endif
 #ifndef SGS_FWD_WPC              // warps per CTA of the blend kernels: the 8 warps of a tile are autonomous,
 #define SGS_FWD_WPC 4            // so a tile may be spread over 8 / WPC smaller CTAs (finer scheduling grain)
 #endif
 #ifndef SGS_BWD_WPC
 #define SGS_BWD_WPC 4
-#endif
-#ifndef SGS_BLEND_PERSIST        // 1: persistent warps take (tile, pixel block) items from a device-side ticket
-#define SGS_BLEND_PERSIST 0      // counter, longest lists first; 0: one CTA per WPC pixel blocks of a tile
 #endif
 constexpr int FWD_WPC = SGS_FWD_WPC, BWD_WPC = SGS_BWD_WPC;
 constexpr int TILE_WARPS = TILE_PIX / 32;
@@ -142,76 +134,18 @@ __device__ __forceinline__ unsigned tile_of_rank(const BucketScan& bs, const uns
     return __ldg(bucket_list + (size_t)(LEN_BUCKETS - 1 - b) * tiles + (i - excl));
 }
 
-// Work distribution of the two blend kernels.  An item is (tile rank, pixel block): the 8 warps
-// of a tile are autonomous, so items are handed out one per WARP, in rank order (longest lists
-// first), from a device-side ticket counter: no CTA waits for its slowest warp, the ~3/4 of the
-// tiles that are empty cost a loop trip instead of a CTA launch, and the tail is one warp deep.
-// The next ticket is requested before the current item is processed (its latency is hidden).
-// for_each_item(fn): fn(tile, warp) with warp = pixel block 0..7 of the tile.
+// Work distribution of the two blend kernels: a tile is spread over 8 / WPC CTAs of WPC
+// autonomous warps (warp = 8x4 pixel block), CTAs in longest-list-first order.  (Persistent
+// warps / CTAs pulling items from a ticket counter were measured 10 % slower -- a hardware-
+// scheduled CTA thins out as its short warps retire, which speeds up its long ones;
+// profiles/README.md, round 1.)
 template <int WPC, typename Fn>
 __device__ __forceinline__ void for_each_item(const unsigned* __restrict__ bucket_count,
-                                              const unsigned* __restrict__ bucket_list, int tiles,
-                                              int* __restrict__ ticket, Fn fn) {
-    const int lane = threadIdx.x & 31;
-    const BucketScan bs = bucket_scan(bucket_count);
-#if SGS_BLEND_PERSIST == 2
-    // CTA-level tickets: an item is (tile rank, group of WPC pixel blocks); the CTA's warps work on
-    // the same tile at the same time, so its list, masks and records are shared through L1
-    constexpr int PARTS = TILE_WARPS / WPC;
-    __shared__ unsigned s_item;
-    const unsigned n_items = (unsigned)tiles * PARTS;
-    unsigned next = 0;
-    if (threadIdx.x == 0) s_item = (unsigned)atomicAdd(ticket, 1);
-    __syncthreads();
-    for (;;) {
-        const unsigned item = s_item;
-        if (item >= n_items) break;
-        if (threadIdx.x == 0) next = (unsigned)atomicAdd(ticket, 1);     // consumed after the item
-        fn(tile_of_rank(bs, bucket_list, tiles, item / PARTS), (int)(item % PARTS) * WPC + (int)(threadIdx.x >> 5));
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = next;
-        __syncthreads();
-    }
-#elif SGS_BLEND_PERSIST
-    const unsigned n_items = (unsigned)tiles * TILE_WARPS;
-    unsigned next = lane == 0 ? (unsigned)atomicAdd(ticket, 1) : 0u;
-    for (;;) {
-        const unsigned item = __shfl_sync(0xffffffffu, next, 0);
-        if (item >= n_items) break;
-        if (lane == 0) next = (unsigned)atomicAdd(ticket, 1);
-        fn(tile_of_rank(bs, bucket_list, tiles, item / TILE_WARPS), (int)(item % TILE_WARPS));
-        __syncwarp();
-    }
-#else
+                                              const unsigned* __restrict__ bucket_list, int tiles, Fn fn) {
     constexpr int PARTS = TILE_WARPS / WPC;      // CTAs per tile
-#ifdef SGS_DEBUG_TOPK            // timing experiment only: process just the K longest tiles (wrong results)
-    if ((int)(blockIdx.x / PARTS) >= SGS_DEBUG_TOPK) return;
-#endif
+    const BucketScan bs = bucket_scan(bucket_count);
     fn(tile_of_rank(bs, bucket_list, tiles, blockIdx.x / PARTS),
        (int)(blockIdx.x % PARTS) * WPC + (int)(threadIdx.x >> 5));
-#endif
-}
-
-// persistent grid: every SM filled with as many CTAs as fit (cached occupancy query)
-template <typename Kern>
-static int persistent_blocks(Kern k, int threads, size_t smem, long long max_blocks) {
-    static const void* c_k[4];
-    static size_t c_smem[4];
-    static int c_blocks[4];
-    static int c_n = 0;
-    int blocks = 0;
-    for (int i = 0; i < c_n; i++)
-        if (c_k[i] == (const void*)k && c_smem[i] == smem) blocks = c_blocks[i];
-    if (!blocks) {
-        int dev = 0, sms = 0, per_sm = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess || per_sm < 1)
-            return 0;
-        blocks = sms * per_sm;
-        if (c_n < 4) { c_k[c_n] = (const void*)k; c_smem[c_n] = smem; c_blocks[c_n] = blocks; c_n++; }
-    }
-    return (int)(blocks < max_blocks ? blocks : max_blocks);
 }
 
 static inline const unsigned long long* sorted_keys(const RasterLayout& lay, const char* bin) {
@@ -246,12 +180,12 @@ __device__ __forceinline__ bool reaches_block(const float4 q0, const float4 q1, 
 }
 
 struct Rec {
-    float4 q0, q1, q2, q3;
+    float4 q0, q1, q2;
 };
 __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned id) {
     const float4* p = rec + 4 * (size_t)id;
     Rec r;
-    r.q0 = __ldg(p); r.q1 = __ldg(p + 1); r.q2 = __ldg(p + 2); r.q3 = __ldg(p + 3);
+    r.q0 = __ldg(p); r.q1 = __ldg(p + 1); r.q2 = __ldg(p + 2);
     return r;
 }
 
@@ -271,7 +205,6 @@ ranges_masks_kernel(const unsigned long long* __restrict__ keys, const unsigned*
         tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
         return;
     }
-    if (!masks) return;              // the masks came out of the last sort pass (radix_sort.cu)
     const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
     const long long i = (long long)(blockIdx.x - range_blocks) * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -288,14 +221,13 @@ int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* ge
     const int range_blocks = (lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32);
     long long blocks = (L_cap + RANGE_THREADS - 1) / RANGE_THREADS;
     if (blocks < 1) blocks = 1;
-    if (SGS_MASKS_IN_SORT) blocks = 0;       // only the tile-range CTAs
     launch_pdl(ranges_masks_kernel, (unsigned)(range_blocks + blocks), RANGE_THREADS, 0, stream,
         sorted_keys(lay, bin), sorted_vals(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
         reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx, lay.tiles, range_blocks,
         reinterpret_cast<uint2*>(bin + lay.ranges_off),
         reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<unsigned*>(bin + lay.bktlist_off),
-        SGS_MASKS_IN_SORT ? nullptr : reinterpret_cast<unsigned char*>(bin + lay.masks_off));
+        reinterpret_cast<unsigned char*>(bin + lay.masks_off));
     SGS_LAUNCH_OK();
     return 0;
 }
@@ -311,14 +243,70 @@ int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* ge
 // (done) and the colour FMAs, so a lone warp on an SM -- the tail of the kernel is the tile
 // with the longest list -- still retires a pair every few cycles.  No CTA barrier anywhere;
 // a warp leaves as soon as its 32 pixels have saturated.
+//
+// EVAL works on TWO ring entries per instruction (packed binary32 pairs, FFMA2 / FMUL2 /
+// FADD2 of sm_100: the kernel is issue-bound, and the falloff + exp chain is 19 of its ~33
+// floating-point operations per pair).  The ring therefore keeps the geometric part of two
+// consecutive entries interleaved -- (x0, x1, y0, y1), (A0, A1, B0, B1), (C0, C1, o0, o1) --
+// so one broadcast LDS.128 delivers an operand pair in an aligned register pair; the colour
+// part stays one float4 per entry for COMPOSITE.  Lane by lane the operations and their
+// order are those of the scalar formulation: results are unchanged, bit for bit.
 // ------------------------------------------------------------------------------------------
 constexpr int RING_SLOTS = 64;     // >= 32 + FWD_U
+static_assert(FWD_U == 4 && BWD_U == 4, "entries are evaluated in packed pairs; the four list positions of a "
+              "batch come from one LDS.128");
+
+struct RingGeo {                    // two consecutive ring entries per element
+    float4 xy[RING_SLOTS / 2];      // x0, x1, y0, y1
+    float4 ab[RING_SLOTS / 2];      // -a/2 (x2), -b (x2)
+    float4 co[RING_SLOTS / 2];      // -c/2 (x2), opacity (x2)
+};
+__device__ __forceinline__ void ring_clear(RingGeo& g, int lane) {      // ring slots always hold finite values
+    g.xy[lane] = g.ab[lane] = g.co[lane] = make_float4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void ring_put(RingGeo& g, unsigned slot, const float4 q0, const float4 q1) {
+    const unsigned ps = slot >> 1, e = slot & 1u;
+    float* xy = reinterpret_cast<float*>(&g.xy[ps]);
+    float* ab = reinterpret_cast<float*>(&g.ab[ps]);
+    float* co = reinterpret_cast<float*>(&g.co[ps]);
+    xy[e] = q0.x; xy[2 + e] = q0.y;
+    ab[e] = q0.z; ab[2 + e] = q0.w;
+    co[e] = q1.x; co[2 + e] = q1.y;
+}
+// exponent ("power"), falloff G = exp(min(power, 0)) and opacity * G of one packed pair of entries
+struct PairEval {
+    float2 power, G, oG;
+};
+__device__ __forceinline__ PairEval ring_eval(const RingGeo& g, unsigned ps, const float2 npx, const float2 npy) {
+    const float4 a = g.xy[ps], b = g.ab[ps], c = g.co[ps];
+    const float2 dx = fadd2(make_float2(a.x, a.y), npx), dy = fadd2(make_float2(a.z, a.w), npy);
+    const float2 uu = fmul2(make_float2(b.x, b.y), dx), vv = fmul2(make_float2(c.x, c.y), dy);
+    const float2 ww = fmul2(make_float2(b.z, b.w), dx);
+    PairEval r;
+    r.power = ffma2(ww, dy, ffma2(vv, dy, fmul2(uu, dx)));
+    // (no min(power, 0): an entry with power > 0 is rejected by its caller whatever G comes out)
+    r.G = expneg2(r.power);
+    r.oG = fmul2(make_float2(c.z, c.w), r.G);
+    return r;
+}
 
 struct FwdBatch {
-    float al[FWD_U], om[FWD_U], r[FWD_U], g[FWD_U], b[FWD_U], z[FWD_U];
+    float al[FWD_U], om[FWD_U];
+    float4 c[FWD_U];                // r, g, b, depth (AUX) | list position + 1 (bits)
     unsigned pos[FWD_U];
 };
 
+// AUX: the caller wants the depth image too (GaussianRasterizer.forward_aux); the colour entry of
+// the ring is then (r, g, b, depth) and the list positions live in their own array.  Without it
+// the fourth float carries the list position: one LDS.128 less per batch, one packed FMA narrower.
+template <bool AUX>
+struct FwdWarpSmem {
+    RingGeo geo;
+    float4 c[RING_SLOTS];
+    unsigned pos[AUX ? RING_SLOTS : 4];       // list position + 1
+};
+
+template <bool AUX>
 __global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_MINB * (TILE_WARPS / FWD_WPC))
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
@@ -327,34 +315,28 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
-                 float* __restrict__ out_depth, int* __restrict__ ticket) {
-    __shared__ float4 s_q0[FWD_WPC][RING_SLOTS];     // x, y, -a/2, -b
-    __shared__ float4 s_q1[FWD_WPC][RING_SLOTS];     // -c/2, opacity, pmin, r
-    __shared__ float4 s_q2[FWD_WPC][RING_SLOTS];     // g, b, depth, list position + 1
+                 float* __restrict__ out_depth) {
+    __shared__ __align__(16) FwdWarpSmem<AUX> s_fwd[FWD_WPC];
 
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
-    float4* const rq0 = s_q0[cwarp];
-    float4* const rq1 = s_q1[cwarp];
-    float4* const rq2 = s_q2[cwarp];
-    // ring slots always hold finite records (an empty slot contributes colour * 0)
-    rq0[lane] = rq0[lane + 32] = make_float4(0, 0, 0, 0);
-    rq1[lane] = rq1[lane + 32] = make_float4(0, 0, 0, 0);
-    rq2[lane] = rq2[lane + 32] = make_float4(0, 0, 0, 0);
+    FwdWarpSmem<AUX>& sm = s_fwd[cwarp];
+    ring_clear(sm.geo, lane);
+    sm.c[lane] = sm.c[lane + 32] = make_float4(0, 0, 0, 0);
+    if (AUX) sm.pos[lane] = sm.pos[lane + 32] = 0u;
     pdl_sync();
-  for_each_item<FWD_WPC>(bucket_count, bucket_list, tiles, ticket, [&](const unsigned tile, const int warp) {
+  for_each_item<FWD_WPC>(bucket_count, bucket_list, tiles, [&](const unsigned tile, const int warp) {
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
     const int px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float bx0 = (float)(tile_x * TILE + ((warp & 1) << 3)), bx1 = bx0 + 7.0f;
-    const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2)), by1 = by0 + 3.0f;
+    const float2 npx = splat2(-(float)px), npy = splat2(-(float)py);
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
 
     bool done = !inside;
-    float T = 1.0f, T_fin = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dacc = 0.0f;
+    float T = 1.0f;
+    float2 C01 = splat2(0.0f), C2D = splat2(0.0f);     // (red, green), (blue, depth)
     unsigned last = 0;
     unsigned head = 0, tail = 0;       // ring: consumed / produced pair counts (warp-uniform)
 
@@ -362,60 +344,71 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     bool cur_is_b = false;             // which of the two is waiting (warp-uniform)
 #pragma unroll
     for (int u = 0; u < FWD_U; u++) {
-        bat_a.al[u] = 0.0f; bat_a.om[u] = 1.0f; bat_a.r[u] = bat_a.g[u] = bat_a.b[u] = bat_a.z[u] = 0.0f; bat_a.pos[u] = 0;
+        bat_a.al[u] = 0.0f; bat_a.om[u] = 1.0f; bat_a.c[u] = make_float4(0, 0, 0, 0); bat_a.pos[u] = 0;
     }
 
-    // alphas of ring entries [base, base + FWD_U); entries at or beyond `limit` are empty
-    auto eval = [&](FwdBatch& e, unsigned base, unsigned limit) {
+    // alphas of ring entries [base, base + FWD_U) (base is a multiple of FWD_U); with LIMIT,
+    // entries at or beyond `limit` are empty (only the drain meets a partial batch).  A rejected
+    // entry gets alpha 0 (1 - alpha = 1 exactly) and list position 0.
+    auto eval = [&](FwdBatch& e, unsigned base, unsigned limit, auto LIMIT) {
+        const unsigned s0 = base & (RING_SLOTS - 1);
+        unsigned pos4[4] = {0u, 0u, 0u, 0u};
+        if (AUX) {
+            const uint4 pp = *reinterpret_cast<const uint4*>(&sm.pos[s0]);
+            pos4[0] = pp.x; pos4[1] = pp.y; pos4[2] = pp.z; pos4[3] = pp.w;
+        }
 #pragma unroll
-        for (int u = 0; u < FWD_U; u++) {
-            const unsigned slot = (base + u) & (RING_SLOTS - 1);
-            const float4 q0 = rq0[slot];
-            const float4 q1 = rq1[slot];
-            const float4 q2 = rq2[slot];
-            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-            const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
-            const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
-            const float al = fminf(0.99f, __fmul_rn(q1.y, expneg(fminf(power, 0.0f))));
-            const bool ok = (base + u < limit) && !(power > 0.0f) && !(al < 1.0f / 255.0f);
-            e.al[u] = ok ? al : 0.0f;
-            e.om[u] = ok ? __fsub_rn(1.0f, al) : 1.0f;
-            e.r[u] = q1.w; e.g[u] = q2.x; e.b[u] = q2.y; e.z[u] = q2.z;
-            e.pos[u] = __float_as_uint(q2.w);
+        for (int h = 0; h < FWD_U / 2; h++) {
+            const PairEval pe = ring_eval(sm.geo, (s0 >> 1) + h, npx, npy);
+            const float pw[2] = {pe.power.x, pe.power.y}, og[2] = {pe.oG.x, pe.oG.y};
+            float al2[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int u = 2 * h + j;
+                const float al = fminf(0.99f, og[j]);
+                bool ok = !(pw[j] > 0.0f) && !(al < 1.0f / 255.0f);
+                if (decltype(LIMIT)::value) ok = ok && (base + u < limit);
+                al2[j] = ok ? al : 0.0f;
+                e.al[u] = al2[j];
+                e.c[u] = sm.c[s0 + u];
+                e.pos[u] = ok ? (AUX ? pos4[u] : __float_as_uint(e.c[u].w)) : 0u;
+            }
+            const float2 om = ffma2(make_float2(al2[0], al2[1]), splat2(-1.0f), splat2(1.0f));    // 1 - alpha
+            e.om[2 * h] = om.x; e.om[2 * h + 1] = om.y;
         }
     };
-    // fold a batch into the pixel state, in order.  T keeps multiplying after saturation
-    // (T_fin holds the reported value); an empty / rejected entry has al = 0, om = 1.
+    // fold a batch into the pixel state, in order ([upstream] renderCUDA: test_T = T (1 - alpha);
+    // test_T < 1e-4 -> done, the entry is NOT applied; else C += c alpha T, T = test_T, the entry
+    // becomes the last contributor).  Branch-free: T freezes when the pixel saturates (so it ends
+    // as the reported final_T), the weight of every later entry is 0.  A rejected entry has
+    // alpha 0: test_T = T exactly, and T >= 1e-4 as long as the pixel is live, so it needs no test
+    // of its own.  Colour and depth accumulate in two packed FMAs (C0, C1), (C2, depth).
     auto composite = [&](const FwdBatch& e) {
 #pragma unroll
         for (int u = 0; u < FWD_U; u++) {
             const float test_T = __fmul_rn(T, e.om[u]);
-            const bool hit = e.al[u] > 0.0f;
-            const bool kill = hit && !done && test_T < 0.0001f;
-            T_fin = kill ? T : T_fin;
-            done = done || kill;
+            done = done || test_T < 0.0001f;
             const float wgt = done ? 0.0f : __fmul_rn(e.al[u], T);
-            C0 = __fmaf_rn(e.r[u], wgt, C0);
-            C1 = __fmaf_rn(e.g[u], wgt, C1);
-            C2 = __fmaf_rn(e.b[u], wgt, C2);
-            Dacc = __fmaf_rn(e.z[u], wgt, Dacc);
-            last = (hit && !done) ? e.pos[u] : last;
-            T = test_T;
+            C01 = ffma2(make_float2(e.c[u].x, e.c[u].y), splat2(wgt), C01);
+            if (AUX) C2D = ffma2(make_float2(e.c[u].z, e.c[u].w), splat2(wgt), C2D);
+            else C2D.x = __fmaf_rn(e.c[u].z, wgt, C2D.x);
+            if (!done) last = max(last, e.pos[u]);
+            T = done ? T : test_T;
         }
     };
+    const std::true_type with_limit;
+    const std::false_type no_limit;
 
     // Staging pipeline, per chunk of 32 list entries (one per lane): reach-mask bytes run four
     // chunks ahead, Gaussian ids of the relevant entries two chunks ahead, their records one
     // chunk ahead -- the dependent mask -> id -> record gather never sits on the critical path,
-    // and a chunk without relevant entries costs a ballot.  (Streaming the masks as 32-bit words,
-    // 128 entries per load and three loads in flight, measured the same 88 us: the mask wait the
-    // profiler shows is covered by the other warps -- the kernel is issue-bound.)
+    // and a chunk without relevant entries costs a ballot.
     const unsigned char* mk = masks + range.x;
     const unsigned* pl = point_list + range.x;
     auto mask_at = [&](int at) { return at + lane < len ? (unsigned)__ldg(mk + at + lane) : 0u; };
     unsigned m0 = mask_at(0), m1 = mask_at(32), m2 = mask_at(64), m3 = mask_at(96);
     Rec p;
-    p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
+    p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
     if ((m0 >> warp) & 1u) p = load_rec(rec, __ldg(pl + lane));
     unsigned nid = ((m1 >> warp) & 1u) ? __ldg(pl + 32 + lane) : 0u;
     for (int pos = 0; pos < len; pos += 32) {
@@ -425,9 +418,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         __syncwarp();                  // earlier ring reads are complete before slots are reused
         if (rel) {
             const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
-            rq0[slot] = p.q0;
-            rq1[slot] = p.q1;
-            rq2[slot] = make_float4(p.q2.x, p.q2.y, p.q2.z, __uint_as_float((unsigned)(pos + lane + 1)));
+            ring_put(sm.geo, slot, p.q0, p.q1);
+            sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, AUX ? p.q2.z : __uint_as_float((unsigned)(pos + lane + 1)));
+            if (AUX) sm.pos[slot] = (unsigned)(pos + lane + 1);
         }
         tail += __popc(bits);
         __syncwarp();
@@ -436,8 +429,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(pos + 128);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= FWD_U) {
-            if (!cur_is_b) { eval(bat_b, head, tail); composite(bat_a); }
-            else           { eval(bat_a, head, tail); composite(bat_b); }
+            if (!cur_is_b) { eval(bat_b, head, tail, no_limit); composite(bat_a); }
+            else           { eval(bat_a, head, tail, no_limit); composite(bat_b); }
             cur_is_b = !cur_is_b;
             head += FWD_U;
         }
@@ -446,19 +439,18 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     // entry ever reached this pixel block -- three quarters of the tiles of an avatar frame are
     // empty, and their warps would spend ~400 instructions compositing empty batches.
     if (tail != 0) {
-        if (!cur_is_b) { eval(bat_b, head, tail); composite(bat_a); composite(bat_b); }
-        else           { eval(bat_a, head, tail); composite(bat_b); composite(bat_a); }
+        if (!cur_is_b) { eval(bat_b, head, tail, with_limit); composite(bat_a); composite(bat_b); }
+        else           { eval(bat_a, head, tail, with_limit); composite(bat_b); composite(bat_a); }
     }
     if (inside) {
         const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
-        const float Tr = done ? T_fin : T;       // a saturated pixel reports the T it stopped at
-        final_T[pix] = Tr;
+        final_T[pix] = T;                        // a saturated pixel reports the T it stopped at
         n_contrib[pix] = last;
-        out_color[pix] = __fmaf_rn(Tr, bg[0], C0);
-        out_color[plane + pix] = __fmaf_rn(Tr, bg[1], C1);
-        out_color[2 * plane + pix] = __fmaf_rn(Tr, bg[2], C2);
-        if (out_alpha) out_alpha[pix] = __fsub_rn(1.0f, Tr);
-        if (out_depth) out_depth[pix] = Dacc;
+        out_color[pix] = __fmaf_rn(T, bg[0], C01.x);
+        out_color[plane + pix] = __fmaf_rn(T, bg[1], C01.y);
+        out_color[2 * plane + pix] = __fmaf_rn(T, bg[2], C2D.x);
+        if (out_alpha) out_alpha[pix] = __fsub_rn(1.0f, T);
+        if (out_depth) out_depth[pix] = C2D.y;
     }
   });
 }
@@ -466,21 +458,15 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
                      float* out_depth, cudaStream_t stream) {
-    long long blocks = (long long)lay.tiles * (TILE_WARPS / FWD_WPC);
-#if SGS_BLEND_PERSIST
-    blocks = persistent_blocks(blend_fwd_kernel, FWD_WPC * 32, 0, blocks);
-    if (blocks < 1) return SGS_ERR_BAD_ARG;
-#endif
-    launch_pdl(blend_fwd_kernel, (unsigned)blocks, FWD_WPC * 32, 0, stream,
+    const long long blocks = (long long)lay.tiles * (TILE_WARPS / FWD_WPC);
+    SGS_CUDA_OK(launch_pdl(out_depth ? blend_fwd_kernel<true> : blend_fwd_kernel<false>, (unsigned)blocks, FWD_WPC * 32, 0, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
-        reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth,
-        reinterpret_cast<int*>(const_cast<char*>(bin) + lay.cnt_off) + CNT_BLEND_TICKET);
-    SGS_LAUNCH_OK();
+        reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth));
     return 0;
 }
 
@@ -488,33 +474,35 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
 // backward.  Same warp-autonomous streaming and ring queue, back to front, starting at the
 // largest contributor count among the warp's 32 pixels.  Two phases per warp:
 //  phase 1 (lane = pixel): the order-dependent part.  EVAL computes falloff G, alpha and
-//    1/(1-alpha) of the next BWD_U pairs while SEQ advances the pixel state (T, the colour
-//    behind the pair) over the previous BWD_U, branch-free.  Of everything the nine parameter
-//    gradients need, only TWO numbers per (pixel, pair) depend on the order: w = G dL/dalpha
-//    and d = alpha T.  SEQ parks them in a warp-private [pair][pixel] tile (row stride 33).
+//    1/(1-alpha) of the next BWD_U pairs (two entries per packed instruction, like the
+//    forward) while SEQ advances the pixel state (T, the colour behind the pair) over the
+//    previous BWD_U, branch-free.  Of everything the nine parameter gradients need, only TWO
+//    numbers per (pixel, pair) depend on the order: w = G dL/dalpha and d = alpha T.  SEQ parks
+//    them in a warp-private [pair][pixel] tile (row stride 36: conflict-free both ways, rows
+//    16-byte aligned).
 //  phase 2 (lane = pair, every 32 queued pairs): each lane walks the 32 pixels of its pair's
-//    row and accumulates  sum w, w dx, w dy, w dx^2, w dx dy, w dy^2, d dL/dpix_rgb  in
-//    registers -- the reduction over pixels costs no shuffles at all -- then folds them into
-//    the nine gradients and issues 2 vector + 1 scalar reduction for its Gaussian.
+//    row FOUR AT A TIME (LDS.128 + packed FMAs) and accumulates  sum w, w dx, w dy, w dx^2,
+//    w dx dy, w dy^2, d dL/dpix_rgb  in registers -- the reduction over pixels costs no
+//    shuffles at all -- then folds them into the nine gradients and issues 2 vector + 1
+//    scalar reduction for its Gaussian.
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_ROW = 33;        // padded row of the [pair][pixel] tiles: conflict-free both ways
-constexpr int BWD_ROWS = SGS_BWD_ROWS;          // pair rows per [pair][pixel] tile: 32, or 16 (half the shared memory)
-constexpr int BWD_HALVES = 32 / BWD_ROWS;       // phase-2 lanes per pair row; each walks 32 / BWD_HALVES pixels
-static_assert(BWD_ROWS == 32 || BWD_ROWS == 16, "BWD_ROWS must be 16 or 32");
+constexpr int BWD_ROW = 36;        // padded row of the [pair][pixel] tiles (16-byte aligned rows)
+constexpr int BWD_ROWS = 32;       // pair rows per [pair][pixel] tile
 static_assert(BWD_ROWS % BWD_U == 0, "a [pair][pixel] tile must hold whole batches");
 
 struct BwdBatch {
-    float al[BWD_U], G[BWD_U], inv[BWD_U], r[BWD_U], g[BWD_U], b[BWD_U];
+    float al[BWD_U], G[BWD_U], inv[BWD_U], b[BWD_U];
+    float2 rg[BWD_U];
 };
 
+constexpr int ID_SLOTS = 128;       // Gaussian ids by consumption index: must outlive the ring slot (until phase 2)
 struct BwdWarpSmem {
-    float4 q0[RING_SLOTS];          // x, y, -a/2, -b
-    float4 q1[RING_SLOTS];          // -c/2, opacity, list position (bits), r
-    float4 q2[RING_SLOTS];          // g, b, -, Gaussian id (bits)
+    RingGeo geo;
+    float4 c[RING_SLOTS];           // r, g, b, list position (bits)
     float w[BWD_ROWS * BWD_ROW];    // G * dL/dalpha   [pair][pixel]
     float d[BWD_ROWS * BWD_ROW];    // alpha * T       [pair][pixel]
     float dp[3][32];                // dL/dpixel rgb of the warp's 32 pixels
-    unsigned id[2][BWD_ROWS];       // Gaussian of each pair row (double-buffered by tile parity)
+    unsigned id[ID_SLOTS];          // Gaussian of each queued pair
 };
 
 __global__ void __launch_bounds__(BWD_WPC * 32, SGS_BWD_MINB * (TILE_WARPS / BWD_WPC))
@@ -524,24 +512,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                  const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
-                 const float* __restrict__ dL_dpix, float* __restrict__ acc, int* __restrict__ ticket) {
+                 const float* __restrict__ dL_dpix, float* __restrict__ acc) {
     extern __shared__ __align__(16) char s_bwd_raw[];
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
     BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(s_bwd_raw)[cwarp];
-    // ring slots always hold finite records
-    sm.q0[lane] = sm.q0[lane + 32] = make_float4(0, 0, 0, 0);
-    sm.q1[lane] = sm.q1[lane + 32] = make_float4(0, 0, 0, 0);
-    sm.q2[lane] = sm.q2[lane + 32] = make_float4(0, 0, 0, 0);
+    ring_clear(sm.geo, lane);
+    sm.c[lane] = sm.c[lane + 32] = make_float4(0, 0, 0, 0);
     pdl_sync();
-  for_each_item<BWD_WPC>(bucket_count, bucket_list, tiles, ticket, [&](const unsigned tile, const int warp) {
+  for_each_item<BWD_WPC>(bucket_count, bucket_list, tiles, [&](const unsigned tile, const int warp) {
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
     const int px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float bx0 = (float)(tile_x * TILE + ((warp & 1) << 3)), bx1 = bx0 + 7.0f;
-    const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2)), by1 = by0 + 3.0f;
+    const float2 npx = splat2(-(float)px), npy = splat2(-(float)py);
+    const float bx0 = (float)(tile_x * TILE + ((warp & 1) << 3));
+    const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2));
     const uint2 range = ranges[tile];
     if (range.y == range.x) return;
     const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
@@ -558,7 +544,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
 
     float T = T_final;
-    float B0 = 0.0f, B1 = 0.0f, B2 = 0.0f;     // colour accumulated behind the current pair
+    float2 B01 = splat2(0.0f);                 // colour accumulated behind the current pair (red, green)
+    float B2 = 0.0f;                           // ... blue
     unsigned head = 0, tail = 0;               // ring: consumed / produced pair counts
     unsigned row0 = 0;                         // first pair (consumption index) of the open [pair][pixel] tile; multiple of BWD_ROWS
 
@@ -567,28 +554,30 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 #pragma unroll
     for (int u = 0; u < BWD_U; u++) {
         bat_a.al[u] = 0.0f; bat_a.G[u] = 0.0f; bat_a.inv[u] = 1.0f;
-        bat_a.r[u] = bat_a.g[u] = bat_a.b[u] = 0.0f;
+        bat_a.rg[u] = splat2(0.0f); bat_a.b[u] = 0.0f;
     }
 
-    auto eval = [&](BwdBatch& e, unsigned base, unsigned limit) {
+    auto eval = [&](BwdBatch& e, unsigned base, unsigned limit, auto LIMIT) {
+        const unsigned s0 = base & (RING_SLOTS - 1);
 #pragma unroll
-        for (int u = 0; u < BWD_U; u++) {
-            const unsigned slot = (base + u) & (RING_SLOTS - 1);
-            const float4 q0 = sm.q0[slot];
-            const float4 q1 = sm.q1[slot];
-            const float4 q2 = sm.q2[slot];
-            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-            const float uu = __fmul_rn(q0.z, dx), vv = __fmul_rn(q1.x, dy), ww = __fmul_rn(q0.w, dx);
-            const float power = __fmaf_rn(ww, dy, __fmaf_rn(vv, dy, __fmul_rn(uu, dx)));
-            const float G = expneg(fminf(power, 0.0f));
-            const float al = fminf(0.99f, __fmul_rn(q1.y, G));
-            const bool ok = (base + u < limit) && __float_as_uint(q1.z) < last && !(power > 0.0f) &&
-                            !(al < 1.0f / 255.0f);
-            e.al[u] = ok ? al : 0.0f;
-            e.G[u] = ok ? G : 0.0f;
-            e.inv[u] = __fdividef(1.0f, 1.0f - e.al[u]);
-            e.r[u] = q1.w; e.g[u] = q2.x; e.b[u] = q2.y;
-            if (lane == u) sm.id[((base + u) / BWD_ROWS) & 1][(base + u) % BWD_ROWS] = __float_as_uint(q2.w);
+        for (int h = 0; h < BWD_U / 2; h++) {
+            const PairEval pe = ring_eval(sm.geo, (s0 >> 1) + h, npx, npy);
+            const float pw[2] = {pe.power.x, pe.power.y}, og[2] = {pe.oG.x, pe.oG.y}, Gj[2] = {pe.G.x, pe.G.y};
+            float al2[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int u = 2 * h + j;
+                const float4 c = sm.c[s0 + u];
+                const float al = fminf(0.99f, og[j]);
+                bool ok = __float_as_uint(c.w) < last && !(pw[j] > 0.0f) && !(al < 1.0f / 255.0f);
+                if (decltype(LIMIT)::value) ok = ok && (base + u < limit);
+                al2[j] = ok ? al : 0.0f;
+                e.al[u] = al2[j];
+                e.G[u] = ok ? Gj[j] : 0.0f;
+                e.rg[u] = make_float2(c.x, c.y); e.b[u] = c.z;
+            }
+            const float2 om = ffma2(make_float2(al2[0], al2[1]), splat2(-1.0f), splat2(1.0f));
+            e.inv[2 * h] = __fdividef(1.0f, om.x); e.inv[2 * h + 1] = __fdividef(1.0f, om.y);
         }
     };
     // advance the pixel state over a batch whose first pair has consumption index `base`
@@ -597,88 +586,82 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         for (int u = 0; u < BWD_U; u++) {
             T = T * e.inv[u];
             const float dch = e.al[u] * T;
-            const float t0 = e.r[u] - B0, t1 = e.g[u] - B1, t2 = e.b[u] - B2;
-            const float dot = fmaf(t2, dp2, fmaf(t1, dp1, t0 * dp0));
+            const float2 t01 = ffma2(B01, splat2(-1.0f), e.rg[u]);      // colour - colour behind
+            const float t2 = e.b[u] - B2;
+            const float dot = fmaf(t2, dp2, fmaf(t01.y, dp1, t01.x * dp0));
             const float dLda = fmaf(T, dot, nTf_bg * e.inv[u]);
             const unsigned row = (base + u) % BWD_ROWS;
             sm.w[row * BWD_ROW + lane] = e.G[u] * dLda;
             sm.d[row * BWD_ROW + lane] = dch;
-            B0 = fmaf(e.al[u], t0, B0);       // = al * c + (1 - al) * B
-            B1 = fmaf(e.al[u], t1, B1);
+            B01 = ffma2(splat2(e.al[u]), t01, B01);       // = al * c + (1 - al) * B
             B2 = fmaf(e.al[u], t2, B2);
         }
     };
-    // phase 2 over the `cnt` (<= BWD_ROWS) pair rows of the open tile.  Lane = (pair row r,
-    // pixel half h); it walks its 32 / BWD_HALVES pixels accumulating RAW moments of w about the
-    // block origin -- the pixel offsets kx, ky are compile-time constants of the unrolled loop,
-    // so a moment costs one FMA with an immediate -- and re-centres them on the Gaussian after
-    // the loop:  sum w dx = ax S0 - Mx,  sum w dx^2 = ax (ax S0 - 2 Mx) + Mxx, ... (dx = ax - kx).
+    // phase 2 over the `cnt` (<= BWD_ROWS) pair rows of the open tile.  Lane = pair row r; it
+    // walks the 32 pixels four at a time (even / odd columns in the two halves of a packed
+    // pair) accumulating RAW moments of w about the block origin and re-centres them on the
+    // Gaussian after the loop:
+    //   sum w dx = ax S0 - Mx,  sum w dx^2 = ax (ax S0 - 2 Mx) + Mxx, ... (dx = ax - kx).
+    // With kx = 2k (+1 in the odd half) the moments need only broadcast scalar factors:
+    //   sum kx w = sum 2k (we + wo) + sum wo,   sum kx^2 w = sum 4k^2 (we + wo) + 2 sum 2k wo + sum wo.
     auto reduce_rows = [&](unsigned cnt) {
         __syncwarp();
-        const unsigned r = lane % BWD_ROWS, h = lane / BWD_ROWS;
+        const unsigned r = lane;
         const bool valid = r < cnt;
-        const unsigned id = valid ? sm.id[(row0 / BWD_ROWS) & 1][r] : 0u;
+        const unsigned id = valid ? sm.id[(row0 + r) & (ID_SLOTS - 1)] : 0u;
         const float4 q0 = __ldg(rec + 4 * (size_t)id);
         const float4 q1 = __ldg(rec + 4 * (size_t)id + 1);
-        float S0 = 0, Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, Sr = 0, Sg = 0, Sb = 0;
-        const float* wr = sm.w + r * BWD_ROW + h * BWD_ROWS;
-        const float* dr = sm.d + r * BWD_ROW + h * BWD_ROWS;
-        const float* dpp = &sm.dp[0][h * BWD_ROWS];
-#if SGS_BWD_P2ROW
+        float S0 = 0, Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0;
+        float2 Sr = splat2(0.0f), Sg = splat2(0.0f), Sb = splat2(0.0f);
+        const float4* wr = reinterpret_cast<const float4*>(sm.w + r * BWD_ROW);
+        const float4* dr = reinterpret_cast<const float4*>(sm.d + r * BWD_ROW);
+        const float4* dpr = reinterpret_cast<const float4*>(&sm.dp[0][0]);
 #pragma unroll 1
-        for (int yy = 0; yy < BWD_ROWS / 8; yy++) {           // one pixel row of the 8x4 block per trip
+        for (int yy = 0; yy < 4; yy++) {                      // one pixel row of the 8x4 block per trip
             const float ky = (float)yy;
-            float R0 = 0, Rx = 0, Rxx = 0;                    // this row's moments in x
+            float2 R0 = splat2(0.0f), Rx = splat2(0.0f), Rxx = splat2(0.0f);      // this row's moments in x (even, odd columns)
 #pragma unroll
-            for (int kx = 0; kx < 8; kx++) {
-                const int k = yy * 8 + kx;
-                const float w = wr[k], d = dr[k];
-                R0 += w;
-                if (kx != 0) { Rx = fmaf(w, (float)kx, Rx); Rxx = fmaf(w, (float)(kx * kx), Rxx); }
-                Sr = fmaf(d, dpp[k], Sr); Sg = fmaf(d, dpp[32 + k], Sg); Sb = fmaf(d, dpp[64 + k], Sb);
+            for (int k4 = 0; k4 < 2; k4++) {
+                const float4 w4 = wr[yy * 2 + k4], d4 = dr[yy * 2 + k4];
+                const float4 pr = dpr[yy * 2 + k4], pg = dpr[8 + yy * 2 + k4], pb = dpr[16 + yy * 2 + k4];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int kp = 2 * k4 + j;                // columns 2 kp, 2 kp + 1
+                    const float2 w = j ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
+                    const float2 d = j ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
+                    R0 = fadd2(R0, w);
+                    if (kp != 0) {
+                        Rx = ffma2(w, splat2((float)(2 * kp)), Rx);
+                        Rxx = ffma2(w, splat2((float)(4 * kp * kp)), Rxx);
+                    }
+                    Sr = ffma2(d, j ? make_float2(pr.z, pr.w) : make_float2(pr.x, pr.y), Sr);
+                    Sg = ffma2(d, j ? make_float2(pg.z, pg.w) : make_float2(pg.x, pg.y), Sg);
+                    Sb = ffma2(d, j ? make_float2(pb.z, pb.w) : make_float2(pb.x, pb.y), Sb);
+                }
             }
-            S0 += R0; Mx += Rx; Mxx += Rxx;
-            My = fmaf(R0, ky, My); Myy = fmaf(R0, ky * ky, Myy); Mxy = fmaf(Rx, ky, Mxy);
+            const float r0 = R0.x + R0.y, rx = (Rx.x + Rx.y) + R0.y, rxx = (Rxx.x + Rxx.y) + fmaf(2.0f, Rx.y, R0.y);
+            S0 += r0; Mx += rx; Mxx += rxx;
+            My = fmaf(r0, ky, My); Myy = fmaf(r0, ky * ky, Myy); Mxy = fmaf(rx, ky, Mxy);
         }
-#else
-#pragma unroll
-        for (int k = 0; k < BWD_ROWS; k++) {
-            const float w = wr[k], d = dr[k];
-            const float kx = (float)(k & 7), ky = (float)(k >> 3);
-            S0 += w;
-            if ((k & 7) != 0) { Mx = fmaf(w, kx, Mx); Mxx = fmaf(w, kx * kx, Mxx); }
-            if ((k >> 3) != 0) { My = fmaf(w, ky, My); Myy = fmaf(w, ky * ky, Myy); }
-            if ((k & 7) != 0 && (k >> 3) != 0) Mxy = fmaf(w, kx * ky, Mxy);
-            Sr = fmaf(d, dpp[k], Sr); Sg = fmaf(d, dpp[32 + k], Sg); Sb = fmaf(d, dpp[64 + k], Sb);
-        }
-#endif
-        const float ax = q0.x - bx0, ay = q0.y - (by0 + (float)(h * (BWD_ROWS / 8)));
-        float Sx = fmaf(ax, S0, -Mx), Sy = fmaf(ay, S0, -My);
-        float Sxx = fmaf(ax, fmaf(ax, S0, -2.0f * Mx), Mxx);
-        float Syy = fmaf(ay, fmaf(ay, S0, -2.0f * My), Myy);
-        float Sxy = fmaf(ax, fmaf(ay, S0, -My), fmaf(-ay, Mx, Mxy));
-        if (BWD_HALVES == 2) {
-            S0 += __shfl_xor_sync(0xffffffffu, S0, 16); Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
-            Sy += __shfl_xor_sync(0xffffffffu, Sy, 16); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
-            Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16); Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
-            Sr += __shfl_xor_sync(0xffffffffu, Sr, 16); Sg += __shfl_xor_sync(0xffffffffu, Sg, 16);
-            Sb += __shfl_xor_sync(0xffffffffu, Sb, 16);
-        }
+        const float ax = q0.x - bx0, ay = q0.y - by0;
+        const float Sx = fmaf(ax, S0, -Mx), Sy = fmaf(ay, S0, -My);
+        const float Sxx = fmaf(ax, fmaf(ax, S0, -2.0f * Mx), Mxx);
+        const float Syy = fmaf(ay, fmaf(ay, S0, -2.0f * My), Myy);
+        const float Sxy = fmaf(ax, fmaf(ay, S0, -My), fmaf(-ay, Mx, Mxy));
         if (valid) {
             // conic entries: a = -2*q0.z, b = -q0.w, c = -2*q1.x
             const float ca = -2.0f * q0.z, cb = -q0.w, cc = -2.0f * q1.x, o = q1.y;
             float* dst = acc + (size_t)id * ACC_FLOATS;
             // accumulator slots 0..8: mean2D.x, .y, conic a, b, c, opacity, r, g, b
-            if (BWD_HALVES == 1 || h == 0)
-                red_add_f4(dst, -o * ddelx_dx * (ca * Sx + cb * Sy), -o * ddely_dy * (cc * Sy + cb * Sx),
-                           -0.5f * o * Sxx, -0.5f * o * Sxy);
-            if (BWD_HALVES == 1 || h == 1) {
-                red_add_f4(dst + 4, -0.5f * o * Syy, S0, Sr, Sg);
-                atomicAdd(dst + 8, Sb);
-            }
+            red_add_f4(dst, -o * ddelx_dx * (ca * Sx + cb * Sy), -o * ddely_dy * (cc * Sy + cb * Sx),
+                       -0.5f * o * Sxx, -0.5f * o * Sxy);
+            red_add_f4(dst + 4, -0.5f * o * Syy, S0, Sr.x + Sr.y, Sg.x + Sg.y);
+            atomicAdd(dst + 8, Sb.x + Sb.y);
         }
         __syncwarp();
     };
+    const std::true_type with_limit;
+    const std::false_type no_limit;
 
     // Same staging pipeline as the forward (masks four chunks ahead, ids two, records one),
     // walking the list back to front: chunk c covers list positions top-lane, top =
@@ -689,7 +672,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     unsigned m0 = mask_at(wlast - 1), m1 = mask_at(wlast - 33), m2 = mask_at(wlast - 65), m3 = mask_at(wlast - 97);
     Rec p;
     unsigned pid = 0;
-    p.q0 = p.q1 = p.q2 = p.q3 = make_float4(0, 0, 0, 0);
+    p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
     if ((m0 >> warp) & 1u) {
         pid = __ldg(pl + (wlast - 1 - lane));
         p = load_rec(rec, pid);
@@ -704,9 +687,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         __syncwarp();
         if (rel) {
             const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
-            sm.q0[slot] = p.q0;
-            sm.q1[slot] = make_float4(p.q1.x, p.q1.y, __uint_as_float((unsigned)(top - lane)), p.q1.w);
-            sm.q2[slot] = make_float4(p.q2.x, p.q2.y, 0.0f, __uint_as_float(pid));
+            const unsigned idx = tail + __popc(bits & lanemask_lt());      // consumption index of this entry
+            ring_put(sm.geo, slot, p.q0, p.q1);
+            sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, __uint_as_float((unsigned)(top - lane)));
+            sm.id[idx & (ID_SLOTS - 1)] = pid;
         }
         tail += __popc(bits);
         __syncwarp();
@@ -718,8 +702,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(top - 128);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= BWD_U) {
-            if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
-            else           { eval(bat_a, head, tail); seq(bat_b, pend); }
+            if (!cur_is_b) { eval(bat_b, head, tail, no_limit); seq(bat_a, pend); }
+            else           { eval(bat_a, head, tail, no_limit); seq(bat_b, pend); }
             cur_is_b = !cur_is_b;
             if (pend + BWD_U - row0 == BWD_ROWS) {       // the open tile is full
                 reduce_rows(BWD_ROWS);
@@ -730,8 +714,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
     }
     // drain: the waiting batch, the partial remainder of the ring, the partial tile
-    if (!cur_is_b) { eval(bat_b, head, tail); seq(bat_a, pend); }
-    else           { eval(bat_a, head, tail); seq(bat_b, pend); }
+    if (!cur_is_b) { eval(bat_b, head, tail, with_limit); seq(bat_a, pend); }
+    else           { eval(bat_a, head, tail, with_limit); seq(bat_b, pend); }
     if (pend + BWD_U - row0 == BWD_ROWS) {
         reduce_rows(BWD_ROWS);
         row0 += BWD_ROWS;
@@ -744,24 +728,19 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
 }
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
-                     const char* img, const float* bg, const float* dL_dpix, float* acc, int* ticket,
+                     const char* img, const float* bg, const float* dL_dpix, float* acc,
                      cudaStream_t stream) {
     const size_t smem = sizeof(BwdWarpSmem) * BWD_WPC;
-    SGS_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (long long)lay.tiles * (TILE_WARPS / BWD_WPC);
-#if SGS_BLEND_PERSIST
-    blocks = persistent_blocks(blend_bwd_kernel, BWD_WPC * 32, smem, blocks);
-    if (blocks < 1) return SGS_ERR_BAD_ARG;
-#endif
-    launch_pdl(blend_bwd_kernel, (unsigned)blocks, BWD_WPC * 32, smem, stream,
+    SGS_CUDA_OK(set_max_smem(blend_bwd_kernel, smem));
+    const long long blocks = (long long)lay.tiles * (TILE_WARPS / BWD_WPC);
+    SGS_CUDA_OK(launch_pdl(blend_bwd_kernel, (unsigned)blocks, BWD_WPC * 32, smem, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
         reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
-        reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc, ticket);
-    SGS_LAUNCH_OK();
+        reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc));
     return 0;
 }
 

@@ -29,25 +29,6 @@
 namespace sgs {
 
 constexpr int GEO_THREADS = 256;
-// A/B knobs (tools/sweep.sh)
-#ifndef SGS_EMIT_WIDE             // emission scan: look-back by the whole CTA (1) or one warp (0)
-#define SGS_EMIT_WIDE 0
-#endif
-#ifndef SGS_EMIT_MATCH            // tile-digit histogram: one shared atomic per group of equal digits
-#define SGS_EMIT_MATCH 0
-#endif
-// Pair list by count / scan / scatter (1) or by emit_pairs + tile-id radix passes (0).  Both give
-// the same bytes (all GPU parity tests pass either way).  Measured at 200k Gaussians / 1024^2
-// (profiles/README.md, v7): count 26 us + scan 8.5 us + scatter 52 us = 86 us against 53 us for
-// emit + two passes -- the enumeration is ~6k dependent instructions per warp (binary search,
-// division, match_any, counter update) with only 8-16 warps per SM because of the 64-100 KB
-// counter arrays, i.e. latency-bound at 19 % issue.  Default off until that chain is shortened.
-#ifndef SGS_BIN_CSS
-#define SGS_BIN_CSS 0
-#endif
-constexpr int BIN_THREADS = 256;
-constexpr int BIN_GAUSS = 1024;           // depth-ordered Gaussians per chunk (CTA): 128 per warp
-constexpr int BIN_MAX_TILES = 8192;       // 8 warps x tiles u16 counters + tiles u32 bases must fit in shared memory
 constexpr unsigned long long FLAG_AGG = 1ull << 62;
 constexpr unsigned long long FLAG_INCL = 2ull << 62;
 constexpr unsigned long long FLAG_MASK = 3ull << 62;
@@ -103,9 +84,11 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.masks_off = o;    o += align_up(cap, 256);
     l.bin_ctas = (P + BIN_GAUSS - 1) / BIN_GAUSS;
     if (l.bin_ctas < 1) l.bin_ctas = 1;
-    l.bcount_off = o;   o += align_up((size_t)l.bin_ctas * l.tiles * 2, 256);
-    l.bbase_off = o;    o += align_up((size_t)l.bin_ctas * l.tiles * 4, 256);
-    l.btotal_off = o;   o += align_up((size_t)l.tiles * 4, 256);
+    l.bin_tp = (int)align_up((size_t)l.tiles, 512);
+    const bool css = l.tiles <= BIN_MAX_TILES && l.gx <= 255 && l.gy <= 255;     // bin_css_supported()
+    l.bcount_off = o;   o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 2, 256) : 0;
+    l.bbase_off = o;    o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 4, 256) : 0;
+    l.btotal_off = o;   o += css ? align_up((size_t)l.bin_tp * 4, 256) : 0;
     l.bin_bytes = o;
     // image state
     size_t pix = (size_t)W * H;
@@ -331,8 +314,6 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     __shared__ unsigned s_warp[GEO_THREADS / 32];
     __shared__ unsigned s_hist[(MAX_PASSES - DEPTH_PASSES) * RADIX];
     __shared__ int s_ticket;
-    __shared__ unsigned long long s_wsum[GEO_THREADS / 32];
-    __shared__ int s_wincl[GEO_THREADS / 32];
     __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -373,58 +354,6 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     incl += warp_off;
     s_incl[tid] = incl;
 
-#if SGS_EMIT_WIDE
-    // ---- chained scan across CTAs: decoupled look-back by the WHOLE CTA, 256 predecessors
-    // per round trip.  All emission CTAs are normally resident and publish their aggregates
-    // at the same time, so a walk of 32 predecessors per round trip (one warp) would make
-    // chunk k wait ~k/64 dependent L2 round trips; here it is ~k/512 + 1.
-    if (tid == 0)
-        st_relaxed_u64(&a.scan_status[chunk], (chunk == 0 ? FLAG_INCL : FLAG_AGG) | block_total);
-    unsigned long long excl = 0;                     // CTA-uniform
-    if (chunk > 0) {
-        for (int look = chunk - 1;; look -= GEO_THREADS) {
-            const int j = look - tid;
-            unsigned long long s = j >= 0 ? ld_relaxed_u64(&a.scan_status[j]) : FLAG_INCL;
-            while ((s & FLAG_MASK) == 0) s = ld_relaxed_u64(&a.scan_status[j]);
-            const unsigned inc_mask = __ballot_sync(0xffffffffu, (s & FLAG_MASK) == FLAG_INCL);
-            const int first = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-            unsigned long long v = lane <= first ? (s & ~FLAG_MASK) : 0ull;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (lane == 0) {
-                s_wsum[warp] = v;
-                s_wincl[warp] = inc_mask != 0;
-            }
-            __syncthreads();
-            bool done = false;                       // warp 0 holds the nearest predecessors
-#pragma unroll
-            for (int w = 0; w < GEO_THREADS / 32; w++) {
-                if (!done) {
-                    excl += s_wsum[w];
-                    done = s_wincl[w] != 0;
-                }
-            }
-            __syncthreads();                         // before the next round overwrites s_wsum
-            if (done) break;
-        }
-        if (tid == 0) st_relaxed_u64(&a.scan_status[chunk], FLAG_INCL | (excl + block_total));
-    }
-    if (tid == 0) {
-        unsigned long long total = excl + block_total;
-        if (chunk == (int)gridDim.x - 1) {
-            a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-            if (a.host_counters) {     // the grand total decides the overflow: the last chunk knows both
-                a.host_counters[0] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-                a.host_counters[1] = total > (unsigned long long)a.L_cap ? 1 : 0;
-                __threadfence_system();
-            }
-        }
-        if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
-    }
-    __syncthreads();          // s_incl, s_rect
-
-    const unsigned long long prefix = excl;
-#else
     // ---- chained scan across CTAs (decoupled look-back, one warp) ----
     if (warp == 0) {
         unsigned long long excl = 0;
@@ -467,7 +396,6 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     __syncthreads();          // s_prefix, s_incl, s_rect
 
     const unsigned long long prefix = s_prefix;
-#endif
     // ---- emit (tile|depth) keys and Gaussian ids ----
     for (unsigned e = tid; e < block_total; e += GEO_THREADS) {
         int lo = 0, hi = GEO_THREADS - 1;          // first g with s_incl[g] > e
@@ -486,19 +414,8 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
         if (pos < (unsigned long long)a.L_cap) {
             a.keys[pos] = key;
             a.vals[pos] = s_gid[g];
-#if SGS_EMIT_MATCH
-            // neighbouring pairs are neighbouring tiles: the upper digits are shared by most
-            // of the warp, so equal digits are counted once (one shared atomic per group)
-            const unsigned act = __activemask();
-            for (int p = 0; p < tile_passes; p++) {
-                const unsigned d = (tile_id >> (p * RADIX_BITS)) & (RADIX - 1);
-                const unsigned peers = __match_any_sync(act, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * RADIX + d], (unsigned)__popc(peers));
-            }
-#else
             for (int p = 0; p < tile_passes; p++)
                 atomicAdd(&s_hist[p * RADIX + ((tile_id >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
-#endif
         }
     }
     __syncthreads();
@@ -533,327 +450,16 @@ int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// The pair list by count / scan / scatter.
-//
-// With the Gaussians in depth order (launch_depth_sort), the sorted (tile|depth, id) list is a
-// STABLE counting sort of the pairs by tile id: tile t's segment holds, in depth order, the
-// Gaussians whose rectangle covers t.  Three kernels replace emit_pairs + the tile-id radix
-// passes and write the sorted list directly (bit-identical: a stable sort has one answer):
-//   bin_count  : chunk c = BIN_GAUSS consecutive depth-ordered Gaussians -> counts[c][t]
-//   bin_scan   : per tile, exclusive prefix of counts over the chunks -> base[c][t], total[t]
-//   bin_scatter: tile starts (scan of total[], redone per CTA: a few thousand values), then the
-//                chunk is enumerated again and every pair goes to start[t] + base[c][t] + rank.
-// Enumeration (shared by count and scatter): a warp owns 128 consecutive Gaussians and walks
-// their pairs in Gaussian-major order, 32 per step; the running per-(warp, tile) counters live
-// in shared memory (u16), ranks inside a step come from match_any, so the order is stable by
-// construction and no atomics are needed.  (Taking one Gaussian per step with lanes = its
-// tiles was measured first: 33 us per pass -- 128 dependent steps per warp.)
-// (A decoupled look-back does not carry over from the 256-bin radix passes: with one bin per
-// tile the walk over predecessors would be 16x the traffic -- hence the separate scan.)
-// ------------------------------------------------------------------------------------------
-struct BinArgs {
-    int P, tiles, gx, ctas;
-    const unsigned* nkeys[2];   // depth-sorted keys are in buffer depth_sort_parity(varbits)
-    const unsigned* nvals[2];
-    const unsigned* varbits;
-    const uint2* rects;
-    unsigned short* counts;     // [ctas][tiles]
-    unsigned* base;             // [ctas][tiles]
-    unsigned* total;            // [tiles]
-    int* counters;
-    int* host_counters;         // mapped host memory for {num_rendered, overflow}, or null
-    unsigned long long* keys;   // sorted list (output)
-    unsigned* vals;
-    long long L_cap;
-};
-
-// Per-warp staging of the enumeration: the warp's 128 Gaussians (4 consecutive ones per lane)
-// with the inclusive prefix of their tile counts.
-constexpr int BIN_WARP_GAUSS = BIN_GAUSS / (BIN_THREADS / 32);        // 128
-struct BinWarpStage {
-    unsigned pref[BIN_WARP_GAUSS];      // inclusive prefix of tiles touched
-    uint4 info[BIN_WARP_GAUSS];         // x0 | y0 << 16, rect width, Gaussian id, depth bits
-};
-
-// PLACE = false: cnt[w][t] += 1 per pair.  PLACE = true: pair -> s_base[t] + cnt[w][t]++.
-// The warp's pairs are taken 32 at a time in Gaussian-major order, one per lane (binary search
-// of the staged prefix, like emit_pairs_kernel).  Pairs of one window that fall on the same
-// tile come from different Gaussians and sit in lane order = depth order: match_any gives each
-// its rank among them, the lowest lane advances the running per-(warp, tile) counter once.
-template <bool PLACE>
-__device__ __forceinline__ void bin_enumerate(const BinArgs& a, int chunk, unsigned short* s_cnt,
-                                              const unsigned* s_base, BinWarpStage* s_stage) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int par = depth_sort_parity(a.varbits, DEPTH_PASSES);
-    const unsigned* __restrict__ nk = par ? a.nkeys[1] : a.nkeys[0];
-    const unsigned* __restrict__ nv = par ? a.nvals[1] : a.nvals[0];
-    unsigned short* const cnt = s_cnt + (size_t)warp * a.tiles;
-    BinWarpStage& st = s_stage[warp];
-    const int g0 = chunk * BIN_GAUSS + warp * BIN_WARP_GAUSS + 4 * lane;
-    // ---- stage: 4 consecutive Gaussians per lane ----
-    unsigned n[4], tot = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int pos = g0 + i;
-        unsigned gid = 0, dkey = 0;
-        uint2 r = make_uint2(0u, 0u);
-        if (pos < a.P) {
-            gid = nv[pos];
-            dkey = nk[pos];
-            r = __ldg(a.rects + gid);
-        }
-        const unsigned rw = r.y & 0xffffu;
-        n[i] = rw * (r.y >> 16);
-        tot += n[i];
-        st.info[4 * lane + i] = make_uint4(r.x, rw, gid, dkey);
-    }
-    unsigned incl = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned x = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += x;
-    }
-    unsigned run = incl - tot;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        run += n[i];
-        st.pref[4 * lane + i] = run;
-    }
-    const unsigned warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    __syncwarp();
-    // ---- pairs, 32 per window ----
-    for (unsigned e0 = 0; e0 < warp_total; e0 += 32) {
-        const unsigned e = e0 + lane;
-        const bool active = e < warp_total;
-        unsigned t = 0xffff0000u | (unsigned)lane;      // inactive lanes: unique, matches nobody
-        unsigned gid = 0, dkey = 0;
-        if (active) {
-            int lo = 0, hi = BIN_WARP_GAUSS - 1;        // first Gaussian whose inclusive prefix exceeds e
-#pragma unroll
-            for (int it = 0; it < 7; it++) {
-                const int mid = (lo + hi) >> 1;
-                if (st.pref[mid] > e) hi = mid; else lo = mid + 1;
-            }
-            const uint4 f = st.info[lo];
-            const unsigned k = e - (lo ? st.pref[lo - 1] : 0u);
-            const unsigned ty = k / f.y, tx = k - ty * f.y;
-            t = ((f.x >> 16) + ty) * (unsigned)a.gx + (f.x & 0xffffu) + tx;
-            gid = f.z; dkey = f.w;
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, t);
-        const int leader = __ffs(peers) - 1;
-        unsigned c = 0;
-        if (active && lane == leader) {
-            c = cnt[t];
-            cnt[t] = (unsigned short)(c + (unsigned)__popc(peers));
-        }
-        c = __shfl_sync(0xffffffffu, c, leader) + (unsigned)__popc(peers & lanemask_lt());
-        if (PLACE && active) {
-            const unsigned long long p = (unsigned long long)s_base[t] + c;
-            if (p < (unsigned long long)a.L_cap) {
-                a.keys[p] = ((unsigned long long)t << 32) | dkey;
-                a.vals[p] = gid;
-            }
-        }
-        __syncwarp();                                   // the next window may hit the same tiles
-    }
-    __syncwarp();                                       // the stage is rewritten by the next pass
-}
-
-__device__ __forceinline__ void bin_zero_counters(unsigned short* s_cnt, int tiles) {
-    uint4* z = reinterpret_cast<uint4*>(s_cnt);         // 8 * tiles * 2 bytes, tiles even -> multiple of 16
-    const int n16 = (BIN_THREADS / 32) * tiles * 2 / 16;
-    for (int i = threadIdx.x; i < n16; i += BIN_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-}
-
-__global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(BinArgs a) {
-    extern __shared__ __align__(16) unsigned char s_bin[];
-    unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_bin);      // [8][tiles]
-    BinWarpStage* s_stage = reinterpret_cast<BinWarpStage*>(s_bin + (size_t)(BIN_THREADS / 32) * a.tiles * 2);
-    bin_zero_counters(s_cnt, a.tiles);
-    pdl_sync();
-    __syncthreads();
-    const int chunk = blockIdx.x;
-    bin_enumerate<false>(a, chunk, s_cnt, nullptr, s_stage);
-    __syncthreads();
-    // chunk totals per tile: two tiles per 32-bit word (counts <= 1024: no carry between halves)
-    const unsigned* w32 = reinterpret_cast<const unsigned*>(s_cnt);
-    unsigned* out = reinterpret_cast<unsigned*>(a.counts + (size_t)chunk * a.tiles);
-    const int half = a.tiles / 2;
-    for (int i = threadIdx.x; i < half; i += BIN_THREADS) {
-        unsigned sum = 0;
-#pragma unroll
-        for (int w = 0; w < BIN_THREADS / 32; w++) sum += w32[(size_t)w * half + i];
-        out[i] = sum;
-    }
-}
-
-// Prefix over the chunks, per tile.  A CTA takes a slab of 32 tiles; its 8 warps split the chunk
-// rows into 8 contiguous groups: sum the group (independent loads, all in flight), exchange the
-// eight partial sums through shared memory, then walk the group again writing the prefixes.
-// (One thread per tile walking all rows is a chain of dependent L2 round trips: measured 85 us.)
-__global__ void __launch_bounds__(256) bin_scan_kernel(BinArgs a) {
-    __shared__ unsigned s_part[8][32];
-    pdl_sync();
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + lane;
-    const bool ok = t < a.tiles;
-    const int rows = (a.ctas + 7) / 8;
-    const int r0 = min(a.ctas, grp * rows), r1 = min(a.ctas, r0 + rows);
-    const unsigned short* __restrict__ cn = a.counts + (ok ? t : 0);
-    unsigned* __restrict__ bs = a.base + (ok ? t : 0);
-    const size_t stride = (size_t)a.tiles;
-    unsigned sum = 0;
-    if (ok) {
-#pragma unroll 8
-        for (int c = r0; c < r1; c++) sum += cn[(size_t)c * stride];
-    }
-    s_part[grp][lane] = sum;
-    __syncthreads();
-    unsigned run = 0;
-#pragma unroll
-    for (int g = 0; g < 8; g++)
-        if (g < grp) run += s_part[g][lane];
-    if (!ok) return;
-    int c = r0;
-    for (; c + 8 <= r1; c += 8) {               // loads first, then the dependent prefix and the stores
-        unsigned v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = cn[(size_t)(c + k) * stride];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            bs[(size_t)(c + k) * stride] = run;
-            run += v[k];
-        }
-    }
-    for (; c < r1; c++) {
-        const unsigned v = cn[(size_t)c * stride];
-        bs[(size_t)c * stride] = run;
-        run += v;
-    }
-    if (grp == 7) a.total[t] = run;             // the last group ends on the grand total
-}
-
-__global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinArgs a) {
-    extern __shared__ __align__(16) unsigned char s_bin[];
-    unsigned short* s_cnt = reinterpret_cast<unsigned short*>(s_bin);                          // [8][tiles]
-    unsigned* s_base = reinterpret_cast<unsigned*>(s_bin + (size_t)(BIN_THREADS / 32) * a.tiles * 2);   // [tiles]
-    BinWarpStage* s_stage = reinterpret_cast<BinWarpStage*>(s_bin + (size_t)(BIN_THREADS / 32) * a.tiles * 2 + (size_t)a.tiles * 4);
-    __shared__ unsigned s_wsum[BIN_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    bin_zero_counters(s_cnt, a.tiles);
-    pdl_sync();
-    const int chunk = blockIdx.x;
-    // ---- tile starts: exclusive scan of total[] (every CTA redoes it: tiles <= 8192 values) ----
-    const int per = (a.tiles + BIN_THREADS - 1) / BIN_THREADS;          // consecutive tiles per thread
-    const int t0 = tid * per;
-    unsigned mine = 0;
-    for (int k = 0; k < per; k++)
-        if (t0 + k < a.tiles) mine += a.total[t0 + k];
-    unsigned incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned x = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += x;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    unsigned off = 0, grand = 0;
-#pragma unroll
-    for (int w = 0; w < BIN_THREADS / 32; w++) {
-        const unsigned v = s_wsum[w];
-        if (w < warp) off += v;
-        grand += v;
-    }
-    unsigned start = off + incl - mine;
-    const unsigned* brow = a.base + (size_t)chunk * a.tiles;
-    for (int k = 0; k < per; k++) {
-        if (t0 + k < a.tiles) {
-            s_base[t0 + k] = start + brow[t0 + k];
-            start += a.total[t0 + k];
-        }
-    }
-    if (chunk == 0 && tid == 0) {
-        const unsigned long long total = grand;
-        a.counters[CNT_NUM_RENDERED] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-        if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
-        if (a.host_counters) {
-            a.host_counters[0] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
-            a.host_counters[1] = total > (unsigned long long)a.L_cap ? 1 : 0;
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    // ---- pass A: per-warp counts; then exclusive over the warps (two tiles per word) ----
-    bin_enumerate<false>(a, chunk, s_cnt, nullptr, s_stage);
-    __syncthreads();
-    unsigned* w32 = reinterpret_cast<unsigned*>(s_cnt);
-    const int half = a.tiles / 2;
-    for (int i = tid; i < half; i += BIN_THREADS) {
-        unsigned run = 0;
-#pragma unroll
-        for (int w = 0; w < BIN_THREADS / 32; w++) {
-            const unsigned v = w32[(size_t)w * half + i];
-            w32[(size_t)w * half + i] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-    // ---- pass B: place ----
-    bin_enumerate<true>(a, chunk, s_cnt, s_base, s_stage);
-}
-
-bool bin_css_supported(const RasterLayout& lay) {
-    return SGS_BIN_CSS && !SGS_MASKS_IN_SORT && lay.tiles <= BIN_MAX_TILES && (lay.tiles % 8) == 0;
-}
-
-int launch_bin_css(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
-                   cudaStream_t stream, int debug) {
-    if (P <= 0) return 0;
-    BinArgs a;
-    a.P = P; a.tiles = lay.tiles; a.gx = lay.gx; a.ctas = lay.bin_ctas;
-    a.nkeys[0] = reinterpret_cast<const unsigned*>(bin + lay.nkeys0_off);
-    a.nkeys[1] = reinterpret_cast<const unsigned*>(bin + lay.nkeys1_off);
-    a.nvals[0] = reinterpret_cast<const unsigned*>(bin + lay.nvals0_off);
-    a.nvals[1] = reinterpret_cast<const unsigned*>(bin + lay.nvals1_off);
-    a.counters = reinterpret_cast<int*>(bin + lay.cnt_off);
-    a.varbits = reinterpret_cast<const unsigned*>(a.counters + CNT_VARBITS);
-    a.rects = reinterpret_cast<const uint2*>(bin + lay.rects_off);
-    a.counts = reinterpret_cast<unsigned short*>(bin + lay.bcount_off);
-    a.base = reinterpret_cast<unsigned*>(bin + lay.bbase_off);
-    a.total = reinterpret_cast<unsigned*>(bin + lay.btotal_off);
-    a.host_counters = host_counters;
-    a.keys = reinterpret_cast<unsigned long long*>(bin + (lay.sorted_in_1() ? lay.keys1_off : lay.keys0_off));
-    a.vals = reinterpret_cast<unsigned*>(bin + (lay.sorted_in_1() ? lay.vals1_off : lay.vals0_off));
-    a.L_cap = L_cap;
-    const size_t smem_stage = sizeof(BinWarpStage) * (BIN_THREADS / 32);
-    const size_t smem_count = (size_t)(BIN_THREADS / 32) * lay.tiles * 2 + smem_stage;
-    const size_t smem_scatter = (size_t)(BIN_THREADS / 32) * lay.tiles * 2 + (size_t)lay.tiles * 4 + smem_stage;
-    SGS_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
-    SGS_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-    launch_pdl(bin_count_kernel, lay.bin_ctas, BIN_THREADS, smem_count, stream, a);
-    SGS_LAUNCH_OK();
-    SGS_STAGE_OK(debug, stream);
-    launch_pdl(bin_scan_kernel, (lay.tiles + 31) / 32, 256, 0, stream, a);
-    SGS_LAUNCH_OK();
-    SGS_STAGE_OK(debug, stream);
-    launch_pdl(bin_scatter_kernel, lay.bin_ctas, BIN_THREADS, smem_scatter, stream, a);
-    SGS_LAUNCH_OK();
-    SGS_STAGE_OK(debug, stream);
-    return 0;
-}
-
 template <int D, bool HAS_SH>
 static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec16, cudaStream_t st) {
     size_t smem = HAS_SH ? (size_t)GEO_THREADS * sh_stride4(sh_nvec(D)) * 16 : 0;
     if (vec16) {
         auto k = geometry_kernel<D, HAS_SH, true>;
-        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGS_CUDA_OK(set_max_smem(k, smem));
         launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
     } else {
         auto k = geometry_kernel<D, HAS_SH, false>;
-        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGS_CUDA_OK(set_max_smem(k, smem));
         launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
     }
     SGS_LAUNCH_OK();

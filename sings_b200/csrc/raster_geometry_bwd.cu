@@ -294,11 +294,11 @@ static int launch_gb_t(const GeomBwdArgs& b, const float4* rec, int blocks, bool
     size_t smem = HAS_SH ? (size_t)GB_THREADS * sh_stride4(sh_nvec(D)) * 16 : 0;
     if (vec16) {
         auto k = geometry_bwd_kernel<D, HAS_SH, true>;
-        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGS_CUDA_OK(set_max_smem(k, smem));
         launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
     } else {
         auto k = geometry_bwd_kernel<D, HAS_SH, false>;
-        if (smem > 48 * 1024) SGS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGS_CUDA_OK(set_max_smem(k, smem));
         launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
     }
     SGS_LAUNCH_OK();
