@@ -332,10 +332,12 @@ def gpu_arm(args):
         barrier()
         hot_coarse = float(np.mean([s["step"].interval_ms(8, 3) for s in sets]))
     stage = {k: float(np.mean(v)) for k, v in stage.items()}
-    stage["binning"] = stage.pop("sort") + stage.pop("ranges")
     Lm = float(np.mean([s["L"] for s in sets]))
     n_vis = float(np.mean([int((s["step"].radii > 0).sum().item()) for s in sets]))
     ab = algorithmic_bytes(N_GAUSS, N_JOINTS, 16, Lm, W_IMG, H_IMG, n_vis)
+    if "deform_geometry" in stage:      # fused kernels: the stages merge, their algorithmic bytes add
+        ab["deform_geometry"] = ab.pop("lbs_fwd") + ab.pop("geometry")
+        ab["geometry_lbs_bwd"] = ab.pop("geometry_bwd") + ab.pop("lbs_bwd")
     stages_out = {}
     for k, b in ab.items():
         ms = stage.get(k)
@@ -344,7 +346,7 @@ def gpu_arm(args):
             stages_out[k] = {"ms": round(ms, 4), "alg_mb": round(b / 1e6, 2), "gbs": round(gbs, 1),
                              "frac": round(gbs / hbm_peak, 4)}
     dom = max((k for k in stages_out), key=lambda k: stages_out[k]["ms"])
-    hot = ["lbs_fwd", "geometry", "binning"]
+    hot = [k for k in ("lbs_fwd", "geometry", "deform_geometry", "binning") if k in ab]
     hot_b = sum(ab[k] for k in hot)
     hot_ms = sum(stage[k] for k in hot)
     hot_one = hot_coarse if hot_coarse else hot_ms
@@ -353,7 +355,8 @@ def gpu_arm(args):
     if os.path.exists(tp):      # DRAM bytes per launch from the committed `ncu --set full` capture
         with open(tp) as f:
             tj = json.load(f)
-        kern = {"lbs_fwd": "lbs_fwd_kernel", "lbs_bwd": "lbs_bwd_kernel", "geometry": "geometry_kernel",
+        kern = {"deform_geometry": "geometry_kernel", "geometry_lbs_bwd": "geometry_bwd_kernel",
+                "lbs_fwd": "lbs_fwd_kernel", "lbs_bwd": "lbs_bwd_kernel", "geometry": "geometry_kernel",
                 "binning": "bin_scatter_kernel", "blend_fwd": "blend_fwd_kernel",
                 "blend_bwd": "blend_bwd_kernel", "geometry_bwd": "geometry_bwd_kernel"}[dom]
         if kern in tj.get("kernels", {}):

@@ -253,6 +253,68 @@ int sgs_rot6d_to_axis_angle(const float* d6, int n, float* aa_out, sgs_stream_t 
 int sgs_rot6d_to_axis_angle_bwd(const float* d6, const float* dL_daa, int n, float* dL_dd6,
                                 sgs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The whole frame in two calls: pose -> A, the deform segment and the rasterizer with the
+ * deformer FUSED into the rasterizer's per-Gaussian kernels (forward: LBS in the prologue of the
+ * preprocess kernel; backward: the LBS backward in the epilogue of the preprocess backward), so
+ * the deformed means / quaternions / scales and their gradients make no round trip through
+ * memory between two kernels.  Same results as sgs_pose_lbs_fwd + sgs_raster_forward and
+ * sgs_raster_backward + sgs_lbs_bwd + sgs_pose_to_A_bwd (one iteration of the reference's hot
+ * loop, gs_trainer.py:229-244 and :400; sings_hybrid.py:398-419; no ext_tfs).
+ *
+ * The skinning weights come packed: lbs_weights is constant between densifications
+ * (sings_hybrid.py:724) with a handful of non-zero entries per row, so the caller packs it once
+ * with sgs_lbs_pack_weights into K slots per Gaussian (K in {4, 8, 12, 16}); *max_nnz (device
+ * int, zeroed by the caller) receives the longest row -- pack again with a larger K, or stay on
+ * the unfused entry points, if it exceeds K.  wq and iq take sgs_lbs_packed_bytes(N, K) and
+ * sgs_lbs_packed_bytes(N, K) / 4 bytes.
+ * ------------------------------------------------------------------------------------- */
+size_t sgs_lbs_packed_bytes(int N, int K);
+int sgs_lbs_pack_weights(int N, int J, const float* W, int K, float* wq, unsigned int* iq, int* max_nnz,
+                         sgs_stream_t stream);
+
+typedef struct sgs_deform_args {
+    int N, J, K, rot6d;          /* Gaussians, joints, packed slots, rot_canon is (N,6) */
+    const float* pose;           /* (J,3) axis-angle, joint 0 = global orientation */
+    const float* rest;           /* (J,3) rest joints */
+    const int* parents;          /* (J) */
+    const float* inv_A_t2cano;   /* (J,16) or null */
+    const float* xyz_canon;      /* (N,3) */
+    const float* scales;         /* (N,3) */
+    const float* rot_canon;      /* (N,9) | (N,6) | null (identity) */
+    const float* wq;             /* packed weights */
+    const unsigned int* iq;      /* packed joint indices */
+    const float* smpl_scale;     /* (1) or null */
+    const float* transl;         /* (3) or null */
+    float* A;                    /* (J,16) out: cano->pose transforms (read again by the backward) */
+    float* G;                    /* (J,12) out: global joint transforms (read again by the backward) */
+    float* xyz;                  /* (N,3) out: deformed means = the rasterizer's means3D */
+    float* rotq;                 /* (N,4) out */
+    float* scales_out;           /* (N,3) out */
+    float* d_xyz_canon;          /* backward outputs: (N,3) */
+    float* d_rot_canon;          /* (N,9) | (N,6) | null */
+    float* d_scales;             /* (N,3) */
+    float* d_A;                  /* (J,16) accumulated: the caller zeroes it (sgs_raster_clear `extra`) */
+    float* d_transl;             /* (3) accumulated likewise, or null */
+    float* d_pose;               /* (J,3) */
+} sgs_deform_args;
+
+/* Rasterizer arguments as in sgs_raster_forward / sgs_raster_backward (SH colours, scales +
+ * quaternions; stage events: [8] frame start, [10] before and [11] after the pose backward). */
+int sgs_avatar_forward(const sgs_deform_args* d, int D, int M, int W, int H, const float* bg,
+                       const float* opacities, float scale_modifier, const float* viewmatrix,
+                       const float* projmatrix, const float* campos, float tanfovx, float tanfovy,
+                       const float* shs, long long L_cap, void* geom, void* binning, void* img,
+                       float* out_color, int* radii, float* out_alpha, float* out_depth, int* host_counters,
+                       sgs_stream_t stream, int debug, void* timing);
+int sgs_avatar_backward(const sgs_deform_args* d, int D, int M, int W, int H, const float* bg,
+                        float scale_modifier, const float* viewmatrix, const float* projmatrix,
+                        const float* campos, float tanfovx, float tanfovy, const float* shs, const int* radii,
+                        const float* dL_dout_color, long long L_cap, const void* geom, const void* binning,
+                        const void* img, void* acc, float* dL_dmeans2D, float* dL_dopacity, float* dL_dsh,
+                        float* xyz_gradient_accum, float* denom, float* max_radii2D, sgs_stream_t stream,
+                        int debug, void* timing);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,15 @@ _lib = None
 c_f32p = C.c_void_p   # device pointers travel as integers
 _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 
+class DeformArgs(C.Structure):
+    """sgs_deform_args (include/sings_b200.h): the deformer side of the fused frame calls."""
+    _fields_ = [("N", _i), ("J", _i), ("K", _i), ("rot6d", _i)] + [
+        (name, _vp) for name in (
+            "pose", "rest", "parents", "inv_A_t2cano", "xyz_canon", "scales", "rot_canon", "wq", "iq",
+            "smpl_scale", "transl", "A", "G", "xyz", "rotq", "scales_out", "d_xyz_canon", "d_rot_canon",
+            "d_scales", "d_A", "d_transl", "d_pose")]
+
+
 _SIGNATURES = {
     "sgs_version": (C.c_int, []),
     "sgs_error_string": (C.c_char_p, [_i]),
@@ -50,6 +59,12 @@ _SIGNATURES = {
     "sgs_pose_lbs_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i] + [_vp] * 12),
     "sgs_lbs_fwd_rot6d": (_i, [_i, _i, _i] + [_vp] * 15),
     "sgs_lbs_bwd_rot6d": (_i, [_i, _i, _i] + [_vp] * 21),
+    "sgs_lbs_packed_bytes": (_sz, [_i, _i]),
+    "sgs_lbs_pack_weights": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "sgs_avatar_forward": (_i, [C.POINTER(DeformArgs), _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _vp,
+                                _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sgs_avatar_backward": (_i, [C.POINTER(DeformArgs), _i, _i, _i, _i, _vp, _f, _vp, _vp, _vp, _f, _f, _vp, _vp,
+                                 _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "sgs_rot6d_to_matrix": (_i, [_vp, _i, _vp, _vp]),
     "sgs_rot6d_to_matrix_bwd": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sgs_rot6d_to_axis_angle": (_i, [_vp, _i, _vp, _vp]),

@@ -26,13 +26,14 @@ std::vector<FuncState> g_funcs;
 FuncState& func_state(const void* f, int dev) {
     for (auto& s : g_funcs)
         if (s.f == f && s.dev == dev) return s;
-    g_funcs.push_back(FuncState{f, dev, 48 * 1024, 0, 0, -1});
+    g_funcs.push_back(FuncState{f, dev, 0, 0, 0, -1});
     return g_funcs.back();
 }
 }  // namespace
 
 cudaError_t sgs::ensure_max_smem(const void* func, size_t bytes) {
-    if (bytes <= 48 * 1024) return cudaSuccess;
+    // (no shortcut below 48 KB: the limit without opt-in counts the kernel's STATIC shared memory too)
+    if (bytes == 0) return cudaSuccess;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -222,14 +223,17 @@ static int fill_geom_args(GeomArgs& a, int P, int D, int M, int W, int H, const 
     return 0;
 }
 
-int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+}  // extern "C"
+
+// lf != null: the deform segment runs inside the geometry kernel (sgs_avatar_forward)
+static int raster_forward_impl(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
                        const float* colors_precomp, const float* opacities, const float* scales,
                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
                        const float* viewmatrix, const float* projmatrix, const float* campos,
                        float tanfovx, float tanfovy, const float* shs, int prefiltered,
                        long long L_cap, void* geom, void* binning, void* img, float* out_color,
                        int* radii, float* out_alpha, float* out_depth, int* host_counters,
-                       sgs_stream_t stream_, int debug, void* timing) {
+                       sgs_stream_t stream_, int debug, void* timing, const LbsFuse* lf) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GeomArgs a;
     int rc = fill_geom_args(a, P, D, M, W, H, means3D, colors_precomp, opacities, scales,
@@ -252,7 +256,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
         (void)cudaGetLastError();
     }
     tick(timing, 0, stream);
-    rc = launch_geometry(a, lay, L_cap, radii, g, b, stream, !precleared);
+    rc = launch_geometry(a, lay, L_cap, radii, g, b, stream, !precleared, lf);
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
@@ -291,7 +295,7 @@ int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const
     return 0;
 }
 
-int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+static int raster_backward_impl(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
                         const float* colors_precomp, const float* scales, float scale_modifier,
                         const float* rotations, const float* cov3D_precomp,
                         const float* viewmatrix, const float* projmatrix, const float* campos,
@@ -301,16 +305,17 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                         float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
                         float* xyz_gradient_accum, float* denom, float* max_radii2D,
-                        sgs_stream_t stream_, int debug, void* timing) {
+                        sgs_stream_t stream_, int debug, void* timing, const LbsFuse* lf) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GeomBwdArgs b;
     int rc = fill_geom_args(b.fwd, P, D, M, W, H, means3D, colors_precomp, nullptr, scales,
                             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix,
                             campos, tanfovx, tanfovy, shs, 0);
     if (rc) return rc;
-    if (!bg || !geom || !binning || !img || !acc || !dL_dout_color || !dL_dmeans3D || !dL_dmeans2D ||
-        !dL_dcolors || !dL_dopacity || (P > 0 && !radii) || (shs && !dL_dsh) || L_cap < 1)
+    if (!bg || !geom || !binning || !img || !acc || !dL_dout_color || !dL_dmeans2D || !dL_dopacity ||
+        (P > 0 && !radii) || (shs && !dL_dsh) || L_cap < 1)
         return SGS_ERR_BAD_ARG;
+    if (!lf && (!dL_dmeans3D || !dL_dcolors)) return SGS_ERR_BAD_ARG;
     if (((uintptr_t)acc & 15) || (dL_drots && ((uintptr_t)dL_drots & 15))) return SGS_ERR_MISALIGNED;
     const int n_stat = (xyz_gradient_accum != nullptr) + (denom != nullptr) + (max_radii2D != nullptr);
     if (n_stat != 0 && n_stat != 3) return SGS_ERR_BAD_ARG;
@@ -331,10 +336,117 @@ int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, cons
     b.dL_dopacity = dL_dopacity; b.dL_dcov3D = dL_dcov3D; b.dL_dsh = dL_dsh;
     b.dL_dscales = dL_dscales; b.dL_drots = dL_drots;
     b.stat_accum = xyz_gradient_accum; b.stat_denom = denom; b.stat_max_radii = max_radii2D;
-    rc = launch_geometry_bwd(b, (const char*)geom, stream);
+    rc = launch_geometry_bwd(b, (const char*)geom, stream, lf);
     if (rc) return rc;
     tick(timing, 7, stream);
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+extern "C" {
+
+int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* campos,
+                       float tanfovx, float tanfovy, const float* shs, int prefiltered,
+                       long long L_cap, void* geom, void* binning, void* img, float* out_color,
+                       int* radii, float* out_alpha, float* out_depth, int* host_counters,
+                       sgs_stream_t stream, int debug, void* timing) {
+    return raster_forward_impl(P, D, M, W, H, bg, means3D, colors_precomp, opacities, scales, scale_modifier,
+                               rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs,
+                               prefiltered, L_cap, geom, binning, img, out_color, radii, out_alpha, out_depth,
+                               host_counters, stream, debug, timing, nullptr);
+}
+
+int sgs_raster_backward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
+                        const float* colors_precomp, const float* scales, float scale_modifier,
+                        const float* rotations, const float* cov3D_precomp,
+                        const float* viewmatrix, const float* projmatrix, const float* campos,
+                        float tanfovx, float tanfovy, const float* shs, const int* radii,
+                        const float* dL_dout_color, long long L_cap, const void* geom,
+                        const void* binning, const void* img, void* acc, float* dL_dmeans3D,
+                        float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                        float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drots,
+                        float* xyz_gradient_accum, float* denom, float* max_radii2D,
+                        sgs_stream_t stream, int debug, void* timing) {
+    return raster_backward_impl(P, D, M, W, H, bg, means3D, colors_precomp, scales, scale_modifier, rotations,
+                                cov3D_precomp, viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii,
+                                dL_dout_color, L_cap, geom, binning, img, acc, dL_dmeans3D, dL_dmeans2D, dL_dcolors,
+                                dL_dopacity, dL_dcov3D, dL_dsh, dL_dscales, dL_drots, xyz_gradient_accum, denom,
+                                max_radii2D, stream, debug, timing, nullptr);
+}
+
+static int fill_fuse(LbsFuse& f, const sgs_deform_args* d) {
+    if (!d || d->N < 0) return SGS_ERR_BAD_ARG;
+    if (d->J < 1 || d->J > 64) return SGS_ERR_BAD_JOINTS;
+    if (d->K < 4 || d->K > LBS_PACK_MAX_K || (d->K & 3)) return SGS_ERR_BAD_ARG;
+    if (!d->pose || !d->rest || !d->parents || !d->A || !d->G || !d->xyz_canon || !d->scales || !d->wq || !d->iq ||
+        !d->xyz || !d->rotq || !d->scales_out)
+        return SGS_ERR_BAD_ARG;
+    if (((uintptr_t)d->A & 15) || ((uintptr_t)d->rotq & 15)) return SGS_ERR_MISALIGNED;
+    f = LbsFuse{};
+    f.J = d->J; f.K = d->K; f.rot6d = d->rot6d;
+    f.A = d->A; f.xyz = d->xyz_canon; f.scales = d->scales; f.rot = d->rot_canon;
+    f.wq = d->wq; f.iq = d->iq; f.smpl_scale = d->smpl_scale; f.transl = d->transl;
+    f.xyz_out = d->xyz; f.rotq_out = d->rotq; f.scales_out = d->scales_out;
+    f.d_xyz = d->d_xyz_canon; f.d_rot = d->d_rot_canon; f.d_scales = d->d_scales; f.d_A = d->d_A;
+    f.d_transl = d->d_transl;
+    return 0;
+}
+
+size_t sgs_lbs_packed_bytes(int N, int K) {
+    return lbs_packed_tiles(N) * (size_t)(K > 0 ? K : 0) * LBS_PACK_TILE * 4;
+}
+
+int sgs_lbs_pack_weights(int N, int J, const float* W, int K, float* wq, unsigned int* iq, int* max_nnz,
+                         sgs_stream_t stream) {
+    if (N < 0 || (N > 0 && (!W || !wq || !iq || !max_nnz))) return SGS_ERR_BAD_ARG;
+    return launch_lbs_pack_weights(N, J, W, K, wq, iq, max_nnz, (cudaStream_t)stream);
+}
+
+int sgs_avatar_forward(const sgs_deform_args* d, int D, int M, int W, int H, const float* bg,
+                       const float* opacities, float scale_modifier, const float* viewmatrix,
+                       const float* projmatrix, const float* campos, float tanfovx, float tanfovy,
+                       const float* shs, long long L_cap, void* geom, void* binning, void* img,
+                       float* out_color, int* radii, float* out_alpha, float* out_depth, int* host_counters,
+                       sgs_stream_t stream, int debug, void* timing) {
+    LbsFuse f;
+    int rc = fill_fuse(f, d);
+    if (rc) return rc;
+    if (!shs) return SGS_ERR_BAD_ARG;
+    tick(timing, 8, (cudaStream_t)stream);
+    rc = launch_pose_to_A(d->pose, d->rest, d->parents, d->inv_A_t2cano, 1, d->J, d->A, d->G, (cudaStream_t)stream);
+    if (rc) return rc;
+    // the kernel in front of the fused geometry kernel is pose -> A: parameters may be fetched early
+    return raster_forward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, opacities, d->scales_out, scale_modifier,
+                               d->rotq, nullptr, viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, 0, L_cap,
+                               geom, binning, img, out_color, radii, out_alpha, out_depth, host_counters, stream,
+                               debug | SGS_FLAG_EARLY_PARAMS, timing, &f);
+}
+
+int sgs_avatar_backward(const sgs_deform_args* d, int D, int M, int W, int H, const float* bg,
+                        float scale_modifier, const float* viewmatrix, const float* projmatrix,
+                        const float* campos, float tanfovx, float tanfovy, const float* shs, const int* radii,
+                        const float* dL_dout_color, long long L_cap, const void* geom, const void* binning,
+                        const void* img, void* acc, float* dL_dmeans2D, float* dL_dopacity, float* dL_dsh,
+                        float* xyz_gradient_accum, float* denom, float* max_radii2D, sgs_stream_t stream,
+                        int debug, void* timing) {
+    LbsFuse f;
+    int rc = fill_fuse(f, d);
+    if (rc) return rc;
+    if (!d->d_xyz_canon || !d->d_scales || !d->d_A || !d->d_pose || (d->rot_canon && !d->d_rot_canon))
+        return SGS_ERR_BAD_ARG;
+    rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
+                              viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
+                              geom, binning, img, acc, nullptr, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
+                              nullptr, nullptr, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing, &f);
+    if (rc) return rc;
+    tick(timing, 10, (cudaStream_t)stream);
+    rc = launch_pose_to_A_bwd(d->pose, d->rest, d->parents, d->inv_A_t2cano, d->G, d->d_A, 1, d->J, d->d_pose,
+                              (cudaStream_t)stream);
+    if (rc) return rc;
+    tick(timing, 11, (cudaStream_t)stream);
     return 0;
 }
 

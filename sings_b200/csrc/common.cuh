@@ -171,6 +171,27 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     return r;
 }
 
+// 128-bit read-only load that stays where it is written: the compiler may neither sink it to its
+// first use nor merge it with a later one (software prefetch / memory-level parallelism)
+__device__ __forceinline__ float4 ldg_f4_pinned(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ unsigned ldg_u32_pinned(const unsigned* p) {
+    unsigned r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ldg_u64_pinned(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+
 // ---- cp.async (LDGSTS): 16-byte global -> shared, L2 only ----
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

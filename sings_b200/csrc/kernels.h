@@ -46,7 +46,7 @@ struct RasterLayout {
     // count / scan / scatter binning (raster_binning.cu): per-(chunk, tile) pair counts (u16),
     // their exclusive prefix over the chunks (u32), per-tile totals (u32); bin_ctas chunks of
     // BIN_GAUSS depth-ordered Gaussians, rows of bin_tp tiles (tiles padded to 512)
-    size_t bcount_off, bbase_off, btotal_off;
+    size_t bcount_off, bbase_off, btotal_off, bstart_off;
     int bin_ctas, bin_tp;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
@@ -78,8 +78,9 @@ struct GeomArgs {
     int early_params = 0;
 };
 
+struct LbsFuse;      // kernels_lbs.h: non-null = the deform segment runs inside the geometry kernel
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
-                    char* geom, char* bin, cudaStream_t stream, bool clear = true);
+                    char* geom, char* bin, cudaStream_t stream, bool clear = true, const LbsFuse* lf = nullptr);
 
 // depth passes over the P per-Gaussian items (passes whose digit is constant are skipped)
 int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t stream, int debug);
@@ -129,7 +130,7 @@ struct GeomBwdArgs {
     float* stat_denom;         // (P) denom += 1                                | densification statistics
     float* stat_max_radii;     // (P) max_radii2D = max(., radii)               | of the visible Gaussians
 };
-int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t stream);
+int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t stream, const LbsFuse* lf = nullptr);
 
 int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
                         cudaStream_t stream);

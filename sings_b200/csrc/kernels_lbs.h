@@ -44,6 +44,43 @@ struct LbsGrads {
     float* d_transl;        // (B,3) accumulated (caller zeroes) or null
 };
 
+// Packed skinning weights.  lbs_weights is a constant buffer between densifications
+// (sings_hybrid.py:724) and each row has only a handful of non-zero entries (<= 4 on SMPL
+// vertices, up to ~12 after repeated midpoint subdivision, geometry_ops.py:65-73), so the fused
+// per-frame kernels read a compact copy: per tile of 256 Gaussians, K slots, slot-major so a
+// warp's loads are contiguous --
+//   wq[(tile * K + k) * 256 + t]        k-th non-zero weight of Gaussian tile * 256 + t (0 = unused slot)
+//   iq[(tile * K/4 + k/4) * 256 + t]    four joint indices, 8 bits each (byte k % 4)
+// in ascending joint order.  Skipping exact zeros leaves T = sum_j w_j A_j unchanged.
+constexpr int LBS_PACK_TILE = 256;
+constexpr int LBS_PACK_MAX_K = 16;
+inline size_t lbs_packed_tiles(int N) { return (size_t)((N > 0 ? N : 1) + LBS_PACK_TILE - 1) / LBS_PACK_TILE; }
+int launch_lbs_pack_weights(int N, int J, const float* W, int K, float* wq, unsigned* iq, int* max_nnz,
+                            cudaStream_t stream);
+
+// What the fused LBS + rasterizer-geometry kernels need of the deformer (one frame, B = 1).
+struct LbsFuse {
+    int J, K, rot6d;
+    const float* A;           // (J,16) cano->pose joint transforms of this frame
+    const float* xyz;         // (N,3) canonical means
+    const float* scales;      // (N,3)
+    const float* rot;         // (N,9) / (N,6) when rot6d / null (= identity)
+    const float* wq;          // packed weights
+    const unsigned* iq;       // packed joint indices
+    const float* smpl_scale;  // (1) or null
+    const float* transl;      // (3) or null
+    // forward outputs = the rasterizer's inputs (kept for inspection and for the drop-in boundary)
+    float* xyz_out;           // (N,3)
+    float* rotq_out;          // (N,4)
+    float* scales_out;        // (N,3)
+    // backward outputs
+    float* d_xyz;             // (N,3)
+    float* d_rot;             // (N,9) / (N,6) or null
+    float* d_scales;          // (N,3)
+    float* d_A;               // (J,16) accumulated (caller zeroes)
+    float* d_transl;          // (3) accumulated (caller zeroes) or null
+};
+
 int launch_pose_to_A(const float* pose, const float* rest, const int* parents, const float* inv_A,
                      int B, int J, float* A_out, float* G_out, cudaStream_t stream);
 int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parents,

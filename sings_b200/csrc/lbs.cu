@@ -19,6 +19,7 @@
 // warp-broadcast LDS.128.  Tensor cores are deliberately unused: K = J <= 52, ~6 flop/byte.
 #include "common.cuh"
 #include "kernels_lbs.h"
+#include "lbs_math.cuh"
 
 namespace sgs {
 
@@ -315,179 +316,6 @@ int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parent
 }
 
 // ------------------------------------------------------------------------------------------
-// matrix -> quaternion (rotations.py:98-149) and its backward through the selected candidate
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int mat_to_quat(const float* m, float* q) {
-    const float arg[4] = {1.0f + m[0] + m[4] + m[8], 1.0f + m[0] - m[4] - m[8],
-                          1.0f - m[0] + m[4] - m[8], 1.0f - m[0] - m[4] + m[8]};
-    float qa[4];
-    int best = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) qa[i] = arg[i] > 0.0f ? sqrtf(arg[i]) : 0.0f;
-#pragma unroll
-    for (int i = 1; i < 4; i++)
-        if (qa[i] > qa[best]) best = i;          // first maximum, like torch.argmax
-    const float m01 = m[1], m02 = m[2], m10 = m[3], m12 = m[5], m20 = m[6], m21 = m[7];
-    float c[4];
-    const float sq = qa[best] * qa[best];
-    if (best == 0)      { c[0] = sq;        c[1] = m21 - m12; c[2] = m02 - m20; c[3] = m10 - m01; }
-    else if (best == 1) { c[0] = m21 - m12; c[1] = sq;        c[2] = m10 + m01; c[3] = m02 + m20; }
-    else if (best == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = sq;        c[3] = m12 + m21; }
-    else                { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = sq; }
-    // den >= 0.2: one reciprocal (numerator 1, operands in the normal range) instead of four
-    // divisions whose zero numerators would take the slow IEEE path for the whole warp
-    const float inv_den = 1.0f / (2.0f * fmaxf(qa[best], 0.1f));
-#pragma unroll
-    for (int k = 0; k < 4; k++) q[k] = c[k] * inv_den;
-    return best;
-}
-
-// gradient of q w.r.t. the 3x3 matrix (row-major gm[9]) given dL/dq (g[4])
-__device__ __forceinline__ void mat_to_quat_bwd(const float* m, const float* g, float* gm) {
-    const float arg[4] = {1.0f + m[0] + m[4] + m[8], 1.0f + m[0] - m[4] - m[8],
-                          1.0f - m[0] + m[4] - m[8], 1.0f - m[0] - m[4] + m[8]};
-    float qa[4];
-    int best = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) qa[i] = arg[i] > 0.0f ? sqrtf(arg[i]) : 0.0f;
-#pragma unroll
-    for (int i = 1; i < 4; i++)
-        if (qa[i] > qa[best]) best = i;
-    const float m01 = m[1], m02 = m[2], m10 = m[3], m12 = m[5], m20 = m[6], m21 = m[7];
-    const float qb = qa[best];
-    const float sq = qb * qb;
-    float c[4];
-    if (best == 0)      { c[0] = sq;        c[1] = m21 - m12; c[2] = m02 - m20; c[3] = m10 - m01; }
-    else if (best == 1) { c[0] = m21 - m12; c[1] = sq;        c[2] = m10 + m01; c[3] = m02 + m20; }
-    else if (best == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = sq;        c[3] = m12 + m21; }
-    else                { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = sq; }
-    const float inv_den = 1.0f / (2.0f * fmaxf(qb, 0.1f));
-    float gc[4];
-    float gden = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { gc[k] = g[k] * inv_den; gden -= g[k] * c[k] * inv_den * inv_den; }
-    // den = 2 max(qb, 0.1): gradient reaches qb only above the floor; c[best] = qb^2
-    float gqb = (qb > 0.1f ? 2.0f * gden : 0.0f) + 2.0f * qb * gc[best];
-    const float garg = arg[best] > 0.0f ? gqb * (0.5f / fmaxf(qb, 1e-30f)) : 0.0f;   // zero sub-gradient at 0
-#pragma unroll
-    for (int k = 0; k < 9; k++) gm[k] = 0.0f;
-    const float s0 = (best == 0 || best == 1) ? 1.0f : -1.0f;
-    const float s1 = (best == 0 || best == 2) ? 1.0f : -1.0f;
-    const float s2 = (best == 0 || best == 3) ? 1.0f : -1.0f;
-    gm[0] = s0 * garg; gm[4] = s1 * garg; gm[8] = s2 * garg;
-    // off-diagonal candidates: (index into m, sign) pairs per output slot
-    if (best == 0) {
-        gm[7] += gc[1]; gm[5] -= gc[1]; gm[2] += gc[2]; gm[6] -= gc[2]; gm[3] += gc[3]; gm[1] -= gc[3];
-    } else if (best == 1) {
-        gm[7] += gc[0]; gm[5] -= gc[0]; gm[3] += gc[2]; gm[1] += gc[2]; gm[2] += gc[3]; gm[6] += gc[3];
-    } else if (best == 2) {
-        gm[2] += gc[0]; gm[6] -= gc[0]; gm[3] += gc[1]; gm[1] += gc[1]; gm[5] += gc[3]; gm[7] += gc[3];
-    } else {
-        gm[3] += gc[0]; gm[1] -= gc[0]; gm[6] += gc[1]; gm[2] += gc[1]; gm[7] += gc[2]; gm[5] += gc[2];
-    }
-}
-
-__device__ __forceinline__ void quat_mul(const float* a, const float* b, float* o) {
-    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
-    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
-    o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
-    o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
-}
-
-// ------------------------------------------------------------------------------------------
-// 6D rotation (Zhou et al.) -> matrix by Gram-Schmidt, rows b1, b2, b3 (rotations.py:545-566:
-// F.normalize(a1); a2 - (b1.a2) b1; F.normalize; cross; stack on dim -2) and its backward.
-// F.normalize divides by max(||v||, 1e-12).
-// ------------------------------------------------------------------------------------------
-constexpr float NORMALIZE_EPS = 1e-12f;
-
-__device__ __forceinline__ void rot6d_to_mat(const float* d6, float* R) {
-    const float n1 = sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]);
-    const float i1 = 1.0f / fmaxf(n1, NORMALIZE_EPS);
-    const float b1[3] = {d6[0] * i1, d6[1] * i1, d6[2] * i1};
-    const float d = b1[0] * d6[3] + b1[1] * d6[4] + b1[2] * d6[5];
-    const float u[3] = {d6[3] - d * b1[0], d6[4] - d * b1[1], d6[5] - d * b1[2]};
-    const float n2 = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-    const float i2 = 1.0f / fmaxf(n2, NORMALIZE_EPS);
-    const float b2[3] = {u[0] * i2, u[1] * i2, u[2] * i2};
-    R[0] = b1[0]; R[1] = b1[1]; R[2] = b1[2];
-    R[3] = b2[0]; R[4] = b2[1]; R[5] = b2[2];
-    R[6] = b1[1] * b2[2] - b1[2] * b2[1];
-    R[7] = b1[2] * b2[0] - b1[0] * b2[2];
-    R[8] = b1[0] * b2[1] - b1[1] * b2[0];
-}
-
-// v / max(||v||, eps) backward: g_v = (g - b (b.g)) / n above the floor, g / eps below it
-__device__ __forceinline__ void normalize_bwd(const float* b, float n, const float* g, float* gv) {
-    if (n > NORMALIZE_EPS) {
-        const float bg = b[0] * g[0] + b[1] * g[1] + b[2] * g[2];
-        const float inv = 1.0f / n;
-#pragma unroll
-        for (int k = 0; k < 3; k++) gv[k] = (g[k] - b[k] * bg) * inv;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; k++) gv[k] = g[k] * (1.0f / NORMALIZE_EPS);
-    }
-}
-
-// dL/dR (row-major 9) -> dL/dd6 (6)
-__device__ __forceinline__ void rot6d_to_mat_bwd(const float* d6, const float* gR, float* g6) {
-    const float n1 = sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]);
-    const float i1 = 1.0f / fmaxf(n1, NORMALIZE_EPS);
-    const float b1[3] = {d6[0] * i1, d6[1] * i1, d6[2] * i1};
-    const float a2[3] = {d6[3], d6[4], d6[5]};
-    const float d = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
-    const float u[3] = {a2[0] - d * b1[0], a2[1] - d * b1[1], a2[2] - d * b1[2]};
-    const float n2 = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-    const float i2 = 1.0f / fmaxf(n2, NORMALIZE_EPS);
-    const float b2[3] = {u[0] * i2, u[1] * i2, u[2] * i2};
-    const float* g3 = gR + 6;
-    // b3 = b1 x b2:  dL/db1 += b2 x g3,  dL/db2 += g3 x b1
-    float gb1[3] = {gR[0] + (b2[1] * g3[2] - b2[2] * g3[1]), gR[1] + (b2[2] * g3[0] - b2[0] * g3[2]),
-                    gR[2] + (b2[0] * g3[1] - b2[1] * g3[0])};
-    const float gb2[3] = {gR[3] + (g3[1] * b1[2] - g3[2] * b1[1]), gR[4] + (g3[2] * b1[0] - g3[0] * b1[2]),
-                          gR[5] + (g3[0] * b1[1] - g3[1] * b1[0])};
-    float gu[3];
-    normalize_bwd(b2, n2, gb2, gu);
-    // u = a2 - (b1.a2) b1
-    const float gub1 = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        g6[3 + k] = gu[k] - gub1 * b1[k];
-        gb1[k] += -gub1 * a2[k] - d * gu[k];
-    }
-    normalize_bwd(b1, n1, gb1, g6);
-}
-
-// quaternion (real first) -> axis-angle (rotations.py:514-542): half = atan2(||v||, w),
-// angle = 2 half, v / (sin(half)/angle), series 0.5 - angle^2/48 below 1e-6
-__device__ __forceinline__ void quat_to_axis_angle(const float* q, float* aa) {
-    const float n = sqrtf(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    const float half = atan2f(n, q[0]);
-    const float angle = 2.0f * half;
-    const float s = fabsf(angle) < 1e-6f ? 0.5f - (angle * angle) / 48.0f : sinf(half) / angle;
-    aa[0] = q[1] / s; aa[1] = q[2] / s; aa[2] = q[3] / s;
-}
-
-__device__ __forceinline__ void quat_to_axis_angle_bwd(const float* q, const float* g, float* gq) {
-    const float n = sqrtf(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    const float half = atan2f(n, q[0]);
-    const float angle = 2.0f * half;
-    const bool small = fabsf(angle) < 1e-6f;
-    const float s = small ? 0.5f - (angle * angle) / 48.0f : sinf(half) / angle;
-    // d s / d half: series -angle/24 per unit angle (x2); else (cos(half) angle - 2 sin(half)) / angle^2
-    const float ds_dhalf = small ? -angle / 12.0f : (cosf(half) * angle - 2.0f * sinf(half)) / (angle * angle);
-    const float gs = -(g[0] * q[1] + g[1] * q[2] + g[2] * q[3]) / (s * s);
-    const float gh = gs * ds_dhalf;
-    const float r2 = n * n + q[0] * q[0];
-    const float gn = r2 > 0.0f ? gh * q[0] / r2 : 0.0f;
-    gq[0] = r2 > 0.0f ? -gh * n / r2 : 0.0f;
-    const float gn_over_n = n > 0.0f ? gn / n : 0.0f;      // torch.norm has a zero sub-gradient at 0
-#pragma unroll
-    for (int k = 0; k < 3; k++) gq[1 + k] = g[k] / s + gn_over_n * q[1 + k];
-}
-
-// ------------------------------------------------------------------------------------------
 // shared-memory tile of one CTA (256 consecutive Gaussians).  Every per-Gaussian array is a
 // contiguous block in global memory, so it is moved as a block: one TMA bulk copy
 // (cp.async.bulk + mbarrier) when the block is 16-byte aligned and a multiple of 16 bytes,
@@ -630,19 +458,6 @@ __device__ __forceinline__ void blend_T(const LbsTile& s, int b, int J, int t, f
             T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
             T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
         }
-    }
-}
-
-__device__ __forceinline__ void compose_rot(const float* T, const float* Rc, bool iso, float* Rp) {
-    if (iso) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) { Rp[3 * r] = T[4 * r]; Rp[3 * r + 1] = T[4 * r + 1]; Rp[3 * r + 2] = T[4 * r + 2]; }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                Rp[3 * r + c] = T[4 * r] * Rc[c] + T[4 * r + 1] * Rc[3 + c] + T[4 * r + 2] * Rc[6 + c];
     }
 }
 
@@ -988,6 +803,48 @@ int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
     if (smem > 220 * 1024) return SGS_ERR_CAPACITY;
     SGS_CUDA_OK(set_max_smem(lbs_bwd_kernel, smem));
     launch_pdl(lbs_bwd_kernel, (a.N + LBS_THREADS - 1) / LBS_THREADS, LBS_THREADS, smem, stream, a, g);
+    SGS_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// packed skinning weights (kernels_lbs.h): one thread per Gaussian collects the non-zero entries
+// of its row in ascending joint order; *max_nnz receives the longest row (the caller checks it
+// against K once -- the buffer only changes at densification).
+// ------------------------------------------------------------------------------------------
+__global__ void lbs_pack_weights_kernel(int N, int J, const float* __restrict__ W, int K, float* __restrict__ wq,
+                                        unsigned* __restrict__ iq, int* __restrict__ max_nnz) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int nnz = 0;
+    if (n < N) {
+        const size_t tile = (size_t)n / LBS_PACK_TILE, t = (size_t)n % LBS_PACK_TILE;
+        unsigned word = 0;
+        for (int j = 0; j < J; j++) {
+            const float w = W[(size_t)n * J + j];
+            if (w != 0.0f) {
+                if (nnz < K) {
+                    wq[(tile * K + nnz) * LBS_PACK_TILE + t] = w;
+                    word |= (unsigned)j << (8 * (nnz & 3));
+                    if ((nnz & 3) == 3) { iq[(tile * (K / 4) + nnz / 4) * LBS_PACK_TILE + t] = word; word = 0; }
+                }
+                nnz++;
+            }
+        }
+        for (int k = nnz; k < K; k++) {           // unused slots: weight 0 (joint 0)
+            wq[(tile * K + k) * LBS_PACK_TILE + t] = 0.0f;
+            if ((k & 3) == 3) { iq[(tile * (K / 4) + k / 4) * LBS_PACK_TILE + t] = word; word = 0; }
+        }
+    }
+    const int m = __reduce_max_sync(0xffffffffu, nnz);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_nnz, m);
+}
+
+int launch_lbs_pack_weights(int N, int J, const float* W, int K, float* wq, unsigned* iq, int* max_nnz,
+                            cudaStream_t stream) {
+    if (N <= 0) return 0;
+    if (J < 1 || J > 64) return SGS_ERR_BAD_JOINTS;
+    if (K < 4 || K > LBS_PACK_MAX_K || (K & 3)) return SGS_ERR_BAD_ARG;
+    lbs_pack_weights_kernel<<<(N + 255) / 256, 256, 0, stream>>>(N, J, W, K, wq, iq, max_nnz);
     SGS_LAUNCH_OK();
     return 0;
 }

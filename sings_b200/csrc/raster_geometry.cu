@@ -25,6 +25,7 @@
 // block-local offsets), so key and value stores are fully coalesced.
 #include "geom_math.cuh"
 #include "kernels.h"
+#include "lbs_math.cuh"
 
 namespace sgs {
 
@@ -89,6 +90,7 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.bcount_off = o;   o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 2, 256) : 0;
     l.bbase_off = o;    o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 4, 256) : 0;
     l.btotal_off = o;   o += css ? align_up((size_t)l.bin_tp * 4, 256) : 0;
+    l.bstart_off = o;   o += css ? align_up((size_t)l.bin_tp * 4, 256) : 0;
     l.bin_bytes = o;
     // image state
     size_t pix = (size_t)W * H;
@@ -112,9 +114,13 @@ struct GeoOut {
 
 // NVEC: float4 per SH row staged to shared memory; 0 = colours precomputed.
 // VEC16: SH rows are 16-byte aligned (M*3 % 4 == 0 and base aligned) -> 16-byte cp.async.
-template <int D, bool HAS_SH, bool VEC16>
-__global__ void __launch_bounds__(GEO_THREADS)
-geometry_kernel(GeomArgs a, GeoOut o) {
+// FUSE: the deform segment of SinGS.forward (sings_hybrid.py:398-419) runs in this kernel's
+// prologue -- canonical attributes and packed skinning weights in, deformed mean / quaternion /
+// scale straight into the projection math (and out to global memory once, for the backward and
+// for inspection) -- instead of a separate LBS kernel writing them and this one reading them back.
+template <int D, bool HAS_SH, bool VEC16, bool FUSE>
+__global__ void __launch_bounds__(GEO_THREADS, FUSE ? 3 : 1)
+geometry_kernel(GeomArgs a, GeoOut o, LbsFuse lf) {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
     constexpr int S4 = HAS_SH ? sh_stride4(NVEC) : 0;
@@ -122,6 +128,7 @@ geometry_kernel(GeomArgs a, GeoOut o) {
     __shared__ float s_cam[36];
     __shared__ unsigned s_hist[DEPTH_PASSES * RADIX];
     __shared__ unsigned s_var[2];
+    __shared__ float4 s_A[FUSE ? 64 * 3 : 1];        // rows 0..2 of the joint transforms
 
     const int tid = threadIdx.x;
     const int base = blockIdx.x * GEO_THREADS;
@@ -150,19 +157,48 @@ geometry_kernel(GeomArgs a, GeoOut o) {
             cp_async_commit();
         }
     };
+    const int idx = base + tid;
+    const bool in_range = idx < a.P;
     if (a.early_params) stage_sh();
+    // the canonical attributes are model parameters too: fetched ahead of the wait (the kernel in
+    // front is pose -> A, which writes none of them)
+    CanonG cg;
+    if constexpr (FUSE) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) cg.Rc[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+        if (in_range) load_canon(lf, idx, cg);
+    }
     pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
     else if (tid < 35) s_cam[tid] = a.campos[tid - 32];
     else if (tid < 37) s_var[tid - 35] = 0;
     for (int i = tid; i < DEPTH_PASSES * RADIX; i += GEO_THREADS) s_hist[i] = 0;
+    if constexpr (FUSE) {
+        for (int f = tid; f < lf.J * 3; f += GEO_THREADS)
+            s_A[f] = reinterpret_cast<const float4*>(lf.A)[(f / 3) * 4 + f % 3];
+    }
     __syncthreads();
-    const int idx = base + tid;
-    const bool in_range = idx < a.P;
     const float* V = s_cam;
     const float* Mx = s_cam + 16;
     if (!a.early_params) stage_sh();
+    float m3[3] = {0, 0, 0}, sc3[3] = {0, 0, 0};
+    float4 qrot = make_float4(1, 0, 0, 0);
+    if constexpr (FUSE) {
+        if (in_range) {
+            const float sm = lf.smpl_scale ? __ldg(lf.smpl_scale) : 1.0f;
+            float tr[3] = {0, 0, 0};
+            if (lf.transl) { tr[0] = __ldg(lf.transl); tr[1] = __ldg(lf.transl + 1); tr[2] = __ldg(lf.transl + 2); }
+            float q[4], T[12];
+            deform_one(lf, s_A, cg, sm, tr, m3, q, sc3, T);
+            qrot = make_float4(q[0], q[1], q[2], q[3]);
+            lf.xyz_out[3 * (size_t)idx] = m3[0]; lf.xyz_out[3 * (size_t)idx + 1] = m3[1]; lf.xyz_out[3 * (size_t)idx + 2] = m3[2];
+            reinterpret_cast<float4*>(lf.rotq_out)[idx] = qrot;
+            lf.scales_out[3 * (size_t)idx] = sc3[0]; lf.scales_out[3 * (size_t)idx + 1] = sc3[1]; lf.scales_out[3 * (size_t)idx + 2] = sc3[2];
+        }
+    } else if (in_range) {
+        m3[0] = a.means3D[3 * idx]; m3[1] = a.means3D[3 * idx + 1]; m3[2] = a.means3D[3 * idx + 2];
+    }
 
     // ---- per-Gaussian geometry ----
     unsigned tiles = 0;
@@ -171,7 +207,7 @@ geometry_kernel(GeomArgs a, GeoOut o) {
     float px = 0, py = 0, pz = 0, depth = 0, ix = 0, iy = 0;
     float conA = 0, conB = 0, conC = 0, opac = 0;
     if (in_range) {
-        px = a.means3D[3 * idx]; py = a.means3D[3 * idx + 1]; pz = a.means3D[3 * idx + 2];
+        px = m3[0]; py = m3[1]; pz = m3[2];
         depth = xform_row(V, 2, px, py, pz);
         if (depth > 0.2f) {      // [upstream] in_frustum: p_view.z <= 0.2 culls
             float pvx = xform_row(V, 0, px, py, pz), pvy = xform_row(V, 1, px, py, pz);
@@ -184,9 +220,11 @@ geometry_kernel(GeomArgs a, GeoOut o) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[6 * (size_t)idx + k];
             } else {
-                float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-                cov3d_from_scale_rot(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2],
-                                     a.scale_modifier, q.x, q.y, q.z, q.w, c3);
+                if constexpr (!FUSE) {
+                    qrot = reinterpret_cast<const float4*>(a.rotations)[idx];
+                    sc3[0] = a.scales[3 * idx]; sc3[1] = a.scales[3 * idx + 1]; sc3[2] = a.scales[3 * idx + 2];
+                }
+                cov3d_from_scale_rot(sc3[0], sc3[1], sc3[2], a.scale_modifier, qrot.x, qrot.y, qrot.z, qrot.w, c3);
             }
             Cov2D cv;
             cov2d(pvx, pvy, depth, o.fx, o.fy, a.tanfovx, a.tanfovy, c3, V, cv);
@@ -451,23 +489,34 @@ int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin
 }
 
 template <int D, bool HAS_SH>
-static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec16, cudaStream_t st) {
+static int launch_geo_t(const GeomArgs& a, const GeoOut& o, int blocks, bool vec16, cudaStream_t st, const LbsFuse* lf) {
     size_t smem = HAS_SH ? (size_t)GEO_THREADS * sh_stride4(sh_nvec(D)) * 16 : 0;
-    if (vec16) {
-        auto k = geometry_kernel<D, HAS_SH, true>;
-        SGS_CUDA_OK(set_max_smem(k, smem));
-        launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
-    } else {
-        auto k = geometry_kernel<D, HAS_SH, false>;
-        SGS_CUDA_OK(set_max_smem(k, smem));
-        launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o);
+    const LbsFuse none{};
+    if (lf) {
+        if constexpr (HAS_SH) {
+            if (!vec16) return SGS_ERR_MISALIGNED;
+            auto k = geometry_kernel<D, true, true, true>;
+            SGS_CUDA_OK(set_max_smem(k, smem));
+            SGS_CUDA_OK(launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o, *lf));
+            return 0;
+        } else {
+            return SGS_ERR_BAD_ARG;
+        }
     }
-    SGS_LAUNCH_OK();
+    if (vec16) {
+        auto k = geometry_kernel<D, HAS_SH, true, false>;
+        SGS_CUDA_OK(set_max_smem(k, smem));
+        SGS_CUDA_OK(launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o, none));
+    } else {
+        auto k = geometry_kernel<D, HAS_SH, false, false>;
+        SGS_CUDA_OK(set_max_smem(k, smem));
+        SGS_CUDA_OK(launch_pdl(k, blocks, GEO_THREADS, smem, st, a, o, none));
+    }
     return 0;
 }
 
 int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap, int* radii,
-                    char* geom, char* bin, cudaStream_t stream, bool clear) {
+                    char* geom, char* bin, cudaStream_t stream, bool clear, const LbsFuse* lf) {
     // one memset clears counters, histograms, scan + sort look-back status and the tile-length bucket counts
     if (clear) SGS_CUDA_OK(cudaMemsetAsync(bin, 0, lay.zero_bytes, stream));
     if (a.P <= 0) return 0;
@@ -484,14 +533,14 @@ int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap,
     o.fx = (float)a.W / (2.0f * a.tanfovx);
     o.fy = (float)a.H / (2.0f * a.tanfovy);
     const bool has_sh = a.colors_precomp == nullptr;
-    if (!has_sh) return launch_geo_t<0, false>(a, o, lay.scan_blocks, false, stream);
+    if (!has_sh) return launch_geo_t<0, false>(a, o, lay.scan_blocks, false, stream, lf);
     const bool vec16 = ((a.M * 3) % 4 == 0) && (((uintptr_t)a.shs & 15) == 0) &&
                        (a.M * 3 >= sh_nvec(a.D) * 4);
     switch (a.D) {
-        case 0: return launch_geo_t<0, true>(a, o, lay.scan_blocks, vec16, stream);
-        case 1: return launch_geo_t<1, true>(a, o, lay.scan_blocks, vec16, stream);
-        case 2: return launch_geo_t<2, true>(a, o, lay.scan_blocks, vec16, stream);
-        case 3: return launch_geo_t<3, true>(a, o, lay.scan_blocks, vec16, stream);
+        case 0: return launch_geo_t<0, true>(a, o, lay.scan_blocks, vec16, stream, lf);
+        case 1: return launch_geo_t<1, true>(a, o, lay.scan_blocks, vec16, stream, lf);
+        case 2: return launch_geo_t<2, true>(a, o, lay.scan_blocks, vec16, stream, lf);
+        case 3: return launch_geo_t<3, true>(a, o, lay.scan_blocks, vec16, stream, lf);
         default: return SGS_ERR_BAD_SH_DEGREE;
     }
 }

@@ -12,18 +12,26 @@
 // rows and written back with coalesced 16-byte stores.
 #include "geom_math.cuh"
 #include "kernels.h"
+#include "lbs_math.cuh"
 
 namespace sgs {
 
 constexpr int GB_THREADS = 256;
 
-template <int D, bool HAS_SH, bool VEC16>
-__global__ void __launch_bounds__(GB_THREADS)
-geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
+// FUSE: the backward of the deform segment (what autograd computes for sings_hybrid.py:398-419,
+// SURVEY.md Appendix B) runs in this kernel's epilogue on the gradients it has just produced --
+// dL/d(mean, scale, quaternion) never travel through global memory; out come the canonical-
+// parameter gradients, dL/dA and dL/dtransl.  dL/dA[j] = sum_n W[n,j] dT_n uses the packed
+// weights: every warp folds its 32 rows, one after the other, into a private J x 12 tile in
+// shared memory (lanes = (slot, entry) of the row: distinct addresses, plain read-modify-write);
+// the CTA then adds its warps' tiles and issues one atomic per non-zero entry.
+template <int D, bool HAS_SH, bool VEC16, bool FUSE>
+__global__ void __launch_bounds__(GB_THREADS, FUSE ? 2 : 1)
+geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
     constexpr int S4 = HAS_SH ? sh_stride4(NVEC) : 0;
-    extern __shared__ float4 s_sh[];
+    extern __shared__ float4 s_sh[];                 // SH rows; FUSE: then A (J x 3 float4), dT, per-warp dA tiles
     __shared__ float s_cam[36];
     const GeomArgs& a = b.fwd;
     const int tid = threadIdx.x;
@@ -54,6 +62,20 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
         }
     };
     if (a.early_params) stage_sh();
+    // FUSE: canonical attributes (model parameters) and this frame's joint transforms (written by
+    // the forward, many kernels ago) are fetched ahead of the wait too
+    float4* const s_A = s_sh + (size_t)GB_THREADS * S4;                               // [J][3]
+    float* const s_dT = reinterpret_cast<float*>(s_A + 64 * 3);                        // [256][12]
+    float* const s_part = s_dT + GB_THREADS * 12;                                      // [8][J][12]
+    CanonG cg;
+    if constexpr (FUSE) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) cg.Rc[k] = (k % 4 == 0) ? 1.0f : 0.0f;
+        if (in_range) load_canon(lf, idx, cg);
+        for (int f = tid; f < lf.J * 3; f += GB_THREADS)
+            s_A[f] = reinterpret_cast<const float4*>(lf.A)[(f / 3) * 4 + f % 3];
+        for (int f = tid; f < (GB_THREADS / 32) * lf.J * 12; f += GB_THREADS) s_part[f] = 0.0f;
+    }
     pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
     else if (tid < 32) s_cam[tid] = a.proj[tid - 16];
@@ -273,52 +295,168 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec) {
         b.stat_max_radii[idx] = fmaxf(b.stat_max_radii[idx], (float)b.radii[idx]);
     }
     if (in_range) {
-        b.dL_dmeans3D[3 * idx] = dmean[0]; b.dL_dmeans3D[3 * idx + 1] = dmean[1]; b.dL_dmeans3D[3 * idx + 2] = dmean[2];
         b.dL_dmeans2D[3 * idx] = g2x; b.dL_dmeans2D[3 * idx + 1] = g2y; b.dL_dmeans2D[3 * idx + 2] = 0.0f;
         b.dL_dopacity[idx] = gop;
-        b.dL_dcolors[3 * idx] = gcol[0]; b.dL_dcolors[3 * idx + 1] = gcol[1]; b.dL_dcolors[3 * idx + 2] = gcol[2];
+        if (b.dL_dcolors) {
+            b.dL_dcolors[3 * idx] = gcol[0]; b.dL_dcolors[3 * idx + 1] = gcol[1]; b.dL_dcolors[3 * idx + 2] = gcol[2];
+        }
         if (b.dL_dcov3D) {
 #pragma unroll
             for (int k = 0; k < 6; k++) b.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
         }
-        if (b.dL_dscales) {
-            b.dL_dscales[3 * idx] = dscale[0]; b.dL_dscales[3 * idx + 1] = dscale[1]; b.dL_dscales[3 * idx + 2] = dscale[2];
+    }
+    if constexpr (!FUSE) {
+        if (in_range) {
+            b.dL_dmeans3D[3 * idx] = dmean[0]; b.dL_dmeans3D[3 * idx + 1] = dmean[1]; b.dL_dmeans3D[3 * idx + 2] = dmean[2];
+            if (b.dL_dscales) {
+                b.dL_dscales[3 * idx] = dscale[0]; b.dL_dscales[3 * idx + 1] = dscale[1]; b.dL_dscales[3 * idx + 2] = dscale[2];
+            }
+            if (b.dL_drots)
+                reinterpret_cast<float4*>(b.dL_drots)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
         }
-        if (b.dL_drots)
-            reinterpret_cast<float4*>(b.dL_drots)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    } else {
+        // ---- deform-segment backward on g_x = dmean, g_q = drot, g_s = dscale ----
+        const int lane = tid & 31, warp = tid >> 5;
+        const bool iso = lf.rot == nullptr;
+        float dT[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) dT[k] = 0.0f;
+        float gtr[3] = {0, 0, 0};
+        if (in_range) {
+            const float sm = lf.smpl_scale ? __ldg(lf.smpl_scale) : 1.0f;
+            float T[12];
+            blend_T_packed(s_A, cg.pw, lf.K, T);
+            float Rp[9], gR[9];
+            compose_rot(T, cg.Rc, iso, Rp);
+            mat_to_quat_bwd(Rp, drot, gR);
+            gtr[0] = dmean[0]; gtr[1] = dmean[1]; gtr[2] = dmean[2];
+            const float h[3] = {dmean[0] * sm, dmean[1] * sm, dmean[2] * sm};      // dL/d(verts)
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float rot = iso ? gR[3 * r + c]
+                                          : gR[3 * r] * cg.Rc[3 * c] + gR[3 * r + 1] * cg.Rc[3 * c + 1] + gR[3 * r + 2] * cg.Rc[3 * c + 2];
+                    dT[4 * r + c] = h[r] * cg.x[c] + rot;
+                }
+                dT[4 * r + 3] = h[r];
+            }
+            // d xyz_canon = T3^T h ; d scales = g_s * smpl_scale ; d R_canon = T3^T gR
+            lf.d_xyz[3 * (size_t)idx] = T[0] * h[0] + T[4] * h[1] + T[8] * h[2];
+            lf.d_xyz[3 * (size_t)idx + 1] = T[1] * h[0] + T[5] * h[1] + T[9] * h[2];
+            lf.d_xyz[3 * (size_t)idx + 2] = T[2] * h[0] + T[6] * h[1] + T[10] * h[2];
+            lf.d_scales[3 * (size_t)idx] = dscale[0] * sm; lf.d_scales[3 * (size_t)idx + 1] = dscale[1] * sm;
+            lf.d_scales[3 * (size_t)idx + 2] = dscale[2] * sm;
+            if (lf.d_rot && !iso) {
+                float dRc[9];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        dRc[3 * r + c] = T[r] * gR[c] + T[4 + r] * gR[3 + c] + T[8 + r] * gR[6 + c];
+                if (lf.rot6d) {
+                    float in6[6], g6[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) in6[k] = __ldg(lf.rot + 6 * (size_t)idx + k);
+                    rot6d_to_mat_bwd(in6, dRc, g6);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) lf.d_rot[6 * (size_t)idx + k] = g6[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) lf.d_rot[9 * (size_t)idx + k] = dRc[k];
+                }
+            }
+        }
+        if (lf.d_transl) {
+            const float t0 = warp_sum(gtr[0]), t1 = warp_sum(gtr[1]), t2 = warp_sum(gtr[2]);
+            if (lane == 0) { atomicAdd(lf.d_transl, t0); atomicAdd(lf.d_transl + 1, t1); atomicAdd(lf.d_transl + 2, t2); }
+        }
+        // ---- dA: this warp's 32 rows, one after the other.  Row l: lanes (slot k2, entry e) for two
+        // slots at a time add w_k dT_l[e] to tile[j_k][e] -- the joints of one row are distinct.
+        float4* dTrow = reinterpret_cast<float4*>(s_dT) + tid * 3;
+        dTrow[0] = make_float4(dT[0], dT[1], dT[2], dT[3]);
+        dTrow[1] = make_float4(dT[4], dT[5], dT[6], dT[7]);
+        dTrow[2] = make_float4(dT[8], dT[9], dT[10], dT[11]);
+        // the row's packed weights go through shared memory too (the SH rows are done with: every
+        // thread has written its dL/dsh row and the block has passed the barrier in front of the
+        // write-out ... which reads them: so use the dT tile's neighbour, the per-warp staging below)
+        __shared__ float s_w[GB_THREADS / 32][32][LBS_PACK_MAX_K];
+        __shared__ unsigned char s_j[GB_THREADS / 32][32][LBS_PACK_MAX_K];
+#pragma unroll
+        for (int k = 0; k < LBS_PACK_MAX_K; k++) {
+            if (k < lf.K) {
+                s_w[warp][lane][k] = in_range ? cg.pw.w[k] : 0.0f;
+                s_j[warp][lane][k] = (unsigned char)((cg.pw.idx[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            }
+        }
+        __syncwarp();
+        float* const tile = s_part + (size_t)warp * lf.J * 12;
+        const int k2 = lane / 12, e = lane - 12 * k2;            // lanes 0..23: slot pair member, entry
+        if (lane < 24) {
+            for (int l = 0; l < 32; l++) {
+                const float dte = s_dT[(warp * 32 + l) * 12 + e];
+                for (int kb = 0; kb < lf.K; kb += 2) {
+                    const float w = s_w[warp][l][kb + k2];
+                    if (w != 0.0f) {
+                        const int j = s_j[warp][l][kb + k2];
+                        tile[j * 12 + e] = fmaf(w, dte, tile[j * 12 + e]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int oidx = tid; oidx < lf.J * 12; oidx += GB_THREADS) {
+            float accv = 0.0f;
+#pragma unroll
+            for (int w = 0; w < GB_THREADS / 32; w++) accv += s_part[(size_t)w * lf.J * 12 + oidx];
+            const int j = oidx / 12, c = oidx - j * 12;
+            if (accv != 0.0f) atomicAdd(lf.d_A + (size_t)j * 16 + 4 * (c >> 2) + (c & 3), accv);
+        }
     }
 }
 
 template <int D, bool HAS_SH>
-static int launch_gb_t(const GeomBwdArgs& b, const float4* rec, int blocks, bool vec16, cudaStream_t st) {
+static int launch_gb_t(const GeomBwdArgs& b, const float4* rec, int blocks, bool vec16, cudaStream_t st, const LbsFuse* lf) {
     size_t smem = HAS_SH ? (size_t)GB_THREADS * sh_stride4(sh_nvec(D)) * 16 : 0;
-    if (vec16) {
-        auto k = geometry_bwd_kernel<D, HAS_SH, true>;
-        SGS_CUDA_OK(set_max_smem(k, smem));
-        launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
-    } else {
-        auto k = geometry_bwd_kernel<D, HAS_SH, false>;
-        SGS_CUDA_OK(set_max_smem(k, smem));
-        launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec);
+    const LbsFuse none{};
+    if (lf) {
+        if constexpr (HAS_SH) {
+            if (!vec16) return SGS_ERR_MISALIGNED;
+            smem += (size_t)64 * 3 * 16 + (size_t)GB_THREADS * 48 + (size_t)(GB_THREADS / 32) * lf->J * 48;
+            auto k = geometry_bwd_kernel<D, true, true, true>;
+            SGS_CUDA_OK(set_max_smem(k, smem));
+            SGS_CUDA_OK(launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec, *lf));
+            return 0;
+        } else {
+            return SGS_ERR_BAD_ARG;
+        }
     }
-    SGS_LAUNCH_OK();
+    if (vec16) {
+        auto k = geometry_bwd_kernel<D, HAS_SH, true, false>;
+        SGS_CUDA_OK(set_max_smem(k, smem));
+        SGS_CUDA_OK(launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec, none));
+    } else {
+        auto k = geometry_bwd_kernel<D, HAS_SH, false, false>;
+        SGS_CUDA_OK(set_max_smem(k, smem));
+        SGS_CUDA_OK(launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec, none));
+    }
     return 0;
 }
 
-int launch_geometry_bwd(const GeomBwdArgs& b, const char* geom, cudaStream_t stream) {
+int launch_geometry_bwd(const GeomBwdArgs& b, const char* geom, cudaStream_t stream, const LbsFuse* lf) {
     const GeomArgs& a = b.fwd;
     if (a.P <= 0) return 0;
     const float4* rec = reinterpret_cast<const float4*>(geom);
     const int blocks = (a.P + GB_THREADS - 1) / GB_THREADS;
     const bool has_sh = a.colors_precomp == nullptr;
-    if (!has_sh) return launch_gb_t<0, false>(b, rec, blocks, false, stream);
+    if (!has_sh) return launch_gb_t<0, false>(b, rec, blocks, false, stream, lf);
     const bool vec16 = ((a.M * 3) % 4 == 0) && (((uintptr_t)a.shs & 15) == 0) &&
                        (((uintptr_t)b.dL_dsh & 15) == 0) && (a.M * 3 >= sh_nvec(a.D) * 4);
     switch (a.D) {
-        case 0: return launch_gb_t<0, true>(b, rec, blocks, vec16, stream);
-        case 1: return launch_gb_t<1, true>(b, rec, blocks, vec16, stream);
-        case 2: return launch_gb_t<2, true>(b, rec, blocks, vec16, stream);
-        case 3: return launch_gb_t<3, true>(b, rec, blocks, vec16, stream);
+        case 0: return launch_gb_t<0, true>(b, rec, blocks, vec16, stream, lf);
+        case 1: return launch_gb_t<1, true>(b, rec, blocks, vec16, stream, lf);
+        case 2: return launch_gb_t<2, true>(b, rec, blocks, vec16, stream, lf);
+        case 3: return launch_gb_t<3, true>(b, rec, blocks, vec16, stream, lf);
         default: return SGS_ERR_BAD_SH_DEGREE;
     }
 }

@@ -92,6 +92,7 @@ class AvatarStep:
         self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
         self._bwd_clean = False
+        self._pack_weights()
         # shs is a model parameter: the kernels in front of the geometry kernels (LBS forward,
         # blend backward) are this library's and never write it, so its rows may be prefetched
         # ahead of the dependency wait (SGS_FLAG_EARLY_PARAMS)
@@ -107,6 +108,47 @@ class AvatarStep:
             h = C.c_void_p()
             _lib.check(self.L.sgs_timing_create(16, C.byref(h)), "sgs_timing_create")
             self.timing = h
+
+    def _pack_weights(self):
+        """Compact copy of lbs_weights for the fused kernels (include/sings_b200.h: packed skinning
+        weights).  The buffer is constant between densifications (sings_hybrid.py:724); call
+        again after it changes.  Rows with more than 16 non-zero joints (or SGS_NO_FUSE=1) keep the
+        step on the unfused kernels."""
+        L_, p = self.L, _lib.ptr
+        self.K, self.wq, self.iq = 0, None, None
+        if os.environ.get("SGS_NO_FUSE"):
+            return
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        nnz = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        K = 4
+        while K <= 16:
+            nb = int(L_.sgs_lbs_packed_bytes(self.N, K))
+            wq = torch.empty(nb // 4, device=self.dev, dtype=torch.float32)
+            iq = torch.empty(max(nb // 16, 1), device=self.dev, dtype=torch.int32)
+            nnz.zero_()
+            _lib.check(L_.sgs_lbs_pack_weights(self.N, self.J, p(self.W_lbs), K, p(wq), p(iq), p(nnz), st),
+                       "sgs_lbs_pack_weights")
+            m = int(nnz.item())
+            if m <= K:
+                self.K, self.wq, self.iq = K, wq, iq
+                return
+            K = (m + 3) // 4 * 4
+
+    def _deform_args(self, fr) -> "_lib.DeformArgs":
+        p = _lib.ptr
+        d = _lib.DeformArgs()
+        d.N, d.J, d.K, d.rot6d = self.N, self.J, self.K, 0
+        pose = fr.pose.reshape(1, self.J, 3)
+        for name, tns in (("pose", pose), ("rest", self.rest), ("parents", self.parents),
+                          ("inv_A_t2cano", self.inv_A), ("xyz_canon", self.xyz_canon), ("scales", self.scales),
+                          ("rot_canon", self.rot_canon), ("wq", self.wq), ("iq", self.iq),
+                          ("smpl_scale", fr.smpl_scale), ("transl", fr.transl), ("A", self.A), ("G", self.G),
+                          ("xyz", self.xyz), ("rotq", self.rotq), ("scales_out", self.sc),
+                          ("d_xyz_canon", self.d_xyz_canon), ("d_rot_canon", self.d_rot_canon),
+                          ("d_scales", self.d_scales), ("d_A", self.d_A), ("d_transl", self.d_transl),
+                          ("d_pose", self.d_pose)):
+            setattr(d, name, p(tns))
+        return d
 
     def _alloc_scratch(self):
         gb, bb, ib, ab = _sizes(self.N, self.Wd, self.H, self.L_cap)
@@ -127,6 +169,15 @@ class AvatarStep:
                                        p(self.small_grads), self.small_grads.numel() * 4, st),   # d_A and d_transl
                    "sgs_raster_clear")
         self._bwd_clean = True             # one backward may rely on the up-front clearing
+        if self.K:
+            # the fused path: pose -> A, then LBS inside the rasterizer's preprocess kernel
+            d = self._deform_args(fr)
+            _lib.check(L_.sgs_avatar_forward(
+                C.byref(d), self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.opacity), 1.0, p(fr.viewmatrix),
+                p(fr.projmatrix), p(fr.campos), float(fr.tanfovx), float(fr.tanfovy), p(self.shs), self.L_cap,
+                p(self.geom), p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
+                self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_avatar_forward")
+            return self.color
         if tm:
             L_.sgs_timing_record(tm, 8, st)
         _lib.check(L_.sgs_pose_lbs_fwd(p(pose), p(self.rest), p(self.parents), p(self.inv_A), 1, self.N,
@@ -154,6 +205,16 @@ class AvatarStep:
         if not self._bwd_clean:            # a second backward of the same forward: clear again
             self.small_grads.zero_()
         self._bwd_clean = False
+        if self.K:
+            d = self._deform_args(fr)
+            _lib.check(L_.sgs_avatar_backward(
+                C.byref(d), self.D, self.M, self.Wd, self.H, p(fr.bg), 1.0, p(fr.viewmatrix), p(fr.projmatrix),
+                p(fr.campos), float(fr.tanfovx), float(fr.tanfovy), p(self.shs), p(self.radii), p(dL_dimage),
+                self.L_cap, p(self.geom), p(self.binning), p(self.img), p(self.acc), p(self.g_means2D),
+                p(self.d_opacity), p(self.d_shs), p(self.grad_accum) if stats else None,
+                p(self.denom) if stats else None, p(self.max_radii2D) if stats else None, st, flags, tm),
+                "sgs_avatar_backward")
+            return
         _lib.check(L_.sgs_raster_backward(
             self.N, self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.xyz), None, p(self.sc), 1.0,
             p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos), float(fr.tanfovx),
@@ -262,9 +323,13 @@ class AvatarStep:
             raise _lib.SgsError("AvatarStep(timing=True) required")
         out = {}
         ms = C.c_float()
-        for name, i, j in [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("sort", 1, 2), ("ranges", 2, 3),
-                           ("blend_fwd", 3, 4), ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7),
-                           ("lbs_bwd", 10, 11), ("total", 8, 11)]:
+        if self.K:      # fused kernels: deform + preprocess is one stage, so is their backward
+            stages = [("deform_geometry", 8, 1), ("binning", 1, 3), ("blend_fwd", 3, 4), ("blend_bwd", 5, 6),
+                      ("geometry_lbs_bwd", 6, 11), ("total", 8, 11)]
+        else:
+            stages = [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("binning", 1, 3), ("blend_fwd", 3, 4),
+                      ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7), ("lbs_bwd", 10, 11), ("total", 8, 11)]
+        for name, i, j in stages:
             _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
             out[name] = float(ms.value)
         return out

@@ -131,6 +131,46 @@ def test_avatar_step_matches_autograd_path():
     assert torch.allclose(step.grad_accum[vis], torch.norm(m2.grad[vis, :2], dim=-1), rtol=1e-4, atol=1e-12)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("J,iso,smooth", [(24, False, 0), (52, True, 2), (52, False, 1)])
+def test_fused_deform_kernels_equal_the_separate_ones(J, iso, smooth, monkeypatch):
+    """sgs_avatar_forward / _backward (LBS fused into the rasterizer's per-Gaussian kernels, packed
+    skinning weights with K = 4 .. 16 slots) against the separate kernels on the same inputs:
+    same image bits, same radii, gradients to fp32 re-association."""
+    from sings_b200 import synthetic as syn
+    from sings_b200.step import AvatarStep, FrameInputs
+    H, W, N = 144, 112, 5000
+    av = syn.make_avatar(N, J, seed=31, isotropic=iso, smooth_weights=smooth)
+    view = syn.make_view(H, W)
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), device="cuda")
+    fr = FrameInputs(pose=t(syn.random_pose(J, seed=33)), transl=t(syn.default_transl(H, focal=5000.0 * H / 896.0)),
+                     viewmatrix=t(view.world_view_transform), projmatrix=t(view.full_proj_transform),
+                     campos=t(view.camera_center), bg=t(np.array([0.3, 0.6, 0.9], np.float32)),
+                     tanfovx=view.tanfovx, tanfovy=view.tanfovy, smpl_scale=t(np.array([1.07], np.float32)))
+    G = torch.randn(3, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    out = {}
+    for mode in ("fused", "separate"):
+        if mode == "separate":
+            monkeypatch.setenv("SGS_NO_FUSE", "1")
+        st = AvatarStep(t(av.xyz_canon), None if iso else t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs),
+                        t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano), H, W, 3)
+        assert (st.K > 0) == (mode == "fused")
+        if mode == "fused":
+            nnz = int((av.lbs_weights != 0).sum(1).max())
+            assert st.K >= nnz and st.K - nnz < 4 and (smooth == 0 or st.K > 4)
+        img = st.forward(fr).clone()
+        st.backward(G)
+        torch.cuda.synchronize()
+        assert st.check_capacity() > 0
+        out[mode] = dict(img=img, radii=st.radii.clone(), xyz=st.xyz.clone(), q=st.rotq.clone(), bucket=st.bucket.clone(),
+                         d_pose=st.d_pose.clone(), d_transl=st.d_transl.clone(), m2=st.g_means2D.clone())
+    a, b = out["fused"], out["separate"]
+    assert torch.equal(a["xyz"], b["xyz"]) and torch.equal(a["q"], b["q"])
+    assert torch.equal(a["img"], b["img"]) and torch.equal(a["radii"], b["radii"])
+    for k in ("bucket", "d_pose", "d_transl", "m2"):
+        assert rel_err(a[k].cpu().numpy(), b[k].cpu().numpy()) < 2e-5, k
+
+
 def _avatar_step(sc, H, W, D=3, timing=False):
     from sings_b200.step import AvatarStep
     av = sc["avatar"]
