@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsings_b200.so")
+# SGS_LIB_PATH: an alternative build of the same library (A/B variants built by tools/variants.sh)
+LIB_PATH = os.environ.get("SGS_LIB_PATH") or os.path.join(_HERE, "lib", "libsings_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 _lib = None
 

@@ -34,16 +34,16 @@ def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0
     while first < hi:
         overflow_at = None
         for f in range(first, hi):
-            img = step.forward(frames[f])
+            # every frame of a block reports {num_rendered, overflow} into its own pinned row, so one
+            # stream sync per block of COUNTER_SLOTS frames sees the flag of each of them
+            img = step.forward(frames[f], slot=(f - first) % step.COUNTER_SLOTS)
             out[f - lo].copy_(img)
-            # the counters of frame f are only valid until the next forward overwrites them, so
-            # examine them lazily: one event-free read after a stream sync every 32 frames
-            if (f - first) % 32 == 31 or f == hi - 1:
+            if (f - first) % step.COUNTER_SLOTS == step.COUNTER_SLOTS - 1 or f == hi - 1:
                 torch.cuda.current_stream(step.dev).synchronize()
                 try:
                     step.check_capacity()
                 except SgsError:
-                    overflow_at = max(first, f - 31)
+                    overflow_at = first + (f - first) // step.COUNTER_SLOTS * step.COUNTER_SLOTS
                     break
         if overflow_at is None:
             break

@@ -260,29 +260,17 @@ static int raster_forward_impl(int P, int D, int M, int W, int H, const float* b
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 1, stream);
-    // the binning by count / scan / scatter needs Gaussians to bin; an empty frame takes the
-    // search-based range kernel, which files every tile as empty
-    const bool css = P > 0 && bin_css_supported(lay) && !getenv("SGS_RADIX_BINNING");
     if (P > 0) {
         rc = launch_depth_sort(P, lay, b, stream, debug);     // Gaussians by depth (N items)
         if (rc) return rc;
-        if (css) {
-            // count / scan / scatter: sorted pair list, tile ranges, length buckets, reach masks
-            rc = launch_bin_css(P, lay, L_cap, g, b, host_dev, stream, debug);
-            if (rc) return rc;
-        } else {
-            rc = launch_emit_pairs(P, lay, L_cap, b, host_dev, stream);     // scan + (tile|depth, id) pairs in depth order
-            if (rc) return rc;
-            rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
-            if (rc) return rc;
-        }
-    }
-    tick(timing, 2, stream);
-    if (!css) {
-        // ranges + tiles bucketed by list length; per-pair reach mask over the 8 pixel blocks of a tile
-        rc = launch_ranges_masks(lay, L_cap, g, b, stream);
+        rc = launch_emit_pairs(P, lay, L_cap, g, b, host_dev, stream);  // scan + (tile|depth, id|reach mask) pairs in depth order
+        if (rc) return rc;
+        rc = launch_tile_sort(lay, L_cap, g, b, stream, debug);  // stable passes over the tile-id digits (L items)
         if (rc) return rc;
     }
+    tick(timing, 2, stream);
+    rc = launch_tile_ranges(lay, L_cap, b, stream);      // ranges + tiles bucketed by list length
+    if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
     rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);

@@ -99,20 +99,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Where the per-pair reach masks are computed (A/B knob): 1 = by the last tile-id pass of the
-// pair sort, for every pair it scatters (the pair's tile and Gaussian id are in registers
-// there); 0 = by a pass of its own over the sorted list (ranges_masks_kernel).  Measured (v7):
-// in the sort the stage pair sort + ranges goes 74.8 + 20.5 -> 86.0 + 10.2 us, i.e. nothing is
-// gained -- the record gather delays the pass's scatter as much as the separate pass costs.
-#ifndef SGS_MASKS_IN_SORT
-#define SGS_MASKS_IN_SORT 0
-#endif
-
 // Reach mask of a (tile, Gaussian) pair: bit w says whether the Gaussian's alpha >= 1/255
 // footprint can touch 8x4 pixel block w of the tile (w = blend warp index): reaches_block for
-// the 2 x 4 blocks, sharing the per-column / per-row terms.  Computed ONCE per frame and pair;
-// the forward and the backward blend then stream one byte per pair and gather the 64-byte
-// record only for the ~10 % of (warp, pair) combinations that can contribute.
+// the 2 x 4 blocks, sharing the per-column / per-row terms.  Computed ONCE per frame and pair, by
+// the emission kernel (one pair per lane, the Gaussian's record staged in shared memory), and
+// packed into the top byte of the pair's 32-bit value -- so it rides through the tile-id radix
+// passes for free, and the forward and the backward blend gather the 64-byte record only for
+// the ~10 % of (warp, pair) combinations that can contribute.
 __device__ __forceinline__ unsigned reach_mask(const float4 q0, const float4 q1, const float4 q3,
                                                float tx, float ty) {
     const float a = -2.0f * q0.z, b2 = -2.0f * q0.w, c = -2.0f * q1.x;

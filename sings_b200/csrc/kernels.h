@@ -32,9 +32,11 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
 constexpr int DEPTH_PASSES = 4;            // radix passes over the 32 depth bits, run once per Gaussian
-constexpr int BIN_THREADS = 128;           // count / scatter CTA: 4 warps ...
-constexpr int BIN_GAUSS = 512;             // ... of 128 depth-ordered Gaussians each
-constexpr int BIN_MAX_TILES = 8192;        // per-warp u16 counters + u32 bases per tile must fit in shared memory
+// A pair's 32-bit value = Gaussian id (low 24 bits) | reach mask (high 8 bits: which of the tile's
+// eight 8x4 pixel blocks the Gaussian's alpha >= 1/255 footprint can touch).  The mask rides
+// through the tile-id radix passes for free; the blend kernels read both with one load.
+constexpr int ID_BITS = 24;
+constexpr unsigned ID_MASK = (1u << ID_BITS) - 1u;
 
 struct RasterLayout {
     // geometry state (per Gaussian)
@@ -42,12 +44,7 @@ struct RasterLayout {
     // zeroed scratch + binning state
     size_t cnt_off, hist_off, scan_off, nstat_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
     size_t nkeys0_off, nkeys1_off, nvals0_off, nvals1_off, rects_off;   // per-Gaussian depth-sort items
-    size_t keys0_off, keys1_off, vals0_off, vals1_off, masks_off, bin_bytes;
-    // count / scan / scatter binning (raster_binning.cu): per-(chunk, tile) pair counts (u16),
-    // their exclusive prefix over the chunks (u32), per-tile totals (u32); bin_ctas chunks of
-    // BIN_GAUSS depth-ordered Gaussians, rows of bin_tp tiles (tiles padded to 512)
-    size_t bcount_off, bbase_off, btotal_off, bstart_off;
-    int bin_ctas, bin_tp;
+    size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
     // image state
     size_t finalT_off, ncontrib_off, img_bytes;
     int scan_blocks, sort_blocks, nsort_blocks, tiles, gx, gy, end_bit, passes;
@@ -84,15 +81,9 @@ int launch_geometry(const GeomArgs& a, const RasterLayout& lay, long long L_cap,
 
 // depth passes over the P per-Gaussian items (passes whose digit is constant are skipped)
 int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t stream, int debug);
-// chained scan of tiles touched + (tile|depth, id) emission in depth order
-int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
-                      cudaStream_t stream);
-// the pair list by count / scan / scatter instead of emit_pairs + tile-id passes + range search:
-// writes the SORTED list, the tile ranges, the length buckets and the reach masks.
-// bin_css_supported: tile grid within the shared-memory budget of the kernels (else the radix path).
-bool bin_css_supported(const RasterLayout& lay);
-int launch_bin_css(int P, const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
-                   int* host_counters, cudaStream_t stream, int debug);
+// chained scan of tiles touched + (tile|depth, id|reach mask) emission in depth order
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                      int* host_counters, cudaStream_t stream);
 // stable passes over the tile-id digits of the emitted pairs
 int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom, char* bin, cudaStream_t stream,
                      int debug);
@@ -102,9 +93,8 @@ int launch_sort_pairs_u64(unsigned long long* keys, unsigned* vals, unsigned lon
                           int end_bit, int* result_in_tmp, cudaStream_t stream);
 size_t sort_scratch_bytes(long long n);
 
-// tile ranges (+ tiles bucketed by list length) and per-pair reach masks, one launch
-int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
-                        cudaStream_t stream);
+// tile ranges (+ tiles bucketed by list length)
+int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,

@@ -46,11 +46,6 @@ struct SortPass {
     int shift;
     unsigned mask;            // (1 << bits of this digit) - 1; < 255 only in a partial last pass
     int par;                  // source buffer (without varbits) / pass index (with varbits)
-    // last tile-id pass of the rasterizer's pair sort only (else null): the pass also writes the
-    // reach mask of every pair it scatters (common.cuh reach_mask; geometry records `rec`)
-    const float4* rec;
-    unsigned char* masks_out;
-    int gx_tiles;
 };
 
 // exclusive scan of two values per thread over a 256-thread block (one barrier)
@@ -244,16 +239,6 @@ __global__ void __launch_bounds__(SORT_THREADS, sizeof(K) == 8 ? SGS_SORT_MINB_L
             const unsigned v = s_vals[p];
             keys_out[dst] = kk;
             vals_out[dst] = v;
-            if constexpr (sizeof(K) == 8) {
-                if (a.masks_out) {       // pair (tile = key >> 32, Gaussian v): which pixel blocks can it reach?
-                    const unsigned tile = (unsigned)((unsigned long long)kk >> 32);
-                    const float4* r = a.rec + 4 * (size_t)v;
-                    const float4 q0 = __ldg(r), q1 = __ldg(r + 1), q3 = __ldg(r + 3);
-                    const float tx = (float)((tile % (unsigned)a.gx_tiles) * TILE);
-                    const float ty = (float)((tile / (unsigned)a.gx_tiles) * TILE);
-                    a.masks_out[dst] = (unsigned char)reach_mask(q0, q1, q3, tx, ty);
-                }
-            }
         }
     }
 }
@@ -289,8 +274,7 @@ static bool all_resident(Kern k, int blocks, size_t smem) {
 static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* k1, unsigned* v1,
                       const unsigned* hist, unsigned* status, int* tickets, const int* n_ptr,
                       long long n_cap, int p0, int p1, int end_bit, int blocks, cudaStream_t stream,
-                      int debug, const float4* rec = nullptr, unsigned char* masks_out = nullptr,
-                      int gx_tiles = 1) {
+                      int debug) {
     for (int p = p0; p < p1; p++) {
         SortPass<unsigned long long> a;
         a.keys[0] = k0; a.keys[1] = k1;
@@ -304,9 +288,6 @@ static int run_passes(unsigned long long* k0, unsigned* v0, unsigned long long* 
         a.shift = p * RADIX_BITS;
         a.mask = (1u << min(RADIX_BITS, end_bit - p * RADIX_BITS)) - 1u;
         a.par = (p - p0) & 1;
-        a.rec = rec;
-        a.masks_out = p == p1 - 1 ? masks_out : nullptr;
-        a.gx_tiles = gx_tiles;
         auto k = onesweep_pass_kernel<unsigned long long, SORT_ITEMS_L, SGS_LOOKBACK_L>;
         const size_t smem = (size_t)SORT_TILE_L * 12;
         SGS_CUDA_OK(set_max_smem(k, smem));
@@ -335,7 +316,6 @@ int launch_depth_sort(int P, const RasterLayout& lay, char* bin, cudaStream_t st
         a.shift = p * RADIX_BITS;
         a.mask = RADIX - 1;
         a.par = p;
-        a.rec = nullptr; a.masks_out = nullptr; a.gx_tiles = 1;
         auto k = onesweep_pass_kernel<unsigned, SORT_ITEMS_N, SGS_LOOKBACK_N>;
         const size_t smem = (size_t)SORT_TILE_N * 8;
         if (all_resident(k, lay.nsort_blocks, smem)) a.ticket = nullptr;
@@ -356,9 +336,7 @@ int launch_tile_sort(const RasterLayout& lay, long long L_cap, const char* geom,
                       reinterpret_cast<const unsigned*>(bin + lay.hist_off),
                       reinterpret_cast<unsigned*>(bin + lay.sortstat_off),
                       counters + CNT_SORT_TICKET0, counters + CNT_NUM_RENDERED, L_cap, DEPTH_PASSES,
-                      lay.passes, lay.end_bit, lay.sort_blocks, stream, debug,
-                      reinterpret_cast<const float4*>(geom + lay.rec_off),
-                      nullptr, lay.gx);
+                      lay.passes, lay.end_bit, lay.sort_blocks, stream, debug);
 }
 
 size_t sort_scratch_bytes(long long n) {

@@ -160,25 +160,6 @@ __device__ __forceinline__ void pixel_of_thread(int warp, int lane, int& lx, int
     ly = ((warp >> 1) << 2) + (lane >> 3);
 }
 
-// Can the footprint {alpha >= 1/255} of a Gaussian reach the pixel block [bx0,bx1]x[by0,by1]?
-// Exact test: the minimum over the rectangle of the quadratic form q(d) = a dx^2 + 2b dx dy +
-// c dy^2 (d = pixel - centre; power = -q/2) is compared with t = -2 pmin (+ margin).  For a
-// convex form the minimum lies at the centre (if inside) or on one of the two edges nearest
-// to it; both edge minima are evaluated in closed form.  q3 = (t with margin, -b/c, -b/a,
-// flags) comes from the geometry kernel.  A block that fails can only produce pairs the blend
-// loop would reject, so skipping it changes nothing.
-__device__ __forceinline__ bool reaches_block(const float4 q0, const float4 q1, const float4 q3,
-                                              float bx0, float bx1, float by0, float by1) {
-    const float a = -2.0f * q0.z, b = -q0.w, c = -2.0f * q1.x;
-    const float X0 = bx0 - q0.x, X1 = bx1 - q0.x, Y0 = by0 - q0.y, Y1 = by1 - q0.y;
-    const float cx = fminf(fmaxf(0.0f, X0), X1), cy = fminf(fmaxf(0.0f, Y0), Y1);
-    const float dy1 = fminf(fmaxf(q3.y * cx, Y0), Y1);        // minimiser on the edge x = cx
-    const float dx2 = fminf(fmaxf(q3.z * cy, X0), X1);        // minimiser on the edge y = cy
-    const float qa = a * cx * cx + 2.0f * b * cx * dy1 + c * dy1 * dy1;
-    const float qb = a * dx2 * dx2 + 2.0f * b * dx2 * cy + c * cy * cy;
-    return fminf(qa, qb) <= q3.x;
-}
-
 struct Rec {
     float4 q0, q1, q2;
 };
@@ -189,46 +170,22 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
     return r;
 }
 
-// Tile ranges and reach masks in ONE launch (both only read the sorted list): the first
-// `range_blocks` CTAs search the ranges of 8 tiles each (a chain of dependent probes, so they
-// start first), the others compute one reach mask per thread.  (A per-tile shared-memory
-// bitonic sort of the depth bits that also produced these masks was tried in place of the depth
-// passes of the radix sort: n log^2 n compare-exchanges cost as many instructions; rejected.)
+// [upstream] identifyTileRanges (+ the length buckets): 8 tiles per CTA, a warp each.
 __global__ void __launch_bounds__(RANGE_THREADS)
-ranges_masks_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ point_list,
-                    const int* __restrict__ counters, long long n_cap, const float4* __restrict__ rec,
-                    int gx_tiles, int tiles, int range_blocks, uint2* __restrict__ ranges,
-                    unsigned* __restrict__ bucket_count, unsigned* __restrict__ bucket_list,
-                    unsigned char* __restrict__ masks) {
+tile_ranges_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ counters, long long n_cap,
+                   int tiles, uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
+                   unsigned* __restrict__ bucket_list) {
     pdl_sync();
-    if ((int)blockIdx.x < range_blocks) {
-        tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
-        return;
-    }
-    const long long n = min((long long)counters[CNT_NUM_RENDERED], n_cap);
-    const long long i = (long long)(blockIdx.x - range_blocks) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned tile = (unsigned)(__ldg(keys + i) >> 32);
-    const unsigned id = __ldg(point_list + i);
-    const float4* p = rec + 4 * (size_t)id;
-    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q3 = __ldg(p + 3);
-    const float tx = (float)((tile % (unsigned)gx_tiles) * TILE), ty = (float)((tile / (unsigned)gx_tiles) * TILE);
-    masks[i] = (unsigned char)reach_mask(q0, q1, q3, tx, ty);
+    tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
 }
 
-int launch_ranges_masks(const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
-                        cudaStream_t stream) {
+int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream) {
     const int range_blocks = (lay.tiles + RANGE_THREADS / 32 - 1) / (RANGE_THREADS / 32);
-    long long blocks = (L_cap + RANGE_THREADS - 1) / RANGE_THREADS;
-    if (blocks < 1) blocks = 1;
-    launch_pdl(ranges_masks_kernel, (unsigned)(range_blocks + blocks), RANGE_THREADS, 0, stream,
-        sorted_keys(lay, bin), sorted_vals(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap,
-        reinterpret_cast<const float4*>(geom + lay.rec_off), lay.gx, lay.tiles, range_blocks,
+    SGS_CUDA_OK(launch_pdl(tile_ranges_kernel, (unsigned)range_blocks, RANGE_THREADS, 0, stream,
+        sorted_keys(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap, lay.tiles,
         reinterpret_cast<uint2*>(bin + lay.ranges_off),
         reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
-        reinterpret_cast<unsigned*>(bin + lay.bktlist_off),
-        reinterpret_cast<unsigned char*>(bin + lay.masks_off));
-    SGS_LAUNCH_OK();
+        reinterpret_cast<unsigned*>(bin + lay.bktlist_off)));
     return 0;
 }
 
@@ -310,8 +267,7 @@ template <bool AUX>
 __global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_MINB * (TILE_WARPS / FWD_WPC))
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
-                 const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
-                 const float4* __restrict__ rec,
+                 const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
                  unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
@@ -399,21 +355,21 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const std::true_type with_limit;
     const std::false_type no_limit;
 
-    // Staging pipeline, per chunk of 32 list entries (one per lane): reach-mask bytes run four
-    // chunks ahead, Gaussian ids of the relevant entries two chunks ahead, their records one
-    // chunk ahead -- the dependent mask -> id -> record gather never sits on the critical path,
-    // and a chunk without relevant entries costs a ballot.
-    const unsigned char* mk = masks + range.x;
+    // Staging pipeline, per chunk of 32 list entries (one per lane): the entries (id | mask) run
+    // three chunks ahead, the records of the relevant ones one chunk ahead -- the dependent
+    // entry -> record gather never sits on the critical path, and a chunk without relevant
+    // entries costs a ballot.
+    // a list entry = Gaussian id | reach mask << 24: bit (24 + w) says pixel block w can be reached
     const unsigned* pl = point_list + range.x;
-    auto mask_at = [&](int at) { return at + lane < len ? (unsigned)__ldg(mk + at + lane) : 0u; };
-    unsigned m0 = mask_at(0), m1 = mask_at(32), m2 = mask_at(64), m3 = mask_at(96);
+    const unsigned wbit = 1u << (ID_BITS + warp);
+    auto entry_at = [&](int at) { return at + lane < len ? __ldg(pl + at + lane) : 0u; };
+    unsigned m0 = entry_at(0), m1 = entry_at(32), m2 = entry_at(64);
     Rec p;
     p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
-    if ((m0 >> warp) & 1u) p = load_rec(rec, __ldg(pl + lane));
-    unsigned nid = ((m1 >> warp) & 1u) ? __ldg(pl + 32 + lane) : 0u;
+    if (m0 & wbit) p = load_rec(rec, m0 & ID_MASK);
     for (int pos = 0; pos < len; pos += 32) {
         if (__all_sync(0xffffffffu, done)) break;
-        const bool rel = (m0 >> warp) & 1u;
+        const bool rel = (m0 & wbit) != 0u;
         const unsigned bits = __ballot_sync(0xffffffffu, rel);
         __syncwarp();                  // earlier ring reads are complete before slots are reused
         if (rel) {
@@ -424,9 +380,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
         tail += __popc(bits);
         __syncwarp();
-        if ((m1 >> warp) & 1u) p = load_rec(rec, nid);
-        if ((m2 >> warp) & 1u) nid = __ldg(pl + pos + 64 + lane);
-        m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(pos + 128);
+        if (m1 & wbit) p = load_rec(rec, m1 & ID_MASK);
+        m0 = m1; m1 = m2; m2 = entry_at(pos + 96);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= FWD_U) {
             if (!cur_is_b) { eval(bat_b, head, tail, no_limit); composite(bat_a); }
@@ -463,7 +418,6 @@ int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, co
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
-        reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
         reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth));
@@ -508,8 +462,7 @@ struct BwdWarpSmem {
 __global__ void __launch_bounds__(BWD_WPC * 32, SGS_BWD_MINB * (TILE_WARPS / BWD_WPC))
 blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
-                 const unsigned* __restrict__ point_list, const unsigned char* __restrict__ masks,
-                 const float4* __restrict__ rec,
+                 const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, float* __restrict__ acc) {
@@ -663,26 +616,25 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     const std::true_type with_limit;
     const std::false_type no_limit;
 
-    // Same staging pipeline as the forward (masks four chunks ahead, ids two, records one),
+    // Same staging pipeline as the forward (entries three chunks ahead, records one),
     // walking the list back to front: chunk c covers list positions top-lane, top =
     // wlast-1-32c, so lane order is back-to-front order.
-    const unsigned char* mk = masks + range.x;
     const unsigned* pl = point_list + range.x;
-    auto mask_at = [&](int top) { return top - lane >= 0 ? (unsigned)__ldg(mk + top - lane) : 0u; };
-    unsigned m0 = mask_at(wlast - 1), m1 = mask_at(wlast - 33), m2 = mask_at(wlast - 65), m3 = mask_at(wlast - 97);
+    const unsigned wbit = 1u << (ID_BITS + warp);
+    auto entry_at = [&](int top) { return top - lane >= 0 ? __ldg(pl + top - lane) : 0u; };
+    unsigned m0 = entry_at(wlast - 1), m1 = entry_at(wlast - 33), m2 = entry_at(wlast - 65);
     Rec p;
     unsigned pid = 0;
     p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
-    if ((m0 >> warp) & 1u) {
-        pid = __ldg(pl + (wlast - 1 - lane));
+    if (m0 & wbit) {
+        pid = m0 & ID_MASK;
         p = load_rec(rec, pid);
     }
-    unsigned nid = ((m1 >> warp) & 1u) ? __ldg(pl + (wlast - 33 - lane)) : 0u;
     // `cur` starts as an empty batch at consumption index -BWD_U: its SEQ writes zeros into
     // rows that real pairs overwrite before any reduction reads them.
     unsigned pend = 0u - BWD_U;
     for (int top = wlast - 1; top >= 0; top -= 32) {
-        const bool rel = (m0 >> warp) & 1u;
+        const bool rel = (m0 & wbit) != 0u;
         const unsigned bits = __ballot_sync(0xffffffffu, rel);
         __syncwarp();
         if (rel) {
@@ -694,12 +646,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         }
         tail += __popc(bits);
         __syncwarp();
-        if ((m1 >> warp) & 1u) {
-            pid = nid;
+        if (m1 & wbit) {
+            pid = m1 & ID_MASK;
             p = load_rec(rec, pid);
         }
-        if ((m2 >> warp) & 1u) nid = __ldg(pl + (top - 64 - lane));
-        m0 = m1; m1 = m2; m2 = m3; m3 = mask_at(top - 128);
+        m0 = m1; m1 = m2; m2 = entry_at(top - 96);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= BWD_U) {
             if (!cur_is_b) { eval(bat_b, head, tail, no_limit); seq(bat_a, pend); }
@@ -737,7 +688,6 @@ int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, co
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
-        reinterpret_cast<const unsigned char*>(bin + lay.masks_off),
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
         reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc));

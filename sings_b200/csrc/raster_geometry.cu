@@ -29,7 +29,10 @@
 
 namespace sgs {
 
-constexpr int GEO_THREADS = 256;
+#ifndef SGS_GEO_THREADS
+#define SGS_GEO_THREADS 256
+#endif
+constexpr int GEO_THREADS = SGS_GEO_THREADS;
 constexpr unsigned long long FLAG_AGG = 1ull << 62;
 constexpr unsigned long long FLAG_INCL = 2ull << 62;
 constexpr unsigned long long FLAG_MASK = 3ull << 62;
@@ -82,15 +85,6 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.keys1_off = o;    o += align_up(cap * 8, 256);
     l.vals0_off = o;    o += align_up(cap * 4, 256);
     l.vals1_off = o;    o += align_up(cap * 4, 256);
-    l.masks_off = o;    o += align_up(cap, 256);
-    l.bin_ctas = (P + BIN_GAUSS - 1) / BIN_GAUSS;
-    if (l.bin_ctas < 1) l.bin_ctas = 1;
-    l.bin_tp = (int)align_up((size_t)l.tiles, 512);
-    const bool css = l.tiles <= BIN_MAX_TILES && l.gx <= 255 && l.gy <= 255;     // bin_css_supported()
-    l.bcount_off = o;   o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 2, 256) : 0;
-    l.bbase_off = o;    o += css ? align_up((size_t)l.bin_ctas * l.bin_tp * 4, 256) : 0;
-    l.btotal_off = o;   o += css ? align_up((size_t)l.bin_tp * 4, 256) : 0;
-    l.bstart_off = o;   o += css ? align_up((size_t)l.bin_tp * 4, 256) : 0;
     l.bin_bytes = o;
     // image state
     size_t pix = (size_t)W * H;
@@ -119,7 +113,7 @@ struct GeoOut {
 // scale straight into the projection math (and out to global memory once, for the backward and
 // for inspection) -- instead of a separate LBS kernel writing them and this one reading them back.
 template <int D, bool HAS_SH, bool VEC16, bool FUSE>
-__global__ void __launch_bounds__(GEO_THREADS, FUSE ? 3 : 1)
+__global__ void __launch_bounds__(GEO_THREADS, FUSE ? (768 / GEO_THREADS) : 1)
 geometry_kernel(GeomArgs a, GeoOut o, LbsFuse lf) {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
@@ -338,7 +332,8 @@ struct EmitArgs {
     unsigned* hist;             // [pass][256]; this kernel fills passes >= DEPTH_PASSES
     unsigned long long* scan_status;
     unsigned long long* keys;
-    unsigned* vals;
+    unsigned* vals;             // Gaussian id | reach mask << 24
+    const float4* rec;          // geometry records (reach masks)
     long long L_cap;
     int passes;
     int gx;
@@ -349,6 +344,8 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     __shared__ unsigned s_incl[GEO_THREADS];         // block-local inclusive tile offsets
     __shared__ int4 s_rect[GEO_THREADS];             // x0, y0, width, depth bits
     __shared__ unsigned s_gid[GEO_THREADS];
+    __shared__ float4 s_q0[GEO_THREADS], s_q3[GEO_THREADS];     // record parts the reach mask needs ...
+    __shared__ float s_q1x[GEO_THREADS];                        // ... fetched once per Gaussian, not once per pair
     __shared__ unsigned s_warp[GEO_THREADS / 32];
     __shared__ unsigned s_hist[(MAX_PASSES - DEPTH_PASSES) * RADIX];
     __shared__ int s_ticket;
@@ -373,6 +370,10 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
         tiles = (unsigned)(w * h);
         s_rect[tid] = make_int4((int)(r.x & 0xffffu), (int)(r.x >> 16), w, (int)dkey);
         s_gid[tid] = gid;
+        if (tiles) {
+            const float4* rp = a.rec + 4 * (size_t)gid;
+            s_q0[tid] = __ldg(rp); s_q1x[tid] = __ldg(reinterpret_cast<const float*>(rp + 1)); s_q3[tid] = __ldg(rp + 3);
+        }
     }
     unsigned incl = tiles;
 #pragma unroll
@@ -425,8 +426,7 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
                 if (a.host_counters) {     // the grand total decides the overflow: the last chunk knows both
                     a.host_counters[0] = total > 0x7fffffffull ? 0x7fffffff : (int)total;
                     a.host_counters[1] = total > (unsigned long long)a.L_cap ? 1 : 0;
-                    __threadfence_system();
-                }
+                        }
             }
             if (total > (unsigned long long)a.L_cap) a.counters[CNT_OVERFLOW] = 1;
         }
@@ -450,8 +450,10 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
         const unsigned long long key = ((unsigned long long)tile_id << 32) | (unsigned)r.w;
         const unsigned long long pos = prefix + e;
         if (pos < (unsigned long long)a.L_cap) {
+            const float4 q1 = make_float4(s_q1x[g], 0.0f, 0.0f, 0.0f);
+            const unsigned mask = reach_mask(s_q0[g], q1, s_q3[g], (float)((r.x + (int)tx) * TILE), (float)((r.y + (int)ty) * TILE));
             a.keys[pos] = key;
-            a.vals[pos] = s_gid[g];
+            a.vals[pos] = s_gid[g] | (mask << ID_BITS);
             for (int p = 0; p < tile_passes; p++)
                 atomicAdd(&s_hist[p * RADIX + ((tile_id >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
         }
@@ -463,9 +465,10 @@ __global__ void __launch_bounds__(GEO_THREADS) emit_pairs_kernel(EmitArgs a) {
     }
 }
 
-int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin, int* host_counters,
-                      cudaStream_t stream) {
+int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, const char* geom, char* bin,
+                      int* host_counters, cudaStream_t stream) {
     if (P <= 0) return 0;
+    if (P > (int)ID_MASK) return SGS_ERR_CAPACITY;      // ids share their 32-bit word with the reach mask
     EmitArgs a;
     a.P = P;
     a.nkeys[0] = reinterpret_cast<const unsigned*>(bin + lay.nkeys0_off);
@@ -479,6 +482,7 @@ int launch_emit_pairs(int P, const RasterLayout& lay, long long L_cap, char* bin
     a.scan_status = reinterpret_cast<unsigned long long*>(bin + lay.scan_off);
     a.keys = reinterpret_cast<unsigned long long*>(bin + lay.keys0_off);
     a.vals = reinterpret_cast<unsigned*>(bin + lay.vals0_off);
+    a.rec = reinterpret_cast<const float4*>(geom + lay.rec_off);
     a.L_cap = L_cap;
     a.passes = lay.passes;
     a.gx = lay.gx;

@@ -16,7 +16,10 @@
 
 namespace sgs {
 
-constexpr int GB_THREADS = 256;
+#ifndef SGS_GB_THREADS
+#define SGS_GB_THREADS 256
+#endif
+constexpr int GB_THREADS = SGS_GB_THREADS;
 
 // FUSE: the backward of the deform segment (what autograd computes for sings_hybrid.py:398-419,
 // SURVEY.md Appendix B) runs in this kernel's epilogue on the gradients it has just produced --
@@ -26,7 +29,7 @@ constexpr int GB_THREADS = 256;
 // shared memory (lanes = (slot, entry) of the row: distinct addresses, plain read-modify-write);
 // the CTA then adds its warps' tiles and issues one atomic per non-zero entry.
 template <int D, bool HAS_SH, bool VEC16, bool FUSE>
-__global__ void __launch_bounds__(GB_THREADS, FUSE ? 2 : 1)
+__global__ void __launch_bounds__(GB_THREADS, FUSE ? (512 / GB_THREADS) : 1)
 geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
@@ -390,16 +393,24 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
             }
         }
         __syncwarp();
-        float* const tile = s_part + (size_t)warp * lf.J * 12;
-        const int k2 = lane / 12, e = lane - 12 * k2;            // lanes 0..23: slot pair member, entry
-        if (lane < 24) {
+        // lane = (slot kk of a round of 8 slots, float4 group g of the 3x4 entry block): row l adds
+        // w_k dT_l to tile[j_k] with one LDS.128 / 4 FMA / STS.128 per lane; rows in sequence.
+        float4* const tile4 = reinterpret_cast<float4*>(s_part + (size_t)warp * lf.J * 12);
+        const float4* const dT4 = reinterpret_cast<const float4*>(s_dT) + (size_t)warp * 32 * 3;
+        const int kk = lane / 3, g = lane - 3 * kk;
+        if (kk < 8) {
+#pragma unroll 1
             for (int l = 0; l < 32; l++) {
-                const float dte = s_dT[(warp * 32 + l) * 12 + e];
-                for (int kb = 0; kb < lf.K; kb += 2) {
-                    const float w = s_w[warp][l][kb + k2];
+#pragma unroll 1
+                for (int r0 = 0; r0 < lf.K; r0 += 8) {
+                    const int k = r0 + kk;
+                    const float w = k < lf.K ? s_w[warp][l][k] : 0.0f;
                     if (w != 0.0f) {
-                        const int j = s_j[warp][l][kb + k2];
-                        tile[j * 12 + e] = fmaf(w, dte, tile[j * 12 + e]);
+                        const int j = s_j[warp][l][k];
+                        const float4 d = dT4[l * 3 + g];
+                        float4 v = tile4[j * 3 + g];
+                        v.x = fmaf(w, d.x, v.x); v.y = fmaf(w, d.y, v.y); v.z = fmaf(w, d.z, v.z); v.w = fmaf(w, d.w, v.w);
+                        tile4[j * 3 + g] = v;
                     }
                 }
             }

@@ -69,7 +69,12 @@ class AvatarStep:
         self.radii = e(N, dt=torch.int32)
         self.L_cap = int(pair_capacity) if pair_capacity else max(8 * N, 1 << 16)
         self._alloc_scratch()
-        self.counters = torch.zeros(2, dtype=torch.int32).pin_memory()
+        # {num_rendered, overflow} of a forward, written by the device into mapped pinned memory.  One
+        # row per in-flight frame (forward(slot=...)): a later forward must not overwrite the flag of
+        # a frame that has not been examined yet (check_capacity looks at every row).
+        self.COUNTER_SLOTS = 32
+        self.counters = torch.zeros(self.COUNTER_SLOTS, 2, dtype=torch.int32).pin_memory()
+        self._gen = 0                      # bumped when scratch is reallocated: captured graphs go stale
         # backward intermediates (rasterizer boundary gradients)
         self.g_means3D, self.g_means2D, self.g_colors = e(N, 3), e(N, 3), e(N, 3)
         self.g_cov = e(N, 6)
@@ -156,9 +161,11 @@ class AvatarStep:
         self.geom, self.binning, self.img, self.acc = e(gb), e(bb), e(ib), e(ab)
 
     # ---------------------------------------------------------------------------------
-    def forward(self, fr: FrameInputs, stream=None):
-        """pose -> A -> LBS -> rasterize.  Returns the (3,H,W) image (a persistent buffer)."""
+    def forward(self, fr: FrameInputs, stream=None, slot: int = 0):
+        """pose -> A -> LBS -> rasterize.  Returns the (3,H,W) image (a persistent buffer).
+        `slot` selects the pinned {num_rendered, overflow} row this frame reports into."""
         L_, p = self.L, _lib.ptr
+        cnt_ptr = self.counters.data_ptr() + 8 * (int(slot) % self.COUNTER_SLOTS)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         self._fr = fr
         pose = fr.pose.reshape(1, self.J, 3)
@@ -176,7 +183,7 @@ class AvatarStep:
                 C.byref(d), self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.opacity), 1.0, p(fr.viewmatrix),
                 p(fr.projmatrix), p(fr.campos), float(fr.tanfovx), float(fr.tanfovy), p(self.shs), self.L_cap,
                 p(self.geom), p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-                self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_avatar_forward")
+                cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_avatar_forward")
             return self.color
         if tm:
             L_.sgs_timing_record(tm, 8, st)
@@ -191,7 +198,7 @@ class AvatarStep:
             p(self.sc), 1.0, p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos),
             float(fr.tanfovx), float(fr.tanfovy), p(self.shs), 0, self.L_cap, p(self.geom),
             p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-            self.counters.data_ptr(), st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_raster_forward")
+            cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_raster_forward")
         return self.color
 
     def backward(self, dL_dimage: torch.Tensor, stream=None, stats: bool = True):
@@ -283,8 +290,12 @@ class AvatarStep:
                 rc = self.L.sgs_graph_end(side.cuda_stream, C.byref(h))
             _lib.check(rc, "sgs_graph_end")
             self._graphs.append(h)
-            launch, dev = self.L.sgs_graph_launch, self.dev
-            return lambda: _lib.check(launch(h, torch.cuda.current_stream(dev).cuda_stream), "sgs_graph_launch")
+            launch, dev, gen = self.L.sgs_graph_launch, self.dev, self._gen
+
+            def replay():
+                self._check_gen(gen)
+                _lib.check(launch(h, torch.cuda.current_stream(dev).cuda_stream), "sgs_graph_launch")
+            return replay
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if prologue is not None:
@@ -294,7 +305,17 @@ class AvatarStep:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
             self.backward(dL_dimage)
         self.graph = g
-        return g.replay
+        gen = self._gen
+
+        def replay_torch():
+            self._check_gen(gen)
+            g.replay()
+        return replay_torch
+
+    def _check_gen(self, gen: int) -> None:
+        if gen != self._gen:
+            raise _lib.SgsError("this captured frame is stale: the scratch buffers it was recorded with were "
+                                "reallocated (pair-list capacity raised); call capture() again")
 
     def reset_stats(self):
         self.grad_accum.zero_()
@@ -304,11 +325,19 @@ class AvatarStep:
     def check_capacity(self) -> int:
         """After a synchronisation: (num_rendered); grows the pair list and raises if the last
         forward overflowed (the frame must then be re-rendered)."""
-        L, ovf = int(self.counters[0]), int(self.counters[1])
+        L, ovf = int(self.counters[:, 0].max()), bool(self.counters[:, 1].any())
+        self.counters.zero_()
         if ovf:
             self.L_cap = int(L * 1.3) + 4096
+            # graphs recorded with the old buffers must not be replayed: their pointers and L_cap are baked in
+            for h in self._graphs:
+                self.L.sgs_graph_destroy(h)
+            self._graphs = []
+            self.graph = None
+            self._gen += 1
             self._alloc_scratch()
-            raise _lib.SgsError(f"pair list overflowed (needed {L}); capacity raised to {self.L_cap}, re-render")
+            raise _lib.SgsError(f"pair list overflowed (needed {L}); capacity raised to {self.L_cap}: re-render the "
+                                f"frame(s) and capture() again")
         return L
 
     def interval_ms(self, i: int, j: int) -> float:

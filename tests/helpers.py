@@ -61,9 +61,12 @@ def inspect_state(ctx_tensors, P, W, H, L_cap):
     L = int(cnt[0])
     out = dict(num_rendered=L, overflow=int(cnt[1]))
     out["keys_unsorted"] = b[info["keys_unsorted"]:info["keys_unsorted"] + 8 * L].view(np.uint64).copy()
-    out["vals_unsorted"] = b[info["vals_unsorted"]:info["vals_unsorted"] + 4 * L].view(np.uint32).copy()
+    out["vals_unsorted"] = b[info["vals_unsorted"]:info["vals_unsorted"] + 4 * L].view(np.uint32).copy() & np.uint32(0xffffff)
     out["keys"] = b[info["keys_sorted"]:info["keys_sorted"] + 8 * L].view(np.uint64).copy()
-    out["point_list"] = b[info["vals_sorted"]:info["vals_sorted"] + 4 * L].view(np.uint32).copy()
+    # a list entry = Gaussian id (low 24 bits) | reach mask (high 8 bits, include/sings_b200.h)
+    entries = b[info["vals_sorted"]:info["vals_sorted"] + 4 * L].view(np.uint32).copy()
+    out["point_list"] = entries & np.uint32(0xffffff)
+    out["reach_masks"] = (entries >> np.uint32(24)).astype(np.uint8)
     out["ranges"] = b[info["ranges"]:info["ranges"] + 8 * info["tiles"]].view(np.uint32).reshape(-1, 2).copy()
     out["final_T"] = im[info["final_T"]:info["final_T"] + 4 * W * H].view(np.float32).reshape(H, W).copy()
     out["n_contrib"] = im[info["n_contrib"]:info["n_contrib"] + 4 * W * H].view(np.uint32).reshape(H, W).copy()

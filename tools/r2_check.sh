@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 GPU check: parity tests, short bench (stage table), A/B against the radix binning, launch list
+# round-2 GPU check: parity tests, short bench (stage table), launch list
 TAG=${1:-r2}
 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/${TAG}_tests.txt
 cat gpurun_out/${TAG}_tests.txt | tail -3
@@ -12,9 +12,6 @@ print(" hot", d["roofline"]["lbs_preprocess_sort"])
 '
 python bench.py --steps 200 --warmup 10 --no-cpu --no-dropin 2> gpurun_out/${TAG}_bench.err | tail -1 > gpurun_out/${TAG}_bench.json
 python -c "$show" < gpurun_out/${TAG}_bench.json
-echo "--- radix binning (SGS_RADIX_BINNING=1)"
-SGS_RADIX_BINNING=1 python bench.py --steps 200 --warmup 10 --no-cpu --no-e2e 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_radix.json
-python -c "$show" < gpurun_out/${TAG}_bench_radix.json
 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 80 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 8 --warmup 4 --no-e2e --no-cpu > gpurun_out/${TAG}_launches.log 2>&1
 python tools/launch_shares.py gpurun_out/${TAG}_launches.csv 2>/dev/null | head -30
