@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- deformed-avatar fwd+bwd frames/s (BASELINE.json metric) on N B200s.
+"""bench.py -- deformed-avatar frames/s (BASELINE.json metric) on N B200s.
 
-    python bench.py --gpus 1 --steps K --warmup W               # this repo's CUDA path
+    python bench.py --gpus 1 --steps K --warmup W               # this repo's CUDA path, config c2
     torchrun ... bench.py --gpus N --steps K --warmup W         # one rank per GPU, views sharded
     python bench.py --impl reference --steps K --warmup W       # CPU arm (oracle port)
+    python bench.py --config c1|c2|c3|c4|c5|shipped             # the other north-star workloads
 
-A step = one pass of the hot path over one synthetic frame: pose -> A -> LBS of every
-Gaussian -> rasterize (1024^2, SH degree 3) -> dL/dimage -> rasterizer backward -> LBS
-backward -> densification statistics (+ the gradient all-reduce when N > 1).
-Workload = BASELINE.json configs[1]: 200k Gaussians, J=24, random pose, synthetic data.
+A step = one pass of the hot path over one synthetic frame: pose -> A -> LBS of every Gaussian
+-> rasterize -> dL/dimage -> rasterizer backward -> LBS backward -> densification statistics
+(+ the gradient all-reduce when N > 1); configs c1 and c4 (animation) are forward only.
+Default workload = BASELINE.json configs[1] (c2): 200k Gaussians, SH degree 3, 1024^2, J = 24.
 
-`value`  : device-resident inputs, AvatarStep (sync-free launch sequence), CUDA events.
-`e2e`    : the public API (sings_b200.deform + diff_gaussian_rasterization autograd) with HOST
-           buffers: per step pose/transl/dL-dimage are copied from pinned memory and the loss
-           is read back, all inside the timed region.
-L2      : inputs rotate over a ring of distinct avatars larger than the 126 MB L2.
-Nothing here reads /root/reference.  The CPU arm / cpu_baseline time the oracle port
+`value`  : device-resident inputs, AvatarStep (sync-free launch sequence), CUDA events.  For N > 1
+           it is the SYNCHRONOUS data-parallel step (the all-reduce of a step's gradients
+           finishes before the next forward starts, as an optimizer step needs); the pipelined
+           figure (exchange overlapping the next frames) is reported beside it as `dp.pipelined`.
+`e2e`    : the same through the C ABI / the public autograd API with HOST buffers: per step
+           pose/transl/dL-dimage are copied from pinned memory and the loss is read back, all
+           inside the timed region; the box's measured pinned H2D rate is reported with it.
+`ab`     : stock comparators on the same box: cub::DeviceRadixSort::SortPairs vs
+           sgs_sort_pairs_u64 on the frame's keys; the reference's LBS as eager torch ops on the
+           GPU vs sgs_lbs_fwd + sgs_lbs_bwd.
+L2       : inputs rotate over a ring of distinct avatars larger than the 126 MB L2.
+Nothing here reads /root/reference.  The CPU arm / cpu_baseline / ab.lbs time the oracle port
 (oracle/lbs_oracle.py + oracle/c/raster_oracle.c, OpenMP) -- the only use of oracle/ here.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -34,11 +42,37 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_GAUSS, H_IMG, W_IMG, SH_DEG, N_JOINTS = 200_000, 1024, 1024, 3, 24
 RING = 4
 U8_SCALE = 42.0       # uint8 target = rint(G * 42 + 127.5): +-3 sigma of the N(0,1) gradient image in 8 bits
-WORKLOAD = "single B200: LBS + rasterize fwd+bwd, 200k Gaussians, SH degree 3, 1024x1024 view, random pose"
 METRIC = "deformed-avatar fwd+bwd frames/s @200k Gaussians 1024^2"
+
+# BASELINE.json configs (c1..c5) + the configuration the reference ships (human_complex.yaml:34,54,86)
+CONFIGS = {
+    "c1": dict(workload="CPU torch reference: SMPL LBS of 50k synthetic Gaussians + forward splat of one 512x512 view "
+                        "(neutral pose, SH degree 0)",
+               N=50_000, H=512, W=512, D=0, J=24, iso=False, neutral=True, mode="fwd"),
+    "c2": dict(workload="single B200: LBS + rasterize fwd+bwd, 200k Gaussians, SH degree 3, 1024x1024 view, random pose",
+               N=200_000, H=1024, W=1024, D=3, J=24, iso=False, mode="train"),
+    "c3": dict(workload="human_complex-style training step: 300k Gaussians, batch of 8 synthetic turn-around views "
+                        "sharded over 8xB200 with NCCL grad allreduce",
+               N=300_000, H=1024, W=1024, D=3, J=24, iso=False, mode="train", views=8),
+    "c4": dict(workload="animation render: 120-frame synthetic AMASS-shaped pose sequence, 200k Gaussians at 1080p, "
+                        "frames sharded across 1/2/4/8 GPUs (forward only)",
+               N=200_000, H=1080, W=1920, D=3, J=24, iso=False, mode="fwd", frames=120),
+    "c5": dict(workload="stress: 1M Gaussians after densification, 2048x2048 views, fwd+bwd, sort and "
+                        "atomic-contention scaling",
+               N=1_000_000, H=2048, W=2048, D=3, J=24, iso=False, mode="train"),
+    "shipped": dict(workload="the configuration SinGS ships (human_complex.yaml): SMPL-H 52 joints, SH degree 0 "
+                             "(16 stored coefficients), isotropic Gaussians, 512x896 view, 200k Gaussians, fwd+bwd",
+                    N=200_000, H=896, W=512, D=0, J=52, iso=True, mode="train"),
+}
+
+
+def config_dict(cfg):
+    """The `config` entry of the bench line: identical in both arms (the driver compares them)."""
+    return {"workload": cfg["workload"], "gaussians": cfg["N"], "image": [cfg["H"], cfg["W"]],
+            "sh_degree": cfg["D"], "joints": cfg["J"], "isotropic": bool(cfg["iso"]),
+            "pass": "forward only" if cfg["mode"] == "fwd" else "forward + backward"}
 
 
 def peaks():
@@ -49,13 +83,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_frame_inputs(seed: int, n=N_GAUSS, H=H_IMG, W=W_IMG, J=N_JOINTS):
+def build_frame_inputs(cfg, seed: int, yaw: float = 0.0):
     """numpy inputs of one avatar + one frame."""
     from sings_b200 import synthetic as syn
-    av = syn.make_avatar(n, J, seed=seed)
-    pose = syn.random_pose(J, seed=seed + 2)
+    n, H, W, J = cfg["N"], cfg["H"], cfg["W"], cfg["J"]
+    av = syn.make_avatar(n, J, seed=seed, isotropic=cfg["iso"])
+    pose = syn.random_pose(J, seed=seed + 2, neutral=cfg.get("neutral", False))
     transl = syn.default_transl(H)
-    view = syn.make_view(H, W)
+    view = syn.make_view(H, W, yaw=yaw, centre=(0.0, 0.0, float(transl[2])))
     rng = np.random.default_rng(seed + 3)
     G = rng.normal(size=(3, H, W)).astype(np.float32)
     bg = np.ones(3, np.float32)
@@ -65,67 +100,71 @@ def build_frame_inputs(seed: int, n=N_GAUSS, H=H_IMG, W=W_IMG, J=N_JOINTS):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (reference torch LBS restated + C rasterizer), all host threads
 # ------------------------------------------------------------------------------------------
-def cpu_frame(av, pose, transl, view, G, bg, D=SH_DEG):
+def cpu_frame(cfg, av, pose, transl, view, G, bg):
     import torch
     from oracle import lbs_oracle as lo
     from oracle import raster_oracle as ro
     t = torch.from_numpy
-    xyz_c = t(av.xyz_canon).requires_grad_(True)
-    sc_c = t(av.scales).requires_grad_(True)
-    rot_c = t(av.rotmat_canon).requires_grad_(True)
-    pose_t = t(pose)[None].clone().requires_grad_(True)
-    tr = t(transl)[None].clone().requires_grad_(True)
+    train = cfg["mode"] == "train"
+    xyz_c = t(av.xyz_canon).requires_grad_(train)
+    sc_c = t(av.scales).requires_grad_(train)
+    rot_c = None if cfg["iso"] else t(av.rotmat_canon).requires_grad_(train)
+    pose_t = t(pose)[None].clone().requires_grad_(train)
+    tr = t(transl)[None].clone().requires_grad_(train)
     A = lo.pose_to_A(pose_t, t(av.rest), av.parents, t(av.inv_A_t2cano))
     xyz, q, sc, _ = lo.deform(A, xyz_c, t(av.lbs_weights), sc_c, rot_c, None, tr)
     cam = ro.Camera(W=view.image_width, H=view.image_height, tanfovx=view.tanfovx, tanfovy=view.tanfovy,
                     view=view.world_view_transform.reshape(-1), proj=view.full_proj_transform.reshape(-1),
                     campos=view.camera_center)
     st = ro.forward(cam, xyz[0].detach().numpy(), av.opacity, bg, shs=av.shs,
-                    scales=sc[0].detach().numpy(), rotations=q[0].detach().numpy(), sh_degree=D)
-    gr = ro.backward(st, G)
-    torch.autograd.backward([xyz, q, sc], [t(gr["means3D"])[None], t(gr["rotations"])[None], t(gr["scales"])[None]])
+                    scales=sc[0].detach().numpy(), rotations=q[0].detach().numpy(), sh_degree=cfg["D"])
+    if train:
+        gr = ro.backward(st, G)
+        torch.autograd.backward([xyz, q, sc], [t(gr["means3D"])[None], t(gr["rotations"])[None], t(gr["scales"])[None]])
     return st.num_rendered, float((st.color * G).sum())
 
 
-def run_cpu(steps: int, warmup: int, frames):
+def run_cpu(cfg, steps: int, warmup: int, frames):
     import torch
     from oracle import raster_oracle as ro
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ro.set_threads(cores)
     for i in range(warmup):
-        cpu_frame(*frames[i % len(frames)])
+        cpu_frame(cfg, *frames[i % len(frames)])
     t0 = time.perf_counter()
     for i in range(steps):
-        cpu_frame(*frames[i % len(frames)])
+        cpu_frame(cfg, *frames[i % len(frames)])
     dt = time.perf_counter() - t0
     return steps / dt, dt / steps * 1e3, cores
 
 
-def reference_arm(args):
+def cpu_sample_note(cfg, n):
+    what = "fwd+bwd" if cfg["mode"] == "train" else "forward only"
+    return (f"{n} full frames of the same workload on the host ({what}): torch restatement of the reference's "
+            f"lbs_extra / rotations + OpenMP C rasterizer oracle (the reference has no CPU rasterizer and its CUDA "
+            f"one is not vendored)")
+
+
+def reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = [build_frame_inputs(100)]
-    steps, warmup = args.steps, args.warmup
+    frames = [build_frame_inputs(cfg, 100)]
     # bound the run to a few minutes: probe one frame, then cap the step count
     t0 = time.perf_counter()
-    cpu_frame(*frames[0])
+    cpu_frame(cfg, *frames[0])
     t1 = time.perf_counter() - t0
-    budget = 150.0
-    steps_run = max(1, min(steps, int(budget / max(t1, 1e-3))))
-    warm_run = min(warmup, 1)
-    fps, ms, cores = run_cpu(steps_run, warm_run, frames)
+    steps_run = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
+    warm_run = min(args.warmup, 1)
+    fps, ms, cores = run_cpu(cfg, steps_run, warm_run, frames)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps_run, "warmup": warm_run, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": [H_IMG, W_IMG],
-                   "sh_degree": SH_DEG, "joints": N_JOINTS},
+        "config": config_dict(cfg),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps_run} full frames (LBS fwd+bwd via the torch restatement of the "
-                                   f"reference's lbs_extra/rotations, rasterizer fwd+bwd via the OpenMP C oracle); "
-                                   f"the reference has no CPU rasterizer and its CUDA one is not vendored"},
+                         "sample": cpu_sample_note(cfg, steps_run)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,15 +218,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def algorithmic_bytes(N, J, M, L, W, H, n_vis, passes=6):
-    """Per-launch algorithmic bytes of each stage (DESIGN.md 'Algorithmic bytes')."""
+def algorithmic_bytes(N, J, M, L, W, H, n_vis, iso, passes):
+    """Per-launch algorithmic bytes of each stage (SURVEY.md 8d; DESIGN.md 'Algorithmic bytes')."""
     pix, tiles = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    rot = 0 if iso else 36
     return {
-        "lbs_fwd": N * (100 + 4 * J),
-        "lbs_bwd": N * (148 + 4 * J),
+        "lbs_fwd": N * (64 + rot + 4 * J),
+        "lbs_bwd": N * (112 + rot + 4 * J),
         "geometry": N * (236 + 75),                                 # preprocessCUDA
-        # InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges (SURVEY.md 8d): one stage
-        # here, because the count / scan / scatter binning produces list and ranges together
+        # InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges: one stage
         "binning": 8 * N + 20 * N + 12 * L + (8 + 24 * passes) * L + 8 * L + 8 * tiles,
         "blend_fwd": 40 * L + 20 * pix + 8 * tiles,
         "blend_bwd": 40 * L + 20 * pix + 36 * n_vis,
@@ -195,7 +234,141 @@ def algorithmic_bytes(N, J, M, L, W, H, n_vis, passes=6):
     }
 
 
-def gpu_arm(args):
+def measure_h2d(dev, nbytes):
+    """Pinned host -> device copy rate of THIS box for a buffer the size of the per-step upload."""
+    import torch
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return nbytes * 20 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
+def ab_baselines(cfg, s, dev):
+    """Stock comparators on this box (rank 0, 1 GPU): CUB SortPairs, eager-torch LBS."""
+    import torch
+    from sings_b200 import _lib, deform
+    out = {}
+    L_ = _lib.lib()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    # ---- sort: the frame's keys (tile|depth, 45-47 bits), shuffled, with their ids ----
+    try:
+        step = s["step"]
+        from sings_b200.rasterizer import layout_info
+        info = layout_info(step.N, step.Wd, step.H, step.L_cap)
+        L = int(s["L"])
+        raw = step.binning
+        keys_sorted = raw[info["keys_sorted"]:info["keys_sorted"] + 8 * L].view(torch.int64).clone()
+        perm = torch.randperm(L, device=dev, generator=torch.Generator(dev).manual_seed(1))
+        k0 = keys_sorted[perm].contiguous()
+        v0 = perm.to(torch.int32).contiguous()
+        end_bit = info["end_bit"]
+        kin, vin = k0.clone(), v0.clone()
+        kt, vt = torch.empty_like(k0), torch.empty_like(v0)
+        sb = int(L_.sgs_sort_scratch_bytes(L))
+        scratch = torch.empty(sb, device=dev, dtype=torch.uint8)
+        flag = C.c_int(0)
+
+        def ours():
+            kin.copy_(k0); vin.copy_(v0)
+            _lib.check(L_.sgs_sort_pairs_u64(kin.data_ptr(), vin.data_ptr(), kt.data_ptr(), vt.data_ptr(),
+                                             scratch.data_ptr(), sb, L, end_bit, C.byref(flag), st), "sort")
+
+        def copy_only():
+            kin.copy_(k0); vin.copy_(v0)
+        t_copy = timed(copy_only)
+        t_ours = timed(ours) - t_copy
+        cub_path = os.path.join(ROOT, "tools", "_build", "libcub_ab.so")
+        if os.path.exists(cub_path):
+            cub = C.CDLL(cub_path)
+            cub.cub_ab_sort_pairs_u64.restype = C.c_int
+            cub.cub_ab_sort_pairs_u64.argtypes = [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_void_p,
+                                                                    C.POINTER(C.c_size_t), C.c_void_p]
+            tb = C.c_size_t(0)
+            cub.cub_ab_sort_pairs_u64(None, None, None, None, L, end_bit, None, C.byref(tb), st)
+            temp = torch.empty(max(int(tb.value), 1), device=dev, dtype=torch.uint8)
+
+            def theirs():
+                rc = cub.cub_ab_sort_pairs_u64(k0.data_ptr(), kt.data_ptr(), v0.data_ptr(), vt.data_ptr(), L, end_bit,
+                                               temp.data_ptr(), C.byref(tb), st)
+                assert rc == 0
+            t_cub = timed(theirs)
+            theirs()
+            ck, cv = kt.clone(), vt.clone()
+            ours()
+            torch.cuda.synchronize(dev)
+            rk, rv = (kt, vt) if flag.value else (kin, vin)
+            same = bool(torch.equal(rk, ck) and torch.equal(rv, cv))
+            out["sort"] = {"pairs": L, "end_bit": end_bit, "cub_ms": round(t_cub, 4), "ours_ms": round(t_ours, 4),
+                           "speedup_vs_cub": round(t_cub / t_ours, 3), "identical_output": same,
+                           "note": "cub::DeviceRadixSort::SortPairs(u64, u32) vs sgs_sort_pairs_u64 on the frame's "
+                                   "shuffled keys, whole sort incl. histogram; in the frame itself the four depth digits "
+                                   "are sorted per Gaussian, not per pair, so only two of these passes run over the pairs"}
+        else:
+            out["sort"] = {"unavailable": "tools/_build/libcub_ab.so not built", "ours_ms": round(t_ours, 4)}
+    except Exception as e:       # a failed comparator must not take the bench line down
+        out["sort"] = {"unavailable": repr(e)[:200]}
+
+    # ---- LBS: the reference's torch ops (restated in oracle/lbs_oracle.py) run eagerly on the GPU ----
+    try:
+        from oracle import lbs_oracle as lo
+        av = s["av"]
+        t = lambda a: torch.as_tensor(a, device=dev)
+        A = lo.pose_to_A(t(s["pose"])[None], t(av.rest), av.parents, t(av.inv_A_t2cano))
+        Wd = t(av.lbs_weights)
+        xyz = t(av.xyz_canon).requires_grad_(True)
+        scl = t(av.scales).requires_grad_(True)
+        rot = None if cfg["iso"] else t(av.rotmat_canon).requires_grad_(True)
+        tr = t(s["transl"])[None]
+        n = cfg["N"]
+        gx, gq, gs = torch.randn(1, n, 3, device=dev), torch.randn(1, n, 4, device=dev), torch.randn(1, n, 3, device=dev)
+
+        def torch_lbs():
+            for p in (xyz, scl, rot):
+                if p is not None:
+                    p.grad = None
+            x, q, sc, _ = lo.deform(A, xyz, Wd, scl, rot, None, tr)
+            torch.autograd.backward([x, q, sc], [gx, gq, gs])
+
+        def our_lbs():
+            for p in (xyz, scl, rot):
+                if p is not None:
+                    p.grad = None
+            x, q, sc = deform.deform_gaussians(A[0], xyz, Wd, rot, scl, None, tr[0])
+            torch.autograd.backward([x, q, sc], [gx[0], gq[0], gs[0]])
+        t_torch, t_ours = timed(torch_lbs, 10), timed(our_lbs, 10)
+        out["lbs"] = {"torch_eager_ms": round(t_torch, 4), "ours_ms": round(t_ours, 4),
+                      "speedup_vs_torch": round(t_torch / t_ours, 2), "kind": "port",
+                      "note": "deform segment fwd+bwd (lbs_extra + compose + matrix_to_quaternion, autograd) as eager "
+                              "torch CUDA ops vs sings_b200.deform.deform_gaussians (sgs_lbs_fwd + sgs_lbs_bwd through "
+                              "autograd); the fused per-frame path folds both into the rasterizer's kernels"}
+    except Exception as e:
+        out["lbs"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
+def gpu_arm(args, cfg):
     import torch
     import torch.distributed as dist
     from sings_b200 import dp
@@ -207,46 +380,78 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     hbm_peak, peak_src = peaks()
+    N, H, W, D, J = cfg["N"], cfg["H"], cfg["W"], cfg["D"], cfg["J"]
+    train = cfg["mode"] == "train"
+    ring = RING if N <= 400_000 else 2          # 1M-Gaussian avatars: two are already > L2 several times over
+    views = cfg.get("views", 0)
 
-    # ---- workload: ring of distinct avatars (inputs larger than L2), each rank its own views
+    # ---- workload: ring of distinct avatars (inputs larger than L2), each rank its own views / frames
     sets = []
-    for r in range(RING):
-        av, pose, transl, view, G, bg = build_frame_inputs(1000 * rank + 10 * r)
+    for r in range(ring):
+        yaw = 2 * math.pi * ((rank * ring + r) % views) / views if views else 0.0
+        av, pose, transl, view, G, bg = build_frame_inputs(cfg, 1000 * rank + 10 * r, yaw=yaw)
         t = lambda a: torch.as_tensor(a, device=dev)
-        step = AvatarStep(t(av.xyz_canon), t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs),
-                          t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano),
-                          H_IMG, W_IMG, SH_DEG, timing=True)
+        step = AvatarStep(t(av.xyz_canon), None if cfg["iso"] else t(av.rotmat_canon), t(av.scales), t(av.opacity),
+                          t(av.shs), t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano),
+                          H, W, D, timing=True)
         fr = FrameInputs(pose=t(pose), transl=t(transl), viewmatrix=t(view.world_view_transform),
                          projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(bg),
                          tanfovx=view.tanfovx, tanfovy=view.tanfovy)
         sets.append(dict(step=step, fr=fr, G=t(G), av=av, pose=pose, transl=transl, view=view, G_np=G, bg=bg))
-    exch = dp.GradExchange(N_GAUSS, sets[0]["step"].n_param_grads, dev,
-                           defer_max=not os.environ.get("SGS_DP_MAX_EVERY_STEP")) if world > 1 else None
+    exch = dp.GradExchange(N, sets[0]["step"].n_param_grads, dev,
+                           defer_max=not os.environ.get("SGS_DP_MAX_EVERY_STEP")) if (world > 1 and train) else None
 
-    def one_step(i, pending, staged=False):
-        s = sets[i % RING]
+    def one_step(i, pending, staged=False, sync_dp=False):
+        s = sets[i % ring]
         st = s["step"]
         st.record_stages = bool(staged)    # eager launches: stage events only in the instrumented passes
-        if exch is not None and pending[i % RING] is not None:
-            pending[i % RING]()            # finish the all-reduce that last used this bucket (folds + clears the step statistics)
-            pending[i % RING] = None
+        if exch is not None and pending[i % ring] is not None:
+            pending[i % ring]()            # finish the all-reduce that last used this bucket (folds + clears the step statistics)
+            pending[i % ring] = None
         if "replay" in s:
             s[{False: "replay", True: "replay_staged", "coarse": "replay_coarse"}[staged]]()   # the frame as one CUDA-graph launch
         else:
             st.forward(s["fr"])
-            st.backward(s["G"])
+            if train:
+                st.backward(s["G"])
         if exch is not None:
-            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)
+            fin = exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)
+            if sync_dp:
+                fin()                      # the current stream waits for the reduced bucket: nothing of the next step overlaps it
+            else:
+                pending[i % ring] = fin
+
+    def drain(pending):
+        for k in range(ring):
+            if pending[k] is not None:
+                pending[k]()
+                pending[k] = None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    pending = [None] * RING
+    def timed_region(n, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            one_step(i, pending, **kw)
+        drain(pending)
+        if exch is not None:
+            exch.sync_max()                # the deferred all-reduce(MAX) of max_radii2D, inside the timed region
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    pending = [None] * ring
     from sings_b200._lib import SgsError
     for attempt in range(4):
-        for i in range(max(args.warmup, 3, RING)):
+        for i in range(max(args.warmup, 3, ring)):
             one_step(i, pending)
         torch.cuda.synchronize()
         try:
@@ -260,39 +465,31 @@ def gpu_arm(args):
                 except SgsError:
                     pass
     if not args.no_graph:
-        # capacities are settled: record each avatar's frame (forward + backward) as a CUDA graph
-        for i in range(RING):
-            if pending[i] is not None:
-                pending[i]()
-                pending[i] = None
+        # capacities are settled: record each avatar's frame (forward [+ backward]) as a CUDA graph
+        drain(pending)
         for s in sets:
-            s["replay"] = s["step"].capture(s["fr"], s["G"], stages=False)
-            s["replay_staged"] = s["step"].capture(s["fr"], s["G"], stages=True)
+            cap = (lambda s, **kw: s["step"].capture(s["fr"], s["G"] if train else None, **kw))
+            s["replay"] = cap(s, stages=False)
+            s["replay_staged"] = cap(s, stages=True)
             # coarse: only the events around LBS + preprocess + sort + ranges (8 = frame start, 3 = after ranges)
-            s["replay_coarse"] = s["step"].capture(s["fr"], s["G"], stages=True, stage_mask=(1 << 8) | (1 << 3))
-        for i in range(2 * RING):
+            s["replay_coarse"] = cap(s, stages=True, stage_mask=(1 << 8) | (1 << 3))
+        for i in range(2 * ring):
             one_step(i, pending)
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        one_step(i, pending)
-    for i in range(RING):
-        if pending[i] is not None:
-            pending[i]()
-            pending[i] = None
+    dp_info = None
     if exch is not None:
-        exch.sync_max()                    # the deferred all-reduce(MAX) of max_radii2D, inside the timed region
-    e1.record()
-    barrier()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
+        ms_pipe = timed_region(args.steps)                       # exchange overlapping the next frames
+        ms_total = timed_region(args.steps, sync_dp=True)        # synchronous step: the headline for N > 1
+        dp_info = {"mode": "synchronous (all-reduce of a step finishes before the next forward starts)",
+                   "pipelined": {"value": world * args.steps / (ms_pipe / 1e3), "ms_per_step": ms_pipe / args.steps,
+                                 "note": f"the all-reduce of a step overlaps the next {ring - 1} frames (distinct avatars)"},
+                   "bucket_mb": round(sets[0]["step"].bucket.numel() * 4 / 1e6, 1),
+                   "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
+    else:
+        ms_total = timed_region(args.steps)
     for s in sets:
         s["step"].check_capacity()
     value = world * args.steps / (ms_total / 1e3)
@@ -300,44 +497,32 @@ def gpu_arm(args):
     # ---- per-stage device times: a second timed pass over the same frames with CUDA events
     # recorded at the stage boundaries.  The records sit between kernels (graph nodes), which
     # turns the kernels' overlapped programmatic launch into full dependencies -- ~4 us per
-    # event, ~45 us per frame (tools/probe_events.py) -- so they stay out of the headline region
-    # above; the stage times below therefore sum to more than ms_per_step.
-    n_stage = max(RING, min(args.steps, 100))
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(n_stage):
-        one_step(i, pending, staged=True)
-    for i in range(RING):
-        if pending[i] is not None:
-            pending[i]()
-            pending[i] = None
-    s1.record()
-    barrier()
-    ms_staged = s0.elapsed_time(s1) / n_stage
+    # event -- so they stay out of the headline region above; the stage times below therefore sum
+    # to more than ms_per_step.
+    n_stage = max(ring, min(args.steps, 100))
+    ms_staged = timed_region(n_stage, staged=True) / n_stage
     stage = {}
     for s in sets:
-        for k, v in s["step"].stage_ms().items():
+        for k, v in s["step"].stage_ms(train).items():
             stage.setdefault(k, []).append(v)
     # third pass: one interval over the north star's target set (LBS + preprocess + sort + ranges),
     # two event records instead of five inside it -- less perturbation than the sum of its stages
     hot_coarse = None
     if not args.no_graph:
-        for i in range(n_stage):
-            one_step(i, pending, staged="coarse")
-        for i in range(RING):
-            if pending[i] is not None:
-                pending[i]()
-                pending[i] = None
-        barrier()
+        timed_region(n_stage, staged="coarse")
         hot_coarse = float(np.mean([s["step"].interval_ms(8, 3) for s in sets]))
     stage = {k: float(np.mean(v)) for k, v in stage.items()}
     Lm = float(np.mean([s["L"] for s in sets]))
     n_vis = float(np.mean([int((s["step"].radii > 0).sum().item()) for s in sets]))
-    ab = algorithmic_bytes(N_GAUSS, N_JOINTS, 16, Lm, W_IMG, H_IMG, n_vis)
+    from sings_b200.rasterizer import layout_info
+    passes = layout_info(N, W, H, 1)["passes"]
+    ab = algorithmic_bytes(N, J, 16, Lm, W, H, n_vis, cfg["iso"], passes)
     if "deform_geometry" in stage:      # fused kernels: the stages merge, their algorithmic bytes add
         ab["deform_geometry"] = ab.pop("lbs_fwd") + ab.pop("geometry")
         ab["geometry_lbs_bwd"] = ab.pop("geometry_bwd") + ab.pop("lbs_bwd")
+    if not train:
+        for k in ("blend_bwd", "geometry_bwd", "lbs_bwd", "geometry_lbs_bwd"):
+            ab.pop(k, None)
     stages_out = {}
     for k, b in ab.items():
         ms = stage.get(k)
@@ -357,9 +542,9 @@ def gpu_arm(args):
             tj = json.load(f)
         kern = {"deform_geometry": "geometry_kernel", "geometry_lbs_bwd": "geometry_bwd_kernel",
                 "lbs_fwd": "lbs_fwd_kernel", "lbs_bwd": "lbs_bwd_kernel", "geometry": "geometry_kernel",
-                "binning": "bin_scatter_kernel", "blend_fwd": "blend_fwd_kernel",
+                "binning": "emit_pairs_kernel", "blend_fwd": "blend_fwd_kernel",
                 "blend_bwd": "blend_bwd_kernel", "geometry_bwd": "geometry_bwd_kernel"}[dom]
-        if kern in tj.get("kernels", {}):
+        if kern in tj.get("kernels", {}) and tj.get("config", "c2") == args.config:
             traffic, traffic_src = tj["kernels"][kern]["dram_bytes"], f"profiles/{tj.get('source')} ({kern})"
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": stages_out[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
@@ -371,7 +556,7 @@ def gpu_arm(args):
                                 "frac": round(hot_b / (hot_one * 1e-3) / 1e9 / hbm_peak, 4),
                                 "ms_sum_of_stages": round(hot_ms, 4),
                                 "timing": "one interval, frame start -> after tile ranges (2 event records)"
-                                          if hot_coarse else "sum of the four stage intervals"},
+                                          if hot_coarse else "sum of the stage intervals"},
         "frame_alg_mb": round(sum(ab.values()) / 1e6, 1),
         "pairs_L": Lm, "visible": n_vis,
         "stage_timing": {"steps": n_stage, "ms_per_step": round(ms_staged, 4),
@@ -383,8 +568,12 @@ def gpu_arm(args):
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, sets, dev, world, rank, exch)
+        e2e = run_e2e(args, cfg, sets, dev, world, rank, exch, ring)
     clocks = sampler.stop() if rank == 0 else None
+
+    ab_out = None
+    if rank == 0 and world == 1 and not args.no_ab:
+        ab_out = ab_baselines(cfg, sets[0], dev)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -392,24 +581,27 @@ def gpu_arm(args):
         frames = [(s["av"], s["pose"], s["transl"], s["view"], s["G_np"], s["bg"])]
         # bounded sample of the same workload: ~15 s of host work (probe one frame, then size the run)
         t0 = time.perf_counter()
-        cpu_frame(*frames[0])
+        cpu_frame(cfg, *frames[0])
         n_cpu = max(2, min(200, int(15.0 / max(time.perf_counter() - t0, 1e-3))))
-        fps, ms, cores = run_cpu(n_cpu, 0, frames)
-        cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                    "sample": f"{n_cpu} full frames of the same workload on the host (torch restatement of the "
-                              f"reference LBS + OpenMP C rasterizer oracle, fwd+bwd)"}
+        fps, ms, cores = run_cpu(cfg, n_cpu, 0, frames)
+        cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": cpu_sample_note(cfg, n_cpu)}
     if rank == 0:
+        st0 = sets[0]["step"]
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": [H_IMG, W_IMG], "sh_degree": SH_DEG,
-                       "joints": N_JOINTS, "views_per_gpu_per_step": 1,
-                       "launch": "eager launches" if args.no_graph else "one CUDA graph per frame (forward+backward)",
-                       "l2": f"inputs rotate over a ring of {RING} distinct avatars (~{RING * 70} MB of inputs) > 126 MB L2",
-                       "parallelism": f"dp{world} (views sharded, gradient bucket all-reduced)" if world > 1 else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 16 * args.steps,
+            "config": config_dict(cfg),
+            "run": {"config_name": args.config, "views_per_gpu_per_step": 1,
+                    "launch": "eager launches" if args.no_graph else "one CUDA graph per frame",
+                    "l2": f"inputs rotate over a ring of {ring} distinct avatars (~{ring * (70 if N <= 400_000 else 350)} MB of "
+                          f"inputs) > 126 MB L2",
+                    "deformer": f"fused into the rasterizer's per-Gaussian kernels, skinning weights packed to {st0.K} slots"
+                                if st0.K else "separate LBS kernels (dense skinning weights)",
+                    "parallelism": f"dp{world} (views sharded, gradient bucket all-reduced every step)" if exch is not None
+                                   else (f"dp{world} (frames sharded, no collective)" if world > 1 else "single GPU")},
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks, "dp": dp_info, "ab": ab_out,
+            "gpu_launches": st0.launches_per_frame(train) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -417,9 +609,12 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, sets, dev, world, rank, exch=None):
+def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
     """Same metric end to end with HOST buffers.  Per step, inside the timed region: H2D of
-    pose + transl + dL/dimage from pinned memory, forward, loss, backward, D2H of the loss.
+    pose + transl + dL/dimage from pinned memory, forward, loss, backward, D2H of the loss
+    (forward-only configs: H2D of pose + transl, forward, clamp + 8-bit conversion on the
+    device, D2H of the finished uint8 frame into pinned memory -- the reference's
+    `image.cpu()` + cv2 conversion, gs_trainer.py:716-719).
 
     Two callers of the same kernels are timed:
       * `e2e` (headline): the C-ABI path -- `AvatarStep` drives include/sings_b200.h directly
@@ -428,7 +623,7 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         `diff_gaussian_rasterization.GaussianRasterizer`), which add torch.autograd and
         per-call allocation overhead on the host.
     Both use the same input pipeline: inputs are prefetched one step ahead on a copy stream
-    into double-buffered device staging (like a data loader with pinned memory) and the loss
+    into double-buffered device staging (like a data loader with pinned memory) and the result
     is read back through pinned slots one step late (like a logging trainer)."""
     import torch
     import torch.distributed as dist
@@ -437,11 +632,12 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
     from sings_b200 import rasterizer as R
     from sings_b200.step import FrameInputs
 
+    N, H, W, D, J = cfg["N"], cfg["H"], cfg["W"], cfg["D"], cfg["J"]
+    train = cfg["mode"] == "train"
     for s in sets:
         s["step"].record_stages = False     # no stage events on this path (eager launches included)
     host = []
     for s in sets:
-        av = s["av"]
         t = lambda a: torch.as_tensor(a, device=dev)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         # the same dense gradient image quantised to 8 bits: how a target image is stored on disk
@@ -449,15 +645,19 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         host.append(dict(pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]), T8=pin(t8), view=s["view"],
                          bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
                          pm=t(s["view"].full_proj_transform), cp=t(s["view"].camera_center)))
-    h2d = int(host[0]["pose"].numel() * 4 + host[0]["transl"].numel() * 4 + host[0]["G"].numel() * 4)
+    h2d = int(host[0]["pose"].numel() * 4 + host[0]["transl"].numel() * 4 + (host[0]["G"].numel() * 4 if train else 0))
+    d2h = 4 if train else 3 * H * W
+    h2d_gbs = measure_h2d(dev, max(h2d, 1 << 20))
     cur = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
     NBUF = 2
-    stage = [dict(pose=torch.empty(N_JOINTS, 3, device=dev), transl=torch.empty(3, device=dev),
-                  G=torch.empty(3, H_IMG, W_IMG, device=dev),
-                  T8=torch.empty(3, H_IMG, W_IMG, device=dev, dtype=torch.uint8), ready=torch.cuda.Event(),
+    stage = [dict(pose=torch.empty(J, 3, device=dev), transl=torch.empty(3, device=dev),
+                  G=torch.empty(3, H, W, device=dev),
+                  T8=torch.empty(3, H, W, device=dev, dtype=torch.uint8), ready=torch.cuda.Event(),
                   free=torch.cuda.Event()) for _ in range(NBUF)]
     loss_host = torch.zeros(NBUF).pin_memory()
+    frame_host = None if train else torch.zeros(NBUF, H, W, 3, dtype=torch.uint8).pin_memory()
+    frame_dev = None if train else [torch.empty(H, W, 3, device=dev, dtype=torch.uint8) for _ in range(NBUF)]
     loss_ev = [torch.cuda.Event() for _ in range(NBUF)]
     losses = []
     # diagnostics only (tools/e2e_probe.sh): "nog" skips the dL/dimage upload, "nosync" the lagged loss read
@@ -465,73 +665,81 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
     upload = {"u8": False}      # True: the per-step image upload is uint8 and decoded on the device
 
     def prefetch(i):
-        hs, sb = host[i % RING], stage[i % NBUF]
+        hs, sb = host[i % ring], stage[i % NBUF]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sb["free"])          # the step that last used this buffer is done
             sb["pose"].copy_(hs["pose"], non_blocking=True)
             sb["transl"].copy_(hs["transl"], non_blocking=True)
-            if upload["u8"]:
-                sb["T8"].copy_(hs["T8"], non_blocking=True)
-            elif "nog" not in PROBE:
-                sb["G"].copy_(hs["G"], non_blocking=True)
+            if train:
+                if upload["u8"]:
+                    sb["T8"].copy_(hs["T8"], non_blocking=True)
+                elif "nog" not in PROBE:
+                    sb["G"].copy_(hs["G"], non_blocking=True)
             sb["ready"].record(copy_stream)
 
-    def finish_step(i, loss, sb):
+    def finish_step(i, result, sb):
         sb["free"].record(cur)
-        loss_host[i % NBUF:i % NBUF + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        if train:
+            loss_host[i % NBUF:i % NBUF + 1].copy_(result.detach().reshape(1), non_blocking=True)
+        else:
+            # the finished frame: clamp(0,1) (gs_renderer_single.py:96), HWC uint8, into pinned memory
+            from sings_b200.animate import frame_to_uint8
+            frame_to_uint8(result, frame_dev[i % NBUF])
+            frame_host[i % NBUF].copy_(frame_dev[i % NBUF], non_blocking=True)
         loss_ev[i % NBUF].record(cur)
-        if i >= 1 and "nosync" not in PROBE:           # read the previous step's loss
+        if i >= 1 and "nosync" not in PROBE:           # read the previous step's result
             loss_ev[(i - 1) % NBUF].synchronize()
-            losses.append(float(loss_host[(i - 1) % NBUF]))
+            losses.append(float(loss_host[(i - 1) % NBUF]) if train else float(frame_host[(i - 1) % NBUF][0, 0, 0]))
 
     # ---- C-ABI path ----
-    pending = [None] * RING
+    pending = [None] * ring
 
     def drain_exchange():
-        for k in range(RING):
+        for k in range(ring):
             if pending[k] is not None:
                 pending[k]()
                 pending[k] = None
 
-    assert RING % NBUF == 0        # ring slot k always meets staging buffer k % NBUF (graphs bind addresses)
+    assert ring % NBUF == 0        # ring slot k always meets staging buffer k % NBUF (graphs bind addresses)
     frames = [FrameInputs(pose=stage[k % NBUF]["pose"], transl=stage[k % NBUF]["transl"], viewmatrix=host[k]["vm"],
                           projmatrix=host[k]["pm"], campos=host[k]["cp"], bg=host[k]["bg"],
-                          tanfovx=host[k]["view"].tanfovx, tanfovy=host[k]["view"].tanfovy) for k in range(RING)]
-    replays = [None] * RING
+                          tanfovx=host[k]["view"].tanfovx, tanfovy=host[k]["view"].tanfovy) for k in range(ring)]
+    replays = [None] * ring
 
     def step_abi(i, n_total):
-        hs, sb, st = host[i % RING], stage[i % NBUF], sets[i % RING]["step"]
+        sb, st = stage[i % NBUF], sets[i % ring]["step"]
         if i + 1 < n_total:
             prefetch(i + 1)
-        if exch is not None and pending[i % RING] is not None:
-            pending[i % RING]()            # finish the all-reduce that last used this bucket (folds + clears the step statistics)
-            pending[i % RING] = None
         cur.wait_event(sb["ready"])
-        if replays[i % RING] is not None:
-            replays[i % RING]()            # forward + loss + backward as one CUDA-graph launch
-            loss = st.loss
+        if replays[i % ring] is not None:
+            replays[i % ring]()            # forward + loss + backward as one CUDA-graph launch
+            result = st.loss if train else st.color
         else:
-            img = st.forward(frames[i % RING])
-            loss = torch.dot(img.view(-1), sb["G"].view(-1))      # L = sum(image * G); dL/dimage = G
-            st.backward(sb["G"])
+            img = st.forward(frames[i % ring])
+            if train:
+                result = torch.dot(img.view(-1), sb["G"].view(-1))      # L = sum(image * G); dL/dimage = G
+                st.backward(sb["G"])
+            else:
+                result = img
         if exch is not None:
-            pending[i % RING] = exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)
-        finish_step(i, loss, sb)
+            exch.exchange(st.bucket, st.max_radii2D, async_op=True, reset_step=True)()   # synchronous step (see gpu_arm)
+        finish_step(i, result, sb)
 
     # ---- drop-in autograd path ----
     params = []
-    if not args.no_dropin:
+    if not args.no_dropin and train:
         for s in sets:
             av = s["av"]
             t = lambda a: torch.as_tensor(a, device=dev)
-            params.append(dict(xyz=t(av.xyz_canon).requires_grad_(True), rot=t(av.rotmat_canon).requires_grad_(True),
+            params.append(dict(xyz=t(av.xyz_canon).requires_grad_(True),
+                               rot=None if cfg["iso"] else t(av.rotmat_canon).requires_grad_(True),
                                scales=t(av.scales).requires_grad_(True), opacity=t(av.opacity).requires_grad_(True),
                                shs=t(av.shs).requires_grad_(True), W=t(av.lbs_weights), rest=t(av.rest),
                                parents=torch.from_numpy(av.parents).to(device=dev, dtype=torch.int32),
                                inv_A=t(av.inv_A_t2cano)))
 
     def step_dropin(i, n_total):
-        hs, sb, p = host[i % RING], stage[i % NBUF], params[i % RING]
+        hs, sb, p = host[i % ring], stage[i % NBUF], params[i % ring]
         if i + 1 < n_total:
             prefetch(i + 1)
         cur.wait_event(sb["ready"])
@@ -542,14 +750,15 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         v = hs["view"]
         rs = GaussianRasterizationSettings(
             image_height=v.image_height, image_width=v.image_width, tanfovx=v.tanfovx, tanfovy=v.tanfovy,
-            bg=hs["bg"], scale_modifier=1.0, viewmatrix=hs["vm"], projmatrix=hs["pm"], sh_degree=SH_DEG,
+            bg=hs["bg"], scale_modifier=1.0, viewmatrix=hs["vm"], projmatrix=hs["pm"], sh_degree=D,
             campos=hs["cp"], prefiltered=False, debug=False)
         means2D = torch.zeros_like(xyz, requires_grad=True)
         img, radii = GaussianRasterizer(rs)(means3D=xyz, means2D=means2D, shs=p["shs"], opacities=p["opacity"],
                                             scales=sc, rotations=rotq)
         loss = (img * sb["G"]).sum()
         for q in (p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"]):
-            q.grad = None
+            if q is not None:
+                q.grad = None
         loss.backward()
         finish_step(i, loss, sb)
 
@@ -560,7 +769,7 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         for i in range(n):
             step(i, n)
         loss_ev[(n - 1) % NBUF].synchronize()
-        losses.append(float(loss_host[(n - 1) % NBUF]))
+        losses.append(float(loss_host[(n - 1) % NBUF]) if train else float(frame_host[(n - 1) % NBUF][0, 0, 0]))
 
     def timed(step, n):
         if world > 1:
@@ -580,24 +789,27 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         return float(ms.item())
 
     n = max(10, min(args.steps, 400))
-    run(step_abi, RING)
+    run(step_abi, ring)
     if not args.no_graph:
         drain_exchange()
         torch.cuda.synchronize()
-        for k in range(RING):
-            replays[k] = sets[k]["step"].capture(frames[k], stage[k % NBUF]["G"], loss_weight=stage[k % NBUF]["G"], stages=False)
-        run(step_abi, RING)
+        for k in range(ring):
+            replays[k] = sets[k]["step"].capture(frames[k], stage[k % NBUF]["G"] if train else None,
+                                                 loss_weight=stage[k % NBUF]["G"] if train else None, stages=False)
+        run(step_abi, ring)
     ms = timed(step_abi, n)
     for s in sets:
         s["step"].check_capacity()
     out = {"value": world * n / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": n, "ms_per_step": ms / n,
-           "pipeline": "inputs prefetched one step ahead on a copy stream; loss read back one step late; "
+           "d2h_bytes_per_step": d2h, "steps": n, "ms_per_step": ms / n,
+           "h2d_pinned_gbs_measured": round(h2d_gbs, 2),
+           "h2d_gbs_implied": round(h2d * (n / (ms / 1e3)) / 1e9, 2),
+           "pipeline": "inputs prefetched one step ahead on a copy stream; result read back one step late; "
                        "all copies inside the timed region",
            "api": "C ABI (include/sings_b200.h) driven by sings_b200.step.AvatarStep with preallocated buffers"
                   + ("" if args.no_graph else ", one CUDA graph per frame")}
-    if not args.no_graph and not PROBE:
-        # Variant: the per-step image goes up as uint8 (3.1 MB instead of 12.6 MB) and is decoded
+    if train and not args.no_graph and not PROBE:
+        # Variant: the per-step image goes up as uint8 (a quarter of the bytes) and is decoded
         # on the device inside the graph.  Reported beside the float32 headline because the
         # float upload is bound by the box's host link, not by the GPU (tools/e2e_probe.sh).
         upload["u8"] = True
@@ -607,21 +819,21 @@ def run_e2e(args, sets, dev, world, rank, exch=None):
         def decode(k):
             sb = stage[k % NBUF]
             return lambda: torch.mul(torch.sub(sb["T8"].float(), 127.5), 1.0 / U8_SCALE, out=sb["G"])
-        for k in range(RING):
+        for k in range(ring):
             replays[k] = sets[k]["step"].capture(frames[k], stage[k % NBUF]["G"], loss_weight=stage[k % NBUF]["G"],
                                                  prologue=decode(k), stages=False)
-        run(step_abi, RING)
+        run(step_abi, ring)
         ms8 = timed(step_abi, n)
         upload["u8"] = False
         out["u8_upload"] = {"value": world * n / (ms8 / 1e3), "unit": "frames/s", "steps": n, "ms_per_step": ms8 / n,
-                            "h2d_bytes_per_step": h2d - 3 * H_IMG * W_IMG * 3, "d2h_bytes_per_step": 4,
+                            "h2d_bytes_per_step": h2d - 3 * H * W * 3, "d2h_bytes_per_step": 4,
                             "note": "same C-ABI loop; dL/dimage uploaded as uint8 and decoded on the device "
                                     "(torch sub/mul inside the graph)"}
-    if not args.no_dropin:
+    if params:
         nd = max(10, min(args.steps, 100))
-        run(step_dropin, RING)   # checked mode: sizes the pair-list capacity for every avatar of the ring
+        run(step_dropin, ring)   # checked mode: sizes the pair-list capacity for every avatar of the ring
         R.set_async(True)        # then no mid-step host sync: the overflow flag is examined at the next forward
-        run(step_dropin, RING)
+        run(step_dropin, ring)
         msd = timed(step_dropin, nd)
         R.check_pending(block=True)
         R.set_async(False)
@@ -637,15 +849,21 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="workload: BASELINE.json configs c1..c5 or the shipped configuration (default c2, the metric's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ab", action="store_true", help="skip the CUB / eager-torch comparators")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-dropin", action="store_true", help="skip the autograd drop-in variant of the e2e run")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if cfg.get("frames") and args.steps == 400:
+        args.steps = cfg["frames"]
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, cfg)
     else:
-        gpu_arm(args)
+        gpu_arm(args, cfg)
 
 
 if __name__ == "__main__":

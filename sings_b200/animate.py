@@ -17,6 +17,18 @@ from . import dp
 from .step import AvatarStep, FrameInputs
 
 
+def frame_to_uint8(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(3,H,W) float image -> (H,W,3) uint8 on the device: the reference's clamp(0,1)
+    (gs_renderer_single.py:96) followed by the 8-bit conversion its writers apply on the host after
+    `.cpu()` (gs_trainer.py:716-719: `(image * 255).astype(uint8)` for cv2.imwrite) -- done before
+    the device -> host copy, which then moves a quarter of the bytes."""
+    q = torch.mul(img.clamp(0.0, 1.0), 255.0).to(torch.uint8).permute(1, 2, 0)
+    if out is None:
+        return q.contiguous()
+    out.copy_(q)
+    return out
+
+
 def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0, world: int = 1,
                   out: Optional[torch.Tensor] = None, clamp: bool = True) -> Tuple[int, int, torch.Tensor]:
     """Render this rank's share of `frames`; returns (lo, hi, images (hi-lo, 3, H, W)).

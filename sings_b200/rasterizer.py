@@ -23,6 +23,7 @@ Differences by design (B200-first, results identical):
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from typing import NamedTuple, Optional
 
@@ -96,15 +97,21 @@ def _f32c(t: Optional[torch.Tensor], name: str, dev) -> Optional[torch.Tensor]:
         return None
     if t.device != dev:
         raise ValueError(f"{name} must live on {dev}, got {t.device}")
-    if t.dtype != torch.float32:
-        t = t.float()
-    return t.contiguous()
+    if t.dtype is torch.float32 and t.is_contiguous():      # the usual case: no new tensor
+        return t
+    return t.float().contiguous()
 
 
+@functools.lru_cache(maxsize=64)
 def _sizes(P, W, H, L_cap):
+    """(geom, binning, img, acc) scratch bytes; one C call per distinct shape (cached)."""
     s = [C.c_size_t() for _ in range(4)]
     _lib.check(_lib.lib().sgs_raster_sizes(P, W, H, L_cap, *[C.byref(x) for x in s]), "sgs_raster_sizes")
-    return [int(x.value) for x in s]
+    return tuple(int(x.value) for x in s)
+
+
+def _align256(n: int) -> int:
+    return (n + 255) // 256 * 256
 
 
 def layout_info(P, W, H, L_cap) -> dict:
@@ -163,12 +170,25 @@ class _RasterizeGaussians(torch.autograd.Function):
         alpha = torch.empty(H, W, device=dev, dtype=torch.float32) if want_aux else None
         depth = torch.empty(H, W, device=dev, dtype=torch.float32) if want_aux else None
         global last_num_rendered
+        needs_grad = any(x is not None and x.requires_grad for x in
+                         (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
         while True:
-            gb, bb, ib, _ = _sizes(P, W, H, L_cap)
-            geom = torch.empty(gb, device=dev, dtype=torch.uint8)
-            binning = torch.empty(bb, device=dev, dtype=torch.uint8)
-            img = torch.empty(ib, device=dev, dtype=torch.uint8)
+            # ONE allocation for the frame's state (geometry records | binning | image state | backward
+            # accumulator) and ONE kernel that zeroes what forward and backward need zeroed: no memset
+            # node sits between two kernels (each costs them their overlapped launch), and the clear
+            # kernel in front lets the SH rows be fetched ahead of the dependency wait (EARLY_PARAMS:
+            # whatever produced `shs` finished before our clear kernel released its dependents).
+            gb, bb, ib, ab = _sizes(P, W, H, L_cap)
+            o1, o2, o3 = _align256(gb), _align256(gb) + _align256(bb), _align256(gb) + _align256(bb) + _align256(ib)
+            scratch = torch.empty(o3 + (ab if needs_grad else 0), device=dev, dtype=torch.uint8)
+            geom, binning, img = scratch[:gb], scratch[o1:o1 + bb], scratch[o2:o2 + ib]
+            acc = scratch[o3:o3 + ab] if needs_grad else None
             row = _pinned_row(di)
+            flags = int(bool(rs.debug))
+            if P > 0:
+                _lib.check(L_.sgs_raster_clear(P, W, H, L_cap, _lib.ptr(binning), _lib.ptr(acc), None, 0,
+                                               stream.cuda_stream), "sgs_raster_clear")
+                flags |= _lib.FLAG_PRECLEARED | _lib.FLAG_EARLY_PARAMS
             try:
                 rc = L_.sgs_raster_forward(
                     P, D, M, W, H, _lib.ptr(bg), _lib.ptr(m3), _lib.ptr(col), _lib.ptr(opa),
@@ -177,7 +197,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovy), _lib.ptr(shc), int(bool(rs.prefiltered)), L_cap,
                     _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img), _lib.ptr(color),
                     _lib.ptr(radii), _lib.ptr(alpha), _lib.ptr(depth), row.data_ptr(),
-                    stream.cuda_stream, int(bool(rs.debug)), None)
+                    stream.cuda_stream, flags, None)
                 _lib.check(rc, "sgs_raster_forward")
             except Exception:
                 if rs.debug:
@@ -187,8 +207,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise
             ev = torch.cuda.Event()
             ev.record(stream)
+            ctx.fwd_check = None
             if _ASYNC:
                 _pending.append((ev, row, L_cap, di))
+                ctx.fwd_check = (ev, row, L_cap)
                 break
             ev.synchronize()
             L, ovf = int(row[0]), int(row[1])
@@ -202,8 +224,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.dims = (P, D, M, W, H)
         ctx.has = (shc is not None, col is not None, cov is not None)
         ctx.opac_shape = tuple(opacities.shape) if opacities is not None else (P, 1)
+        ctx.acc_clean = acc is not None and P > 0
         ctx.save_for_backward(m3, shc, col, sca, rot, cov, radii, geom, binning, img, bg, view,
-                              proj, campos)
+                              proj, campos, acc)
         ctx.mark_non_differentiable(radii)
         if want_aux:
             ctx.mark_non_differentiable(alpha, depth)
@@ -216,20 +239,36 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         P, D, M, W, H = ctx.dims
         (m3, shc, col, sca, rot, cov, radii, geom, binning, img, bg, view, proj,
-         campos) = ctx.saved_tensors
+         campos, acc) = ctx.saved_tensors
         dev = m3.device
+        if ctx.fwd_check is not None:
+            # async mode: this frame's forward has not been examined yet -- gradients of a truncated pair
+            # list must not reach the optimizer (the event is long complete by now: no real wait)
+            ev, row, cap = ctx.fwd_check
+            ev.synchronize()
+            if int(row[1]):
+                raise _lib.SgsError(f"rasterizer pair list overflowed in the forward of this frame (needed "
+                                    f"{int(row[0])}, capacity {cap}); its gradients are not valid. Re-render the frame.")
         g = grad_out_color
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
         stream = torch.cuda.current_stream(dev)
-        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
-        d_means3D, d_means2D, d_colors, d_opac = e(P, 3), e(P, 3), e(P, 3), e(P, 1)
-        d_cov = e(P, 6)
-        d_sh = e(P, M, 3) if shc is not None else None
-        d_scales, d_rots = e(P, 3), e(P, 4)
-        acc_bytes = _sizes(P, W, H, ctx.L_cap)[3]
-        acc = torch.empty(acc_bytes, device=dev, dtype=torch.uint8)
+        # the per-Gaussian gradients as views of one allocation (rots and sh first: 16-byte aligned)
+        has_sh, has_col, has_cov = ctx.has
+        widths = [4, 3 * M if has_sh else 0, 3, 3, 3, 1, 6, 3]
+        flat = torch.empty(P * sum(widths), device=dev, dtype=torch.float32)
+        views, o = [], 0
+        for w_ in widths:
+            views.append(flat[o:o + P * w_].view(P, w_) if w_ else None)
+            o += P * w_
+        d_rots, d_sh, d_means3D, d_means2D, d_colors, d_opac, d_cov, d_scales = views
+        if d_sh is not None:
+            d_sh = d_sh.view(P, M, 3)
+        flags = int(bool(rs.debug))
+        if ctx.acc_clean:
+            flags |= _lib.FLAG_PRECLEARED      # cleared together with the forward's state, by one kernel
+            ctx.acc_clean = False              # a second backward of the same graph clears it again (memset)
         try:
             rc = L_.sgs_raster_backward(
                 P, D, M, W, H, _lib.ptr(bg), _lib.ptr(m3), _lib.ptr(col), _lib.ptr(sca),
@@ -239,14 +278,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _lib.ptr(binning), _lib.ptr(img), _lib.ptr(acc), _lib.ptr(d_means3D),
                 _lib.ptr(d_means2D), _lib.ptr(d_colors), _lib.ptr(d_opac), _lib.ptr(d_cov),
                 _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), None, None, None,
-                stream.cuda_stream, int(bool(rs.debug)), None)
+                stream.cuda_stream, flags, None)
             _lib.check(rc, "sgs_raster_backward")
         except Exception:
             if rs.debug:
                 torch.save((m3, radii, col, sca, rot, cov, g, shc, tuple(rs)), "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
             raise
-        has_sh, has_col, has_cov = ctx.has
         return (d_means3D, d_means2D, d_sh if has_sh else None, d_colors if has_col else None,
                 d_opac.reshape(ctx.opac_shape), None if has_cov else d_scales, None if has_cov else d_rots,
                 d_cov if has_cov else None, None, None)

@@ -245,10 +245,10 @@ class AvatarStep:
         if tm:
             L_.sgs_timing_record(tm, 11, st)
 
-    def capture(self, fr: FrameInputs, dL_dimage: torch.Tensor, loss_weight: Optional[torch.Tensor] = None,
+    def capture(self, fr: FrameInputs, dL_dimage: Optional[torch.Tensor], loss_weight: Optional[torch.Tensor] = None,
                 prologue=None, stages: bool = True, stage_mask: Optional[int] = None):
         """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
-        graph and return replay().  The launch sequence is static -- capacity-sized pair list,
+        graph and return replay() (dL_dimage None: the forward alone, e.g. animation frames).  The launch sequence is static -- capacity-sized pair list,
         device-side counts, no host round trip -- so the whole frame becomes one graph launch.
         `fr`'s tensors and `dL_dimage` are captured by address: refresh their contents in
         place before each replay.  Stage events keep working (external event-record nodes).
@@ -275,7 +275,8 @@ class AvatarStep:
             img = self.forward(fr)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
-            self.backward(dL_dimage)
+            if dL_dimage is not None:
+                self.backward(dL_dimage)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
         if prologue is None and loss_weight is None and not os.environ.get("SGS_TORCH_GRAPH"):
@@ -285,7 +286,8 @@ class AvatarStep:
             _lib.check(self.L.sgs_graph_begin(side.cuda_stream), "sgs_graph_begin")
             try:
                 self.forward(fr, stream=side)
-                self.backward(dL_dimage, stream=side)
+                if dL_dimage is not None:
+                    self.backward(dL_dimage, stream=side)
             finally:
                 rc = self.L.sgs_graph_end(side.cuda_stream, C.byref(h))
             _lib.check(rc, "sgs_graph_end")
@@ -303,7 +305,8 @@ class AvatarStep:
             img = self.forward(fr)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
-            self.backward(dL_dimage)
+            if dL_dimage is not None:
+                self.backward(dL_dimage)
         self.graph = g
         gen = self._gen
 
@@ -346,8 +349,17 @@ class AvatarStep:
         _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
         return float(ms.value)
 
-    def stage_ms(self) -> dict:
-        """Per-stage device times of the last forward+backward (needs timing=True)."""
+    def launches_per_frame(self, backward: bool = True) -> int:
+        """Kernels of this library that one frame launches (the bench line's gpu_launches)."""
+        info = (C.c_longlong * 16)()
+        _lib.check(self.L.sgs_raster_layout_info(self.N, self.Wd, self.H, self.L_cap, info), "layout")
+        tile_passes = int(info[10]) - 4
+        fwd = 1 + 1 + (0 if self.K else 1) + 1 + 4 + 1 + tile_passes + 1 + 1   # clear, pose->A, [LBS], geometry, 4 depth passes, emit, tile passes, ranges, blend
+        bwd = 1 + 1 + (0 if self.K else 1) + 1                                   # blend bwd, geometry bwd, [LBS bwd], pose bwd
+        return fwd + (bwd if backward else 0)
+
+    def stage_ms(self, backward: bool = True) -> dict:
+        """Per-stage device times of the last forward [+ backward] (needs timing=True)."""
         if not self.timing:
             raise _lib.SgsError("AvatarStep(timing=True) required")
         out = {}
@@ -358,6 +370,9 @@ class AvatarStep:
         else:
             stages = [("lbs_fwd", 8, 9), ("geometry", 0, 1), ("binning", 1, 3), ("blend_fwd", 3, 4),
                       ("blend_bwd", 5, 6), ("geometry_bwd", 6, 7), ("lbs_bwd", 10, 11), ("total", 8, 11)]
+        if not backward:     # forward-only frame (animation): the stages up to the blend
+            stages = [s for s in stages if s[0] in ("deform_geometry", "lbs_fwd", "geometry", "binning", "blend_fwd")]
+            stages.append(("total", 8, 4))
         for name, i, j in stages:
             _lib.check(self.L.sgs_timing_elapsed_ms(self.timing, i, j, C.byref(ms)), "elapsed")
             out[name] = float(ms.value)
