@@ -115,6 +115,14 @@ def check(code: int, what: str = "") -> None:
         raise SgsError(f"{what}: {msg} (code {code})" if what else f"{msg} (code {code})")
 
 
+def raw_stream(dev) -> int:
+    """cudaStream_t of torch's current stream on `dev` (the raw getter: ~1 us instead of the ~12 us of
+    torch.cuda.current_stream(), which the drop-in path would otherwise pay six times per step)."""
+    import torch
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def ptr(t) -> int | None:
     """data_ptr of a CUDA tensor (or None)."""
     if t is None:

@@ -44,7 +44,7 @@ class _PoseToA(torch.autograd.Function):
         B, J = pose_c.shape[0], pose_c.shape[1]
         A = torch.empty(B, J, 4, 4, device=pose.device, dtype=torch.float32)
         G = torch.empty(B, J, 12, device=pose.device, dtype=torch.float32)
-        st = torch.cuda.current_stream(pose.device).cuda_stream
+        st = _lib.raw_stream(pose.device)
         _lib.check(_lib.lib().sgs_pose_to_A(pose_c.data_ptr(), rest_c.data_ptr(), par.data_ptr(),
                                             _lib.ptr(inv_c), B, J, A.data_ptr(), G.data_ptr(), st),
                    "sgs_pose_to_A")
@@ -56,7 +56,7 @@ class _PoseToA(torch.autograd.Function):
         pose_c, rest_c, par, inv_c, G = ctx.saved_tensors
         B, J = pose_c.shape[0], pose_c.shape[1]
         d_pose = torch.empty_like(pose_c)
-        st = torch.cuda.current_stream(pose_c.device).cuda_stream
+        st = _lib.raw_stream(pose_c.device)
         _lib.check(_lib.lib().sgs_pose_to_A_bwd(pose_c.data_ptr(), rest_c.data_ptr(), par.data_ptr(),
                                                 _lib.ptr(inv_c), G.data_ptr(), _c(dA).data_ptr(), B, J,
                                                 d_pose.data_ptr(), st), "sgs_pose_to_A_bwd")
@@ -87,7 +87,7 @@ class _Rot6dConvert(torch.autograd.Function):
         d6_c = _c(d6).reshape(-1, 6)
         n = d6_c.shape[0]
         out = torch.empty((n, 9) if mode == 0 else (n, 3), device=d6.device, dtype=torch.float32)
-        st = torch.cuda.current_stream(d6.device).cuda_stream
+        st = _lib.raw_stream(d6.device)
         fn = _lib.lib().sgs_rot6d_to_matrix if mode == 0 else _lib.lib().sgs_rot6d_to_axis_angle
         _lib.check(fn(d6_c.data_ptr(), n, out.data_ptr(), st), "sgs_rot6d_to_*")
         ctx.save_for_backward(d6_c)
@@ -100,7 +100,7 @@ class _Rot6dConvert(torch.autograd.Function):
         n = d6_c.shape[0]
         g_c = _c(g).reshape(n, -1)
         g6 = torch.empty(n, 6, device=d6_c.device, dtype=torch.float32)
-        st = torch.cuda.current_stream(d6_c.device).cuda_stream
+        st = _lib.raw_stream(d6_c.device)
         fn = _lib.lib().sgs_rot6d_to_matrix_bwd if ctx.mode == 0 else _lib.lib().sgs_rot6d_to_axis_angle_bwd
         _lib.check(fn(d6_c.data_ptr(), g_c.data_ptr(), n, g6.data_ptr(), st), "sgs_rot6d_to_*_bwd")
         return g6.reshape(ctx.in_shape), None
@@ -134,7 +134,7 @@ class _DeformGaussians(torch.autograd.Function):
         rotq_o = torch.empty(B, N, 4, device=dev, dtype=torch.float32)
         sc_o = torch.empty(B, N, 3, device=dev, dtype=torch.float32)
         T_o = torch.empty(B, N, 4, 4, device=dev, dtype=torch.float32) if want_T else None
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = _lib.raw_stream(dev)
         fwd = _lib.lib().sgs_lbs_fwd_rot6d if rot6d else _lib.lib().sgs_lbs_fwd
         _lib.check(fwd(
             B, N, J, A_c.data_ptr(), xyz_c.data_ptr(), W_c.data_ptr(), _lib.ptr(rot_c),
@@ -168,7 +168,7 @@ class _DeformGaussians(torch.autograd.Function):
         d_A = z(B, J, 4, 4)
         d_ss = z(B) if ss_c is not None else None
         d_tr = z(B, 3) if tr_c is not None else None
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = _lib.raw_stream(dev)
         bwd = _lib.lib().sgs_lbs_bwd_rot6d if ctx.rot6d else _lib.lib().sgs_lbs_bwd
         _lib.check(bwd(
             B, N, J, A_c.data_ptr(), xyz_c.data_ptr(), W_c.data_ptr(), _lib.ptr(rot_c),

@@ -136,6 +136,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         if not means3D.is_cuda:
             raise _lib.SgsError("sings_b200 rasterizer needs CUDA tensors (no CPU fallback)")
         dev = means3D.device
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            # the library launches on `dev`'s current stream: make `dev` the current device for the call
+            with torch.cuda.device(dev):
+                return _RasterizeGaussians.forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales,
+                                                   rotations, cov3Ds_precomp, raster_settings, want_aux)
         P = means3D.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
         m3 = _f32c(means3D, "means3D", dev)
@@ -160,7 +165,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
             if opa is None or opa.numel() != P:
                 raise ValueError("opacities must have one value per Gaussian")
-        stream = torch.cuda.current_stream(dev)
+        st = _lib.raw_stream(dev)
         di = dev.index if dev.index is not None else torch.cuda.current_device()
         if _ASYNC:
             check_pending()
@@ -187,7 +192,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             flags = int(bool(rs.debug))
             if P > 0:
                 _lib.check(L_.sgs_raster_clear(P, W, H, L_cap, _lib.ptr(binning), _lib.ptr(acc), None, 0,
-                                               stream.cuda_stream), "sgs_raster_clear")
+                                               st), "sgs_raster_clear")
                 flags |= _lib.FLAG_PRECLEARED | _lib.FLAG_EARLY_PARAMS
             try:
                 rc = L_.sgs_raster_forward(
@@ -197,7 +202,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovy), _lib.ptr(shc), int(bool(rs.prefiltered)), L_cap,
                     _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img), _lib.ptr(color),
                     _lib.ptr(radii), _lib.ptr(alpha), _lib.ptr(depth), row.data_ptr(),
-                    stream.cuda_stream, flags, None)
+                    st, flags, None)
                 _lib.check(rc, "sgs_raster_forward")
             except Exception:
                 if rs.debug:
@@ -206,7 +211,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
             ev = torch.cuda.Event()
-            ev.record(stream)
+            ev.record()                        # current stream of the current device == `dev` (see the guard above)
             ctx.fwd_check = None
             if _ASYNC:
                 _pending.append((ev, row, L_cap, di))
@@ -241,6 +246,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         (m3, shc, col, sca, rot, cov, radii, geom, binning, img, bg, view, proj,
          campos, acc) = ctx.saved_tensors
         dev = m3.device
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return _RasterizeGaussians.backward(ctx, grad_out_color, *_unused)
         if ctx.fwd_check is not None:
             # async mode: this frame's forward has not been examined yet -- gradients of a truncated pair
             # list must not reach the optimizer (the event is long complete by now: no real wait)
@@ -253,7 +261,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         if g.dtype != torch.float32:
             g = g.float()
         g = g.contiguous()
-        stream = torch.cuda.current_stream(dev)
+        st = _lib.raw_stream(dev)
         # the per-Gaussian gradients as views of one allocation (rots and sh first: 16-byte aligned)
         has_sh, has_col, has_cov = ctx.has
         widths = [4, 3 * M if has_sh else 0, 3, 3, 3, 1, 6, 3]
@@ -278,7 +286,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _lib.ptr(binning), _lib.ptr(img), _lib.ptr(acc), _lib.ptr(d_means3D),
                 _lib.ptr(d_means2D), _lib.ptr(d_colors), _lib.ptr(d_opac), _lib.ptr(d_cov),
                 _lib.ptr(d_sh), _lib.ptr(d_scales), _lib.ptr(d_rots), None, None, None,
-                stream.cuda_stream, flags, None)
+                st, flags, None)
             _lib.check(rc, "sgs_raster_backward")
         except Exception:
             if rs.debug:
