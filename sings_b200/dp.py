@@ -59,12 +59,15 @@ class GradExchange:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def exchange(self, bucket: torch.Tensor, max_radii: torch.Tensor, async_op: bool = False,
-                 reset_step: bool = False):
+                 reset_step: bool = True):
         """All-reduce one step's bucket (SUM) and radii (MAX) in place and fold the statistics
         into the persistent accumulators.  With async_op=True returns a finish() callable so
-        the exchange overlaps whatever the caller launches next.  reset_step=True also clears
-        the step's statistics (the bucket's accum / denom slices and max_radii) for the next
-        view; on CUDA the fold and the clearing are one kernel (sgs_fold_stats)."""
+        the exchange overlaps whatever the caller launches next.  reset_step (default) also
+        clears the step's statistics (the bucket's accum / denom slices and max_radii) for the
+        next view; on CUDA the fold and the clearing are one kernel (sgs_fold_stats).
+        AvatarStep ACCUMULATES its statistics into those slices (+=), so a caller that passes
+        reset_step=False must call AvatarStep.reset_stats() itself before the next view --
+        otherwise the next exchange folds the same increments into the accumulators again."""
         handles = []
         if self.world > 1:
             handles.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
@@ -119,12 +122,15 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     when WORLD_SIZE > 1 (backend nccl on CUDA, gloo otherwise)."""
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # The exchange overlaps the next frame (it has RING-1 frames of slack), so it should be thin
-    # rather than fast: a cap on NCCL's CTAs keeps it from taking SMs and HBM bandwidth from the
-    # memory-bound head of the next frame.  Measured (profiles/README.md, v7), frames/s at 2 GPUs:
-    # NCCL's default 3708; capped at 32 CTAs 3831, 16 4006, 8 3967, 6 3875, 4 2770 (the exchange
-    # becomes the bottleneck); at 8 GPUs: 32 CTAs 13548, 16 13752, 8 14334.
-    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("SGS_NCCL_MAX_CTAS", "8"))
+    # NCCL's CTA budget.  A synchronous step (the optimizer needs the reduced gradients before the
+    # next forward) has the all-reduce on its critical path: it should be fast, so the cap is loose
+    # (measured at 2 GPUs, frames/s of the synchronous step: cap 8 -> 2902, 16 -> 3688, 32 -> 4047;
+    # profiles/README.md, round 2).  A pipelined exchange (overlapping the next frames) wants the
+    # opposite -- thin, so it stays out of the way of the memory-bound head of the next frame: cap 8
+    # (round 1: 8 GPUs 13548 frames/s at 32 CTAs, 14334 at 8).  SGS_NCCL_MAX_CTAS overrides; 0 = NCCL's own choice.
+    cap = os.environ.get("SGS_NCCL_MAX_CTAS", "32")
+    if cap != "0":
+        os.environ.setdefault("NCCL_MAX_CTAS", cap)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():

@@ -49,6 +49,30 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-20))
 
 
+def grad_errors(a, b):
+    """Three views of how far gradient tensor a is from the reference b:
+      max_rel  max|a-b| / max|b|            (the north star's "relative error", dominated by the largest entries)
+      l2_rel   ||a-b||_2 / ||b||_2          (per-tensor L2-relative error)
+      bad_frac fraction of ELEMENTS outside |a-b| <= 1e-3 |b| + 1e-6 max|b|  -- a small entry that is
+               100 % wrong passes the first two; this one catches it."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    d = np.abs(a - b)
+    mb = np.abs(b).max() + 1e-300
+    return dict(max_rel=float(d.max() / mb), l2_rel=float(np.linalg.norm(d) / (np.linalg.norm(b) + 1e-300)),
+                bad_frac=float((d > 1e-3 * np.abs(b) + 1e-6 * mb).mean()))
+
+
+def assert_grad_close(a, b, name="", tol=1e-3, pct=99.9):
+    """Gradient parity bar of the tests: tensor-relative and L2-relative error <= tol, and at least
+    `pct` % of the elements individually within 1e-3 relative (+ 1e-6 of the tensor's scale)."""
+    e = grad_errors(a, b)
+    assert e["max_rel"] <= tol, f"grad {name}: max-relative error {e}"
+    assert e["l2_rel"] <= tol, f"grad {name}: L2-relative error {e}"
+    assert e["bad_frac"] <= 1.0 - pct / 100.0, f"grad {name}: element-wise check {e}"
+    return e
+
+
 def inspect_state(ctx_tensors, P, W, H, L_cap):
     """Pull keys / point list / ranges / final_T / n_contrib out of the scratch buffers a
     forward saved (parity tests only)."""

@@ -55,7 +55,7 @@ def _worker(rank, world, port, q):
                 rd = torch.randint(0, 40, (N,), generator=gg).float()
             exp_sum += b
             exp_max = torch.maximum(exp_max, rd)
-        finish = ex.exchange(bucket, radii, async_op=True)
+        finish = ex.exchange(bucket, radii, async_op=True, reset_step=False)    # fresh step buffers every iteration here
         grads = finish()
         assert torch.allclose(grads, exp_sum[:n_param], atol=1e-6)
         accum += exp_sum[n_param:n_param + N]
@@ -106,8 +106,17 @@ def test_exchange_world_size_2_gloo():
 def test_single_process_exchange_is_local_accumulation():
     ex = dp.GradExchange(4, 8, "cpu")
     b = torch.arange(16, dtype=torch.float32)
-    g = ex.exchange(b, torch.tensor([1.0, 5.0, 0.0, 2.0]))
+    b0 = b.clone()
+    g = ex.exchange(b, torch.tensor([1.0, 5.0, 0.0, 2.0]), reset_step=False)
     assert torch.equal(g, b[:8]) and torch.equal(ex.xyz_gradient_accum, b[8:12])
-    ex.exchange(b, torch.tensor([3.0, 1.0, 0.0, 2.0]))
+    ex.exchange(b, torch.tensor([3.0, 1.0, 0.0, 2.0]), reset_step=False)
     assert torch.equal(ex.max_radii2D, torch.tensor([3.0, 5.0, 0.0, 2.0]))
     assert torch.equal(ex.denom, 2 * b[12:16])
+    # default (reset_step=True): the step's statistics are cleared after the fold, so an AvatarStep that
+    # keeps accumulating into the same slices is not counted twice
+    ex2 = dp.GradExchange(4, 8, "cpu")
+    r = torch.tensor([1.0, 5.0, 0.0, 2.0])
+    ex2.exchange(b, r)
+    assert float(b[8:].abs().max()) == 0.0 and float(r.abs().max()) == 0.0 and torch.equal(b[:8], b0[:8])
+    ex2.exchange(b, r)                                   # nothing new was accumulated: nothing is added
+    assert torch.equal(ex2.xyz_gradient_accum, b0[8:12]) and torch.equal(ex2.denom, b0[12:16])

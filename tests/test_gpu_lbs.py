@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import rel_err
+from helpers import assert_grad_close, rel_err
 from oracle import lbs_oracle as lo
 from sings_b200 import deform
 from sings_b200 import synthetic as syn
@@ -45,8 +45,7 @@ def test_against_reference_golden(path):
     if rc is not None:
         checks.append(("d_rotmat_canon", rc))
     for name, t in checks:
-        e = rel_err(t.grad.cpu().numpy(), ref[name].numpy())
-        assert e < GRAD_TOL, f"{name}: {e}"
+        assert_grad_close(t.grad.cpu().numpy(), ref[name].numpy(), name, tol=GRAD_TOL)
 
 
 def test_lbs_extra_signature_and_T_gradient():

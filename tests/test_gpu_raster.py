@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import inspect_state, make_scene, oracle_camera, raster_settings, rel_err
+from helpers import assert_grad_close, inspect_state, make_scene, oracle_camera, raster_settings, rel_err
 from oracle import raster_oracle as ro
 
 pytestmark = pytest.mark.gpu
@@ -85,8 +85,7 @@ def check_backward(sc, st, leaves, color, seed=1):
     for k, t in leaves.items():
         assert t.grad is not None, k
         assert t.grad.shape == t.shape
-        e = rel_err(t.grad.cpu().numpy(), gr[names[k]])
-        assert e <= GRAD_TOL, f"grad {k}: rel err {e}"
+        assert_grad_close(t.grad.cpu().numpy(), gr[names[k]], k, tol=GRAD_TOL)
     assert float(leaves["means2D"].grad[:, 2].abs().max()) == 0.0
 
 
