@@ -41,6 +41,15 @@ class FrameInputs:
     tanfovy: float
     smpl_scale: Optional[torch.Tensor] = None   # (1,)
 
+    def __post_init__(self):
+        # the library reads raw memory: every tensor must be float32 and C-contiguous.  (A camera
+        # matrix built as `W2C.T` in numpy is an F-ordered view; torch.as_tensor keeps its strides and
+        # data_ptr() would then hand the kernels the TRANSPOSE -- harmless only for an identity pose.)
+        for name in ("pose", "transl", "viewmatrix", "projmatrix", "campos", "bg", "smpl_scale"):
+            v = getattr(self, name)
+            if v is not None and (v.dtype != torch.float32 or not v.is_contiguous()):
+                setattr(self, name, v.float().contiguous())
+
 
 class AvatarStep:
     def __init__(self, xyz_canon, rotmat_canon, scales, opacity, shs, lbs_weights, rest_joints,
