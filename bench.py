@@ -656,9 +656,8 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
                   T8=torch.empty(3, H, W, device=dev, dtype=torch.uint8), ready=torch.cuda.Event(),
                   free=torch.cuda.Event()) for _ in range(NBUF)]
     loss_host = torch.zeros(NBUF).pin_memory()
-    frame_host = None if train else torch.zeros(NBUF, H, W, 3, dtype=torch.uint8).pin_memory()
-    frame_dev = None if train else [torch.empty(H, W, 3, device=dev, dtype=torch.uint8) for _ in range(NBUF)]
     loss_ev = [torch.cuda.Event() for _ in range(NBUF)]
+    writer = {"w": None}        # forward-only configs: the asynchronous frame writer (sings_b200.animate.FrameWriter)
     losses = []
     # diagnostics only (tools/e2e_probe.sh): "nog" skips the dL/dimage upload, "nosync" the lagged loss read
     PROBE = os.environ.get("SGS_E2E_PROBE", "")
@@ -679,17 +678,16 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
 
     def finish_step(i, result, sb):
         sb["free"].record(cur)
-        if train:
-            loss_host[i % NBUF:i % NBUF + 1].copy_(result.detach().reshape(1), non_blocking=True)
-        else:
-            # the finished frame: clamp(0,1) (gs_renderer_single.py:96), HWC uint8, into pinned memory
-            from sings_b200.animate import frame_to_uint8
-            frame_to_uint8(result, frame_dev[i % NBUF])
-            frame_host[i % NBUF].copy_(frame_dev[i % NBUF], non_blocking=True)
+        if not train:
+            # the finished frame: 8-bit conversion on the device, async copy into pinned memory, hand-over
+            # to the encoder threads (JPEG with --encode, else the frame is only delivered)
+            writer["w"].submit(result, f"{i:05d}")
+            return
+        loss_host[i % NBUF:i % NBUF + 1].copy_(result.detach().reshape(1), non_blocking=True)
         loss_ev[i % NBUF].record(cur)
         if i >= 1 and "nosync" not in PROBE:           # read the previous step's result
             loss_ev[(i - 1) % NBUF].synchronize()
-            losses.append(float(loss_host[(i - 1) % NBUF]) if train else float(frame_host[(i - 1) % NBUF][0, 0, 0]))
+            losses.append(float(loss_host[(i - 1) % NBUF]))
 
     # ---- C-ABI path ----
     pending = [None] * ring
@@ -765,11 +763,21 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
     def run(step, n):
         for sb in stage:
             sb["free"].record(cur)
+        if not train:
+            from sings_b200.animate import FrameWriter
+            out_dir = os.path.join(ROOT, "gpurun_out", f"anim_rank{rank}") if args.encode else None
+            writer["w"] = FrameWriter(out_dir, H, W, dev, depth=8, workers=8, ext="jpg", encode=args.encode,
+                                      sink=lambda name, arr: losses.append(float(arr[0, 0, 0])))
         prefetch(0)
         for i in range(n):
             step(i, n)
+        if not train:
+            assert writer["w"].close() == n                # every frame copied out (and encoded) inside the timed region
+            if args.encode:
+                losses.extend([0.0] * n)
+            return
         loss_ev[(n - 1) % NBUF].synchronize()
-        losses.append(float(loss_host[(n - 1) % NBUF]) if train else float(frame_host[(n - 1) % NBUF][0, 0, 0]))
+        losses.append(float(loss_host[(n - 1) % NBUF]))
 
     def timed(step, n):
         if world > 1:
@@ -805,7 +813,10 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
            "h2d_pinned_gbs_measured": round(h2d_gbs, 2),
            "h2d_gbs_implied": round(h2d * (n / (ms / 1e3)) / 1e9, 2),
            "pipeline": "inputs prefetched one step ahead on a copy stream; result read back one step late; "
-                       "all copies inside the timed region",
+                       "all copies inside the timed region" if train else
+                       "pose prefetched one step ahead; frame converted to 8 bits on the device, copied to pinned memory on "
+                       "a side stream and handed to host threads" + (" that JPEG-encode it (cv2)" if args.encode else "") +
+                       "; the timed region ends when the last frame has been delivered",
            "api": "C ABI (include/sings_b200.h) driven by sings_b200.step.AvatarStep with preallocated buffers"
                   + ("" if args.no_graph else ", one CUDA graph per frame")}
     if train and not args.no_graph and not PROBE:
@@ -856,6 +867,9 @@ def main():
     ap.add_argument("--no-ab", action="store_true", help="skip the CUB / eager-torch comparators")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-dropin", action="store_true", help="skip the autograd drop-in variant of the e2e run")
+    ap.add_argument("--encode", action="store_true",
+                    help="forward-only configs: the e2e loop also JPEG-encodes every frame to gpurun_out/anim_rank*/ (cv2, "
+                         "host threads), like the reference's animation loop")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if cfg.get("frames") and args.steps == 400:

@@ -163,6 +163,13 @@ int sgs_densify_stats(int P, const float* grad_means2D, const int* radii,
 int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii,
                    float* xyz_gradient_accum, float* denom, float* max_radii2D, sgs_stream_t stream);
 
+/* Animation output, device half: (3,H,W) float image -> (H,W,3) uint8 with the arithmetic of
+ * sings/rec/trainer/gs_trainer.py:716-717 -- clamp(0,1), float32 multiply by 255, truncation
+ * (`.astype('uint8')`), CHW -> HWC -- and, with bgr != 0, the RGB -> BGR swap of :718
+ * (cv2.cvtColor) folded in.  One pass on the device instead of a float32 device->host copy and
+ * four numpy passes on the host; `out` (4-byte aligned) is then copied out at a quarter of the bytes. */
+int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* out, sgs_stream_t stream);
+
 /* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
  * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]
  * rasterizer_impl.cu).  The result is in (keys,vals) when *result_in_tmp (host) == 0, else

@@ -17,16 +17,103 @@ from . import dp
 from .step import AvatarStep, FrameInputs
 
 
-def frame_to_uint8(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(3,H,W) float image -> (H,W,3) uint8 on the device: the reference's clamp(0,1)
-    (gs_renderer_single.py:96) followed by the 8-bit conversion its writers apply on the host after
-    `.cpu()` (gs_trainer.py:716-719: `(image * 255).astype(uint8)` for cv2.imwrite) -- done before
-    the device -> host copy, which then moves a quarter of the bytes."""
-    q = torch.mul(img.clamp(0.0, 1.0), 255.0).to(torch.uint8).permute(1, 2, 0)
+def frame_to_uint8(img: torch.Tensor, out: Optional[torch.Tensor] = None, bgr: bool = False) -> torch.Tensor:
+    """(3,H,W) float32 CUDA image -> (H,W,3) uint8 on the device (sgs_frame_to_u8): the reference's
+    `(image.cpu().clamp(0, 1).permute(1, 2, 0).numpy() * 255).astype('uint8')` (gs_trainer.py:716-717)
+    and, with bgr=True, its `cv2.cvtColor(..., COLOR_RGB2BGR)` (:718) -- same bits, done BEFORE the
+    device -> host copy, which then moves a quarter of the bytes."""
+    from . import _lib
+    if not img.is_cuda:
+        raise _lib.SgsError("frame_to_uint8 needs a CUDA image (no CPU fallback)")
+    img = img.detach()
+    if img.dtype != torch.float32 or not img.is_contiguous():
+        img = img.float().contiguous()
+    _, H, W = img.shape
     if out is None:
-        return q.contiguous()
-    out.copy_(q)
+        out = torch.empty(H, W, 3, device=img.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().sgs_frame_to_u8(img.data_ptr(), H, W, int(bgr), out.data_ptr(), _lib.raw_stream(img.device)),
+               "sgs_frame_to_u8")
     return out
+
+
+class FrameWriter:
+    """Asynchronous output path of the animation loop (gs_trainer.py:716-728 writes every frame
+    synchronously: blocking float32 D2H, numpy conversion, cv2.imwrite, all on the render thread).
+
+    submit(image, name) converts the frame to 8 bits on the device, starts its copy into one of
+    `depth` pinned host buffers on a side stream and returns at once; encoder threads pick the
+    buffer up when its copy event has completed and write `<dir>/<name>.<ext>` with cv2 (the
+    reference's encoder; BGR order is produced on the device).  Rendering, copy and encoding of
+    different frames overlap; submit() only blocks when all `depth` buffers are in flight.
+    `encode=False` stops after the copy (frames are handed to `sink(name, array)` if given)."""
+
+    def __init__(self, out_dir: Optional[str], H: int, W: int, device, depth: int = 8, workers: int = 4,
+                 ext: str = "jpg", encode: bool = True, sink=None):
+        import queue
+        import threading
+        self.dir, self.ext, self.encode, self.sink = out_dir, ext, encode and out_dir is not None, sink
+        if self.encode:
+            import os
+            os.makedirs(out_dir, exist_ok=True)
+        self.dev = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.slots = [dict(dev=torch.empty(H, W, 3, device=self.dev, dtype=torch.uint8),
+                           host=torch.empty(H, W, 3, dtype=torch.uint8).pin_memory(),
+                           ready=torch.cuda.Event(), done=threading.Event()) for _ in range(depth)]
+        for s in self.slots:
+            s["done"].set()
+        self.q = queue.Queue()
+        self.n = 0
+        self.bytes = 0
+        self.errors = []
+        self.threads = [threading.Thread(target=self._work, daemon=True) for _ in range(max(1, workers))]
+        for th in self.threads:
+            th.start()
+
+    def _work(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            slot, name = item
+            try:
+                slot["ready"].synchronize()                    # this frame's copy has landed
+                arr = slot["host"].numpy()
+                if self.encode:
+                    import cv2
+                    if not cv2.imwrite(f"{self.dir}/{name}.{self.ext}", arr):
+                        raise IOError(f"cv2.imwrite failed for {name}")
+                elif self.sink is not None:
+                    self.sink(name, arr)
+            except Exception as e:                             # surfaced by close()
+                self.errors.append(e)
+            finally:
+                slot["done"].set()
+
+    def submit(self, image: torch.Tensor, name: str) -> None:
+        slot = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        slot["done"].wait()                                    # the encoder is finished with this buffer
+        slot["done"].clear()
+        frame_to_uint8(image, slot["dev"], bgr=self.encode)    # on the render stream, right behind the blend
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ev)
+            slot["host"].copy_(slot["dev"], non_blocking=True)
+            slot["ready"].record(self.copy_stream)
+        self.bytes += slot["host"].numel()
+        self.q.put((slot, name))
+
+    def close(self) -> int:
+        """Wait for every submitted frame; returns the number written.  Raises the first encoder error."""
+        for _ in self.threads:
+            self.q.put(None)
+        for th in self.threads:
+            th.join()
+        if self.errors:
+            raise self.errors[0]
+        return self.n
 
 
 def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0, world: int = 1,

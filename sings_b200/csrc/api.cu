@@ -79,7 +79,7 @@ static inline void tick(void* timing, int i, cudaStream_t s) {
 
 extern "C" {
 
-int sgs_version(void) { return 100; }
+int sgs_version(void) { return 200; }
 
 int sgs_timing_create(int n_events, void** handle) {
     if (n_events < 1 || !handle) return SGS_ERR_BAD_ARG;
@@ -458,6 +458,12 @@ int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_
         return SGS_ERR_BAD_ARG;
     return launch_fold_stats(P, step_accum, step_denom, step_max_radii, xyz_gradient_accum, denom, max_radii2D,
                              (cudaStream_t)stream);
+}
+
+int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* out, sgs_stream_t stream) {
+    if (H < 0 || W < 0 || (H > 0 && W > 0 && (!image || !out))) return SGS_ERR_BAD_ARG;
+    if ((uintptr_t)out & 3) return SGS_ERR_MISALIGNED;
+    return launch_frame_to_u8(image, H, W, bgr, out, (cudaStream_t)stream);
 }
 
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }

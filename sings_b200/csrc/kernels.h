@@ -125,6 +125,9 @@ int launch_geometry_bwd(const GeomBwdArgs& a, const char* geom, cudaStream_t str
 int launch_mark_visible(int P, const float* means3D, const float* view, unsigned char* present,
                         cudaStream_t stream);
 
+// (3,H,W) float image -> (H,W,3) uint8: clamp(0,1) * 255 truncated, optional RGB -> BGR (frame_out.cu)
+int launch_frame_to_u8(const float* img, int H, int W, int bgr, unsigned char* out, cudaStream_t stream);
+
 int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream);
 int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
                       float* denom, float* max_radii, cudaStream_t stream);

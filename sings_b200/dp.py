@@ -131,6 +131,9 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     cap = os.environ.get("SGS_NCCL_MAX_CTAS", "32")
     if cap != "0":
         os.environ.setdefault("NCCL_MAX_CTAS", cap)
+    # the 52.8 MB gradient bucket at 8 GPUs (tools/nccl_ar_probe.sh, profiles/r02_nccl_allreduce_n8.txt):
+    # NCCL's own choice 0.233 ms, Ring 0.206 ms, Tree 0.273 ms (NVLS is not offered on this box)
+    os.environ.setdefault("NCCL_ALGO", "Ring")
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():

@@ -9,7 +9,7 @@ for c in $CFGS; do
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/${TAG}_n${N}_$c.json"))
+    d = json.loads(open("gpurun_out/${TAG}_n${N}_$c.json").read().strip().splitlines()[-1])
     dp = d.get("dp") or {}
     print("$c N=$N value", round(d["value"], 1), "ms", round(d["ms_per_step"], 4), "| pipelined", dp.get("pipelined", {}).get("value"), "| e2e", round(d["e2e"]["value"], 1), "| clocks", d["clocks"])
 except Exception as e:
