@@ -303,7 +303,7 @@ static int raster_backward_impl(int P, int D, int M, int W, int H, const float* 
     if (!bg || !geom || !binning || !img || !acc || !dL_dout_color || !dL_dmeans2D || !dL_dopacity ||
         (P > 0 && !radii) || (shs && !dL_dsh) || L_cap < 1)
         return SGS_ERR_BAD_ARG;
-    if (!lf && (!dL_dmeans3D || !dL_dcolors)) return SGS_ERR_BAD_ARG;
+    if (!lf && (!dL_dmeans3D || (colors_precomp && !dL_dcolors))) return SGS_ERR_BAD_ARG;
     if (((uintptr_t)acc & 15) || (dL_drots && ((uintptr_t)dL_drots & 15))) return SGS_ERR_MISALIGNED;
     const int n_stat = (xyz_gradient_accum != nullptr) + (denom != nullptr) + (max_radii2D != nullptr);
     if (n_stat != 0 && n_stat != 3) return SGS_ERR_BAD_ARG;
@@ -425,10 +425,22 @@ int sgs_avatar_backward(const sgs_deform_args* d, int D, int M, int W, int H, co
     if (rc) return rc;
     if (!d->d_xyz_canon || !d->d_scales || !d->d_A || !d->d_pose || (d->rot_canon && !d->d_rot_canon))
         return SGS_ERR_BAD_ARG;
-    rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
-                              viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
-                              geom, binning, img, acc, nullptr, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
-                              nullptr, nullptr, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing, &f);
+    if (d->g_xyz && d->g_rotq && d->g_scales) {
+        // split arrangement: the rasterizer's per-Gaussian backward writes dL/d(mean, quaternion, scale) to
+        // the caller's scratch, the packed-weights LBS backward (same device code as the fused epilogue) reads them
+        rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
+                                  viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
+                                  geom, binning, img, acc, d->g_xyz, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
+                                  d->g_scales, d->g_rotq, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing,
+                                  nullptr);
+        if (rc) return rc;
+        rc = launch_lbs_bwd_packed(f, d->N, d->g_xyz, d->g_rotq, d->g_scales, (cudaStream_t)stream);
+    } else {
+        rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
+                                  viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
+                                  geom, binning, img, acc, nullptr, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
+                                  nullptr, nullptr, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing, &f);
+    }
     if (rc) return rc;
     tick(timing, 10, (cudaStream_t)stream);
     rc = launch_pose_to_A_bwd(d->pose, d->rest, d->parents, d->inv_A_t2cano, d->G, d->d_A, 1, d->J, d->d_pose,

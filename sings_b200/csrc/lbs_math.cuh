@@ -273,4 +273,119 @@ __device__ __forceinline__ void deform_one(const LbsFuse& f, const float4* sA, c
     mat_to_quat(Rp, q);
 }
 
+// ---- backward of the deform segment for one Gaussian: upstream gradients
+// g_x (deformed mean), g_q (quaternion), g_s (deformed scale) -> canonical-parameter gradients
+// (written to lf.d_xyz / d_scales / d_rot) and this Gaussian's dT (3x4) for dL/dA = sum_n W dT_n ----
+__device__ __forceinline__ void lbs_bwd_one(const LbsFuse& lf, const float4* sA, const CanonG& cg, int idx,
+                                            const float* g_x, const float* g_q, const float* g_s, float* dT) {
+    const bool iso = lf.rot == nullptr;
+    const float sm = lf.smpl_scale ? __ldg(lf.smpl_scale) : 1.0f;
+    float T[12];
+    blend_T_packed(sA, cg.pw, lf.K, T);
+    float Rp[9], gR[9];
+    compose_rot(T, cg.Rc, iso, Rp);
+    mat_to_quat_bwd(Rp, g_q, gR);
+    const float h[3] = {g_x[0] * sm, g_x[1] * sm, g_x[2] * sm};      // dL/d(verts)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float rot = iso ? gR[3 * r + c]
+                                  : gR[3 * r] * cg.Rc[3 * c] + gR[3 * r + 1] * cg.Rc[3 * c + 1] + gR[3 * r + 2] * cg.Rc[3 * c + 2];
+            dT[4 * r + c] = h[r] * cg.x[c] + rot;
+        }
+        dT[4 * r + 3] = h[r];
+    }
+    // d xyz_canon = T3^T h ; d scales = g_s * smpl_scale ; d R_canon = T3^T gR
+    lf.d_xyz[3 * (size_t)idx] = T[0] * h[0] + T[4] * h[1] + T[8] * h[2];
+    lf.d_xyz[3 * (size_t)idx + 1] = T[1] * h[0] + T[5] * h[1] + T[9] * h[2];
+    lf.d_xyz[3 * (size_t)idx + 2] = T[2] * h[0] + T[6] * h[1] + T[10] * h[2];
+    lf.d_scales[3 * (size_t)idx] = g_s[0] * sm; lf.d_scales[3 * (size_t)idx + 1] = g_s[1] * sm;
+    lf.d_scales[3 * (size_t)idx + 2] = g_s[2] * sm;
+    if (lf.d_rot && !iso) {
+        float dRc[9];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                dRc[3 * r + c] = T[r] * gR[c] + T[4 + r] * gR[3 + c] + T[8 + r] * gR[6 + c];
+        if (lf.rot6d) {
+            float in6[6], g6[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) in6[k] = __ldg(lf.rot + 6 * (size_t)idx + k);
+            rot6d_to_mat_bwd(in6, dRc, g6);
+#pragma unroll
+            for (int k = 0; k < 6; k++) lf.d_rot[6 * (size_t)idx + k] = g6[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) lf.d_rot[9 * (size_t)idx + k] = dRc[k];
+        }
+    }
+}
+
+// Shared memory of the CTA-level reduction below, for a CTA of THREADS threads and J joints.
+template <int THREADS>
+__host__ __device__ constexpr size_t lbs_reduce_smem_bytes(int J, int K) {
+    return (size_t)THREADS * 48 + (size_t)THREADS * K * 8 + (size_t)(THREADS / 32) * J * 48;
+}
+
+// dL/dA[j] = sum_n W[n,j] dT_n and dL/dtransl = sum_n g_x over the CTA's Gaussians, with the
+// packed weights: every warp folds its 32 rows, one after the other, into a private J x 12 tile
+// (lane = (slot, float4 group of the 3x4 block): the joints of one row are distinct, so a row is
+// one conflict-free LDS.128 / 4 FMA / STS.128 per lane); the CTA then adds its warps' tiles and
+// issues one atomic per non-zero entry.  `raw`: lbs_reduce_smem_bytes, 16-byte aligned.  All
+// threads of the CTA call it (dT = 0 and weights 0 for threads without a Gaussian).
+template <int THREADS>
+__device__ __forceinline__ void lbs_bwd_reduce(const LbsFuse& lf, char* raw, const float* dT, const float* g_x,
+                                               const PackedW& pw, bool live) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* const s_dT = reinterpret_cast<float4*>(raw);                                  // [THREADS][3]
+    float2* const s_wj = reinterpret_cast<float2*>(raw + (size_t)THREADS * 48);           // [THREADS][K] (weight, joint bits)
+    float* const s_part = reinterpret_cast<float*>(raw + (size_t)THREADS * 48 + (size_t)THREADS * lf.K * 8);   // [warps][J][12]
+    for (int f = tid; f < (THREADS / 32) * lf.J * 12; f += THREADS) s_part[f] = 0.0f;
+    if (lf.d_transl) {
+        const float t0 = warp_sum(live ? g_x[0] : 0.0f), t1 = warp_sum(live ? g_x[1] : 0.0f), t2 = warp_sum(live ? g_x[2] : 0.0f);
+        if (lane == 0) { atomicAdd(lf.d_transl, t0); atomicAdd(lf.d_transl + 1, t1); atomicAdd(lf.d_transl + 2, t2); }
+    }
+    s_dT[tid * 3] = make_float4(dT[0], dT[1], dT[2], dT[3]);
+    s_dT[tid * 3 + 1] = make_float4(dT[4], dT[5], dT[6], dT[7]);
+    s_dT[tid * 3 + 2] = make_float4(dT[8], dT[9], dT[10], dT[11]);
+#pragma unroll
+    for (int k = 0; k < LBS_PACK_MAX_K; k++)
+        if (k < lf.K)
+            s_wj[(size_t)tid * lf.K + k] = make_float2(live ? pw.w[k] : 0.0f,
+                                                       __uint_as_float((pw.idx[k >> 2] >> (8 * (k & 3))) & 0xffu));
+    __syncthreads();                           // the tiles are zero; (the rows below are this warp's own)
+    float4* const tile4 = reinterpret_cast<float4*>(s_part + (size_t)warp * lf.J * 12);
+    const float4* const dT4 = s_dT + (size_t)warp * 32 * 3;
+    const float2* const wj = s_wj + (size_t)warp * 32 * lf.K;
+    const int kk = lane / 3, g = lane - 3 * kk;          // 10 slots x 3 float4 groups per round (lanes 30, 31 idle)
+    for (int r0 = 0; r0 < lf.K; r0 += 10) {
+        const int k = r0 + kk;
+        const bool act = kk < 10 && k < lf.K;
+#pragma unroll 4
+        for (int l = 0; l < 32; l++) {
+            if (act) {
+                const float2 e = wj[l * lf.K + k];
+                if (e.x != 0.0f) {
+                    const unsigned j = __float_as_uint(e.y);
+                    const float4 d = dT4[l * 3 + g];
+                    float4 v = tile4[j * 3 + g];
+                    v.x = fmaf(e.x, d.x, v.x); v.y = fmaf(e.x, d.y, v.y); v.z = fmaf(e.x, d.z, v.z); v.w = fmaf(e.x, d.w, v.w);
+                    tile4[j * 3 + g] = v;
+                }
+            }
+            __syncwarp();      // row l is folded in before any lane reads a tile entry for row l + 1
+        }
+    }
+    __syncthreads();
+    for (int oidx = tid; oidx < lf.J * 12; oidx += THREADS) {
+        float accv = 0.0f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) accv += s_part[(size_t)w * lf.J * 12 + oidx];
+        const int j = oidx / 12, c = oidx - j * 12;
+        if (accv != 0.0f) atomicAdd(lf.d_A + (size_t)j * 16 + 4 * (c >> 2) + (c & 3), accv);
+    }
+}
+
 }  // namespace sgs

@@ -67,9 +67,7 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
     if (a.early_params) stage_sh();
     // FUSE: canonical attributes (model parameters) and this frame's joint transforms (written by
     // the forward, many kernels ago) are fetched ahead of the wait too
-    float4* const s_A = s_sh + (size_t)GB_THREADS * S4;                               // [J][3]
-    float* const s_dT = reinterpret_cast<float*>(s_A + 64 * 3);                        // [256][12]
-    float* const s_part = s_dT + GB_THREADS * 12;                                      // [8][J][12]
+    float4* const s_A = s_sh + (size_t)GB_THREADS * S4;                               // [J][3], then the reduction's arrays
     CanonG cg;
     if constexpr (FUSE) {
 #pragma unroll
@@ -77,7 +75,6 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
         if (in_range) load_canon(lf, idx, cg);
         for (int f = tid; f < lf.J * 3; f += GB_THREADS)
             s_A[f] = reinterpret_cast<const float4*>(lf.A)[(f / 3) * 4 + f % 3];
-        for (int f = tid; f < (GB_THREADS / 32) * lf.J * 12; f += GB_THREADS) s_part[f] = 0.0f;
     }
     pdl_sync();
     if (tid < 16) s_cam[tid] = a.view[tid];
@@ -319,110 +316,11 @@ geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
         }
     } else {
         // ---- deform-segment backward on g_x = dmean, g_q = drot, g_s = dscale ----
-        const int lane = tid & 31, warp = tid >> 5;
-        const bool iso = lf.rot == nullptr;
         float dT[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) dT[k] = 0.0f;
-        float gtr[3] = {0, 0, 0};
-        if (in_range) {
-            const float sm = lf.smpl_scale ? __ldg(lf.smpl_scale) : 1.0f;
-            float T[12];
-            blend_T_packed(s_A, cg.pw, lf.K, T);
-            float Rp[9], gR[9];
-            compose_rot(T, cg.Rc, iso, Rp);
-            mat_to_quat_bwd(Rp, drot, gR);
-            gtr[0] = dmean[0]; gtr[1] = dmean[1]; gtr[2] = dmean[2];
-            const float h[3] = {dmean[0] * sm, dmean[1] * sm, dmean[2] * sm};      // dL/d(verts)
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float rot = iso ? gR[3 * r + c]
-                                          : gR[3 * r] * cg.Rc[3 * c] + gR[3 * r + 1] * cg.Rc[3 * c + 1] + gR[3 * r + 2] * cg.Rc[3 * c + 2];
-                    dT[4 * r + c] = h[r] * cg.x[c] + rot;
-                }
-                dT[4 * r + 3] = h[r];
-            }
-            // d xyz_canon = T3^T h ; d scales = g_s * smpl_scale ; d R_canon = T3^T gR
-            lf.d_xyz[3 * (size_t)idx] = T[0] * h[0] + T[4] * h[1] + T[8] * h[2];
-            lf.d_xyz[3 * (size_t)idx + 1] = T[1] * h[0] + T[5] * h[1] + T[9] * h[2];
-            lf.d_xyz[3 * (size_t)idx + 2] = T[2] * h[0] + T[6] * h[1] + T[10] * h[2];
-            lf.d_scales[3 * (size_t)idx] = dscale[0] * sm; lf.d_scales[3 * (size_t)idx + 1] = dscale[1] * sm;
-            lf.d_scales[3 * (size_t)idx + 2] = dscale[2] * sm;
-            if (lf.d_rot && !iso) {
-                float dRc[9];
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        dRc[3 * r + c] = T[r] * gR[c] + T[4 + r] * gR[3 + c] + T[8 + r] * gR[6 + c];
-                if (lf.rot6d) {
-                    float in6[6], g6[6];
-#pragma unroll
-                    for (int k = 0; k < 6; k++) in6[k] = __ldg(lf.rot + 6 * (size_t)idx + k);
-                    rot6d_to_mat_bwd(in6, dRc, g6);
-#pragma unroll
-                    for (int k = 0; k < 6; k++) lf.d_rot[6 * (size_t)idx + k] = g6[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 9; k++) lf.d_rot[9 * (size_t)idx + k] = dRc[k];
-                }
-            }
-        }
-        if (lf.d_transl) {
-            const float t0 = warp_sum(gtr[0]), t1 = warp_sum(gtr[1]), t2 = warp_sum(gtr[2]);
-            if (lane == 0) { atomicAdd(lf.d_transl, t0); atomicAdd(lf.d_transl + 1, t1); atomicAdd(lf.d_transl + 2, t2); }
-        }
-        // ---- dA: this warp's 32 rows, one after the other.  Row l: lanes (slot k2, entry e) for two
-        // slots at a time add w_k dT_l[e] to tile[j_k][e] -- the joints of one row are distinct.
-        float4* dTrow = reinterpret_cast<float4*>(s_dT) + tid * 3;
-        dTrow[0] = make_float4(dT[0], dT[1], dT[2], dT[3]);
-        dTrow[1] = make_float4(dT[4], dT[5], dT[6], dT[7]);
-        dTrow[2] = make_float4(dT[8], dT[9], dT[10], dT[11]);
-        // the row's packed weights go through shared memory too (the SH rows are done with: every
-        // thread has written its dL/dsh row and the block has passed the barrier in front of the
-        // write-out ... which reads them: so use the dT tile's neighbour, the per-warp staging below)
-        __shared__ float s_w[GB_THREADS / 32][32][LBS_PACK_MAX_K];
-        __shared__ unsigned char s_j[GB_THREADS / 32][32][LBS_PACK_MAX_K];
-#pragma unroll
-        for (int k = 0; k < LBS_PACK_MAX_K; k++) {
-            if (k < lf.K) {
-                s_w[warp][lane][k] = in_range ? cg.pw.w[k] : 0.0f;
-                s_j[warp][lane][k] = (unsigned char)((cg.pw.idx[k >> 2] >> (8 * (k & 3))) & 0xffu);
-            }
-        }
-        __syncwarp();
-        // lane = (slot kk of a round of 8 slots, float4 group g of the 3x4 entry block): row l adds
-        // w_k dT_l to tile[j_k] with one LDS.128 / 4 FMA / STS.128 per lane; rows in sequence.
-        float4* const tile4 = reinterpret_cast<float4*>(s_part + (size_t)warp * lf.J * 12);
-        const float4* const dT4 = reinterpret_cast<const float4*>(s_dT) + (size_t)warp * 32 * 3;
-        const int kk = lane / 3, g = lane - 3 * kk;
-        if (kk < 8) {
-#pragma unroll 1
-            for (int l = 0; l < 32; l++) {
-#pragma unroll 1
-                for (int r0 = 0; r0 < lf.K; r0 += 8) {
-                    const int k = r0 + kk;
-                    const float w = k < lf.K ? s_w[warp][l][k] : 0.0f;
-                    if (w != 0.0f) {
-                        const int j = s_j[warp][l][k];
-                        const float4 d = dT4[l * 3 + g];
-                        float4 v = tile4[j * 3 + g];
-                        v.x = fmaf(w, d.x, v.x); v.y = fmaf(w, d.y, v.y); v.z = fmaf(w, d.z, v.z); v.w = fmaf(w, d.w, v.w);
-                        tile4[j * 3 + g] = v;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int oidx = tid; oidx < lf.J * 12; oidx += GB_THREADS) {
-            float accv = 0.0f;
-#pragma unroll
-            for (int w = 0; w < GB_THREADS / 32; w++) accv += s_part[(size_t)w * lf.J * 12 + oidx];
-            const int j = oidx / 12, c = oidx - j * 12;
-            if (accv != 0.0f) atomicAdd(lf.d_A + (size_t)j * 16 + 4 * (c >> 2) + (c & 3), accv);
-        }
+        if (in_range) lbs_bwd_one(lf, s_A, cg, idx, dmean, drot, dscale, dT);
+        lbs_bwd_reduce<GB_THREADS>(lf, reinterpret_cast<char*>(s_A + 64 * 3), dT, dmean, cg.pw, in_range);
     }
 }
 
@@ -433,7 +331,7 @@ static int launch_gb_t(const GeomBwdArgs& b, const float4* rec, int blocks, bool
     if (lf) {
         if constexpr (HAS_SH) {
             if (!vec16) return SGS_ERR_MISALIGNED;
-            smem += (size_t)64 * 3 * 16 + (size_t)GB_THREADS * 48 + (size_t)(GB_THREADS / 32) * lf->J * 48;
+            smem += (size_t)64 * 3 * 16 + lbs_reduce_smem_bytes<GB_THREADS>(lf->J, lf->K);
             auto k = geometry_bwd_kernel<D, true, true, true>;
             SGS_CUDA_OK(set_max_smem(k, smem));
             SGS_CUDA_OK(launch_pdl(k, blocks, GB_THREADS, smem, st, b, rec, *lf));
