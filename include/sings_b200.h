@@ -304,13 +304,6 @@ typedef struct sgs_deform_args {
     float* d_A;                  /* (J,16) accumulated: the caller zeroes it (sgs_raster_clear `extra`) */
     float* d_transl;             /* (3) accumulated likewise, or null */
     float* d_pose;               /* (J,3) */
-    /* optional scratch (N,3), (N,4) 16-byte aligned, (N,3): when all three are set, the backward runs as
-     * TWO per-Gaussian kernels (rasterizer backward, then the packed-weights LBS backward) with these
-     * gradients in between, instead of one fused kernel -- same results, the faster arrangement when
-     * the fused kernel's register / shared-memory footprint costs more than the round trip saves */
-    float* g_xyz;
-    float* g_rotq;
-    float* g_scales;
 } sgs_deform_args;
 
 /* Rasterizer arguments as in sgs_raster_forward / sgs_raster_backward (SH colours, scales +

@@ -24,7 +24,7 @@ class DeformArgs(C.Structure):
         (name, _vp) for name in (
             "pose", "rest", "parents", "inv_A_t2cano", "xyz_canon", "scales", "rot_canon", "wq", "iq",
             "smpl_scale", "transl", "A", "G", "xyz", "rotq", "scales_out", "d_xyz_canon", "d_rot_canon",
-            "d_scales", "d_A", "d_transl", "d_pose", "g_xyz", "g_rotq", "g_scales")]
+            "d_scales", "d_A", "d_transl", "d_pose")]
 
 
 _SIGNATURES = {

@@ -425,22 +425,13 @@ int sgs_avatar_backward(const sgs_deform_args* d, int D, int M, int W, int H, co
     if (rc) return rc;
     if (!d->d_xyz_canon || !d->d_scales || !d->d_A || !d->d_pose || (d->rot_canon && !d->d_rot_canon))
         return SGS_ERR_BAD_ARG;
-    if (d->g_xyz && d->g_rotq && d->g_scales) {
-        // split arrangement: the rasterizer's per-Gaussian backward writes dL/d(mean, quaternion, scale) to
-        // the caller's scratch, the packed-weights LBS backward (same device code as the fused epilogue) reads them
-        rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
-                                  viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
-                                  geom, binning, img, acc, d->g_xyz, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
-                                  d->g_scales, d->g_rotq, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing,
-                                  nullptr);
-        if (rc) return rc;
-        rc = launch_lbs_bwd_packed(f, d->N, d->g_xyz, d->g_rotq, d->g_scales, (cudaStream_t)stream);
-    } else {
-        rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
-                                  viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
-                                  geom, binning, img, acc, nullptr, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
-                                  nullptr, nullptr, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing, &f);
-    }
+    // (A split arrangement -- the rasterizer's per-Gaussian backward and a packed-weights LBS backward as
+    // two kernels -- was measured slower than the fused kernel: 101 us against 84 us for the stage at
+    // 200k Gaussians; profiles/README.md, round 2.)
+    rc = raster_backward_impl(d->N, D, M, W, H, bg, d->xyz, nullptr, d->scales_out, scale_modifier, d->rotq, nullptr,
+                              viewmatrix, projmatrix, campos, tanfovx, tanfovy, shs, radii, dL_dout_color, L_cap,
+                              geom, binning, img, acc, nullptr, dL_dmeans2D, nullptr, dL_dopacity, nullptr, dL_dsh,
+                              nullptr, nullptr, xyz_gradient_accum, denom, max_radii2D, stream, debug, timing, &f);
     if (rc) return rc;
     tick(timing, 10, (cudaStream_t)stream);
     rc = launch_pose_to_A_bwd(d->pose, d->rest, d->parents, d->inv_A_t2cano, d->G, d->d_A, 1, d->J, d->d_pose,

@@ -81,8 +81,6 @@ struct LbsFuse {
     float* d_transl;          // (3) accumulated (caller zeroes) or null
 };
 
-int launch_lbs_bwd_packed(const LbsFuse& lf, int N, const float* g_xyz, const float* g_rotq, const float* g_scales,
-                          cudaStream_t stream);
 int launch_pose_to_A(const float* pose, const float* rest, const int* parents, const float* inv_A,
                      int B, int J, float* A_out, float* G_out, cudaStream_t stream);
 int launch_pose_to_A_bwd(const float* pose, const float* rest, const int* parents,

@@ -808,53 +808,6 @@ int launch_lbs_bwd(const LbsArgs& a, const LbsGrads& g, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
-// LBS backward with PACKED skinning weights, one frame (the per-frame path of AvatarStep when the
-// rasterizer's backward is not fused with it): same device functions as the fused epilogue of
-// geometry_bwd_kernel (lbs_math.cuh).  Thread = Gaussian; canonical attributes and packed weights
-// are fetched ahead of the dependency wait (model parameters), the upstream gradients after it.
-// ------------------------------------------------------------------------------------------
-constexpr int LBP_THREADS = 256;
-__global__ void __launch_bounds__(LBP_THREADS) lbs_bwd_packed_kernel(LbsFuse lf, int N, const float* __restrict__ g_xyz,
-                                                                     const float* __restrict__ g_rotq,
-                                                                     const float* __restrict__ g_scales) {
-    extern __shared__ __align__(16) char s_lbp[];
-    float4* const s_A = reinterpret_cast<float4*>(s_lbp);            // [64][3]
-    const int tid = threadIdx.x, idx = blockIdx.x * LBP_THREADS + tid;
-    const bool live = idx < N;
-    CanonG cg;
-#pragma unroll
-    for (int k = 0; k < 9; k++) cg.Rc[k] = (k % 4 == 0) ? 1.0f : 0.0f;
-    if (live) load_canon(lf, idx, cg);
-    for (int f = tid; f < lf.J * 3; f += LBP_THREADS)
-        s_A[f] = reinterpret_cast<const float4*>(lf.A)[(f / 3) * 4 + f % 3];
-    pdl_sync();
-    float gx[3] = {0, 0, 0}, gq[4] = {0, 0, 0, 0}, gs[3] = {0, 0, 0};
-    if (live) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { gx[k] = g_xyz[3 * (size_t)idx + k]; gs[k] = g_scales[3 * (size_t)idx + k]; }
-        const float4 q = reinterpret_cast<const float4*>(g_rotq)[idx];
-        gq[0] = q.x; gq[1] = q.y; gq[2] = q.z; gq[3] = q.w;
-    }
-    __syncthreads();
-    float dT[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) dT[k] = 0.0f;
-    if (live) lbs_bwd_one(lf, s_A, cg, idx, gx, gq, gs, dT);
-    lbs_bwd_reduce<LBP_THREADS>(lf, s_lbp + 64 * 3 * 16, dT, gx, cg.pw, live);
-}
-
-int launch_lbs_bwd_packed(const LbsFuse& lf, int N, const float* g_xyz, const float* g_rotq, const float* g_scales,
-                          cudaStream_t stream) {
-    if (N <= 0) return 0;
-    if (((uintptr_t)g_rotq & 15) || ((uintptr_t)lf.A & 15)) return SGS_ERR_MISALIGNED;
-    const size_t smem = (size_t)64 * 3 * 16 + lbs_reduce_smem_bytes<LBP_THREADS>(lf.J, lf.K);
-    SGS_CUDA_OK(set_max_smem(lbs_bwd_packed_kernel, smem));
-    SGS_CUDA_OK(launch_pdl(lbs_bwd_packed_kernel, (N + LBP_THREADS - 1) / LBP_THREADS, LBP_THREADS, smem, stream, lf, N,
-                           g_xyz, g_rotq, g_scales));
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------
 // packed skinning weights (kernels_lbs.h): one thread per Gaussian collects the non-zero entries
 // of its row in ascending joint order; *max_nnz receives the longest row (the caller checks it
 // against K once -- the buffer only changes at densification).

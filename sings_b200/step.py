@@ -106,8 +106,6 @@ class AvatarStep:
         self.d_transl = self.small_grads[J * 16:J * 16 + 3].view(1, 3)
         self.d_pose = e(1, J, 3)
         self._bwd_clean = False
-        # backward arrangement of the fused path: SGS_BWD=fused | split (default: see DESIGN.md, measured)
-        self.split_bwd = os.environ.get("SGS_BWD", "split") == "split"
         self._pack_weights()
         # shs is a model parameter: the kernels in front of the geometry kernels (LBS forward,
         # blend backward) are this library's and never write it, so its rows may be prefetched
@@ -164,8 +162,6 @@ class AvatarStep:
                           ("d_scales", self.d_scales), ("d_A", self.d_A), ("d_transl", self.d_transl),
                           ("d_pose", self.d_pose)):
             setattr(d, name, p(tns))
-        if self.split_bwd:      # two per-Gaussian backward kernels with these gradients in between (see the header)
-            d.g_xyz, d.g_rotq, d.g_scales = p(self.g_means3D), p(self.g_rots), p(self.g_scales_r)
         return d
 
     def _alloc_scratch(self):
@@ -368,7 +364,7 @@ class AvatarStep:
         _lib.check(self.L.sgs_raster_layout_info(self.N, self.Wd, self.H, self.L_cap, info), "layout")
         tile_passes = int(info[10]) - 4
         fwd = 1 + 1 + (0 if self.K else 1) + 1 + 4 + 1 + tile_passes + 1 + 1   # clear, pose->A, [LBS], geometry, 4 depth passes, emit, tile passes, ranges, blend
-        bwd = 1 + 1 + (0 if (self.K and not self.split_bwd) else 1) + 1          # blend bwd, geometry bwd, [LBS bwd], pose bwd
+        bwd = 1 + 1 + (0 if self.K else 1) + 1                                   # blend bwd, geometry bwd, [LBS bwd], pose bwd
         return fwd + (bwd if backward else 0)
 
     def stage_ms(self, backward: bool = True) -> dict:

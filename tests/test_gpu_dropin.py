@@ -149,16 +149,13 @@ def test_fused_deform_kernels_equal_the_separate_ones(J, iso, smooth, monkeypatc
                      tanfovx=view.tanfovx, tanfovy=view.tanfovy, smpl_scale=t(np.array([1.07], np.float32)))
     G = torch.randn(3, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
     out = {}
-    for mode in ("fused", "split", "separate"):
-        # fused: LBS inside the rasterizer's per-Gaussian kernels, forward and backward; split: fused forward,
-        # packed-weights LBS backward as its own kernel; separate: the dense-weight LBS kernels of the drop-in path
-        monkeypatch.setenv("SGS_BWD", "split" if mode == "split" else "fused")
+    for mode in ("fused", "separate"):
         if mode == "separate":
             monkeypatch.setenv("SGS_NO_FUSE", "1")
         st = AvatarStep(t(av.xyz_canon), None if iso else t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs),
                         t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano), H, W, 3)
-        assert (st.K > 0) == (mode != "separate") and st.split_bwd == (mode == "split")
-        if mode != "separate":
+        assert (st.K > 0) == (mode == "fused")
+        if mode == "fused":
             nnz = int((av.lbs_weights != 0).sum(1).max())
             assert st.K >= nnz and st.K - nnz < 4 and (smooth == 0 or st.K > 4)
         img = st.forward(fr).clone()
@@ -167,7 +164,7 @@ def test_fused_deform_kernels_equal_the_separate_ones(J, iso, smooth, monkeypatc
         assert st.check_capacity() > 0
         out[mode] = dict(img=img, radii=st.radii.clone(), xyz=st.xyz.clone(), q=st.rotq.clone(), bucket=st.bucket.clone(),
                          d_pose=st.d_pose.clone(), d_transl=st.d_transl.clone(), m2=st.g_means2D.clone())
-    for name in ("fused", "split"):
+    for name in ("fused",):
         a, b = out[name], out["separate"]
         assert torch.equal(a["xyz"], b["xyz"]) and torch.equal(a["q"], b["q"])
         assert torch.equal(a["img"], b["img"]) and torch.equal(a["radii"], b["radii"])
