@@ -1,13 +1,11 @@
 #!/bin/bash
-# Evidence of one version on one GPU (run under gpurun): GPU tests, the default bench line, the
-# reference arm, the ncu launch list + full-set capture.   usage: bash tools/final_evidence.sh <tag>
-TAG=${1:-vX}
-python -m pytest tests -q -m gpu 2>&1 | tail -5 > gpurun_out/${TAG}_tests.txt
+# end-of-round evidence on 1 GPU (run under gpurun): tests, smoke, default bench (both arms), sanitizers
+TAG=${1:-r02_final}
+python -m pytest tests -q -m gpu 2>&1 | tail -3 > gpurun_out/${TAG}_tests.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.txt 2>&1
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python bench.py --impl reference --steps 20 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
-bash tools/profile.sh ${TAG} > /dev/null 2>&1
-ncu -i gpurun_out/${TAG}.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
-python tools/ncu_compact.py gpurun_out/${TAG}_raw.csv > gpurun_out/${TAG}_ncu_compact.txt
-python tools/launch_shares.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launch_shares.txt
-cat gpurun_out/${TAG}_tests.txt; tail -1 gpurun_out/${TAG}_smoke.txt; tail -c 600 gpurun_out/${TAG}_bench.json; echo; head -14 gpurun_out/${TAG}_launch_shares.txt
+SAN="tests/test_gpu_raster.py::test_sh_paths_forward_backward tests/test_gpu_raster.py::test_empty_and_all_culled tests/test_gpu_dropin.py::test_fused_deform_kernels_equal_the_separate_ones tests/test_gpu_dropin.py::test_avatar_step_matches_autograd_path tests/test_gpu_dropin.py::test_cuda_graph_replay_equals_eager_launches tests/test_gpu_lbs.py::test_against_reference_golden tests/test_gpu_output.py::test_frame_to_uint8_bit_exact"
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest $SAN -x -q 2>&1 | tail -6 > gpurun_out/${TAG}_memcheck.txt
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_dropin.py::test_fused_deform_kernels_equal_the_separate_ones tests/test_gpu_raster.py::test_sh_paths_forward_backward -x -q 2>&1 | tail -6 > gpurun_out/${TAG}_racecheck.txt
+cat gpurun_out/${TAG}_tests.txt; tail -1 gpurun_out/${TAG}_smoke.txt; tail -c 400 gpurun_out/${TAG}_bench.json; echo; tail -3 gpurun_out/${TAG}_memcheck.txt; tail -3 gpurun_out/${TAG}_racecheck.txt
