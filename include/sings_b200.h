@@ -7,8 +7,10 @@
  *  - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host";
  *  - the library never allocates or frees: the caller sizes scratch with sgs_raster_sizes()
  *    / sgs_sort_scratch_bytes() and passes raw pointers (torch tensors' data_ptr());
- *  - every entry point takes the CUDA stream to launch on, is re-entrant, keeps no global
- *    state, and never synchronises the host (except with debug != 0);
+ *  - every entry point takes the CUDA stream to launch on and never synchronises the host
+ *    (except with debug != 0); the only process-wide state is a mutex-guarded cache of kernel
+ *    attributes (raised shared-memory limits, occupancy), so host threads may call
+ *    concurrently, each on its own stream and scratch;
  *  - return value: 0 = ok, < 0 = argument error (SGS_ERR_*), > 0 = a cudaError_t;
  *    sgs_error_string() decodes both.
  * All floating point is IEEE binary32; matrices are 16 contiguous floats read column-major
@@ -49,9 +51,11 @@ const char* sgs_error_string(int code);
 
 /* Stage timing (measurement only).  A timing handle owns n CUDA events; the rasterizer entry
  * points record them at stage boundaries when given a handle (null = no recording):
- *   forward : [0] start, [1] after geometry (memset+preprocess+scan+emit), [2] after the radix
- *             sort, [3] after tile ranges, [4] after the blend;
- *   backward: [5] start, [6] after the blend backward (incl. accumulator memset), [7] end.
+ *   forward : [0] start, [1] after the per-Gaussian kernel (preprocess; with the fused entry point
+ *             also the deform), [2] after binning (depth passes, pair emission, tile-id
+ *             passes), [3] after tile ranges, [4] after the blend;
+ *   backward: [5] start, [6] after the blend backward, [7] after the per-Gaussian backward;
+ *   fused entry points: [8] frame start (before pose -> A), [10] / [11] around the pose backward.
  * sgs_timing_elapsed_ms waits for event j and returns the time from event i to event j. */
 int sgs_timing_create(int n_events, void** handle);
 int sgs_timing_destroy(void* handle);
