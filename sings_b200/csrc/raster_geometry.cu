@@ -79,7 +79,7 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.nvals1_off = o;   o += align_up(np * 4, 256);
     l.rects_off = o;    o += align_up(np * 8, 256);
     l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
-    l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 4, 256);
+    l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 16, 256);   // work items (tile, start, end, -) by length bucket
     size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
     l.keys0_off = o;    o += align_up(cap * 8, 256);
     l.keys1_off = o;    o += align_up(cap * 8, 256);
