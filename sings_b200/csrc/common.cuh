@@ -283,6 +283,12 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+__device__ __forceinline__ unsigned lanemask_le() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
 // exp(x) for x <= 0, bit-identical to oracle/c/raster_oracle.c expneg (numeric contract).
 // FMA/ALU pipes only (no MUFU, no F2I/FRND): round-to-nearest by the 1.5*2^23 magic add,
 // Cody-Waite reduction, degree-5 polynomial in Estrin form (dependency depth 3), exponent

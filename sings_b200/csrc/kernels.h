@@ -42,11 +42,13 @@ struct RasterLayout {
     // geometry state (per Gaussian)
     size_t rec_off, geom_bytes;
     // zeroed scratch + binning state
-    size_t cnt_off, hist_off, scan_off, nstat_off, sortstat_off, bktcnt_off, zero_bytes, ranges_off, bktlist_off;
+    size_t cnt_off, hist_off, scan_off, nstat_off, sortstat_off, bktcnt_off, itemcnt_off, zero_bytes, ranges_off, bktlist_off, itemlist_off;
+    size_t blklist_off;      // 8 planes (one per pixel block of a tile) of L_cap (id, list position) entries
+    size_t plane_entries;    // entries per plane
     size_t nkeys0_off, nkeys1_off, nvals0_off, nvals1_off, rects_off;   // per-Gaussian depth-sort items
     size_t keys0_off, keys1_off, vals0_off, vals1_off, bin_bytes;
     // image state
-    size_t finalT_off, ncontrib_off, img_bytes;
+    size_t finalT_off, ncontrib_off, nblk_off, img_bytes;
     int scan_blocks, sort_blocks, nsort_blocks, tiles, gx, gy, end_bit, passes;
     // the sorted pair list is in keys1/vals1 when the number of tile-id passes is odd
     bool sorted_in_1() const { return ((passes - DEPTH_PASSES) & 1) != 0; }

@@ -5,19 +5,18 @@
 //   backward.cu renderCUDA (K7, K8, K9 of section 2.4),
 // reached from /root/reference/sings/rec/renderer/gs_renderer_single.py:87-95.
 //
-// One CTA per 16x16 tile, one thread per pixel.  B200-first structure (results unchanged):
-//  * tiles are processed longest-list-first (the range kernel files every tile in a bucket by
-//    list length), so the few tiles with thousands of pairs do not form the tail;
-//  * each warp owns an 8x4 pixel block; while staging a batch of 256 pairs every thread also
-//    computes, for its pair, which of the 8 pixel blocks the Gaussian's alpha >= 1/255 footprint
-//    can reach (ellipse bounding box AND bounding circle, conservative); each warp then
-//    compacts the batch to the pairs that can touch ITS block and loops only over those;
-//  * 48-byte geometry records are prefetched into registers one batch ahead and parked in a
-//    double-buffered shared stage: one barrier per batch, broadcast LDS.128 in the loop;
-//  * forward exits a tile as soon as every pixel has saturated (__syncthreads_count);
-//  * the backward reduce-scatters the nine per-pixel partial gradients across the warp
-//    (recursive halving: 14 shuffles instead of 45) and issues ONE reduction instruction
-//    per warp and Gaussian (lanes 0..8 -> nine consecutive floats).
+// A warp per 8x4 pixel block, a thread per pixel, warps autonomous (no CTA barrier anywhere).
+// B200-first structure (results unchanged):
+//  * tiles / pixel blocks are processed longest-first (work items filed in buckets by length);
+//  * a list entry carries, next to the Gaussian id, the mask of the tile's eight pixel blocks the
+//    Gaussian's alpha >= 1/255 footprint can reach; the forward keeps only the entries of its
+//    own block, and writes them out as the block's own list for the backward;
+//  * 48-byte geometry records are gathered one chunk ahead into a warp-private ring in shared
+//    memory whose geometric part is pair-interleaved: EVAL works on two entries per instruction
+//    (packed binary32 pairs), COMPOSITE / SEQ are branch-free;
+//  * the backward parks the two order-dependent numbers per (pixel, pair) in a [pair][pixel]
+//    tile and reduces over pixels with lane = pair: 2 vector + 1 scalar reduction per warp and
+//    Gaussian.
 #include "common.cuh"
 #include "kernels.h"
 #include <type_traits>
@@ -82,19 +81,19 @@ __device__ __forceinline__ unsigned warp_lower_bound(const unsigned long long* _
 __device__ __forceinline__ void tile_ranges_block(int block, const unsigned long long* __restrict__ keys,
                                                   const int* __restrict__ counters, long long n_cap,
                                                   uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
-                                                  uint4* __restrict__ bucket_list, int tiles) {
-    __shared__ unsigned s_len[RANGE_THREADS / 32], s_lo[RANGE_THREADS / 32];
+                                                  unsigned* __restrict__ bucket_list, int tiles) {
+    __shared__ unsigned s_len[RANGE_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = block * (RANGE_THREADS / 32) + warp;
     const unsigned n = (unsigned)min((long long)counters[CNT_NUM_RENDERED], n_cap);
-    unsigned c = 0, lo = 0;
+    unsigned c = 0;
     if (t < tiles) {                                     // warp-uniform
-        lo = warp_lower_bound(keys, n, (unsigned)t, lane);
+        const unsigned lo = warp_lower_bound(keys, n, (unsigned)t, lane);
         const unsigned hi = warp_lower_bound(keys, n, (unsigned)t + 1u, lane);
         c = hi - lo;
         if (lane == 0) ranges[t] = c ? make_uint2(lo, hi) : make_uint2(0u, 0u);
     }
-    if (lane == 0) { s_len[warp] = c; s_lo[warp] = c ? lo : 0u; }
+    if (lane == 0) s_len[warp] = c;
     __syncthreads();
     if (warp != 0) return;
     const int tt = block * (RANGE_THREADS / 32) + lane;
@@ -105,9 +104,7 @@ __device__ __forceinline__ void tile_ranges_block(int block, const unsigned long
     unsigned slot = 0;
     if (ok && lane == leader) slot = atomicAdd(&bucket_count[bk], (unsigned)__popc(peers));
     slot = __shfl_sync(0xffffffffu, slot, leader);
-    // a work item = (tile, first list position, end): the blend kernels need no second look-up
-    if (ok) bucket_list[(size_t)bk * tiles + slot + __popc(peers & lanemask_lt())] =
-                make_uint4((unsigned)tt, s_lo[lane], s_lo[lane] + s_len[lane], 0u);
+    if (ok) bucket_list[(size_t)bk * tiles + slot + __popc(peers & lanemask_lt())] = (unsigned)tt;
 }
 
 // The i-th tile in longest-bucket-first order (whole warp calls it with the same i).  The bucket
@@ -128,41 +125,66 @@ __device__ __forceinline__ BucketScan bucket_scan(const unsigned* __restrict__ b
     }
     return b;
 }
-__device__ __forceinline__ uint4 tile_of_rank(const BucketScan& bs, const uint4* __restrict__ bucket_list,
-                                              int tiles, unsigned i) {
+__device__ __forceinline__ unsigned tile_of_rank(const BucketScan& bs, const unsigned* __restrict__ bucket_list,
+                                                 int tiles, unsigned i) {
     const unsigned before = __ballot_sync(0xffffffffu, bs.incl <= i);       // buckets entirely before i
     const int b = __popc(before);                                           // lane holding the bucket of i
     const unsigned excl = __shfl_sync(0xffffffffu, bs.incl - bs.cnt, b & 31);
     return __ldg(bucket_list + (size_t)(LEN_BUCKETS - 1 - b) * tiles + (i - excl));
 }
 
-// Work distribution of the two blend kernels: a tile is spread over 8 / WPC items of WPC
-// autonomous warps (warp = 8x4 pixel block), items in longest-list-first order.  The grid holds
-// a quarter of the items (GRID_FOLD); CTA b takes items b, b + grid, b + 2 grid, ...: its first
-// item is a heavy one, the later ones ever lighter -- three quarters of the tiles of an avatar
-// frame are EMPTY, and launched as CTAs of their own (8192 of them at 1024^2) they form a
-// 5 us tail of pure launch overhead; folded behind a real item they cost a few instructions.
-// fn returns false when nothing is left to do for any later item.
-// (Persistent warps / CTAs pulling items from a ticket counter were measured 10 % slower -- a
-// hardware-scheduled CTA thins out as its short warps retire, which speeds up its long ones;
+// Work distribution of the two blend kernels: a tile is spread over 8 / WPC CTAs of WPC
+// autonomous warps (warp = 8x4 pixel block), CTAs in longest-list-first order.  (Persistent
+// warps / CTAs pulling items from a ticket counter were measured 10 % slower -- a hardware-
+// scheduled CTA thins out as its short warps retire, which speeds up its long ones;
 // profiles/README.md, round 1.)
+template <int WPC, typename Fn>
+__device__ __forceinline__ void for_each_tile_item(const unsigned* __restrict__ bucket_count,
+                                              const unsigned* __restrict__ bucket_list, int tiles, Fn fn) {
+    constexpr int PARTS = TILE_WARPS / WPC;      // CTAs per tile
+    const BucketScan bs = bucket_scan(bucket_count);
+    fn(tile_of_rank(bs, bucket_list, tiles, blockIdx.x / PARTS),
+       (int)(blockIdx.x % PARTS) * WPC + (int)(threadIdx.x >> 5));
+}
+
+// bucket of a list of c >= 1 entries: two per octave, monotonic in c
+__device__ __forceinline__ unsigned length_bucket(unsigned c) {
+    const unsigned l = 31u - (unsigned)__clz(c);
+    return l == 0u ? 0u : min((unsigned)LEN_BUCKETS - 1u, 2u * l + ((c >> (l - 1u)) & 1u));
+}
+
+__device__ __forceinline__ uint4 item_of_rank(const BucketScan& bs, const uint4* __restrict__ bucket_list,
+                                              size_t items_cap, unsigned i) {
+    const unsigned before = __ballot_sync(0xffffffffu, bs.incl <= i);       // buckets entirely before i
+    const int b = __popc(before);                                           // lane holding the bucket of i
+    const unsigned excl = __shfl_sync(0xffffffffu, bs.incl - bs.cnt, b & 31);
+    return __ldg(bucket_list + (size_t)(LEN_BUCKETS - 1 - b) * items_cap + (i - excl));
+}
+
+// Work items of the backward blend: one (tile, pixel block) whose pixels have at least one
+// contributor, filed by the forward warp that rendered it in a bucket by the EXACT number of list
+// entries the backward will walk (two buckets per octave), a warp per item, the four warps of a
+// CTA taking four consecutive items of the longest-first order (similar lengths: the CTA's warps
+// retire together).  The grid holds a quarter of the possible items (GRID_FOLD) -- most pixel
+// blocks of an avatar frame are empty -- and warps stride over the items that are really there.
 #ifndef SGS_GRID_FOLD
 #define SGS_GRID_FOLD 4
 #endif
 constexpr int GRID_FOLD = SGS_GRID_FOLD;
-template <int WPC, typename Fn>
+constexpr int BLOCKS_PER_TILE = TILE_PIX / 32;            // 8 pixel blocks of 8x4
+template <typename Fn>
 __device__ __forceinline__ void for_each_item(const unsigned* __restrict__ bucket_count,
                                               const uint4* __restrict__ bucket_list, int tiles, Fn fn) {
-    constexpr int PARTS = TILE_WARPS / WPC;      // items per tile
     const BucketScan bs = bucket_scan(bucket_count);
-    const unsigned items = (unsigned)tiles * PARTS;
-    for (unsigned it = blockIdx.x; it < items; it += gridDim.x)
-        if (!fn(tile_of_rank(bs, bucket_list, tiles, it / PARTS), (int)(it % PARTS) * WPC + (int)(threadIdx.x >> 5))) break;
+    const unsigned n_items = __shfl_sync(0xffffffffu, bs.incl, 31);
+    const unsigned wpc = blockDim.x >> 5;
+    for (unsigned it = blockIdx.x * wpc + (threadIdx.x >> 5); it < n_items; it += gridDim.x * wpc)
+        fn(item_of_rank(bs, bucket_list, (size_t)tiles * 8u, it));
 }
 template <int WPC>
 static inline unsigned blend_grid(int tiles) {
-    const long long items = (long long)tiles * (TILE_WARPS / WPC);
-    return (unsigned)((items + GRID_FOLD - 1) / GRID_FOLD);
+    const long long items = (long long)tiles * BLOCKS_PER_TILE;
+    return (unsigned)((items + (long long)WPC * GRID_FOLD - 1) / ((long long)WPC * GRID_FOLD));
 }
 
 static inline const unsigned long long* sorted_keys(const RasterLayout& lay, const char* bin) {
@@ -191,7 +213,7 @@ __device__ __forceinline__ Rec load_rec(const float4* __restrict__ rec, unsigned
 __global__ void __launch_bounds__(RANGE_THREADS)
 tile_ranges_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ counters, long long n_cap,
                    int tiles, uint2* __restrict__ ranges, unsigned* __restrict__ bucket_count,
-                   uint4* __restrict__ bucket_list) {
+                   unsigned* __restrict__ bucket_list) {
     pdl_sync();
     tile_ranges_block((int)blockIdx.x, keys, counters, n_cap, ranges, bucket_count, bucket_list, tiles);
 }
@@ -202,21 +224,28 @@ int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cuda
         sorted_keys(lay, bin), reinterpret_cast<const int*>(bin + lay.cnt_off), L_cap, lay.tiles,
         reinterpret_cast<uint2*>(bin + lay.ranges_off),
         reinterpret_cast<unsigned*>(bin + lay.bktcnt_off),
-        reinterpret_cast<uint4*>(bin + lay.bktlist_off)));
+        reinterpret_cast<unsigned*>(bin + lay.bktlist_off)));
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // forward.  Warp-autonomous: every warp streams the tile's depth-sorted list by itself, 32
-// pairs at a time (one per lane, prefetched one chunk ahead), keeps the pairs that can reach
-// its own 8x4 pixel block (ballot) and appends their records, compacted, to a warp-private
-// ring in shared memory.  The ring is consumed FWD_U pairs at a time by a two-stage software
-// pipeline: EVAL computes the alphas of the next FWD_U pairs (independent chains: falloff,
-// exp, clamp) while COMPOSITE folds the previous FWD_U into the pixel state.  COMPOSITE is
-// branch-free and its only serial dependency per pair is one multiply (T), one predicate
-// (done) and the colour FMAs, so a lone warp on an SM -- the tail of the kernel is the tile
-// with the longest list -- still retires a pair every few cycles.  No CTA barrier anywhere;
-// a warp leaves as soon as its 32 pixels have saturated.
+// entries at a time (one per lane, entries three chunks ahead, records one), keeps those whose
+// reach mask names its own 8x4 pixel block (ballot) and appends their records, compacted, to a
+// warp-private ring in shared memory.  The ring is consumed FWD_U pairs at a time by a two-stage
+// software pipeline: EVAL computes the alphas of the next FWD_U pairs (independent chains:
+// falloff, exp, clamp) while COMPOSITE folds the previous FWD_U into the pixel state.  COMPOSITE
+// is branch-free and its only serial dependency per pair is one multiply (T), one predicate
+// (done) and the colour FMAs.  No CTA barrier anywhere; a warp leaves as soon as its 32 pixels
+// have saturated.
+//
+// By-product for the backward: only ~10 % of a tile's entries reach any one pixel block, and the
+// scan that finds them is a third of this kernel's instructions.  The warp therefore writes the
+// entries it keeps -- (Gaussian id, position in the tile's list) -- to the block's own list
+// (plane `block` of 8, at the tile's start in the sorted list: no allocation, planes as long as
+// the pair list, mostly untouched), records per pixel the last contributor's index in THAT list,
+// and files one backward work item (tile, block, entries to walk).  The backward then streams
+// exactly the entries it needs, longest items first, and empty pixel blocks cost it nothing.
 //
 // EVAL works on TWO ring entries per instruction (packed binary32 pairs, FFMA2 / FMUL2 /
 // FADD2 of sm_100: the kernel is issue-bound, and the falloff + exp chain is 19 of its ~33
@@ -227,7 +256,7 @@ int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cuda
 // order are those of the scalar formulation: results are unchanged, bit for bit.
 // ------------------------------------------------------------------------------------------
 #ifdef SGS_BLEND_TRACE
-// measurement build only (tools/blend_trace.py): one record per warp of the forward blend
+// measurement build only (tools/blend_trace.py): one record per work item of the forward blend
 struct TraceRec { unsigned long long t0, t1; unsigned smid, tile, warp, relevant, len, pad; };
 __device__ TraceRec g_trace[1 << 16];
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -271,82 +300,49 @@ __device__ __forceinline__ PairEval ring_eval(const RingGeo& g, unsigned ps, con
     return r;
 }
 
-// Staging of the list through shared memory with cp.async (LDGSTS).  A register prefetch
-// ("m2 = load(pos + 96)" in a rotating m0/m1/m2 pipeline) does not work: all trips of the loop
-// issue the SAME load instruction, every wait on its scoreboard waits for the newest load too,
-// and the warp stalls for a full L2 round trip per 32 entries however far ahead it asks
-// (ncu: 17 % of the forward's, 11 % of the backward's stall samples on that one instruction).
-// cp.async groups are counted, so a wait can leave the newest ones in flight.
-//   iteration i commits group i = { entries of chunk i + ENT_AHEAD, records of chunk i + REC_AHEAD };
-//   before that it waits for all groups but the newest REC_AHEAD - 1: records of chunk i and the
-//   entries of chunk i + REC_AHEAD (whose records it is about to request) have landed.
-// Every lane reads back only what it copied itself: no barrier.
-#ifndef SGS_REC_AHEAD
-#define SGS_REC_AHEAD 2
-#endif
-constexpr int REC_AHEAD = SGS_REC_AHEAD;          // chunks between a record request and its use
-constexpr int REC_STAGES = REC_AHEAD + 1;
-constexpr int ENT_AHEAD = 2 * REC_AHEAD;          // chunks between an entry request and its use as the list item
-constexpr int ENT_STAGES = 8;
-static_assert(ENT_AHEAD < ENT_STAGES, "entry ring too small");
-struct ListStage {
-    unsigned ent[ENT_STAGES][32];
-    float4 rq[REC_STAGES][3][32];
-};
-
 struct FwdBatch {
     float al[FWD_U], om[FWD_U];
-    float4 c[FWD_U];                // r, g, b, depth (AUX) | list position + 1 (bits)
-    unsigned pos[FWD_U];
+    float4 c[FWD_U];                // r, g, b, depth (AUX)
+    unsigned pos[FWD_U];            // index in the block's list + 1, 0 = rejected
 };
 
-// AUX: the caller wants the depth image too (GaussianRasterizer.forward_aux); the colour entry of
-// the ring is then (r, g, b, depth) and the list positions live in their own array.  Without it
-// the fourth float carries the list position: one LDS.128 less per batch, one packed FMA narrower.
-template <bool AUX>
+// AUX: the caller wants the depth image too (GaussianRasterizer.forward_aux): the fourth float of
+// the ring's colour entry is the depth, accumulated in the spare half of a packed FMA.
 struct FwdWarpSmem {
     RingGeo geo;
     float4 c[RING_SLOTS];
-    unsigned pos[AUX ? RING_SLOTS : 4];       // list position + 1
-    ListStage st;
 };
 
+#ifndef SGS_FWD_CTAS
+#define SGS_FWD_CTAS 5             // resident CTAs per SM the register budget is cut for (102 registers at 128 threads)
+#endif
 template <bool AUX>
-__global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_MINB * (TILE_WARPS / FWD_WPC))
-blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
-                 const uint4* __restrict__ bucket_list, int tiles,
+__global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_CTAS)
+blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
+                 const unsigned* __restrict__ bucket_list, int tiles,
                  const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
+                 uint2* __restrict__ blk_list, size_t list_plane,
+                 unsigned* __restrict__ item_count, uint4* __restrict__ item_list,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
                  float* __restrict__ out_color, float* __restrict__ final_T,
-                 unsigned* __restrict__ n_contrib, float* __restrict__ out_alpha,
+                 unsigned* __restrict__ n_contrib, unsigned* __restrict__ n_blk, float* __restrict__ out_alpha,
                  float* __restrict__ out_depth) {
-    __shared__ __align__(16) FwdWarpSmem<AUX> s_fwd[FWD_WPC];
+    __shared__ __align__(16) FwdWarpSmem s_fwd[FWD_WPC];
 
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
-    FwdWarpSmem<AUX>& sm = s_fwd[cwarp];
+    FwdWarpSmem& sm = s_fwd[cwarp];
     ring_clear(sm.geo, lane);
     sm.c[lane] = sm.c[lane + 32] = make_float4(0, 0, 0, 0);
-    if (AUX) sm.pos[lane] = sm.pos[lane + 32] = 0u;
     pdl_sync();
-  for_each_item<FWD_WPC>(bucket_count, bucket_list, tiles, [&](const uint4 item, const int warp) {
-    const unsigned tile = item.x;
+  for_each_tile_item<FWD_WPC>(bucket_count, bucket_list, tiles, [&](const unsigned tile, const int warp) {
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
     const int px = tile_x * TILE + lx, py = tile_y * TILE + ly;
     const bool inside = px < W && py < H;
     const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
-    const int len = (int)(item.z - item.y);
-    if (len == 0) {                              // an empty tile shows the background
-        if (inside) {
-            final_T[pix] = 1.0f;
-            n_contrib[pix] = 0u;
-            out_color[pix] = bg[0]; out_color[plane + pix] = bg[1]; out_color[2 * plane + pix] = bg[2];
-            if (out_alpha) out_alpha[pix] = 0.0f;
-            if (out_depth) out_depth[pix] = 0.0f;
-        }
-        return true;
-    }
+    const uint2 range = ranges[tile];
+    const int len = (int)(range.y - range.x);
     const float2 npx = splat2(-(float)px), npy = splat2(-(float)py);
 #ifdef SGS_BLEND_TRACE
     const unsigned long long trace_t0 = gtimer();
@@ -367,14 +363,9 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
 
     // alphas of ring entries [base, base + FWD_U) (base is a multiple of FWD_U); with LIMIT,
     // entries at or beyond `limit` are empty (only the drain meets a partial batch).  A rejected
-    // entry gets alpha 0 (1 - alpha = 1 exactly) and list position 0.
+    // entry gets alpha 0 (1 - alpha = 1 exactly) and index 0.
     auto eval = [&](FwdBatch& e, unsigned base, unsigned limit, auto LIMIT) {
         const unsigned s0 = base & (RING_SLOTS - 1);
-        unsigned pos4[4] = {0u, 0u, 0u, 0u};
-        if (AUX) {
-            const uint4 pp = *reinterpret_cast<const uint4*>(&sm.pos[s0]);
-            pos4[0] = pp.x; pos4[1] = pp.y; pos4[2] = pp.z; pos4[3] = pp.w;
-        }
 #pragma unroll
         for (int h = 0; h < FWD_U / 2; h++) {
             const PairEval pe = ring_eval(sm.geo, (s0 >> 1) + h, npx, npy);
@@ -389,7 +380,7 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
                 al2[j] = ok ? al : 0.0f;
                 e.al[u] = al2[j];
                 e.c[u] = sm.c[s0 + u];
-                e.pos[u] = ok ? (AUX ? pos4[u] : __float_as_uint(e.c[u].w)) : 0u;
+                e.pos[u] = ok ? base + u + 1u : 0u;
             }
             const float2 om = ffma2(make_float2(al2[0], al2[1]), splat2(-1.0f), splat2(1.0f));    // 1 - alpha
             e.om[2 * h] = om.x; e.om[2 * h + 1] = om.y;
@@ -417,49 +408,35 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
     const std::true_type with_limit;
     const std::false_type no_limit;
 
-    // Per chunk of 32 list entries (one per lane), staged as described at ListStage.  A list
-    // entry = Gaussian id | reach mask << 24: bit (24 + w) says pixel block w can be reached; a
-    // chunk without relevant entries costs a ballot.
-    const unsigned* pl = point_list + item.y;
+    // Staging pipeline, per chunk of 32 list entries (one per lane): the entries (id | mask) run
+    // three chunks ahead, the records of the relevant ones one chunk ahead -- the dependent
+    // entry -> record gather never sits on the critical path, and a chunk without relevant
+    // entries costs a ballot.
+    // a list entry = Gaussian id | reach mask << 24: bit (24 + w) says pixel block w can be reached
+    const unsigned* pl = point_list + range.x;
+    uint2* bl = blk_list + (size_t)warp * list_plane + range.x;        // this block's own list
     const unsigned wbit = 1u << (ID_BITS + warp);
-    const int nch = (len + 31) >> 5;
-    int rs_put = 0, rs_get = 0;        // record stage being requested / consumed
-    for (int i = -ENT_AHEAD; i < nch; i++) {
-        cp_async_wait_group<REC_AHEAD - 1>();
-        {
-            const int c = i + ENT_AHEAD, at = 32 * c + lane;
-            if (c < nch) cp_async4_zfill(&sm.st.ent[c & (ENT_STAGES - 1)][lane], pl + min(at, len - 1), at < len);
-        }
-        {
-            const int c = i + REC_AHEAD;
-            if (c >= 0 && c < nch) {
-                const unsigned m = sm.st.ent[c & (ENT_STAGES - 1)][lane];
-                if (m & wbit) {
-                    const float4* src = rec + 4 * (size_t)(m & ID_MASK);
-                    cp_async16_ca(&sm.st.rq[rs_put][0][lane], src);
-                    cp_async16_ca(&sm.st.rq[rs_put][1][lane], src + 1);
-                    cp_async16_ca(&sm.st.rq[rs_put][2][lane], src + 2);
-                }
-                rs_put = rs_put == REC_STAGES - 1 ? 0 : rs_put + 1;
-            }
-        }
-        cp_async_commit();
-        if (i < 0) continue;
+    auto entry_at = [&](int at) { return at + lane < len ? __ldg(pl + at + lane) : 0u; };
+    unsigned m0 = entry_at(0), m1 = entry_at(32), m2 = entry_at(64);
+    Rec p;
+    p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
+    if (m0 & wbit) p = load_rec(rec, m0 & ID_MASK);
+    for (int pos = 0; pos < len; pos += 32) {
         if (__all_sync(0xffffffffu, done)) break;
-        const int pos = 32 * i;
-        const bool rel = (sm.st.ent[i & (ENT_STAGES - 1)][lane] & wbit) != 0u;
+        const bool rel = (m0 & wbit) != 0u;
         const unsigned bits = __ballot_sync(0xffffffffu, rel);
         __syncwarp();                  // earlier ring reads are complete before slots are reused
         if (rel) {
-            const float4 q0 = sm.st.rq[rs_get][0][lane], q1 = sm.st.rq[rs_get][1][lane], q2 = sm.st.rq[rs_get][2][lane];
-            const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
-            ring_put(sm.geo, slot, q0, q1);
-            sm.c[slot] = make_float4(q1.w, q2.x, q2.y, AUX ? q2.z : __uint_as_float((unsigned)(pos + lane + 1)));
-            if (AUX) sm.pos[slot] = (unsigned)(pos + lane + 1);
+            const unsigned idx = tail + __popc(bits & lanemask_lt());
+            const unsigned slot = idx & (RING_SLOTS - 1);
+            ring_put(sm.geo, slot, p.q0, p.q1);
+            sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, p.q2.z);
+            bl[idx] = make_uint2(m0 & ID_MASK, (unsigned)(pos + lane));
         }
-        rs_get = rs_get == REC_STAGES - 1 ? 0 : rs_get + 1;
         tail += __popc(bits);
         __syncwarp();
+        if (m1 & wbit) p = load_rec(rec, m1 & ID_MASK);
+        m0 = m1; m1 = m2; m2 = entry_at(pos + 96);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= FWD_U) {
             if (!cur_is_b) { eval(bat_b, head, tail, no_limit); composite(bat_a); }
@@ -468,7 +445,6 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
             head += FWD_U;
         }
     }
-    cp_async_wait_all();               // (an early exit leaves requests in flight: the stage is reused by the next item)
     // drain: the waiting batch, then the (partial) remainder of the ring.  Nothing to do when no
     // entry ever reached this pixel block -- three quarters of the tiles of an avatar frame are
     // empty, and their warps would spend ~400 instructions compositing empty batches.
@@ -476,9 +452,18 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
         if (!cur_is_b) { eval(bat_b, head, tail, with_limit); composite(bat_a); composite(bat_b); }
         else           { eval(bat_a, head, tail, with_limit); composite(bat_b); composite(bat_a); }
     }
+    // the backward's work item: the entries of this block's list up to the last contributor of any pixel
+    const unsigned wlast = __reduce_max_sync(0xffffffffu, last);
+    if (wlast != 0u && lane == 0) {
+        const unsigned bk = length_bucket(wlast);
+        const unsigned slot = atomicAdd(&item_count[bk], 1u);
+        item_list[(size_t)bk * ((size_t)tiles * 8u) + slot] = make_uint4(tile * 8u + (unsigned)warp, range.x, wlast, 0u);
+    }
+    __syncwarp();                                // the list entries written by other lanes are visible
     if (inside) {
         final_T[pix] = T;                        // a saturated pixel reports the T it stopped at
-        n_contrib[pix] = last;
+        n_blk[pix] = last;                       // last contributor: index in the block's list + 1 (the backward starts there)
+        n_contrib[pix] = last ? bl[last - 1u].y + 1u : 0u;            // ... and its position in the tile's list + 1 ([upstream] n_contrib)
         out_color[pix] = __fmaf_rn(T, bg[0], C01.x);
         out_color[plane + pix] = __fmaf_rn(T, bg[1], C01.y);
         out_color[2 * plane + pix] = __fmaf_rn(T, bg[2], C2D.x);
@@ -492,7 +477,6 @@ blend_fwd_kernel(const unsigned* __restrict__ bucket_count,
         g_trace[(tile * TILE_WARPS + warp) & 0xffff] = r;
     }
 #endif
-    return true;
   });
 }
 #ifdef SGS_BLEND_TRACE
@@ -504,12 +488,19 @@ extern "C" int sgs_debug_trace_read(void* host, size_t bytes) {
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
                      float* out_depth, cudaStream_t stream) {
-    SGS_CUDA_OK(launch_pdl(out_depth ? blend_fwd_kernel<true> : blend_fwd_kernel<false>, blend_grid<FWD_WPC>(lay.tiles), FWD_WPC * 32, 0, stream,
+    const long long blocks = (long long)lay.tiles * (TILE_WARPS / FWD_WPC);
+    SGS_CUDA_OK(launch_pdl(out_depth ? blend_fwd_kernel<true> : blend_fwd_kernel<false>, (unsigned)blocks, FWD_WPC * 32, 0, stream,
+        reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
-        reinterpret_cast<const uint4*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
-        reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx, out_color,
+        reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, const_cast<char*>(bin)),
+        reinterpret_cast<const float4*>(geom + lay.rec_off),
+        reinterpret_cast<uint2*>(const_cast<char*>(bin) + lay.blklist_off), lay.plane_entries,
+        reinterpret_cast<unsigned*>(const_cast<char*>(bin) + lay.itemcnt_off),
+        reinterpret_cast<uint4*>(const_cast<char*>(bin) + lay.itemlist_off),
+        bg, W, H, lay.gx, out_color,
         reinterpret_cast<float*>(img + lay.finalT_off),
-        reinterpret_cast<unsigned*>(img + lay.ncontrib_off), out_alpha, out_depth));
+        reinterpret_cast<unsigned*>(img + lay.ncontrib_off),
+        reinterpret_cast<unsigned*>(img + lay.nblk_off), out_alpha, out_depth));
     return 0;
 }
 
@@ -546,20 +537,14 @@ struct BwdWarpSmem {
     float d[BWD_ROWS * BWD_ROW];    // alpha * T       [pair][pixel]
     float dp[3][32];                // dL/dpixel rgb of the warp's 32 pixels
     unsigned id[ID_SLOTS];          // Gaussian of each queued pair
-    unsigned ent[ENT_STAGES][32];   // list entries in flight (cp.async; see ListStage)
 };
-#ifndef SGS_BWD_ENT_AHEAD
-#define SGS_BWD_ENT_AHEAD 4
-#endif
-constexpr int BWD_ENT_AHEAD = SGS_BWD_ENT_AHEAD;
-static_assert(BWD_ENT_AHEAD >= 2 && BWD_ENT_AHEAD < ENT_STAGES, "entries must be known one chunk before their records are requested");
 
 __global__ void __launch_bounds__(BWD_WPC * 32, SGS_BWD_MINB * (TILE_WARPS / BWD_WPC))
 blend_bwd_kernel(const unsigned* __restrict__ bucket_count,
                  const uint4* __restrict__ bucket_list, int tiles,
-                 const unsigned* __restrict__ point_list, const float4* __restrict__ rec,
+                 const uint2* __restrict__ blk_list, size_t list_plane, const float4* __restrict__ rec,
                  const float* __restrict__ bg, int W, int H, int gx_tiles,
-                 const float* __restrict__ final_T, const unsigned* __restrict__ n_contrib,
+                 const float* __restrict__ final_T, const unsigned* __restrict__ n_blk,
                  const float* __restrict__ dL_dpix, float* __restrict__ acc) {
     extern __shared__ __align__(16) char s_bwd_raw[];
     const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
@@ -567,9 +552,9 @@ blend_bwd_kernel(const unsigned* __restrict__ bucket_count,
     ring_clear(sm.geo, lane);
     sm.c[lane] = sm.c[lane + 32] = make_float4(0, 0, 0, 0);
     pdl_sync();
-  for_each_item<BWD_WPC>(bucket_count, bucket_list, tiles, [&](const uint4 item, const int warp) {
-    if (item.z == item.y) return false;        // items come longest first: only empty tiles from here on
-    const unsigned tile = item.x;
+  for_each_item(bucket_count, bucket_list, tiles, [&](const uint4 item) {
+    const unsigned tile = item.x >> 3;
+    const int warp = (int)(item.x & 7u);
     const int tile_x = (int)(tile % (unsigned)gx_tiles), tile_y = (int)(tile / (unsigned)gx_tiles);
     int lx, ly;
     pixel_of_thread(warp, lane, lx, ly);
@@ -580,10 +565,11 @@ blend_bwd_kernel(const unsigned* __restrict__ bucket_count,
     const float by0 = (float)(tile_y * TILE + ((warp >> 1) << 2));
     const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
 
-    const unsigned last = inside ? n_contrib[pix] : 0u;
-    // entries at list positions >= the warp's largest contributor count reach none of its pixels
+    // last contributor of the pixel: index in the block's list + 1
+    const unsigned last = inside ? n_blk[pix] : 0u;
+    // entries at or beyond the warp's largest index reach none of its pixels
     const int wlast = (int)__reduce_max_sync(0xffffffffu, last);
-    if (wlast == 0) return true;
+    if (wlast == 0) return;
     __syncwarp();                              // (a previous item's last reduction has read dp)
     const float T_final = inside ? final_T[pix] : 0.0f;
     float dp0 = 0.0f, dp1 = 0.0f, dp2 = 0.0f;
@@ -712,49 +698,36 @@ blend_bwd_kernel(const unsigned* __restrict__ bucket_count,
     const std::true_type with_limit;
     const std::false_type no_limit;
 
-    // The list back to front: chunk c covers list positions top - lane, top = wlast - 1 - 32 c, so
-    // lane order is back-to-front order.  Entries are staged with cp.async BWD_ENT_AHEAD chunks
-    // ahead (see ListStage); the records of the relevant ones are gathered into registers one
-    // chunk ahead (this kernel has no shared memory to spare for a record stage).
-    const unsigned* pl = point_list + item.y;
-    const unsigned wbit = 1u << (ID_BITS + warp);
-    const int nch = (wlast + 31) >> 5;
+    // The block's list back to front: round r covers indices top - lane, top = wlast - 1 - 32 r, so
+    // lane order is back-to-front order.  Entries two rounds ahead, their records one round
+    // ahead, in registers (like the forward).
+    const uint2* bl = blk_list + (size_t)warp * list_plane + item.y;
+    auto entry_at = [&](int top) { return top - lane >= 0 ? __ldg(bl + top - lane).x : 0u; };
+    unsigned e1 = entry_at(wlast - 33), e2 = entry_at(wlast - 65);
     Rec p;
-    unsigned pid = 0;
+    unsigned pid = entry_at(wlast - 1);
     p.q0 = p.q1 = p.q2 = make_float4(0, 0, 0, 0);
+    if (wlast - 1 - lane >= 0) p = load_rec(rec, pid);
     // `cur` starts as an empty batch at consumption index -BWD_U: its SEQ writes zeros into
     // rows that real pairs overwrite before any reduction reads them.
     unsigned pend = 0u - BWD_U;
-    for (int i = -BWD_ENT_AHEAD; i < nch; i++) {
-        cp_async_wait_group<BWD_ENT_AHEAD - 2>();          // entries of chunk i + 1 have landed
-        {
-            const int c = i + BWD_ENT_AHEAD, at = wlast - 1 - 32 * c - lane;
-            if (c < nch) cp_async4_zfill(&sm.ent[c & (ENT_STAGES - 1)][lane], pl + max(at, 0), at >= 0);
+    for (int top = wlast - 1; top >= 0; top -= 32) {
+        const int nv = min(32, top + 1);
+        __syncwarp();
+        if (lane < nv) {
+            const unsigned idx = tail + lane;              // consumption index of this entry
+            const unsigned slot = idx & (RING_SLOTS - 1);
+            ring_put(sm.geo, slot, p.q0, p.q1);
+            sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, __uint_as_float((unsigned)(top - lane)));
+            sm.id[idx & (ID_SLOTS - 1)] = pid;
         }
-        cp_async_commit();
-        if (i < -1) continue;
-        if (i >= 0) {
-            const int top = wlast - 1 - 32 * i;
-            const bool rel = (sm.ent[i & (ENT_STAGES - 1)][lane] & wbit) != 0u;
-            const unsigned bits = __ballot_sync(0xffffffffu, rel);
-            __syncwarp();
-            if (rel) {
-                const unsigned slot = (tail + __popc(bits & lanemask_lt())) & (RING_SLOTS - 1);
-                const unsigned idx = tail + __popc(bits & lanemask_lt());      // consumption index of this entry
-                ring_put(sm.geo, slot, p.q0, p.q1);
-                sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, __uint_as_float((unsigned)(top - lane)));
-                sm.id[idx & (ID_SLOTS - 1)] = pid;
-            }
-            tail += __popc(bits);
-            __syncwarp();
+        tail += nv;
+        __syncwarp();
+        if (top - 32 - lane >= 0) {
+            pid = e1;
+            p = load_rec(rec, pid);
         }
-        if (i + 1 < nch) {
-            const unsigned m1 = sm.ent[(i + 1) & (ENT_STAGES - 1)][lane];
-            if (m1 & wbit) {
-                pid = m1 & ID_MASK;
-                p = load_rec(rec, pid);
-            }
-        }
+        e1 = e2; e2 = entry_at(top - 96);
         // the two batch register sets swap roles every step (no register copies)
         while (tail - head >= BWD_U) {
             if (!cur_is_b) { eval(bat_b, head, tail, no_limit); seq(bat_a, pend); }
@@ -779,7 +752,6 @@ blend_bwd_kernel(const unsigned* __restrict__ bucket_count,
         if (!cur_is_b) seq(bat_b, head); else seq(bat_a, head);
     }
     if (tail > row0) reduce_rows(tail - row0);
-    return true;
   });
 }
 
@@ -789,11 +761,12 @@ int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, co
     const size_t smem = sizeof(BwdWarpSmem) * BWD_WPC;
     SGS_CUDA_OK(set_max_smem(blend_bwd_kernel, smem));
     SGS_CUDA_OK(launch_pdl(blend_bwd_kernel, blend_grid<BWD_WPC>(lay.tiles), BWD_WPC * 32, smem, stream,
-        reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
-        reinterpret_cast<const uint4*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, bin),
+        reinterpret_cast<const unsigned*>(bin + lay.itemcnt_off),
+        reinterpret_cast<const uint4*>(bin + lay.itemlist_off), lay.tiles,
+        reinterpret_cast<const uint2*>(bin + lay.blklist_off), lay.plane_entries,
         reinterpret_cast<const float4*>(geom + lay.rec_off), bg, W, H, lay.gx,
         reinterpret_cast<const float*>(img + lay.finalT_off),
-        reinterpret_cast<const unsigned*>(img + lay.ncontrib_off), dL_dpix, acc));
+        reinterpret_cast<const unsigned*>(img + lay.nblk_off), dL_dpix, acc));
     return 0;
 }
 

@@ -71,6 +71,7 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.nstat_off = o;    o += align_up((size_t)DEPTH_PASSES * l.nsort_blocks * RADIX * 4, 256);
     l.sortstat_off = o; o += align_up((size_t)(l.passes - DEPTH_PASSES) * l.sort_blocks * RADIX * 4, 256);
     l.bktcnt_off = o;   o += align_up(32 * 4, 256);
+    l.itemcnt_off = o;  o += align_up(32 * 4, 256);                       // work items of the backward blend per length bucket
     l.zero_bytes = o;
     size_t np = (size_t)(P > 0 ? P : 1);
     l.nkeys0_off = o;   o += align_up(np * 4, 256);
@@ -79,8 +80,11 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     l.nvals1_off = o;   o += align_up(np * 4, 256);
     l.rects_off = o;    o += align_up(np * 8, 256);
     l.ranges_off = o;   o += align_up((size_t)l.tiles * 8, 256);
-    l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 16, 256);   // work items (tile, start, end, -) by length bucket
+    l.bktlist_off = o;  o += align_up((size_t)32 * l.tiles * 4, 256);        // tiles by length bucket
+    l.itemlist_off = o; o += align_up((size_t)32 * l.tiles * 8 * 16, 256);   // backward work items (tile * 8 + block, start, entries, -) by length bucket
     size_t cap = (size_t)(L_cap > 0 ? L_cap : 1);
+    l.plane_entries = (cap + 31) / 32 * 32;
+    l.blklist_off = o;  o += align_up(8 * l.plane_entries * 8, 256);
     l.keys0_off = o;    o += align_up(cap * 8, 256);
     l.keys1_off = o;    o += align_up(cap * 8, 256);
     l.vals0_off = o;    o += align_up(cap * 4, 256);
@@ -90,7 +94,8 @@ RasterLayout raster_layout(int P, int W, int H, long long L_cap) {
     size_t pix = (size_t)W * H;
     l.finalT_off = 0;
     l.ncontrib_off = align_up(pix * 4, 256);
-    l.img_bytes = l.ncontrib_off + align_up(pix * 4, 256);
+    l.nblk_off = l.ncontrib_off + align_up(pix * 4, 256);
+    l.img_bytes = l.nblk_off + align_up(pix * 4, 256);
     return l;
 }
 
