@@ -365,6 +365,33 @@ def ab_baselines(cfg, s, dev):
                               "autograd); the fused per-frame path folds both into the rasterizer's kernels"}
     except Exception as e:
         out["lbs"] = {"unavailable": repr(e)[:200]}
+
+    # ---- image loss: the reference's l1_loss + ssim (restated in oracle/loss_oracle.py) run eagerly on the GPU ----
+    try:
+        from oracle import loss_oracle as llo
+        from sings_b200.losses import image_loss
+        H, W = cfg["H"], cfg["W"]
+        gen = torch.Generator(dev).manual_seed(3)
+        gt = torch.rand(3, H, W, device=dev, generator=gen)
+        pred = (gt + 0.1 * torch.randn(3, H, W, device=dev, generator=gen)).clamp(0, 1).requires_grad_(True)
+        mask = (torch.rand(H, W, device=dev, generator=gen) > 0.3).float()
+        bgc = torch.ones(3, device=dev)
+
+        def torch_loss():
+            pred.grad = None
+            llo.human_image_loss(pred, gt, mask, bgc)[0].backward()
+
+        def our_loss():
+            pred.grad = None
+            image_loss(pred, gt, mask, bgc)[0].backward()
+        t_torch, t_ours = timed(torch_loss, 10), timed(our_loss, 10)
+        out["loss"] = {"torch_eager_ms": round(t_torch, 4), "ours_ms": round(t_ours, 4),
+                       "speedup_vs_torch": round(t_torch / t_ours, 2), "kind": "port",
+                       "note": "L1 + SSIM image loss fwd+bwd (HumanLoss.forward's image terms: l1_loss + ssim, five "
+                               "depthwise conv2d + elementwise ops, autograd) as eager torch CUDA ops vs "
+                               "sings_b200.losses.image_loss (sgs_image_loss_fwd + _bwd through autograd)"}
+    except Exception as e:
+        out["loss"] = {"unavailable": repr(e)[:200]}
     return out
 
 
@@ -641,7 +668,7 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
         t = lambda a: torch.as_tensor(a, device=dev)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         # the same dense gradient image quantised to 8 bits: how a target image is stored on disk
-        t8 = np.clip(np.rint(s["G_np"] * U8_SCALE + 127.5), 0, 255).astype(np.uint8)
+        t8 = np.ascontiguousarray(np.clip(np.rint(s["G_np"] * U8_SCALE + 127.5), 0, 255).astype(np.uint8).transpose(1, 2, 0))
         host.append(dict(pose=pin(s["pose"]), transl=pin(s["transl"]), G=pin(s["G_np"]), T8=pin(t8), view=s["view"],
                          bg=t(s["bg"]), vm=t(s["view"].world_view_transform),
                          pm=t(s["view"].full_proj_transform), cp=t(s["view"].camera_center)))
@@ -653,7 +680,7 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
     NBUF = 2
     stage = [dict(pose=torch.empty(J, 3, device=dev), transl=torch.empty(3, device=dev),
                   G=torch.empty(3, H, W, device=dev),
-                  T8=torch.empty(3, H, W, device=dev, dtype=torch.uint8), ready=torch.cuda.Event(),
+                  T8=torch.empty(H, W, 3, device=dev, dtype=torch.uint8), ready=torch.cuda.Event(),
                   free=torch.cuda.Event()) for _ in range(NBUF)]
     loss_host = torch.zeros(NBUF).pin_memory()
     loss_ev = [torch.cuda.Event() for _ in range(NBUF)]
@@ -820,26 +847,34 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
            "api": "C ABI (include/sings_b200.h) driven by sings_b200.step.AvatarStep with preallocated buffers"
                   + ("" if args.no_graph else ", one CUDA graph per frame")}
     if train and not args.no_graph and not PROBE:
-        # Variant: the per-step image goes up as uint8 (a quarter of the bytes) and is decoded
-        # on the device inside the graph.  Reported beside the float32 headline because the
-        # float upload is bound by the box's host link, not by the GPU (tools/e2e_probe.sh).
+        # Variant: what a trainer does -- the step's TARGET image goes up as the dataset's uint8
+        # (H, W, 3) (a quarter of the bytes of a float32 dL/dimage), and the image loss of the
+        # reference (L1 + SSIM, HumanLoss.forward) and its gradient are computed on the device by
+        # the fused loss kernels between forward and backward, inside the graph.  Reported beside
+        # the float32-gradient headline, which is bound by the box's host link, not by the GPU.
+        from sings_b200.losses import ImageLossBuffers
         upload["u8"] = True
         drain_exchange()
         torch.cuda.synchronize()
+        loss_bufs = [ImageLossBuffers(H, W, dev) for _ in range(NBUF)]
 
-        def decode(k):
-            sb = stage[k % NBUF]
-            return lambda: torch.mul(torch.sub(sb["T8"].float(), 127.5), 1.0 / U8_SCALE, out=sb["G"])
+        def loss_of(k):
+            sb, lb, bgk = stage[k % NBUF], loss_bufs[k % NBUF], host[k]["bg"]
+
+            def fn(img):
+                dL = lb.run(img, sb["T8"], None, bgk)
+                return lb.loss_value, dL
+            return fn
         for k in range(ring):
-            replays[k] = sets[k]["step"].capture(frames[k], stage[k % NBUF]["G"], loss_weight=stage[k % NBUF]["G"],
-                                                 prologue=decode(k), stages=False)
+            replays[k] = sets[k]["step"].capture(frames[k], None, loss_fn=loss_of(k), stages=False)
         run(step_abi, ring)
         ms8 = timed(step_abi, n)
         upload["u8"] = False
         out["u8_upload"] = {"value": world * n / (ms8 / 1e3), "unit": "frames/s", "steps": n, "ms_per_step": ms8 / n,
                             "h2d_bytes_per_step": h2d - 3 * H * W * 3, "d2h_bytes_per_step": 4,
-                            "note": "same C-ABI loop; dL/dimage uploaded as uint8 and decoded on the device "
-                                    "(torch sub/mul inside the graph)"}
+                            "note": "same C-ABI loop; the target image is uploaded as uint8 (H, W, 3) and the reference's "
+                                    "image loss (L1 + SSIM) and its gradient are computed on the device by the fused "
+                                    "loss kernels (sgs_image_loss_fwd / _bwd) between forward and backward, inside the graph"}
     if params:
         nd = max(10, min(args.steps, 100))
         run(step_dropin, ring)   # checked mode: sizes the pair-list capacity for every avatar of the ring

@@ -174,6 +174,25 @@ int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_
  * four numpy passes on the host; `out` (4-byte aligned) is then copied out at a quarter of the bytes. */
 int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* out, sgs_stream_t stream);
 
+/* ---- image loss: fused L1 + SSIM of the rendered image against the masked
+ * ground truth.  Replaces /root/reference/sings/rec/losses/loss.py:57-70 (HumanLoss.forward:
+ * gt' = gt m + bg (1 - m); l1 = sum |pred - gt'| / sum m; ssim term = (1 - mean ssim_map) *
+ * (sum m / (H W))) with l1_loss / ssim of /root/reference/sings/rec/losses/utils.py:16-70 (11x11
+ * window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2).
+ *   pred (3,H,W) float; gt (3,H,W) float, or (H,W,3) uint8 when gt_is_u8_hwc (value / 255);
+ *   mask (H,W) float or null (= ones); bg (3); scratch: sgs_image_loss_scratch_floats(H, W) floats,
+ *   written by _fwd and read by _bwd; sums: 4 doubles, 8-byte aligned, written by _fwd:
+ *   [0] = sum |pred - gt'|, [1] = sum of the SSIM map over 3 H W values, [2] = sum m.
+ * The loss is  w_l1 sums[0] / sums[2] + w_ssim (1 - sums[1] / (3 H W)) (sums[2] / (H W))  (the
+ * caller combines the three numbers: they stay on the device).  _bwd writes dL/dpred (3,H,W) of
+ * that loss times *dloss (device scalar, null = 1) and, if loss_out is given, the loss itself. */
+size_t sgs_image_loss_scratch_floats(int H, int W);
+int sgs_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_is_u8_hwc, const float* mask,
+                       const float* bg, float* scratch, double* sums, sgs_stream_t stream);
+int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, const double* sums,
+                       float w_l1, float w_ssim, const float* dloss, float* dL_dpred, float* loss_out,
+                       sgs_stream_t stream);
+
 /* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
  * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]
  * rasterizer_impl.cu).  The result is in (keys,vals) when *result_in_tmp (host) == 0, else

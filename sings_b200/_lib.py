@@ -52,6 +52,9 @@ _SIGNATURES = {
     "sgs_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_fold_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_frame_to_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "sgs_image_loss_scratch_floats": (_sz, [_i, _i]),
+    "sgs_image_loss_fwd": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_image_loss_bwd": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "sgs_sort_scratch_bytes": (_sz, [_ll]),
     "sgs_sort_pairs_u64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _ll, _i, C.POINTER(_i), _vp]),
     "sgs_pose_to_A": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

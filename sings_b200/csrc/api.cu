@@ -469,6 +469,28 @@ int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* ou
     return launch_frame_to_u8(image, H, W, bgr, out, (cudaStream_t)stream);
 }
 
+size_t sgs_image_loss_scratch_floats(int H, int W) {
+    return H > 0 && W > 0 ? (size_t)12 * H * W : 0;     // 9 planes of map derivatives + 3 of the composited target
+}
+
+int sgs_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_is_u8_hwc, const float* mask,
+                       const float* bg, float* scratch, double* sums, sgs_stream_t stream) {
+    if (H <= 0 || W <= 0 || !pred || !gt || !bg || !scratch || !sums) return SGS_ERR_BAD_ARG;
+    if ((uintptr_t)sums & 7) return SGS_ERR_MISALIGNED;
+    const size_t plane = (size_t)H * W;
+    return launch_image_loss_fwd(H, W, pred, gt, gt_is_u8_hwc, mask, bg, scratch, scratch + 9 * plane, sums,
+                                 (cudaStream_t)stream);
+}
+
+int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, const double* sums,
+                       float w_l1, float w_ssim, const float* dloss, float* dL_dpred, float* loss_out,
+                       sgs_stream_t stream) {
+    if (H <= 0 || W <= 0 || !pred || !scratch || !sums || !dL_dpred) return SGS_ERR_BAD_ARG;
+    const size_t plane = (size_t)H * W;
+    return launch_image_loss_bwd(H, W, pred, scratch + 9 * plane, scratch, sums, w_l1, w_ssim, dloss, dL_dpred,
+                                 loss_out, (cudaStream_t)stream);
+}
+
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }
 
 int sgs_sort_pairs_u64(unsigned long long* keys, unsigned int* vals,

@@ -130,6 +130,13 @@ int launch_mark_visible(int P, const float* means3D, const float* view, unsigned
 // (3,H,W) float image -> (H,W,3) uint8: clamp(0,1) * 255 truncated, optional RGB -> BGR (frame_out.cu)
 int launch_frame_to_u8(const float* img, int H, int W, int bgr, unsigned char* out, cudaStream_t stream);
 
+// fused L1 + SSIM image loss (image_loss.cu)
+int launch_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_u8, const float* mask,
+                          const float* bg, float* part, float* gtc, double* sums, cudaStream_t stream);
+int launch_image_loss_bwd(int H, int W, const float* pred, const float* gtc, const float* part,
+                          const double* sums, float w_l1, float w_ssim, const float* dloss,
+                          float* dL_dpred, float* loss_out, cudaStream_t stream);
+
 int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream);
 int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
                       float* denom, float* max_radii, cudaStream_t stream);

@@ -53,10 +53,16 @@ constexpr int FWD_U = SGS_FWD_U;      // pairs evaluated together per pixel in t
 // lower bounds of tile and tile + 1 over the sorted keys -- 4 dependent L2 round trips at a
 // million pairs instead of the 21 of a binary search; no pass over the list, no atomics on
 // the ranges, no memset.  The CTA (8 tiles) then files its tiles in buckets by list length
-// (bucket = bit length of the count, 0 = empty) so the blend kernels can take tiles
+// (two buckets per octave of the length, bucket 0 = empty) so the blend kernels can take tiles
 // longest-first: the few tiles with thousands of pairs must not form the tail.
 constexpr int LEN_BUCKETS = 32;
 constexpr int RANGE_THREADS = 256;
+
+// bucket of a list of c >= 1 entries: two per octave, monotonic in c
+__device__ __forceinline__ unsigned length_bucket(unsigned c) {
+    const unsigned l = 31u - (unsigned)__clz(c);
+    return l == 0u ? 0u : min((unsigned)LEN_BUCKETS - 1u, 2u * l + ((c >> (l - 1u)) & 1u));
+}
 
 // first index in [0, n) whose key's tile id is >= target (warp-cooperative)
 __device__ __forceinline__ unsigned warp_lower_bound(const unsigned long long* __restrict__ keys,
@@ -98,7 +104,8 @@ __device__ __forceinline__ void tile_ranges_block(int block, const unsigned long
     if (warp != 0) return;
     const int tt = block * (RANGE_THREADS / 32) + lane;
     const bool ok = lane < RANGE_THREADS / 32 && tt < tiles;
-    const unsigned bk = ok ? (unsigned)(32 - __clz(s_len[lane])) % LEN_BUCKETS : 0xffffffffu;
+    // bucket 0 = empty tiles (last in the longest-first order), else two buckets per octave of the length
+    const unsigned bk = ok ? (s_len[lane] ? max(1u, length_bucket(s_len[lane])) : 0u) : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, bk);
     const int leader = __ffs(peers) - 1;
     unsigned slot = 0;
@@ -145,12 +152,6 @@ __device__ __forceinline__ void for_each_tile_item(const unsigned* __restrict__ 
     const BucketScan bs = bucket_scan(bucket_count);
     fn(tile_of_rank(bs, bucket_list, tiles, blockIdx.x / PARTS),
        (int)(blockIdx.x % PARTS) * WPC + (int)(threadIdx.x >> 5));
-}
-
-// bucket of a list of c >= 1 entries: two per octave, monotonic in c
-__device__ __forceinline__ unsigned length_bucket(unsigned c) {
-    const unsigned l = 31u - (unsigned)__clz(c);
-    return l == 0u ? 0u : min((unsigned)LEN_BUCKETS - 1u, 2u * l + ((c >> (l - 1u)) & 1u));
 }
 
 __device__ __forceinline__ uint4 item_of_rank(const BucketScan& bs, const uint4* __restrict__ bucket_list,

@@ -255,7 +255,7 @@ class AvatarStep:
             L_.sgs_timing_record(tm, 11, st)
 
     def capture(self, fr: FrameInputs, dL_dimage: Optional[torch.Tensor], loss_weight: Optional[torch.Tensor] = None,
-                prologue=None, stages: bool = True, stage_mask: Optional[int] = None):
+                prologue=None, stages: bool = True, stage_mask: Optional[int] = None, loss_fn=None):
         """Record forward(fr) [+ loss = <image, loss_weight>] + backward(dL_dimage) into a CUDA
         graph and return replay() (dL_dimage None: the forward alone, e.g. animation frames).  The launch sequence is static -- capacity-sized pair list,
         device-side counts, no host round trip -- so the whole frame becomes one graph launch.
@@ -263,18 +263,20 @@ class AvatarStep:
         place before each replay.  Stage events keep working (external event-record nodes).
         `prologue()` (optional) runs first inside the graph -- e.g. the caller's decoding of an
         uploaded target image into `dL_dimage` / `loss_weight`.  stages=False leaves the stage
-        event records out of the graph (see record_stages)."""
+        event records out of the graph (see record_stages).
+        `loss_fn(image) -> (loss, dL_dimage)` (optional, instead of dL_dimage / loss_weight) runs
+        between forward and backward inside the graph -- e.g. sings_b200.losses.ImageLossBuffers."""
         keep, self.record_stages = self.record_stages, bool(stages)
         if self.timing and stage_mask is not None:     # record only these stage events in this graph
             self.L.sgs_timing_set_mask(self.timing, int(stage_mask) & 0xffffffff)
         try:
-            return self._capture(fr, dL_dimage, loss_weight, prologue)
+            return self._capture(fr, dL_dimage, loss_weight, prologue, loss_fn)
         finally:
             self.record_stages = keep
             if self.timing and stage_mask is not None:
                 self.L.sgs_timing_set_mask(self.timing, 0xffffffff)
 
-    def _capture(self, fr, dL_dimage, loss_weight, prologue):
+    def _capture(self, fr, dL_dimage, loss_weight, prologue, loss_fn=None):
         cur = torch.cuda.current_stream(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
@@ -282,13 +284,15 @@ class AvatarStep:
             if prologue is not None:
                 prologue()
             img = self.forward(fr)
+            if loss_fn is not None:
+                self.loss, dL_dimage = loss_fn(img)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
             if dL_dimage is not None:
                 self.backward(dL_dimage)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        if prologue is None and loss_weight is None and not os.environ.get("SGS_TORCH_GRAPH"):
+        if prologue is None and loss_weight is None and loss_fn is None and not os.environ.get("SGS_TORCH_GRAPH"):
             # the pure C-ABI frame: recorded through the library (no torch op inside), replayed
             # with a single cudaGraphLaunch on the current stream
             h = C.c_void_p()
@@ -312,6 +316,8 @@ class AvatarStep:
             if prologue is not None:
                 prologue()
             img = self.forward(fr)
+            if loss_fn is not None:
+                self.loss, dL_dimage = loss_fn(img)
             if loss_weight is not None:
                 self.loss = torch.dot(img.view(-1), loss_weight.view(-1))
             if dL_dimage is not None:
