@@ -421,6 +421,7 @@ def gpu_arm(args, cfg):
         step = AvatarStep(t(av.xyz_canon), None if cfg["iso"] else t(av.rotmat_canon), t(av.scales), t(av.opacity),
                           t(av.shs), t(av.lbs_weights), t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano),
                           H, W, D, timing=True)
+        step.forward_only = not train          # c1 / c4: no backward follows, the forward leaves nothing for one
         fr = FrameInputs(pose=t(pose), transl=t(transl), viewmatrix=t(view.world_view_transform),
                          projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(bg),
                          tanfovx=view.tanfovx, tanfovy=view.tanfovy)

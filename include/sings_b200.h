@@ -45,6 +45,10 @@ typedef void* sgs_stream_t; /* cudaStream_t */
                                    this library's (e.g. sgs_lbs_fwd before the forward, the forward's own
                                    kernels before the backward): the SH rows are then fetched ahead of the
                                    programmatic-dependency wait, while the preceding kernel drains */
+#define SGS_FLAG_FORWARD_ONLY 8 /* no backward will follow this forward (inference / animation): the forward
+                                   blend then skips the per-block lists and work items it otherwise leaves
+                                   for the backward (sgs_raster_backward after such a forward is an error
+                                   the library cannot detect: its gradients are garbage) */
 
 int sgs_version(void);
 const char* sgs_error_string(int code);

@@ -77,7 +77,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-FLAG_SYNC_CHECK, FLAG_PRECLEARED, FLAG_EARLY_PARAMS = 1, 2, 4      # bits of the rasterizer entry points' `debug` argument
+FLAG_SYNC_CHECK, FLAG_PRECLEARED, FLAG_EARLY_PARAMS, FLAG_FORWARD_ONLY = 1, 2, 4, 8   # bits of the rasterizer entry points' `debug` argument
 
 
 class SgsError(RuntimeError):

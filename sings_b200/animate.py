@@ -129,6 +129,7 @@ def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0
     if out is None:
         out = torch.empty(max(n, 0), 3, step.H, step.Wd, device=step.dev, dtype=torch.float32)
     from ._lib import SgsError
+    keep, step.forward_only = step.forward_only, True      # no backward follows an animation frame
     first = lo
     while first < hi:
         overflow_at = None
@@ -147,6 +148,7 @@ def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0
         if overflow_at is None:
             break
         first = overflow_at            # capacity has been raised: redo the last block
+    step.forward_only = keep
     if clamp:
         out[:n].clamp_(0.0, 1.0)
     return lo, hi, out[:n]

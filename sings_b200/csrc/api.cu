@@ -79,7 +79,7 @@ static inline void tick(void* timing, int i, cudaStream_t s) {
 
 extern "C" {
 
-int sgs_version(void) { return 200; }
+int sgs_version(void) { return 210; }
 
 int sgs_timing_create(int n_events, void** handle) {
     if (n_events < 1 || !handle) return SGS_ERR_BAD_ARG;
@@ -247,6 +247,7 @@ static int raster_forward_impl(int P, int D, int M, int W, int H, const float* b
     RasterLayout lay = raster_layout(P, W, H, L_cap);
     char* g = (char*)geom; char* b = (char*)binning; char* im = (char*)img;
     const bool precleared = (debug & SGS_FLAG_PRECLEARED) != 0;
+    const bool forward_only = (debug & SGS_FLAG_FORWARD_ONLY) != 0;
     a.early_params = (debug & SGS_FLAG_EARLY_PARAMS) != 0;
     debug &= SGS_FLAG_SYNC_CHECK;
     // {num_rendered, overflow} for the host: by the emission kernel when the memory is mapped
@@ -273,7 +274,7 @@ static int raster_forward_impl(int P, int D, int M, int W, int H, const float* b
     if (rc) return rc;
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));
     tick(timing, 3, stream);
-    rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, stream);
+    rc = launch_blend_fwd(lay, W, H, g, b, im, bg, out_color, out_alpha, out_depth, !forward_only, stream);
     if (rc) return rc;
     tick(timing, 4, stream);
     if (debug) SGS_CUDA_OK(cudaStreamSynchronize(stream));

@@ -98,9 +98,10 @@ size_t sort_scratch_bytes(long long n);
 // tile ranges (+ tiles bucketed by list length)
 int launch_tile_ranges(const RasterLayout& lay, long long L_cap, char* bin, cudaStream_t stream);
 
+// for_backward: leave the per-block lists and work items the backward blend walks
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
-                     float* out_depth, cudaStream_t stream);
+                     float* out_depth, bool for_backward, cudaStream_t stream);
 
 int launch_blend_bwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      const char* img, const float* bg, const float* dL_dpix, float* acc,

@@ -312,12 +312,15 @@ struct FwdBatch {
 struct FwdWarpSmem {
     RingGeo geo;
     float4 c[RING_SLOTS];
+    unsigned pos[RING_SLOTS];        // position in the tile's list + 1 (forward-only frames, which keep no block lists)
 };
 
 #ifndef SGS_FWD_CTAS
 #define SGS_FWD_CTAS 5             // resident CTAs per SM the register budget is cut for (102 registers at 128 threads)
 #endif
-template <bool AUX>
+// FOR_BWD: leave the block lists, n_blk and the work items for the backward (a forward-only frame --
+// animation, evaluation -- skips them and tracks the tile-list position of the last contributor itself).
+template <bool AUX, bool FOR_BWD>
 __global__ void __launch_bounds__(FWD_WPC * 32, SGS_FWD_CTAS)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ bucket_count,
                  const unsigned* __restrict__ bucket_list, int tiles,
@@ -367,6 +370,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     // entry gets alpha 0 (1 - alpha = 1 exactly) and index 0.
     auto eval = [&](FwdBatch& e, unsigned base, unsigned limit, auto LIMIT) {
         const unsigned s0 = base & (RING_SLOTS - 1);
+        unsigned pos4[4] = {0u, 0u, 0u, 0u};
+        if (!FOR_BWD) {
+            const uint4 pp = *reinterpret_cast<const uint4*>(&sm.pos[s0]);
+            pos4[0] = pp.x; pos4[1] = pp.y; pos4[2] = pp.z; pos4[3] = pp.w;
+        }
 #pragma unroll
         for (int h = 0; h < FWD_U / 2; h++) {
             const PairEval pe = ring_eval(sm.geo, (s0 >> 1) + h, npx, npy);
@@ -381,7 +389,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
                 al2[j] = ok ? al : 0.0f;
                 e.al[u] = al2[j];
                 e.c[u] = sm.c[s0 + u];
-                e.pos[u] = ok ? base + u + 1u : 0u;
+                e.pos[u] = ok ? (FOR_BWD ? base + u + 1u : pos4[u]) : 0u;
             }
             const float2 om = ffma2(make_float2(al2[0], al2[1]), splat2(-1.0f), splat2(1.0f));    // 1 - alpha
             e.om[2 * h] = om.x; e.om[2 * h + 1] = om.y;
@@ -432,7 +440,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
             const unsigned slot = idx & (RING_SLOTS - 1);
             ring_put(sm.geo, slot, p.q0, p.q1);
             sm.c[slot] = make_float4(p.q1.w, p.q2.x, p.q2.y, p.q2.z);
-            bl[idx] = make_uint2(m0 & ID_MASK, (unsigned)(pos + lane));
+            if (FOR_BWD) bl[idx] = make_uint2(m0 & ID_MASK, (unsigned)(pos + lane));
+            else sm.pos[slot] = (unsigned)(pos + lane + 1);
         }
         tail += __popc(bits);
         __syncwarp();
@@ -454,7 +463,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
         else           { eval(bat_a, head, tail, with_limit); composite(bat_b); composite(bat_a); }
     }
     // the backward's work item: the entries of this block's list up to the last contributor of any pixel
-    const unsigned wlast = __reduce_max_sync(0xffffffffu, last);
+    const unsigned wlast = FOR_BWD ? __reduce_max_sync(0xffffffffu, last) : 0u;
     if (wlast != 0u && lane == 0) {
         const unsigned bk = length_bucket(wlast);
         const unsigned slot = atomicAdd(&item_count[bk], 1u);
@@ -463,8 +472,12 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const unsigned* __restrict__ 
     __syncwarp();                                // the list entries written by other lanes are visible
     if (inside) {
         final_T[pix] = T;                        // a saturated pixel reports the T it stopped at
-        n_blk[pix] = last;                       // last contributor: index in the block's list + 1 (the backward starts there)
-        n_contrib[pix] = last ? bl[last - 1u].y + 1u : 0u;            // ... and its position in the tile's list + 1 ([upstream] n_contrib)
+        if (FOR_BWD) {
+            n_blk[pix] = last;                   // last contributor: index in the block's list + 1 (the backward starts there)
+            n_contrib[pix] = last ? bl[last - 1u].y + 1u : 0u;        // ... and its position in the tile's list + 1 ([upstream] n_contrib)
+        } else {
+            n_contrib[pix] = last;
+        }
         out_color[pix] = __fmaf_rn(T, bg[0], C01.x);
         out_color[plane + pix] = __fmaf_rn(T, bg[1], C01.y);
         out_color[2 * plane + pix] = __fmaf_rn(T, bg[2], C2D.x);
@@ -488,9 +501,11 @@ extern "C" int sgs_debug_trace_read(void* host, size_t bytes) {
 
 int launch_blend_fwd(const RasterLayout& lay, int W, int H, const char* geom, const char* bin,
                      char* img, const float* bg, float* out_color, float* out_alpha,
-                     float* out_depth, cudaStream_t stream) {
+                     float* out_depth, bool for_backward, cudaStream_t stream) {
     const long long blocks = (long long)lay.tiles * (TILE_WARPS / FWD_WPC);
-    SGS_CUDA_OK(launch_pdl(out_depth ? blend_fwd_kernel<true> : blend_fwd_kernel<false>, (unsigned)blocks, FWD_WPC * 32, 0, stream,
+    auto kernel = for_backward ? (out_depth ? blend_fwd_kernel<true, true> : blend_fwd_kernel<false, true>)
+                               : (out_depth ? blend_fwd_kernel<true, false> : blend_fwd_kernel<false, false>);
+    SGS_CUDA_OK(launch_pdl(kernel, (unsigned)blocks, FWD_WPC * 32, 0, stream,
         reinterpret_cast<const uint2*>(bin + lay.ranges_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktcnt_off),
         reinterpret_cast<const unsigned*>(bin + lay.bktlist_off), lay.tiles, sorted_vals(lay, const_cast<char*>(bin)),

@@ -190,6 +190,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             acc = scratch[o3:o3 + ab] if needs_grad else None
             row = _pinned_row(di)
             flags = int(bool(rs.debug))
+            if not needs_grad:
+                flags |= _lib.FLAG_FORWARD_ONLY        # no backward can follow: skip what the forward leaves for it
             if P > 0:
                 _lib.check(L_.sgs_raster_clear(P, W, H, L_cap, _lib.ptr(binning), _lib.ptr(acc), None, 0,
                                                st), "sgs_raster_clear")

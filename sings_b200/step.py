@@ -111,6 +111,9 @@ class AvatarStep:
         # blend backward) are this library's and never write it, so its rows may be prefetched
         # ahead of the dependency wait (SGS_FLAG_EARLY_PARAMS)
         self._early = 0 if os.environ.get("SGS_NO_EARLY_PARAMS") else _lib.FLAG_EARLY_PARAMS
+        # set for inference / animation (no backward() will follow a forward()): the forward then
+        # skips the per-block lists and work items it otherwise leaves for the backward blend
+        self.forward_only = False
         self._graphs = []
         self.timing = None
         # stage events are recorded only while this is set.  Inside a captured frame every
@@ -177,6 +180,8 @@ class AvatarStep:
         cnt_ptr = self.counters.data_ptr() + 8 * (int(slot) % self.COUNTER_SLOTS)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         self._fr = fr
+        fo = _lib.FLAG_FORWARD_ONLY if self.forward_only else 0
+        self._fwd_was_forward_only = bool(self.forward_only)
         pose = fr.pose.reshape(1, self.J, 3)
         tm = self.timing if self.record_stages else None
         # everything the frame needs zeroed is cleared here, up front: a memset between two
@@ -192,7 +197,7 @@ class AvatarStep:
                 C.byref(d), self.D, self.M, self.Wd, self.H, p(fr.bg), p(self.opacity), 1.0, p(fr.viewmatrix),
                 p(fr.projmatrix), p(fr.campos), float(fr.tanfovx), float(fr.tanfovy), p(self.shs), self.L_cap,
                 p(self.geom), p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-                cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_avatar_forward")
+                cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early | fo, tm), "sgs_avatar_forward")
             return self.color
         if tm:
             L_.sgs_timing_record(tm, 8, st)
@@ -207,7 +212,7 @@ class AvatarStep:
             p(self.sc), 1.0, p(self.rotq), None, p(fr.viewmatrix), p(fr.projmatrix), p(fr.campos),
             float(fr.tanfovx), float(fr.tanfovy), p(self.shs), 0, self.L_cap, p(self.geom),
             p(self.binning), p(self.img), p(self.color), p(self.radii), None, None,
-            cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early, tm), "sgs_raster_forward")
+            cnt_ptr, st, _lib.FLAG_PRECLEARED | self._early | fo, tm), "sgs_raster_forward")
         return self.color
 
     def backward(self, dL_dimage: torch.Tensor, stream=None, stats: bool = True):
@@ -216,6 +221,8 @@ class AvatarStep:
         L_, p = self.L, _lib.ptr
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         fr = self._fr
+        if getattr(self, "_fwd_was_forward_only", False):
+            raise _lib.SgsError("backward() after a forward_only forward(): the forward left no block lists for it")
         tm = self.timing if self.record_stages else None
         flags = (_lib.FLAG_PRECLEARED if self._bwd_clean else 0) | self._early
         if not self._bwd_clean:            # a second backward of the same forward: clear again
@@ -357,6 +364,15 @@ class AvatarStep:
             raise _lib.SgsError(f"pair list overflowed (needed {L}); capacity raised to {self.L_cap}: re-render the "
                                 f"frame(s) and capture() again")
         return L
+
+    def image_state(self) -> dict:
+        """final_T (H,W) float32 and n_contrib (H,W) int32 of the last forward ([upstream] imgBuffer contents)."""
+        from .rasterizer import layout_info
+        info = layout_info(self.N, self.Wd, self.H, self.L_cap)
+        n = self.H * self.Wd
+        raw = self.img
+        return {"final_T": raw[info["final_T"]:info["final_T"] + 4 * n].view(torch.float32).view(self.H, self.Wd).clone(),
+                "n_contrib": raw[info["n_contrib"]:info["n_contrib"] + 4 * n].view(torch.int32).view(self.H, self.Wd).clone()}
 
     def interval_ms(self, i: int, j: int) -> float:
         """Device time between stage events i and j of the last frame that recorded both."""

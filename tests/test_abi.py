@@ -82,4 +82,4 @@ def test_flag_constants_match_header():
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "sings_b200.h")).read()
     flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SGS_FLAG_(\w+)\s+(\d+)", hdr)}
     assert flags == {"SYNC_CHECK": _lib.FLAG_SYNC_CHECK, "PRECLEARED": _lib.FLAG_PRECLEARED,
-                     "EARLY_PARAMS": _lib.FLAG_EARLY_PARAMS}
+                     "EARLY_PARAMS": _lib.FLAG_EARLY_PARAMS, "FORWARD_ONLY": _lib.FLAG_FORWARD_ONLY}

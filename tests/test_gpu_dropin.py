@@ -351,3 +351,32 @@ def test_config_c3_turnaround_views_gradient_accumulation():
     assert rel_err(ex.xyz_gradient_accum.cpu().numpy(), o_accum) < 1e-3
     assert float(step.bucket[step.n_param_grads:].abs().max()) == 0.0 and float(step.max_radii2D.abs().max()) == 0.0
     assert all(torch.isfinite(p).all() for p in d_pose)
+
+
+def test_forward_only_frames_render_the_same_image_and_refuse_a_backward():
+    """A forward-only AvatarStep (animation / evaluation) leaves nothing for the backward blend: same
+    image, same n_contrib / final_T, and backward() refuses instead of reading lists that were never
+    written."""
+    import numpy as np
+    import torch
+    from helpers import make_scene
+    from sings_b200._lib import SgsError
+    from sings_b200.step import AvatarStep, FrameInputs
+    dev = torch.device("cuda", 0)
+    sc = make_scene(N=6000, H=200, W=176, seed=21)
+    av, view = sc["avatar"], sc["view"]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    fr = FrameInputs(pose=t(sc["pose"]), transl=t(sc["transl"]), viewmatrix=t(view.world_view_transform),
+                     projmatrix=t(view.full_proj_transform), campos=t(view.camera_center), bg=t(np.array([0.2, 0.3, 0.4], np.float32)),
+                     tanfovx=view.tanfovx, tanfovy=view.tanfovy)
+    mk = lambda: AvatarStep(t(av.xyz_canon), t(av.rotmat_canon), t(av.scales), t(av.opacity), t(av.shs), t(av.lbs_weights),
+                            t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano), view.image_height, view.image_width, 3)
+    a, b = mk(), mk()
+    b.forward_only = True
+    ia, ib = a.forward(fr).clone(), b.forward(fr).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(ia, ib)
+    sa, sb = a.image_state(), b.image_state()
+    assert torch.equal(sa["n_contrib"], sb["n_contrib"]) and torch.equal(sa["final_T"], sb["final_T"])
+    with pytest.raises(SgsError):
+        b.backward(torch.ones_like(ib))
