@@ -326,14 +326,15 @@ __device__ __forceinline__ void lbs_bwd_one(const LbsFuse& lf, const float4* sA,
 // Shared memory of the CTA-level reduction below, for a CTA of THREADS threads and J joints.
 template <int THREADS>
 __host__ __device__ constexpr size_t lbs_reduce_smem_bytes(int J, int K) {
-    return (size_t)THREADS * 48 + (size_t)THREADS * K * 8 + (size_t)(THREADS / 32) * J * 48;
+    return (size_t)THREADS * 48 + (size_t)THREADS * K * 8 + (size_t)(THREADS / 32) * 2 * J * 48;      // two tiles per warp
 }
 
 // dL/dA[j] = sum_n W[n,j] dT_n and dL/dtransl = sum_n g_x over the CTA's Gaussians, with the
-// packed weights: every warp folds its 32 rows, one after the other, into a private J x 12 tile
-// (lane = (slot, float4 group of the 3x4 block): the joints of one row are distinct, so a row is
-// one conflict-free LDS.128 / 4 FMA / STS.128 per lane); the CTA then adds its warps' tiles and
-// issues one atomic per non-zero entry.  `raw`: lbs_reduce_smem_bytes, 16-byte aligned.  All
+// packed weights: every warp folds its 32 rows into private J x 12 tiles (lane = (slot, float4
+// group of the 3x4 block): the joints of one row are distinct, so a row is one conflict-free
+// LDS.128 / 4 FMA / STS.128 per lane).  With up to five slots per row -- the usual case, K = 4 --
+// the two halves of the warp take two rows at a time, each into its own tile; the CTA then adds
+// the tiles and issues one atomic per non-zero entry.  `raw`: lbs_reduce_smem_bytes, 16-byte aligned.  All
 // threads of the CTA call it (dT = 0 and weights 0 for threads without a Gaussian).
 template <int THREADS>
 __device__ __forceinline__ void lbs_bwd_reduce(const LbsFuse& lf, char* raw, const float* dT, const float* g_x,
@@ -342,7 +343,7 @@ __device__ __forceinline__ void lbs_bwd_reduce(const LbsFuse& lf, char* raw, con
     float4* const s_dT = reinterpret_cast<float4*>(raw);                                  // [THREADS][3]
     float2* const s_wj = reinterpret_cast<float2*>(raw + (size_t)THREADS * 48);           // [THREADS][K] (weight, joint bits)
     float* const s_part = reinterpret_cast<float*>(raw + (size_t)THREADS * 48 + (size_t)THREADS * lf.K * 8);   // [warps][J][12]
-    for (int f = tid; f < (THREADS / 32) * lf.J * 12; f += THREADS) s_part[f] = 0.0f;
+    for (int f = tid; f < (THREADS / 32) * 2 * lf.J * 12; f += THREADS) s_part[f] = 0.0f;
     if (lf.d_transl) {
         const float t0 = warp_sum(live ? g_x[0] : 0.0f), t1 = warp_sum(live ? g_x[1] : 0.0f), t2 = warp_sum(live ? g_x[2] : 0.0f);
         if (lane == 0) { atomicAdd(lf.d_transl, t0); atomicAdd(lf.d_transl + 1, t1); atomicAdd(lf.d_transl + 2, t2); }
@@ -356,15 +357,16 @@ __device__ __forceinline__ void lbs_bwd_reduce(const LbsFuse& lf, char* raw, con
             s_wj[(size_t)tid * lf.K + k] = make_float2(live ? pw.w[k] : 0.0f,
                                                        __uint_as_float((pw.idx[k >> 2] >> (8 * (k & 3))) & 0xffu));
     __syncthreads();                           // the tiles are zero; (the rows below are this warp's own)
-    float4* const tile4 = reinterpret_cast<float4*>(s_part + (size_t)warp * lf.J * 12);
     const float4* const dT4 = s_dT + (size_t)warp * 32 * 3;
     const float2* const wj = s_wj + (size_t)warp * 32 * lf.K;
-    const int kk = lane / 3, g = lane - 3 * kk;          // 10 slots x 3 float4 groups per round (lanes 30, 31 idle)
-    for (int r0 = 0; r0 < lf.K; r0 += 10) {
-        const int k = r0 + kk;
-        const bool act = kk < 10 && k < lf.K;
+    if (lf.K <= 5) {
+        // two rows per step: lanes 0..14 fold row 2 i, lanes 15..29 row 2 i + 1 (5 slots x 3 float4 groups each)
+        const int h = lane / 15, q = lane - 15 * h, k = q / 3, g = q - 3 * k;
+        const bool act = lane < 30 && k < lf.K;
+        float4* const tile4 = reinterpret_cast<float4*>(s_part + ((size_t)warp * 2 + (h & 1)) * lf.J * 12);
 #pragma unroll 4
-        for (int l = 0; l < 32; l++) {
+        for (int i = 0; i < 16; i++) {
+            const int l = 2 * i + h;
             if (act) {
                 const float2 e = wj[l * lf.K + k];
                 if (e.x != 0.0f) {
@@ -375,14 +377,35 @@ __device__ __forceinline__ void lbs_bwd_reduce(const LbsFuse& lf, char* raw, con
                     tile4[j * 3 + g] = v;
                 }
             }
-            __syncwarp();      // row l is folded in before any lane reads a tile entry for row l + 1
+            __syncwarp();      // rows 2 i, 2 i + 1 are folded in before any lane reads a tile entry for the next two
+        }
+    } else {
+        float4* const tile4 = reinterpret_cast<float4*>(s_part + (size_t)warp * 2 * lf.J * 12);
+        const int kk = lane / 3, g = lane - 3 * kk;          // 10 slots x 3 float4 groups per round (lanes 30, 31 idle)
+        for (int r0 = 0; r0 < lf.K; r0 += 10) {
+            const int k = r0 + kk;
+            const bool act = kk < 10 && k < lf.K;
+#pragma unroll 4
+            for (int l = 0; l < 32; l++) {
+                if (act) {
+                    const float2 e = wj[l * lf.K + k];
+                    if (e.x != 0.0f) {
+                        const unsigned j = __float_as_uint(e.y);
+                        const float4 d = dT4[l * 3 + g];
+                        float4 v = tile4[j * 3 + g];
+                        v.x = fmaf(e.x, d.x, v.x); v.y = fmaf(e.x, d.y, v.y); v.z = fmaf(e.x, d.z, v.z); v.w = fmaf(e.x, d.w, v.w);
+                        tile4[j * 3 + g] = v;
+                    }
+                }
+                __syncwarp();      // row l is folded in before any lane reads a tile entry for row l + 1
+            }
         }
     }
     __syncthreads();
     for (int oidx = tid; oidx < lf.J * 12; oidx += THREADS) {
         float accv = 0.0f;
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) accv += s_part[(size_t)w * lf.J * 12 + oidx];
+        for (int w = 0; w < 2 * (THREADS / 32); w++) accv += s_part[(size_t)w * lf.J * 12 + oidx];
         const int j = oidx / 12, c = oidx - j * 12;
         if (accv != 0.0f) atomicAdd(lf.d_A + (size_t)j * 16 + 4 * (c >> 2) + (c & 3), accv);
     }
