@@ -788,6 +788,25 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
         loss.backward()
         finish_step(i, loss, sb)
 
+    # ---- one-call autograd path (sings_b200.fused.AvatarRenderer) ----
+    renderers = []
+
+    def step_fused(i, n_total):
+        hs, sb, p, r = host[i % ring], stage[i % NBUF], params[i % ring], renderers[i % ring]
+        if i + 1 < n_total:
+            prefetch(i + 1)
+        cur.wait_event(sb["ready"])
+        pose = sb["pose"].detach().requires_grad_(True)
+        transl = sb["transl"].detach().requires_grad_(True)
+        v = hs["view"]
+        img, radii = r(pose, transl, hs["vm"], hs["pm"], hs["cp"], hs["bg"], v.tanfovx, v.tanfovy)
+        loss = (img * sb["G"]).sum()
+        for q in (p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"]):
+            if q is not None:
+                q.grad = None
+        loss.backward()
+        finish_step(i, loss, sb)
+
     def run(step, n):
         for sb in stage:
             sb["free"].record(cur)
@@ -887,6 +906,22 @@ def run_e2e(args, cfg, sets, dev, world, rank, exch, ring):
         out["dropin"] = {"value": world * nd / (msd / 1e3), "unit": "frames/s", "steps": nd, "ms_per_step": msd / nd,
                          "api": "sings_b200.deform.pose_to_A + deform_gaussians + "
                                 "diff_gaussian_rasterization.GaussianRasterizer (torch.autograd)"}
+        from sings_b200.fused import AvatarRenderer
+        for p in params:
+            renderers.append(AvatarRenderer(p["xyz"], p["rot"], p["scales"], p["opacity"], p["shs"], p["W"], p["rest"],
+                                            p["parents"], p["inv_A"], H, W, D, sync_check=False))
+            renderers[-1].step.L_cap = max(renderers[-1].step.L_cap, sets[0]["step"].L_cap)
+            renderers[-1].step._alloc_scratch()
+        run(step_fused, ring)
+        for r in renderers:
+            r.check()
+        msf = timed(step_fused, nd)
+        for r in renderers:
+            r.check()
+        out["fused_autograd"] = {"value": world * nd / (msf / 1e3), "unit": "frames/s", "steps": nd, "ms_per_step": msf / nd,
+                                 "api": "sings_b200.fused.AvatarRenderer: the same computation as ONE torch.autograd "
+                                        "Function over the fused kernels (opt-in, INTEGRATION.md 2b); loss = <image, G> and "
+                                        ".backward() through autograd, gradients cloned out of the bucket"}
     return out
 
 

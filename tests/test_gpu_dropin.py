@@ -380,3 +380,48 @@ def test_forward_only_frames_render_the_same_image_and_refuse_a_backward():
     assert torch.equal(sa["n_contrib"], sb["n_contrib"]) and torch.equal(sa["final_T"], sb["final_T"])
     with pytest.raises(SgsError):
         b.backward(torch.ones_like(ib))
+
+
+def test_avatar_renderer_matches_the_three_function_path():
+    """sings_b200.fused.AvatarRenderer (one autograd Function over the fused kernels) gives the image
+    and every gradient of the reference-shaped path (pose_to_A + deform_gaussians + GaussianRasterizer)."""
+    import numpy as np
+    import torch
+    from helpers import assert_grad_close, make_scene, raster_settings
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from sings_b200 import deform
+    from sings_b200.fused import AvatarRenderer
+    dev = torch.device("cuda", 0)
+    sc = make_scene(N=7000, H=208, W=160, seed=31)
+    av, view = sc["avatar"], sc["view"]
+    t = lambda a, rg=False: torch.tensor(np.ascontiguousarray(a), device=dev, requires_grad=rg)
+    bg = np.array([0.3, 0.1, 0.6], np.float32)
+    G = t(np.random.default_rng(1).normal(size=(3, view.image_height, view.image_width)).astype(np.float32))
+
+    def leaves():
+        return dict(pose=t(sc["pose"], True), transl=t(sc["transl"], True), xyz=t(av.xyz_canon, True),
+                    rot=t(av.rotmat_canon, True), scl=t(av.scales, True), opa=t(av.opacity, True), shs=t(av.shs, True))
+    # reference-shaped path
+    a = leaves()
+    A = deform.pose_to_A(a["pose"], t(av.rest), torch.from_numpy(av.parents), t(av.inv_A_t2cano))
+    xyz, rotq, scl = deform.deform_gaussians(A, a["xyz"], t(av.lbs_weights), a["rot"], a["scl"], None, a["transl"])
+    m2 = torch.zeros_like(xyz, requires_grad=True)
+    img_a, radii_a = GaussianRasterizer(raster_settings(view, bg, 3))(means3D=xyz, means2D=m2, shs=a["shs"], opacities=a["opa"],
+                                                                        scales=scl, rotations=rotq)
+    (img_a * G).sum().backward()
+    # one call
+    b = leaves()
+    r = AvatarRenderer(b["xyz"], b["rot"], b["scl"], b["opa"], b["shs"], t(av.lbs_weights), t(av.rest),
+                       torch.from_numpy(av.parents), t(av.inv_A_t2cano), view.image_height, view.image_width, 3)
+    img_b, radii_b = r(b["pose"], b["transl"], t(view.world_view_transform), t(view.full_proj_transform),
+                       t(view.camera_center), t(bg), view.tanfovx, view.tanfovy)
+    (img_b * G).sum().backward()
+    torch.cuda.synchronize()
+    assert torch.equal(img_a, img_b) and torch.equal(radii_a, radii_b)
+    for k in a:
+        assert_grad_close(b[k].grad.cpu().numpy(), a[k].grad.cpu().numpy(), k)
+    # a second frame reuses the buffers; no-grad call renders the same image
+    with torch.no_grad():
+        img_c, _ = r(b["pose"], b["transl"], t(view.world_view_transform), t(view.full_proj_transform),
+                     t(view.camera_center), t(bg), view.tanfovx, view.tanfovy)
+    assert torch.equal(img_c, img_b)
