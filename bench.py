@@ -392,6 +392,28 @@ def ab_baselines(cfg, s, dev):
                                "sings_b200.losses.image_loss (sgs_image_loss_fwd + _bwd through autograd)"}
     except Exception as e:
         out["loss"] = {"unavailable": repr(e)[:200]}
+
+    # ---- neighbour search of the scale-edge loss (loss_items.py:57-90; pytorch3d.knn_points is not installed:
+    #      the comparator is the same exact search as chunked torch.cdist + topk on the GPU) ----
+    try:
+        from sings_b200.losses import knn_points
+        xyz = torch.as_tensor(s["av"].xyz_canon, device=dev).float().contiguous()
+
+        def torch_knn():
+            outs = []
+            for i in range(0, xyz.shape[0], 4096):
+                d = torch.cdist(xyz[i:i + 4096], xyz)
+                outs.append(torch.topk(d, 9, dim=1, largest=False)[0][:, 1:].mean(1))
+            return torch.cat(outs)
+        t_ours = timed(lambda: knn_points(xyz, 8), 10)
+        t_torch = timed(torch_knn, 3)
+        same = bool(torch.allclose(knn_points(xyz, 8), torch_knn(), rtol=1e-3, atol=1e-7))    # (cdist is the looser side: |a|^2 + |b|^2 - 2ab)
+        out["knn"] = {"points": int(xyz.shape[0]), "K": 8, "torch_cdist_topk_ms": round(t_torch, 3), "ours_ms": round(t_ours, 4),
+                      "speedup_vs_torch": round(t_torch / t_ours, 1), "same_mean_distances": same, "kind": "port",
+                      "note": "mean distance to the 8 nearest other Gaussians (GaussiansEdgeLoss, every iteration in the "
+                              "reference): exact grid search (sgs_knn_mean_dist) vs brute-force chunked torch.cdist + topk"}
+    except Exception as e:
+        out["knn"] = {"unavailable": repr(e)[:200]}
     return out
 
 

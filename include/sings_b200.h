@@ -178,6 +178,20 @@ int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_
  * four numpy passes on the host; `out` (4-byte aligned) is then copied out at a quarter of the bytes. */
 int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* out, sgs_stream_t stream);
 
+/* ---- neighbour distances: exact K nearest neighbours of every point of
+ * xyz (N,3) among the other points of the set, by Euclidean distance.  Replaces
+ * pytorch3d.ops.knn_points(verts[None], verts[None], K + 1) at
+ * /root/reference/sings/rec/losses/loss_items.py:75 (whose first column is the point itself; K here
+ * counts the real neighbours: the reference's K=9 is K=8) and :78-79:
+ *   mean_dist (N)   mean over the K neighbours of |x_j - x_i|      (nullable)
+ *   idx (N,K) int   neighbours, nearest first (-1 where the set has fewer than K + 1 points; ties in
+ *                   arbitrary order)                                (nullable)
+ *   dist2 (N,K)     their squared distances, ascending              (nullable)
+ * 1 <= K <= 16.  scratch: sgs_knn_scratch_bytes(N) bytes, 256-byte aligned. */
+size_t sgs_knn_scratch_bytes(int N);
+int sgs_knn_mean_dist(int N, const float* xyz, int K, void* scratch, size_t scratch_bytes, float* mean_dist,
+                      int* idx, float* dist2, sgs_stream_t stream);
+
 /* ---- image loss: fused L1 + SSIM of the rendered image against the masked
  * ground truth.  Replaces /root/reference/sings/rec/losses/loss.py:57-70 (HumanLoss.forward:
  * gt' = gt m + bg (1 - m); l1 = sum |pred - gt'| / sum m; ssim term = (1 - mean ssim_map) *

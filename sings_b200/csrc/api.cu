@@ -492,6 +492,18 @@ int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, co
                                  loss_out, (cudaStream_t)stream);
 }
 
+size_t sgs_knn_scratch_bytes(int N) {
+    int max_cells = 0;
+    knn_grid_resolution(N, &max_cells);
+    return knn_scratch_bytes(N, max_cells);
+}
+
+int sgs_knn_mean_dist(int N, const float* xyz, int K, void* scratch, size_t scratch_bytes, float* mean_dist,
+                      int* idx, float* dist2, sgs_stream_t stream) {
+    if (N < 0 || (N > 0 && (!xyz || !scratch)) || (!mean_dist && !idx && !dist2)) return SGS_ERR_BAD_ARG;
+    return launch_knn(N, xyz, K, (char*)scratch, scratch_bytes, mean_dist, idx, dist2, (cudaStream_t)stream);
+}
+
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }
 
 int sgs_sort_pairs_u64(unsigned long long* keys, unsigned int* vals,

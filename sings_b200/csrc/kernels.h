@@ -138,6 +138,12 @@ int launch_image_loss_bwd(int H, int W, const float* pred, const float* gtc, con
                           const double* sums, float w_l1, float w_ssim, const float* dloss,
                           float* dL_dpred, float* loss_out, cudaStream_t stream);
 
+// exact K nearest neighbours within a point set + mean neighbour distance (knn.cu)
+size_t knn_scratch_bytes(int N, int max_cells);
+int knn_grid_resolution(int N, int* max_cells);
+int launch_knn(int N, const float* xyz, int K, char* scratch, size_t scratch_bytes, float* mean_dist, int* idx_out,
+               float* d2_out, cudaStream_t stream);
+
 int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream);
 int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
                       float* denom, float* max_radii, cudaStream_t stream);

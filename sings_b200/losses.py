@@ -105,3 +105,49 @@ class ImageLossBuffers:
         hw = float(self.H * self.W)
         s = self.sums
         return (self.w[0] * s[0] / s[2] + self.w[1] * (1.0 - s[1] / (3.0 * hw)) * (s[2] / hw)).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# neighbour distances and the scale-edge loss (loss_items.py:57-90)
+# ------------------------------------------------------------------------------------------
+def knn_points(xyz: torch.Tensor, K: int = 8, return_index: bool = False):
+    """Exact K nearest neighbours of every point of xyz (N, 3) among the OTHER points of the set
+    (sgs_knn_mean_dist): returns mean_dist (N,) = mean |x_j - x_i| over the K neighbours, and with
+    return_index also idx (N, K) int32 nearest first and dist2 (N, K) ascending -- the columns 1..K
+    of pytorch3d.ops.knn_points(xyz[None], xyz[None], K=K + 1), whose column 0 is the point itself.
+    No gradient flows through it (the reference detaches the lengths, loss_items.py:79)."""
+    if not xyz.is_cuda:
+        raise SgsError("sings_b200.losses needs CUDA tensors (there is no CPU path)")
+    x = xyz.detach().to(torch.float32).contiguous()
+    N = x.shape[0]
+    L = _lib.lib()
+    scratch = torch.empty(int(L.sgs_knn_scratch_bytes(N)) + 256, device=x.device, dtype=torch.uint8)
+    base = scratch.data_ptr()
+    off = (-base) % 256
+    mean = torch.empty(N, device=x.device, dtype=torch.float32)
+    idx = torch.empty(N, K, device=x.device, dtype=torch.int32) if return_index else None
+    d2 = torch.empty(N, K, device=x.device, dtype=torch.float32) if return_index else None
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgs_knn_mean_dist(N, _p(x), int(K), base + off, scratch.numel() - off, _p(mean), _p(idx), _p(d2),
+                                       raw_stream(x.device)), "sgs_knn_mean_dist")
+    return (mean, idx, d2) if return_index else mean
+
+
+class GaussiansEdgeLoss(torch.nn.Module):
+    """loss_items.py:57-90, same constructor and call: `loss = GaussiansEdgeLoss(K=9)(human_gs_out)` with
+    human_gs_out['xyz_canon'] (N, 3) and human_gs_out['scales'] (N, 3) (isotropic: column 0 is used).
+    K counts the point itself, as in the reference (K=9 -> 8 neighbours).  The neighbour search -- the
+    expensive part, run over every Gaussian every iteration -- is one call of the library; the loss
+    ((scale_i - mean edge length_i)^2).mean() and its gradient to the scales stay torch ops."""
+
+    def __init__(self, K: int = 9, eps: float = 1e-12):
+        super().__init__()
+        self._K, self._eps = K, eps
+
+    def forward(self, human_gs_out):
+        verts = human_gs_out["xyz_canon"]
+        scales = human_gs_out["scales"][:, 0]
+        edge_lengths = knn_points(verts, self._K - 1).unsqueeze(1)          # (N, 1), detached
+        scale_proj_i = scales.unsqueeze(1)
+        len_factor = 1.0
+        return ((scale_proj_i - len_factor * edge_lengths) ** 2).mean()
