@@ -402,12 +402,12 @@ def ab_baselines(cfg, s, dev):
         def torch_knn():
             outs = []
             for i in range(0, xyz.shape[0], 4096):
-                d = torch.cdist(xyz[i:i + 4096], xyz)
+                d = torch.cdist(xyz[i:i + 4096], xyz, compute_mode="donot_use_mm_for_euclid_dist")
                 outs.append(torch.topk(d, 9, dim=1, largest=False)[0][:, 1:].mean(1))
             return torch.cat(outs)
         t_ours = timed(lambda: knn_points(xyz, 8), 10)
         t_torch = timed(torch_knn, 3)
-        same = bool(torch.allclose(knn_points(xyz, 8), torch_knn(), rtol=1e-3, atol=1e-7))    # (cdist is the looser side: |a|^2 + |b|^2 - 2ab)
+        same = bool(torch.allclose(knn_points(xyz, 8), torch_knn(), rtol=1e-4, atol=1e-7))
         out["knn"] = {"points": int(xyz.shape[0]), "K": 8, "torch_cdist_topk_ms": round(t_torch, 3), "ours_ms": round(t_ours, 4),
                       "speedup_vs_torch": round(t_torch / t_ours, 1), "same_mean_distances": same, "kind": "port",
                       "note": "mean distance to the 8 nearest other Gaussians (GaussiansEdgeLoss, every iteration in the "
