@@ -414,6 +414,39 @@ def ab_baselines(cfg, s, dev):
                               "reference): exact grid search (sgs_knn_mean_dist) vs brute-force chunked torch.cdist + topk"}
     except Exception as e:
         out["knn"] = {"unavailable": repr(e)[:200]}
+
+    # ---- tri-plane features (hexplane.py, shipped configuration: 32 channels, 64^3, multires 1/2/4) ----
+    try:
+        from oracle import hexplane_oracle as hpo
+        from sings_b200.hexplane import HexPlaneField
+        hcfg = {"grid_dimensions": 2, "input_coordinate_dim": 3, "output_coordinate_dim": 32, "resolution": [64, 64, 64],
+                "multires": [1, 2, 4]}
+        field = HexPlaneField(hcfg, bounds=1.3, device=dev)
+        params = [p for gp in field.grids for p in gp]
+        pts = torch.as_tensor(s["av"].xyz_canon, device=dev).float().contiguous().requires_grad_(True)
+        d_out = torch.randn(pts.shape[0], 96, device=dev)
+
+        def clear():
+            pts.grad = None
+            for p in params:
+                p.grad = None
+
+        def torch_hex():
+            clear()
+            f = hpo.hexplane_features(pts, field.aabb, [params[3 * k:3 * k + 3] for k in range(3)])
+            (f * d_out).sum().backward()
+
+        def our_hex():
+            clear()
+            (field(pts) * d_out).sum().backward()
+        t_torch, t_ours = timed(torch_hex, 10), timed(our_hex, 10)
+        out["hexplane"] = {"points": int(pts.shape[0]), "torch_eager_ms": round(t_torch, 4), "ours_ms": round(t_ours, 4),
+                           "speedup_vs_torch": round(t_torch / t_ours, 2), "kind": "port",
+                           "note": "HexPlaneField.forward + backward over all Gaussians (nine grid_sample launches, products, "
+                                   "concatenation, autograd) as eager torch CUDA ops vs sings_b200.hexplane.HexPlaneField "
+                                   "(sgs_hexplane_fwd + _bwd on channel-last planes, incl. the layout copies)"}
+    except Exception as e:
+        out["hexplane"] = {"unavailable": repr(e)[:200]}
     return out
 
 

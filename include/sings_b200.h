@@ -178,6 +178,24 @@ int sgs_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_
  * four numpy passes on the host; `out` (4-byte aligned) is then copied out at a quarter of the bytes. */
 int sgs_frame_to_u8(const float* image, int H, int W, int bgr, unsigned char* out, sgs_stream_t stream);
 
+/* ---- multi-scale tri-plane interpolation (first half of the attribute decode).
+ * Replaces HexPlaneField.forward of /root/reference/sings/rec/models/modules/hexplane.py:165-189
+ * (normalize_aabb :165-166, interpolate_ms_features :70-105 over grid_sample_wrapper :44-68:
+ * bilinear, align_corners=True, padding_mode='border'; per scale the PRODUCT of the planes (0,1),
+ * (0,2), (1,2); scales concatenated), called over all N Gaussians at sings_hybrid.py:252.
+ *   pts (N,3) device; aabb_host: 6 HOST floats = aabb[0] (3), aabb[1] (3) of the module;
+ *   res_host: n_scales x 3 HOST ints (reso x, y, z of each scale); C channels per plane (multiple of 32);
+ *   planes_host: HOST array of 3 * n_scales DEVICE pointers, scale-major, planes in the order above,
+ *   each CHANNEL-LAST (H, W, C) -- i.e. the reference's (1, C, H, W) parameter permuted (0, 2, 3, 1);
+ *   out (N, n_scales * C).  1 <= n_scales <= 4.
+ * _bwd: d_out (N, n_scales * C) -> d_planes_host (HOST array of device pointers, channel-last like
+ * the planes, ACCUMULATED into: zero them first; null = skip) and d_pts (N,3) (null = skip). */
+int sgs_hexplane_fwd(int N, const float* pts, const float* aabb_host, int n_scales, int C, const int* res_host,
+                     const float* const* planes_host, float* out, sgs_stream_t stream);
+int sgs_hexplane_bwd(int N, const float* pts, const float* aabb_host, int n_scales, int C, const int* res_host,
+                     const float* const* planes_host, const float* d_out, float* const* d_planes_host, float* d_pts,
+                     sgs_stream_t stream);
+
 /* ---- neighbour distances: exact K nearest neighbours of every point of
  * xyz (N,3) among the other points of the set, by Euclidean distance.  Replaces
  * pytorch3d.ops.knn_points(verts[None], verts[None], K + 1) at

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "sgs_densify_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_fold_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_frame_to_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "sgs_hexplane_fwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sgs_hexplane_bwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgs_knn_scratch_bytes": (_sz, [_i]),
     "sgs_knn_mean_dist": (_i, [_i, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp]),
     "sgs_image_loss_scratch_floats": (_sz, [_i, _i]),

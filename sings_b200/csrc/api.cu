@@ -492,6 +492,20 @@ int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, co
                                  loss_out, (cudaStream_t)stream);
 }
 
+int sgs_hexplane_fwd(int N, const float* pts, const float* aabb_host, int n_scales, int C, const int* res_host,
+                     const float* const* planes_host, float* out, sgs_stream_t stream) {
+    if (N < 0 || (N > 0 && (!pts || !out))) return SGS_ERR_BAD_ARG;
+    return launch_hexplane_fwd(N, pts, aabb_host, n_scales, C, res_host, planes_host, out, (cudaStream_t)stream);
+}
+
+int sgs_hexplane_bwd(int N, const float* pts, const float* aabb_host, int n_scales, int C, const int* res_host,
+                     const float* const* planes_host, const float* d_out, float* const* d_planes_host, float* d_pts,
+                     sgs_stream_t stream) {
+    if (N < 0 || (N > 0 && (!pts || !d_out)) || (!d_planes_host && !d_pts)) return SGS_ERR_BAD_ARG;
+    return launch_hexplane_bwd(N, pts, aabb_host, n_scales, C, res_host, planes_host, d_out, d_planes_host, d_pts,
+                               (cudaStream_t)stream);
+}
+
 size_t sgs_knn_scratch_bytes(int N) {
     int max_cells = 0;
     knn_grid_resolution(N, &max_cells);

@@ -144,6 +144,13 @@ int knn_grid_resolution(int N, int* max_cells);
 int launch_knn(int N, const float* xyz, int K, char* scratch, size_t scratch_bytes, float* mean_dist, int* idx_out,
                float* d2_out, cudaStream_t stream);
 
+// multi-scale tri-plane interpolation (hexplane.cu); aabb, res, plane pointer arrays are HOST memory
+int launch_hexplane_fwd(int N, const float* pts, const float* aabb_host, int S, int C, const int* res_host,
+                        const float* const* planes_host, float* out, cudaStream_t stream);
+int launch_hexplane_bwd(int N, const float* pts, const float* aabb_host, int S, int C, const int* res_host,
+                        const float* const* planes_host, const float* d_out, float* const* d_planes_host,
+                        float* d_pts, cudaStream_t stream);
+
 int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream);
 int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
                       float* denom, float* max_radii, cudaStream_t stream);
