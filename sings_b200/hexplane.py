@@ -37,7 +37,8 @@ class _Interp(torch.autograd.Function):
         S = len(res) // 3
         p = pts.detach().reshape(-1, 3).to(torch.float32).contiguous()
         N = p.shape[0]
-        # channel-last copies: a bilinear tap becomes one contiguous row of C floats
+        # channel-last (H, W, C): a bilinear tap is one contiguous row of C floats.  For a channels-last
+        # parameter (HexPlaneField below creates them so) this is a view, not a copy.
         cl = [g.detach()[0].permute(1, 2, 0).contiguous() for g in planes]
         out = torch.empty(N, S * Cc, device=p.device, dtype=torch.float32)
         aabb = (C.c_float * 6)(*aabb6)
@@ -93,7 +94,9 @@ class HexPlaneField(nn.Module):
             self._res += reso
             gp = nn.ParameterList()
             for comb in itertools.combinations(range(3), 2):          # (0,1), (0,2), (1,2): init_grid_param, hexplane.py:30-41
-                t = torch.empty([1, Cc] + [reso[cc] for cc in comb[::-1]], device=device)
+                # same shape as the reference's parameter, stored channels-last: the kernels then read the
+                # parameter itself (its (H, W, C) view is contiguous) and no layout copy is made per step
+                t = torch.empty([1, Cc] + [reso[cc] for cc in comb[::-1]], device=device).contiguous(memory_format=torch.channels_last)
                 nn.init.uniform_(t, a=0.1, b=0.5)
                 gp.append(nn.Parameter(t))
             self.feat_dim += Cc
