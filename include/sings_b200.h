@@ -91,8 +91,10 @@ int sgs_graph_destroy(void* graph_exec);
  * ------------------------------------------------------------------------------------- */
 
 /* Scratch sizes in bytes for P Gaussians, a W x H image and room for L_cap (tile,Gaussian)
- * pairs: geom (per-Gaussian records), binning (keys/values/ranges/look-back state),
- * img (final_T, n_contrib), acc (backward accumulator).  Replaces the three resize
+ * pairs: geom (per-Gaussian records), binning (keys/values/ranges/look-back state, and the
+ * per-pixel-block lists + work items the forward leaves for the backward: 8 planes of L_cap
+ * 8-byte entries, mostly untouched), img (final_T, n_contrib, and the last contributor's index in
+ * its block's list), acc (backward accumulator).  Replaces the three resize
  * callbacks of [upstream] rasterize_points.cu (geomBuffer / binningBuffer / imgBuffer). */
 int sgs_raster_sizes(int P, int W, int H, long long L_cap, size_t* geom_bytes,
                      size_t* binning_bytes, size_t* img_bytes, size_t* acc_bytes);
