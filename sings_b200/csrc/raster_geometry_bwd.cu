@@ -29,7 +29,10 @@ constexpr int GB_THREADS = SGS_GB_THREADS;
 // shared memory (lanes = (slot, entry) of the row: distinct addresses, plain read-modify-write);
 // the CTA then adds its warps' tiles and issues one atomic per non-zero entry.
 template <int D, bool HAS_SH, bool VEC16, bool FUSE>
-__global__ void __launch_bounds__(GB_THREADS, FUSE ? (512 / GB_THREADS) : 1)
+#ifndef SGS_GB_CTAS
+#define SGS_GB_CTAS (512 / GB_THREADS)
+#endif
+__global__ void __launch_bounds__(GB_THREADS, FUSE ? SGS_GB_CTAS : 1)
 geometry_bwd_kernel(GeomBwdArgs b, const float4* __restrict__ rec, LbsFuse lf) {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int NVEC = HAS_SH ? sh_nvec(D) : 0;
