@@ -428,7 +428,7 @@ def ab_baselines(cfg, s, dev):
     # ---- tri-plane features (hexplane.py, shipped configuration: 32 channels, 64^3, multires 1/2/4) ----
     try:
         from oracle import hexplane_oracle as hpo
-        from sings_b200.hexplane import HexPlaneField
+        from sings_b200.triplane import HexPlaneField
         hcfg = {"grid_dimensions": 2, "input_coordinate_dim": 3, "output_coordinate_dim": 32, "resolution": [64, 64, 64],
                 "multires": [1, 2, 4]}
         field = HexPlaneField(hcfg, bounds=1.3, device=dev)
@@ -453,7 +453,7 @@ def ab_baselines(cfg, s, dev):
         out["hexplane"] = {"points": int(pts.shape[0]), "torch_eager_ms": round(t_torch, 4), "ours_ms": round(t_ours, 4),
                            "speedup_vs_torch": round(t_torch / t_ours, 2), "kind": "port",
                            "note": "HexPlaneField.forward + backward over all Gaussians (nine grid_sample launches, products, "
-                                   "concatenation, autograd) as eager torch CUDA ops vs sings_b200.hexplane.HexPlaneField "
+                                   "concatenation, autograd) as eager torch CUDA ops vs sings_b200.triplane.HexPlaneField "
                                    "(sgs_hexplane_fwd + _bwd on channel-last planes, incl. the layout copies)"}
     except Exception as e:
         out["hexplane"] = {"unavailable": repr(e)[:200]}

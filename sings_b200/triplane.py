@@ -33,7 +33,7 @@ class _Interp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pts, aabb6, res, Cc, *planes):
         if not pts.is_cuda:
-            raise SgsError("sings_b200.hexplane needs CUDA tensors (there is no CPU path)")
+            raise SgsError("sings_b200.triplane needs CUDA tensors (there is no CPU path)")
         S = len(res) // 3
         p = pts.detach().reshape(-1, 3).to(torch.float32).contiguous()
         N = p.shape[0]
@@ -77,7 +77,7 @@ class HexPlaneField(nn.Module):
     def __init__(self, planeconfig, bounds: float = 1.0, device="cuda"):
         super().__init__()
         if planeconfig["grid_dimensions"] != 2 or planeconfig["input_coordinate_dim"] != 3:
-            raise SgsError("sings_b200.hexplane implements the tri-plane case (grid_dimensions=2, input_coordinate_dim=3)")
+            raise SgsError("sings_b200.triplane implements the tri-plane case (grid_dimensions=2, input_coordinate_dim=3)")
         aabb = torch.tensor([[bounds, bounds, bounds], [-bounds, -bounds, -bounds]], dtype=torch.float32)
         self.aabb = nn.Parameter(aabb, requires_grad=False).to(device)
         self.grid_config = [planeconfig]

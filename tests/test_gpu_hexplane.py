@@ -20,7 +20,7 @@ def close(a, b, name):
 
 
 def field_from(z, dev):
-    from sings_b200.hexplane import HexPlaneField
+    from sings_b200.triplane import HexPlaneField
     cfg = {"grid_dimensions": 2, "input_coordinate_dim": 3, "output_coordinate_dim": int(z["C"]),
            "resolution": [int(v) for v in z["reso"]], "multires": [int(v) for v in z["multires"]]}
     f = HexPlaneField(cfg, bounds=float(z["bounds"]), device=dev)
@@ -50,7 +50,7 @@ def test_matches_reference_golden(path):
 def test_shipped_configuration_against_oracle():
     """human_complex.yaml:39-43: 32 channels, 64^3, multires [1, 2, 4]; 20k points; state_dict keys of the reference."""
     from oracle import hexplane_oracle as ho
-    from sings_b200.hexplane import HexPlaneField
+    from sings_b200.triplane import HexPlaneField
     dev = torch.device("cuda", 0)
     cfg = {"grid_dimensions": 2, "input_coordinate_dim": 3, "output_coordinate_dim": 32, "resolution": [64, 64, 64],
            "multires": [1, 2, 4]}

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sings_b200 import synthetic as syn
-from sings_b200.hexplane import HexPlaneField
+from sings_b200.triplane import HexPlaneField
 from sings_b200.losses import ImageLossBuffers, knn_points
 dev = torch.device("cuda", 0)
 g = torch.Generator(dev).manual_seed(0)
