@@ -78,14 +78,14 @@ class HexPlaneField(nn.Module):
         super().__init__()
         if planeconfig["grid_dimensions"] != 2 or planeconfig["input_coordinate_dim"] != 3:
             raise SgsError("sings_b200.triplane implements the tri-plane case (grid_dimensions=2, input_coordinate_dim=3)")
+        Cc = int(planeconfig["output_coordinate_dim"])
+        if Cc % 32:
+            raise SgsError("output_coordinate_dim must be a multiple of 32")
         aabb = torch.tensor([[bounds, bounds, bounds], [-bounds, -bounds, -bounds]], dtype=torch.float32)
         self.aabb = nn.Parameter(aabb, requires_grad=False).to(device)
         self.grid_config = [planeconfig]
         self.multiscale_res_multipliers = list(planeconfig["multires"])
         self.concat_features = True
-        Cc = int(planeconfig["output_coordinate_dim"])
-        if Cc % 32:
-            raise SgsError("output_coordinate_dim must be a multiple of 32")
         self.grids = nn.ModuleList()
         self.feat_dim = 0
         self._res: List[int] = []

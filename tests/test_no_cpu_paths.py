@@ -34,7 +34,7 @@ def test_triplane_field_mirrors_the_reference_layout_and_refuses_cpu_tensors():
     with pytest.raises(SgsError):
         f(torch.rand(5, 3))
     with pytest.raises(SgsError):
-        HexPlaneField({**cfg, "output_coordinate_dim": 16})
+        HexPlaneField({**cfg, "output_coordinate_dim": 16}, device="cpu")
 
 
 def test_avatar_renderer_refuses_cpu_and_non_contiguous_parameters():
