@@ -83,3 +83,34 @@ def test_flag_constants_match_header():
     flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SGS_FLAG_(\w+)\s+(\d+)", hdr)}
     assert flags == {"SYNC_CHECK": _lib.FLAG_SYNC_CHECK, "PRECLEARED": _lib.FLAG_PRECLEARED,
                      "EARLY_PARAMS": _lib.FLAG_EARLY_PARAMS, "FORWARD_ONLY": _lib.FLAG_FORWARD_ONLY}
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/sings_b200.h compiles as C99 (and C++17) with no torch or CUDA headers, and a C program
+    that takes the address of every declared entry point links against the shared library: the
+    boundary a non-Python host (cgo / JNI / FFI) binds is exactly this header."""
+    import re
+    import shutil
+    import subprocess
+    from sings_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.join(os.path.dirname(__file__), "..")
+    hdr = open(os.path.join(root, "include", "sings_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(sgs_[A-Za-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S))))
+    assert set(names) >= set(_lib.EXPORTS)
+    src = os.path.join(tmp_path, "bind.c")
+    with open(src, "w") as f:
+        f.write('#include "sings_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* fns[] = {\n')
+        f.write("".join(f"    (const void*)&{n},\n" for n in names))
+        f.write('  };\n  printf("%d %d\\n", (int)(sizeof(fns) / sizeof(fns[0])), sgs_version());\n  return 0;\n}\n')
+    inc = os.path.join(root, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-Wno-pedantic", "-fsyntax-only", "-I", inc, src])
+    if shutil.which("g++"):
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", src])
+    _lib.build()
+    libdir = os.path.dirname(_lib.lib_path()) if hasattr(_lib, "lib_path") else os.path.join(root, "sings_b200", "lib")
+    exe = os.path.join(tmp_path, "bind")
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, src, "-o", exe, "-L", libdir, "-lsings_b200", f"-Wl,-rpath,{os.path.abspath(libdir)}"])
+    out = subprocess.check_output([exe]).decode().split()
+    assert int(out[0]) == len(names) and int(out[1]) >= 200
