@@ -221,12 +221,14 @@ int sgs_knn_mean_dist(int N, const float* xyz, int K, void* scratch, size_t scra
  *   mask (H,W) float or null (= ones); bg (3); scratch: sgs_image_loss_scratch_floats(H, W) floats,
  *   written by _fwd and read by _bwd; sums: 4 doubles, 8-byte aligned, written by _fwd:
  *   [0] = sum |pred - gt'|, [1] = sum of the SSIM map over 3 H W values, [2] = sum m.
- * The loss is  w_l1 sums[0] / sums[2] + w_ssim (1 - sums[1] / (3 H W)) (sums[2] / (H W))  (the
- * caller combines the three numbers: they stay on the device).  _bwd writes dL/dpred (3,H,W) of
+ * The loss is  w_l1 sums[0] / sums[2] + w_ssim (1 - sums[1] / (3 H W)) (sums[2] / (H W));  if loss3
+ * (3 device floats) is given, _fwd also writes { loss, l1 = sums[0] / sums[2], ssim term } there
+ * (everything stays on the device).  _bwd writes dL/dpred (3,H,W) of
  * that loss times *dloss (device scalar, null = 1) and, if loss_out is given, the loss itself. */
 size_t sgs_image_loss_scratch_floats(int H, int W);
 int sgs_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_is_u8_hwc, const float* mask,
-                       const float* bg, float* scratch, double* sums, sgs_stream_t stream);
+                       const float* bg, float* scratch, double* sums, float w_l1, float w_ssim, float* loss3,
+                       sgs_stream_t stream);
 int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, const double* sums,
                        float w_l1, float w_ssim, const float* dloss, float* dL_dpred, float* loss_out,
                        sgs_stream_t stream);

@@ -57,7 +57,7 @@ _SIGNATURES = {
     "sgs_knn_scratch_bytes": (_sz, [_i]),
     "sgs_knn_mean_dist": (_i, [_i, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp]),
     "sgs_image_loss_scratch_floats": (_sz, [_i, _i]),
-    "sgs_image_loss_fwd": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sgs_image_loss_fwd": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "sgs_image_loss_bwd": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     "sgs_sort_scratch_bytes": (_sz, [_ll]),
     "sgs_sort_pairs_u64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _ll, _i, C.POINTER(_i), _vp]),

@@ -475,12 +475,13 @@ size_t sgs_image_loss_scratch_floats(int H, int W) {
 }
 
 int sgs_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_is_u8_hwc, const float* mask,
-                       const float* bg, float* scratch, double* sums, sgs_stream_t stream) {
+                       const float* bg, float* scratch, double* sums, float w_l1, float w_ssim, float* loss3,
+                       sgs_stream_t stream) {
     if (H <= 0 || W <= 0 || !pred || !gt || !bg || !scratch || !sums) return SGS_ERR_BAD_ARG;
     if ((uintptr_t)sums & 7) return SGS_ERR_MISALIGNED;
     const size_t plane = (size_t)H * W;
-    return launch_image_loss_fwd(H, W, pred, gt, gt_is_u8_hwc, mask, bg, scratch, scratch + 9 * plane, sums,
-                                 (cudaStream_t)stream);
+    return launch_image_loss_fwd(H, W, pred, gt, gt_is_u8_hwc, mask, bg, scratch, scratch + 9 * plane, sums, w_l1, w_ssim,
+                                 loss3, (cudaStream_t)stream);
 }
 
 int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, const double* sums,

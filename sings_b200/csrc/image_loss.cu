@@ -232,12 +232,25 @@ image_loss_bwd_kernel(int H, int W, const float* __restrict__ pred, const float*
     }
 }
 
+// loss3 = { w_l1 * l1 + w_ssim * ssim_term, l1, ssim_term } from the three sums (one thread)
+__global__ void image_loss_finalize_kernel(int H, int W, const double* __restrict__ sums, float w_l1, float w_ssim,
+                                           float* __restrict__ loss3) {
+    const double hw = (double)H * (double)W;
+    const double l1 = sums[2] > 0.0 ? sums[0] / sums[2] : 0.0;
+    const double ss = (1.0 - sums[1] / (3.0 * hw)) * (sums[2] / hw);
+    loss3[0] = (float)((double)w_l1 * l1 + (double)w_ssim * ss);
+    loss3[1] = (float)l1;
+    loss3[2] = (float)ss;
+}
+
 int launch_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_u8, const float* mask,
-                          const float* bg, float* part, float* gtc, double* sums, cudaStream_t stream) {
+                          const float* bg, float* part, float* gtc, double* sums, float w_l1, float w_ssim,
+                          float* loss3, cudaStream_t stream) {
     SGS_CUDA_OK(cudaMemsetAsync(sums, 0, 4 * sizeof(double), stream));
     const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, 3);
     if (gt_u8) image_loss_fwd_kernel<true><<<grid, LTHREADS, 0, stream>>>(H, W, pred, gt, mask, bg, part, gtc, sums);
     else image_loss_fwd_kernel<false><<<grid, LTHREADS, 0, stream>>>(H, W, pred, gt, mask, bg, part, gtc, sums);
+    if (loss3) image_loss_finalize_kernel<<<1, 1, 0, stream>>>(H, W, sums, w_l1, w_ssim, loss3);
     SGS_LAUNCH_OK();
     return 0;
 }

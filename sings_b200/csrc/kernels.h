@@ -133,7 +133,8 @@ int launch_frame_to_u8(const float* img, int H, int W, int bgr, unsigned char* o
 
 // fused L1 + SSIM image loss (image_loss.cu)
 int launch_image_loss_fwd(int H, int W, const float* pred, const void* gt, int gt_u8, const float* mask,
-                          const float* bg, float* part, float* gtc, double* sums, cudaStream_t stream);
+                          const float* bg, float* part, float* gtc, double* sums, float w_l1, float w_ssim,
+                          float* loss3, cudaStream_t stream);
 int launch_image_loss_bwd(int H, int W, const float* pred, const float* gtc, const float* part,
                           const double* sums, float w_l1, float w_ssim, const float* dloss,
                           float* dL_dpred, float* loss_out, cudaStream_t stream);

@@ -44,15 +44,16 @@ class _ImageLoss(torch.autograd.Function):
         L = _lib.lib()
         scratch = torch.empty(L.sgs_image_loss_scratch_floats(H, W), device=pred.device, dtype=torch.float32)
         sums = torch.empty(4, device=pred.device, dtype=torch.float64)
+        loss3 = torch.empty(3, device=pred.device, dtype=torch.float32)
         with torch.cuda.device(pred.device):
             _lib.check(L.sgs_image_loss_fwd(H, W, _p(pred), _p(gt), int(u8), _p(mask), _p(bg), _p(scratch), _p(sums),
-                                            raw_stream(pred.device)), "sgs_image_loss_fwd")
+                                            float(w_l1), float(w_ssim), _p(loss3), raw_stream(pred.device)),
+                       "sgs_image_loss_fwd")
         ctx.save_for_backward(pred, scratch, sums)
         ctx.hw, ctx.w = (H, W), (float(w_l1), float(w_ssim))
-        hw = float(H * W)
-        l1 = (sums[0] / sums[2]).to(torch.float32)
-        ssim_term = ((1.0 - sums[1] / (3.0 * hw)) * (sums[2] / hw)).to(torch.float32)
-        return w_l1 * l1 + w_ssim * ssim_term, l1.detach(), ssim_term.detach()
+        loss, l1, ss = loss3[0].clone(), loss3[1].clone(), loss3[2].clone()      # (not views of one buffer: autograd outputs)
+        ctx.mark_non_differentiable(l1, ss)
+        return loss, l1, ss
 
     @staticmethod
     def backward(ctx, dloss, _dl1, _dssim):
@@ -96,7 +97,7 @@ class ImageLossBuffers:
         L = _lib.lib()
         st = raw_stream(self.dev) if stream is None else stream
         _lib.check(L.sgs_image_loss_fwd(self.H, self.W, _p(pred), _p(gt), int(gt.dtype == torch.uint8), _p(mask), _p(bg),
-                                        _p(self.scratch), _p(self.sums), st), "sgs_image_loss_fwd")
+                                        _p(self.scratch), _p(self.sums), self.w[0], self.w[1], None, st), "sgs_image_loss_fwd")
         _lib.check(L.sgs_image_loss_bwd(self.H, self.W, _p(pred), _p(self.scratch), _p(self.sums), self.w[0], self.w[1],
                                         None, _p(self.dL_dimage), _p(self.loss_value), st), "sgs_image_loss_bwd")
         return self.dL_dimage
