@@ -19,7 +19,7 @@ def main():
     H = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(H)
     cases = [dict(name="a", reso=[8, 6, 5], multires=[1, 2], C=32, bounds=1.0, N=300, seed=1),
-             dict(name="b", reso=[4, 4, 4], multires=[1, 2, 4], C=64, bounds=1.6, N=257, seed=2)]
+             dict(name="b", reso=[4, 3, 2], multires=[1, 2, 4], C=64, bounds=1.6, N=257, seed=2)]
     for c in cases:
         torch.manual_seed(c["seed"])
         cfg = {"grid_dimensions": 2, "input_coordinate_dim": 3, "output_coordinate_dim": c["C"],
