@@ -457,6 +457,52 @@ def ab_baselines(cfg, s, dev):
                                    "(sgs_hexplane_fwd + _bwd on channel-last planes, incl. the layout copies)"}
     except Exception as e:
         out["hexplane"] = {"unavailable": repr(e)[:200]}
+    # ---- non-image loss terms of gs_trainer.py:363-396: region Laplacians (position, colour, hands) + L2Norm ----
+    try:
+        from oracle import reg_oracle as rgo
+        from sings_b200.regularizers import L2Norm, RegionLaplacianLoss_v2
+        gen = torch.Generator().manual_seed(7)
+        V, R_ = 110_000, 15                    # the subdivided SMPL template the reference trains on
+        labels = torch.sort(torch.randint(0, R_, (V,), generator=gen)).values
+        a = torch.arange(V).repeat_interleave(3)
+        b_ = (a + torch.randint(1, 40, (3 * V,), generator=gen)).clamp(max=V - 1)
+        edges = torch.unique(torch.sort(torch.stack([a, b_], 1), dim=1).values, dim=0)
+        edges = edges[edges[:, 0] != edges[:, 1]].to(dev)
+        labels = labels.to(dev)
+        w = np.linspace(0.5, 1.5, R_)
+        verts = torch.randn(V, 3, device=dev)
+        ours_lap = RegionLaplacianLoss_v2(verts, edges, labels, region_weights=w)
+        ref_lap = rgo.RegionLaplacian(verts, edges, labels, w, sparse=True)
+        N = int(s["av"].xyz_canon.shape[0])
+        xa = torch.randn(V, 3, device=dev, requires_grad=True)
+        sh = torch.randn(V, 16, 3, device=dev, requires_grad=True)
+        off = (0.01 * torch.randn(N, 3, device=dev)).requires_grad_(True)
+        sc = (0.002 + 0.01 * torch.rand(N, 1, device=dev)).repeat(1, 3).requires_grad_(True)
+        opa = torch.rand(N, 1, device=dev, requires_grad=True)
+        l2cfg = dict(lambda_xyz_offsets=0.001, lambda_scales_diff=0.005, max_scale_threshold=0.005, lambda_max_scale=0.01,
+                     min_opacity_threshold=0.2, lambda_min_opacity=0.001)
+        ours_l2 = L2Norm(**l2cfg)
+        leaves = (xa, sh, off, sc, opa)
+
+        def run(lap, l2):
+            for t in leaves:
+                t.grad = None
+            d = {"xyz_offsets": off, "scales": sc, "opacity": opa}
+            loss = 500.0 * lap.forward(xa) + 5.0 * lap.forward(sh[:, 0]) + 1e-5 * lap.forward_hands(xa) + l2(d)
+            loss.backward()
+            return loss
+        l_ref = float(run(ref_lap, lambda d: rgo.l2norm(d, **l2cfg)))
+        l_our = float(run(ours_lap, ours_l2))
+        t_torch = timed(lambda: run(ref_lap, lambda d: rgo.l2norm(d, **l2cfg)), 10)
+        t_ours = timed(lambda: run(ours_lap, ours_l2), 10)
+        out["regularizers"] = {"vertices": V, "gaussians": N, "torch_eager_ms": round(t_torch, 4), "ours_ms": round(t_ours, 4),
+                               "speedup_vs_torch": round(t_torch / t_ours, 2), "kind": "port",
+                               "same_loss": bool(abs(l_ref - l_our) <= 1e-4 * abs(l_ref)),
+                               "note": "RegionLaplacianLoss_v2 on positions, colours and hands + L2Norm, fwd+bwd (per region a "
+                                       "torch.sparse matmul, pow, mean; boolean-mask norms) as eager torch CUDA ops vs "
+                                       "sings_b200.regularizers (one CSR operator; sgs_laplacian_loss_* and sgs_l2norm_*)"}
+    except Exception as e:
+        out["regularizers"] = {"unavailable": repr(e)[:200]}
     return out
 
 

@@ -233,6 +233,49 @@ int sgs_image_loss_bwd(int H, int W, const float* pred, const float* scratch, co
                        float w_l1, float w_ssim, const float* dloss, float* dL_dpred, float* loss_out,
                        sgs_stream_t stream);
 
+/* ---- regularisers on the canonical Gaussians (the non-image terms of
+ * gs_trainer.py:363-396).
+ *
+ * Laplacian terms: y = L x for a FIXED sparse operator L (n x n, CSR: row_ptr (n+1), col_idx, vals;
+ * built once per densification by the host from pytorch3d.ops.laplacian's definition L = D^-1 A - I),
+ * loss = sum_r row_w[r] f(y_r):
+ *   mode 0  f = |y_r|^2 : RegionLaplacianLoss_v2.forward / forward_hands,
+ *           /root/reference/sings/rec/losses/loss_items.py:173-190 -- sum over regions of
+ *           w_region * mean((L_region x_region)^2); all regions are ONE operator with
+ *           row_w[r] = w_region(r) / (n_region(r) * C)
+ *   mode 1  f = |y_r|   : pcd_laplacian_smoothing, loss_items.py:205-214 (row_w = 1 / n)
+ *   x (n, C) floats with row stride ldx >= C (so shs[:n, 0] is taken in place), 1 <= C <= 4;
+ *   y (n, C) dense, written by _fwd and read by _bwd; sum: 1 double (8-byte aligned) = the loss;
+ *   loss_out (1 device float, nullable) = (float)sum.
+ * _bwd: dx (n, C) dense = *dloss (device scalar, null = 1) * L^T (row_w f'(y)) -- a gather over
+ * the CSR of L^T (t_ptr (n+1), t_row, t_val), no atomics; f'(0) = 0 in mode 1 (torch's norm backward). */
+int sgs_laplacian_loss_fwd(int n, int C, const int* row_ptr, const int* col_idx, const float* vals,
+                           const float* row_w, int mode, const float* x, int ldx, float* y, double* sum,
+                           float* loss_out, sgs_stream_t stream);
+int sgs_laplacian_loss_bwd(int n, int C, const int* t_ptr, const int* t_row, const float* t_val,
+                           const float* row_w, int mode, const float* y, const float* dloss, float* dx,
+                           sgs_stream_t stream);
+
+/* L2Norm.forward, /root/reference/sings/rec/losses/loss_items.py:36-54, with s = scales[:, 0]:
+ *   loss = lambda_xyz_offsets |xyz_offsets| + lambda_scales_diff |s - mean(s)|
+ *        + lambda_max_scale |s[s > max_scale_threshold]| + lambda_min_opacity |0.5 - o[o < min_opacity_threshold]|
+ * (Frobenius norms).  xyz_offsets (N,3) dense; scales: column 0 is read with row stride lds floats;
+ * opacity (N); each of the three may be null (its terms are 0, as when the key is absent from the
+ * reference's dict).  sums: 9 doubles (8-byte aligned) written by _fwd and read by _bwd -- [0..4] the
+ * five sums, [5..8] the four norms; loss_out (1 device float, nullable).
+ * _bwd: d_xyz_offsets (N,3), d_scales (N, scale_cols; column 0 carries the gradient, the others are
+ * zeroed), d_opacity (N), each nullable, times *dloss (device scalar, null = 1); the gradient of a
+ * norm that is 0 is 0 (torch's norm backward). */
+int sgs_l2norm_fwd(int N, const float* xyz_offsets, const float* scales, int lds, const float* opacity,
+                   float max_scale_threshold, float min_opacity_threshold, float lambda_xyz_offsets,
+                   float lambda_scales_diff, float lambda_max_scale, float lambda_min_opacity, double* sums,
+                   float* loss_out, sgs_stream_t stream);
+int sgs_l2norm_bwd(int N, const float* xyz_offsets, const float* scales, int lds, int scale_cols,
+                   const float* opacity, float max_scale_threshold, float min_opacity_threshold,
+                   const double* sums, float lambda_xyz_offsets, float lambda_scales_diff, float lambda_max_scale,
+                   float lambda_min_opacity, const float* dloss, float* d_xyz_offsets, float* d_scales,
+                   float* d_opacity, sgs_stream_t stream);
+
 /* Stand-alone stable radix sort of n (u64 key, u32 value) pairs on key bits [0,end_bit):
  * what the rasterizer uses in place of cub::DeviceRadixSort::SortPairs ([upstream]
  * rasterizer_impl.cu).  The result is in (keys,vals) when *result_in_tmp (host) == 0, else

@@ -59,6 +59,10 @@ _SIGNATURES = {
     "sgs_image_loss_scratch_floats": (_sz, [_i, _i]),
     "sgs_image_loss_fwd": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     "sgs_image_loss_bwd": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "sgs_laplacian_loss_fwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "sgs_laplacian_loss_bwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "sgs_l2norm_fwd": (_i, [_i, _vp, _vp, _i, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "sgs_l2norm_bwd": (_i, [_i, _vp, _vp, _i, _i, _vp, _f, _f, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "sgs_sort_scratch_bytes": (_sz, [_ll]),
     "sgs_sort_pairs_u64": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _ll, _i, C.POINTER(_i), _vp]),
     "sgs_pose_to_A": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

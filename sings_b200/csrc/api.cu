@@ -519,6 +519,49 @@ int sgs_knn_mean_dist(int N, const float* xyz, int K, void* scratch, size_t scra
     return launch_knn(N, xyz, K, (char*)scratch, scratch_bytes, mean_dist, idx, dist2, (cudaStream_t)stream);
 }
 
+int sgs_laplacian_loss_fwd(int n, int C, const int* row_ptr, const int* col_idx, const float* vals,
+                           const float* row_w, int mode, const float* x, int ldx, float* y, double* sum,
+                           float* loss_out, sgs_stream_t stream) {
+    if (n < 0 || C < 1 || C > 4 || (mode != 0 && mode != 1) || ldx < C || !sum) return SGS_ERR_BAD_ARG;
+    if (n > 0 && (!row_ptr || !col_idx || !vals || !row_w || !x || !y)) return SGS_ERR_BAD_ARG;
+    if ((uintptr_t)sum & 7) return SGS_ERR_MISALIGNED;
+    return launch_laplacian_loss_fwd(n, C, row_ptr, col_idx, vals, row_w, mode, x, ldx, y, sum, loss_out,
+                                     (cudaStream_t)stream);
+}
+
+int sgs_laplacian_loss_bwd(int n, int C, const int* t_ptr, const int* t_row, const float* t_val,
+                           const float* row_w, int mode, const float* y, const float* dloss, float* dx,
+                           sgs_stream_t stream) {
+    if (n < 0 || C < 1 || C > 4 || (mode != 0 && mode != 1)) return SGS_ERR_BAD_ARG;
+    if (n > 0 && (!t_ptr || !t_row || !t_val || !row_w || !y || !dx)) return SGS_ERR_BAD_ARG;
+    return launch_laplacian_loss_bwd(n, C, t_ptr, t_row, t_val, row_w, mode, y, dloss, dx, (cudaStream_t)stream);
+}
+
+int sgs_l2norm_fwd(int N, const float* xyz_offsets, const float* scales, int lds, const float* opacity,
+                   float max_scale_threshold, float min_opacity_threshold, float lambda_xyz_offsets,
+                   float lambda_scales_diff, float lambda_max_scale, float lambda_min_opacity, double* sums,
+                   float* loss_out, sgs_stream_t stream) {
+    if (N < 0 || !sums || (scales && lds < 1)) return SGS_ERR_BAD_ARG;
+    if ((uintptr_t)sums & 7) return SGS_ERR_MISALIGNED;
+    return launch_l2norm_fwd(N, xyz_offsets, scales, lds, opacity, max_scale_threshold, min_opacity_threshold,
+                             lambda_xyz_offsets, lambda_scales_diff, lambda_max_scale, lambda_min_opacity, sums,
+                             loss_out, (cudaStream_t)stream);
+}
+
+int sgs_l2norm_bwd(int N, const float* xyz_offsets, const float* scales, int lds, int scale_cols,
+                   const float* opacity, float max_scale_threshold, float min_opacity_threshold,
+                   const double* sums, float lambda_xyz_offsets, float lambda_scales_diff, float lambda_max_scale,
+                   float lambda_min_opacity, const float* dloss, float* d_xyz_offsets, float* d_scales,
+                   float* d_opacity, sgs_stream_t stream) {
+    if (N < 0 || !sums) return SGS_ERR_BAD_ARG;
+    if ((d_xyz_offsets && !xyz_offsets) || (d_scales && (!scales || lds < 1 || scale_cols < 1)) ||
+        (d_opacity && !opacity))
+        return SGS_ERR_BAD_ARG;
+    return launch_l2norm_bwd(N, xyz_offsets, scales, lds, scale_cols, opacity, max_scale_threshold,
+                             min_opacity_threshold, sums, lambda_xyz_offsets, lambda_scales_diff, lambda_max_scale,
+                             lambda_min_opacity, dloss, d_xyz_offsets, d_scales, d_opacity, (cudaStream_t)stream);
+}
+
 size_t sgs_sort_scratch_bytes(long long n) { return sort_scratch_bytes(n < 0 ? 0 : n); }
 
 int sgs_sort_pairs_u64(unsigned long long* keys, unsigned int* vals,

@@ -152,6 +152,20 @@ int launch_hexplane_bwd(int N, const float* pts, const float* aabb_host, int S, 
                         const float* const* planes_host, const float* d_out, float* const* d_planes_host,
                         float* d_pts, cudaStream_t stream);
 
+// Laplacian terms and L2Norm of the canonical Gaussians (regularizers.cu)
+int launch_laplacian_loss_fwd(int n, int C, const int* row_ptr, const int* col_idx, const float* vals,
+                              const float* row_w, int mode, const float* x, int ldx, float* y, double* sum,
+                              float* loss_out, cudaStream_t stream);
+int launch_laplacian_loss_bwd(int n, int C, const int* t_ptr, const int* t_row, const float* t_val,
+                              const float* row_w, int mode, const float* y, const float* dloss, float* dx,
+                              cudaStream_t stream);
+int launch_l2norm_fwd(int N, const float* off, const float* scales, int lds, const float* opacity, float thr_s,
+                      float thr_o, float l_off, float l_diff, float l_max, float l_op, double* sums, float* loss_out,
+                      cudaStream_t stream);
+int launch_l2norm_bwd(int N, const float* off, const float* scales, int lds, int S, const float* opacity, float thr_s,
+                      float thr_o, const double* sums, float l_off, float l_diff, float l_max, float l_op,
+                      const float* dloss, float* d_off, float* d_scales, float* d_opacity, cudaStream_t stream);
+
 int launch_clear3(void* a, size_t na, void* b, size_t nb, void* c, size_t nc, cudaStream_t stream);
 int launch_fold_stats(int P, float* step_accum, float* step_denom, float* step_max_radii, float* accum,
                       float* denom, float* max_radii, cudaStream_t stream);
