@@ -15,6 +15,33 @@ _COMMON = '''#pragma once
 #include "emu.h"
 #define SGS_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return (int)_e; } while (0)
 #define SGS_LAUNCH_OK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return (int)_e; } while (0)
+#define SGS_ERR_BAD_ARG -1
+#define SGS_ERR_BAD_SH_DEGREE -2
+#define SGS_ERR_BAD_JOINTS -3
+#define SGS_ERR_MISALIGNED -4
+#define SGS_ERR_CAPACITY -5
+namespace sgs {
+// stand-ins for the helpers of the real common.cuh that are PTX there: programmatic dependent launch
+// (ordering only), the streaming load (a cache hint)
+inline void pdl_wait() {}
+inline void pdl_launch_dependents() {}
+inline void pdl_sync() {}
+inline float4 ldg_stream_f4(const float4* p) { return *p; }
+// packed-pair arithmetic (fma / mul / add .rn.f32x2 in the real header): two independent IEEE operations
+inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline float2 fmul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 fadd2(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+inline float2 splat2(float v) { return float2{v, v}; }
+inline float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
+    emu::launch(kernel, grid, block, static_cast<KArgs>(args)...);
+    return cudaSuccess;
+}
+}  // namespace sgs
 '''
 
 _LAUNCH = re.compile(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^<>;]*>)?)\s*<<<\s*([^;]*?)>>>\s*\(")
