@@ -25,6 +25,7 @@ from __future__ import annotations
 import ctypes as C
 import functools
 import os
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -38,6 +39,7 @@ _pinned: dict = {}             # device index -> (pinned int32 [slots,2], next s
 _pending: list = []            # async mode: (event, pinned row, L_cap) not yet checked
 _SLOTS = 256
 last_num_rendered = 0          # informational: pair count of the last checked forward
+_state_lock = threading.Lock() # host threads rendering concurrently (each on its own stream) share the tables above
 
 
 def set_async(flag: bool) -> None:
@@ -48,32 +50,47 @@ def set_async(flag: bool) -> None:
 
 
 def _pinned_row(dev: int):
-    buf, nxt = _pinned.get(dev, (None, 0))
-    if buf is None:
-        buf = torch.zeros(_SLOTS, 2, dtype=torch.int32).pin_memory()
-    _pinned[dev] = (buf, (nxt + 1) % _SLOTS)
+    with _state_lock:
+        buf, nxt = _pinned.get(dev, (None, 0))
+        if buf is None:
+            buf = torch.zeros(_SLOTS, 2, dtype=torch.int32).pin_memory()
+        _pinned[dev] = (buf, (nxt + 1) % _SLOTS)
     return buf[nxt]
+
+
+def _raise_cap_hint(dev: int, L: int) -> int:
+    with _state_lock:
+        _cap_hint[dev] = max(_cap_hint.get(dev, 0), int(L * 1.3) + 4096)
+        return _cap_hint[dev]
 
 
 def check_pending(block: bool = False) -> None:
     """Async mode: examine finished forwards; raise if one overflowed its pair-list capacity."""
     global last_num_rendered
+    with _state_lock:
+        todo = list(_pending)
+        _pending.clear()
     keep = []
-    for ev, row, cap, dev in _pending:
-        if block:
-            ev.synchronize()
-        if ev.query():
-            L, ovf = int(row[0]), int(row[1])
-            last_num_rendered = L
-            _cap_hint[dev] = max(_cap_hint.get(dev, 0), int(L * 1.3) + 4096)
-            if ovf:
-                _pending.clear()
-                raise _lib.SgsError(
-                    f"rasterizer pair list overflowed (needed {L}, capacity {cap}) in async mode; "
-                    "the frame is incomplete. Capacity has been raised; re-render the frame.")
-        else:
-            keep.append((ev, row, cap, dev))
-    _pending[:] = keep
+    try:
+        while todo:
+            ev, row, cap, dev = todo.pop(0)
+            if block:
+                ev.synchronize()
+            if ev.query():
+                L, ovf = int(row[0]), int(row[1])
+                last_num_rendered = L
+                _raise_cap_hint(dev, L)
+                if ovf:
+                    todo.clear()
+                    keep.clear()
+                    raise _lib.SgsError(
+                        f"rasterizer pair list overflowed (needed {L}, capacity {cap}) in async mode; "
+                        "the frame is incomplete. Capacity has been raised; re-render the frame.")
+            else:
+                keep.append((ev, row, cap, dev))
+    finally:
+        with _state_lock:
+            _pending[:0] = keep + todo
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -216,16 +233,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             ev.record()                        # current stream of the current device == `dev` (see the guard above)
             ctx.fwd_check = None
             if _ASYNC:
-                _pending.append((ev, row, L_cap, di))
+                with _state_lock:
+                    _pending.append((ev, row, L_cap, di))
                 ctx.fwd_check = (ev, row, L_cap)
                 break
             ev.synchronize()
             L, ovf = int(row[0]), int(row[1])
             last_num_rendered = L
-            _cap_hint[di] = max(_cap_hint.get(di, 0), int(L * 1.3) + 4096)
+            hint = _raise_cap_hint(di, L)
             if not ovf:
                 break
-            L_cap = _cap_hint[di]
+            L_cap = hint
         ctx.raster_settings = rs
         ctx.L_cap = L_cap
         ctx.dims = (P, D, M, W, H)
