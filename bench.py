@@ -685,6 +685,13 @@ def gpu_arm(args, cfg):
                 "blend_bwd": "blend_bwd_kernel", "geometry_bwd": "geometry_bwd_kernel"}[dom]
         if kern in tj.get("kernels", {}) and tj.get("config", "c2") == args.config:
             traffic, traffic_src = tj["kernels"][kern]["dram_bytes"], f"profiles/{tj.get('source')} ({kern})"
+            if dom == "binning":        # a stage of several kernels: DRAM bytes of all its launches, not of the emission alone
+                try:
+                    parts = [("onesweep_pass_kernel", 4 + (passes - 4)), ("emit_pairs_kernel", 1), ("tile_ranges_kernel", 1)]
+                    traffic = int(sum(tj["kernels"][k]["dram_bytes"] * n for k, n in parts))
+                    traffic_src = f"profiles/{tj.get('source')} (" + " + ".join(f"{n} x {k}" for k, n in parts) + ")"
+                except Exception:
+                    pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": stages_out[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
         "frac": stages_out[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,

@@ -1,11 +1,13 @@
 """A complete optimisation loop on the device with the pieces of this repository: pose -> deform ->
-rasterize (one autograd call), the reference's image loss (L1 + SSIM) and scale-edge loss, Adam on
-the Gaussian parameters.  Synthetic avatar and target (no SMPL assets needed):
+rasterize (one autograd call), the reference's image loss (L1 + SSIM), scale-edge loss, L2Norm regulariser
+and a Laplacian smoothing term, Adam on the Gaussian parameters.  Synthetic avatar and target (no SMPL assets needed):
 
     python examples/train_step.py [--steps 50] [--gaussians 50000] [--size 512]
 
 What maps to what in SinGS: AvatarRenderer = sings_hybrid.py:390-428 + gs_renderer_single.py:48-101,
-image_loss = HumanLoss.forward's image terms (loss.py:57-70), GaussiansEdgeLoss = loss_items.py:57-90.
+image_loss = HumanLoss.forward's image terms (loss.py:57-70), GaussiansEdgeLoss = loss_items.py:57-90,
+L2Norm = loss_items.py:15-54, pcd_laplacian_smoothing = loss_items.py:205-214 (the region Laplacians of the
+trainer need the SMPL vertex segmentation; the K-NN graph stands in for the mesh here).
 """
 import argparse
 import os
@@ -19,6 +21,7 @@ import torch
 from sings_b200 import synthetic as syn
 from sings_b200.fused import AvatarRenderer
 from sings_b200.losses import GaussiansEdgeLoss, image_loss
+from sings_b200.regularizers import L2Norm, build_edges, laplacian, pcd_laplacian_smoothing
 
 
 def main():
@@ -55,12 +58,18 @@ def main():
     opt = torch.optim.Adam([{"params": [p["xyz"]], "lr": 2e-4}, {"params": [p["shs"]], "lr": 5e-3},
                             {"params": [p["scales"], p["opacity"]], "lr": 1e-3}])
     edge = GaussiansEdgeLoss(K=9)
+    l2 = L2Norm(lambda_xyz_offsets=0.001, lambda_scales_diff=0.005, max_scale_threshold=0.005, lambda_max_scale=0.01,
+                min_opacity_threshold=0.2, lambda_min_opacity=0.001)             # human_complex.yaml:148-154
+    xyz0 = p["xyz"].detach().clone()
+    lap = laplacian(xyz0, build_edges(xyz0, 6))        # constant between densifications, like the trainer's operators
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for it in range(args.steps):
         image, radii = r(pose, transl, *cam)
         loss, items = image_loss(image, gt_u8, None, cam[3])
         loss = loss + 0.1 * edge({"xyz_canon": p["xyz"], "scales": p["scales"]})
+        loss = loss + l2({"xyz_offsets": p["xyz"] - xyz0, "scales": p["scales"], "opacity": p["opacity"]})
+        loss = loss + 0.01 * pcd_laplacian_smoothing(p["xyz"], lap)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
