@@ -711,6 +711,46 @@ def gpu_arm(args, cfg):
                                  "(~4 us each), so that pass is slower than the headline region, which has none"},
     }
 
+    # ---- informational: two independent frames in flight (two streams, each replaying the graphs of its own
+    # avatars).  NOT the headline: a training step with one view per step is serial by the optimizer.  It applies
+    # where frames really are independent -- animation (c4), several views per rank and step (c3 below 8 GPUs) --
+    # and shows how much of the frame is latency rather than throughput: the per-Gaussian and binning kernels of
+    # one frame leave the SMs partly idle, a second frame's kernels fill them.
+    concurrent = None
+    if rank == 0 and world == 1 and not args.no_graph and ring >= 2 and ring % 2 == 0:
+        try:
+            lanes = [torch.cuda.Stream(dev) for _ in range(2)]
+            n_c = max(2 * ring, min(args.steps, 200))
+
+            def concurrent_region(n):
+                torch.cuda.synchronize(dev)
+                cur = torch.cuda.current_stream(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                for ln in lanes:
+                    ln.wait_event(e0)
+                for i in range(n):                      # avatar i % ring always runs on lane i % 2: its buffers never cross lanes
+                    with torch.cuda.stream(lanes[i % 2]):
+                        sets[i % ring]["replay"]()
+                for ln in lanes:
+                    done = torch.cuda.Event()
+                    done.record(ln)
+                    cur.wait_event(done)
+                e1.record(cur)
+                torch.cuda.synchronize(dev)
+                return e0.elapsed_time(e1)
+            concurrent_region(2 * ring)
+            ms_c = concurrent_region(n_c)
+            for s_ in sets:
+                s_["step"].check_capacity()
+            concurrent = {"frames_in_flight": 2, "value": n_c / (ms_c / 1e3), "unit": "frames/s", "steps": n_c,
+                          "ms_per_frame": ms_c / n_c, "vs_serial": round((n_c / (ms_c / 1e3)) / value, 3),
+                          "note": "two streams, each replaying the frame graphs of its own avatars; informational (independent "
+                                  "frames only: animation, several views per rank and step), not the headline"}
+        except Exception as e:       # a failed probe must not take the bench line down
+            concurrent = {"unavailable": repr(e)[:200]}
+        torch.cuda.synchronize(dev)
+
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -747,6 +787,7 @@ def gpu_arm(args, cfg):
                     "parallelism": f"dp{world} (views sharded, gradient bucket all-reduced every step)" if exch is not None
                                    else (f"dp{world} (frames sharded, no collective)" if world > 1 else "single GPU")},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks, "dp": dp_info, "ab": ab_out,
+            "concurrent": concurrent,
             "gpu_launches": st0.launches_per_frame(train) * args.steps,
         }
         print(json.dumps(line), flush=True)
