@@ -116,14 +116,75 @@ class FrameWriter:
         return self.n
 
 
-def render_frames(step: AvatarStep, frames: Sequence[FrameInputs], rank: int = 0, world: int = 1,
+def _render_lanes(steps, frames, lo: int, hi: int, out: torch.Tensor) -> None:
+    """Frames lo..hi dealt round-robin to `steps`, each AvatarStep on its own stream: the per-Gaussian and
+    binning kernels of one frame leave SMs idle that the other frame's kernels fill (measured with two
+    frames in flight: 1.23x at 1080p / 200k Gaussians, bench.py key `concurrent`).  Every step owns its
+    scratch, image buffer and pinned counters, so nothing crosses lanes; a block of frames is redone if a
+    pair list overflowed in it."""
+    from ._lib import SgsError
+    dev, R = steps[0].dev, len(steps)
+    cur = torch.cuda.current_stream(dev)
+    lanes = [torch.cuda.Stream(dev) for _ in steps]
+    start = torch.cuda.Event()
+    start.record(cur)
+    for ln in lanes:
+        ln.wait_event(start)                 # `out` and the frames' tensors were produced on the caller's stream
+    slots = min(s.COUNTER_SLOTS for s in steps)
+    first = lo
+    while first < hi:
+        end = min(hi, first + slots * R)
+        for f in range(first, end):
+            k = (f - first) % R
+            with torch.cuda.stream(lanes[k]):
+                img = steps[k].forward(frames[f], slot=(f - first) // R)
+                out[f - lo].copy_(img)
+        for ln in lanes:
+            ln.synchronize()
+        grown = False
+        for s in steps:
+            try:
+                s.check_capacity()
+            except SgsError:
+                grown = True                 # its capacity has been raised: redo this block
+        if not grown:
+            first = end
+    for ln in lanes:                         # (already drained; keeps the caller's stream ordered after the lanes)
+        cur.wait_stream(ln)
+
+
+def render_frames(step, frames: Sequence[FrameInputs], rank: int = 0, world: int = 1,
                   out: Optional[torch.Tensor] = None, clamp: bool = True) -> Tuple[int, int, torch.Tensor]:
     """Render this rank's share of `frames`; returns (lo, hi, images (hi-lo, 3, H, W)).
 
     `out` (optional, (>= hi-lo, 3, H, W) on the device) receives the images; `clamp` applies
     the reference's `torch.clamp(rendered_image, 0, 1)` (gs_renderer_single.py:96).  The
     launch sequence per frame has no host synchronisation; the pair-list capacity is checked
-    once at the end (and the affected frames re-rendered if it had to grow)."""
+    once at the end (and the affected frames re-rendered if it had to grow).
+    `step` may be a list of AvatarSteps built over the same avatar: the frames are then dealt
+    round-robin to them, each on its own stream (frames are independent; same images)."""
+    if isinstance(step, (list, tuple)):
+        steps = list(step)
+        if len(steps) == 1:
+            step = steps[0]
+        else:
+            if any((s.H, s.Wd, s.dev) != (steps[0].H, steps[0].Wd, steps[0].dev) for s in steps):
+                raise ValueError("render_frames: the AvatarSteps must share image size and device")
+            lo, hi = dp.shard_frames(len(frames), rank, world)
+            n = hi - lo
+            if out is None:
+                out = torch.empty(max(n, 0), 3, steps[0].H, steps[0].Wd, device=steps[0].dev, dtype=torch.float32)
+            keep = [s.forward_only for s in steps]
+            for s in steps:
+                s.forward_only = True
+            try:
+                _render_lanes(steps, frames, lo, hi, out)
+            finally:
+                for s, k in zip(steps, keep):
+                    s.forward_only = k
+            if clamp:
+                out[:n].clamp_(0.0, 1.0)
+            return lo, hi, out[:n]
     lo, hi = dp.shard_frames(len(frames), rank, world)
     n = hi - lo
     if out is None:

@@ -259,6 +259,46 @@ def test_animation_frames_1080p_sharded_forward_only():
         assert np.array_equal(got[f], st.color)
 
 
+def test_animation_two_lanes_equal_one_lane():
+    """render_frames over two AvatarSteps (two streams, frames dealt round-robin) returns the same bits as over
+    one, also when a pair list overflows in the middle of the sequence (the block is redone)."""
+    from sings_b200 import synthetic as syn
+    from sings_b200.animate import render_frames
+    from sings_b200.step import AvatarStep
+    H, W, F = 272, 400, 9
+    sc = make_scene(N=6000, H=H, W=W, seed=41, scale_range=(0.004, 0.03))
+    frames = [_frame(sc, pose=syn.random_pose(24, seed=300 + f), bg=(0.2, 0.4, 0.6)) for f in range(F)]
+    one = _avatar_step(sc, H, W, D=3)
+    _, _, ref = render_frames(one, frames, clamp=True)
+    ref = ref.clone()
+    lanes = [_avatar_step(sc, H, W, D=3), _avatar_step(sc, H, W, D=3)]
+    lo_, hi_, got = render_frames(lanes, frames, clamp=True)
+    assert (lo_, hi_) == (0, F) and torch.equal(got, ref)
+    assert not lanes[0].forward_only and not lanes[1].forward_only
+    # sharded: rank 1 of 2 gets the second half
+    lo_, hi_, got = render_frames(lanes, frames, rank=1, world=2)
+    assert torch.equal(got, ref[lo_:hi_])
+
+
+def test_animation_lanes_redo_a_block_after_overflow():
+    """Huge Gaussians: every frame needs more pairs than the initial capacity of an AvatarStep; one lane or two,
+    the capacities grow once, the block is rendered again, the images are the same."""
+    from sings_b200 import synthetic as syn
+    from sings_b200.animate import render_frames
+    H, W, F = 272, 400, 5
+    sc = make_scene(N=3000, H=H, W=W, seed=42, scale_range=(0.2, 0.4))
+    frames = [_frame(sc, pose=syn.random_pose(24, seed=400 + f), bg=(0.0, 0.0, 0.0)) for f in range(F)]
+    one = _avatar_step(sc, H, W, D=3)
+    cap0 = one.L_cap
+    _, _, ref = render_frames(one, frames)
+    ref = ref.clone()
+    assert one.L_cap > cap0                                  # the single lane overflowed and recovered
+    lanes = [_avatar_step(sc, H, W, D=3), _avatar_step(sc, H, W, D=3)]
+    _, _, got = render_frames(lanes, frames)
+    assert min(s.L_cap for s in lanes) > cap0
+    assert torch.equal(got, ref)
+
+
 def test_config_c1_neutral_pose_sh0_512():
     """BASELINE.json configs[0]: 50k Gaussians, neutral pose, SH degree 0, one 512x512 view --
     LBS + forward splat through the C ABI against the CPU reference path."""
