@@ -11,70 +11,194 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
-_COMMON = '''#pragma once
-#include "emu.h"
-#define SGS_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return (int)_e; } while (0)
-#define SGS_LAUNCH_OK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return (int)_e; } while (0)
-#define SGS_ERR_BAD_ARG -1
-#define SGS_ERR_BAD_SH_DEGREE -2
-#define SGS_ERR_BAD_JOINTS -3
-#define SGS_ERR_MISALIGNED -4
-#define SGS_ERR_CAPACITY -5
+# Emulation bodies for the helpers of sings_b200/csrc/common.cuh that are inline PTX there.  Everything else of
+# that header (numeric helpers such as expneg / reach_mask / xform_row, enums, launch_pdl) is compiled as it is.
+_EMU_BODIES = {
+    "pdl_launch_dependents": "{}",
+    "pdl_wait": "{}",
+    "ld_relaxed_u64": "{ return __atomic_load_n(p, __ATOMIC_SEQ_CST); }",
+    "st_relaxed_u64": "{ __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }",
+    "ld_relaxed_u32": "{ return __atomic_load_n(p, __ATOMIC_SEQ_CST); }",
+    "st_relaxed_u32": "{ __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }",
+    "ldg_stream_f4": "{ return *p; }",
+    "ldg_f4_pinned": "{ return *p; }",
+    "ldg_u32_pinned": "{ return *p; }",
+    "ldg_u64_pinned": "{ return *p; }",
+    # cp.async: the copy happens at once (a legal execution: data only has to be there after the wait)
+    "cp_async16": "{ memcpy(smem_dst, gmem_src, 16); }",
+    "cp_async4": "{ memcpy(smem_dst, gmem_src, 4); }",
+    "cp_async16_ca": "{ memcpy(smem_dst, gmem_src, 16); }",
+    "cp_async4_zfill": "{ if (valid) memcpy(smem_dst, gmem_src, 4); else memset(smem_dst, 0, 4); }",
+    "cp_async_wait_group": "{}",
+    "cp_async_commit": "{}",
+    "cp_async_wait_all": "{}",
+    # mbarrier + TMA bulk load, for the one pattern the kernels use: thread 0 arms the barrier with the byte total
+    # and issues the copies (synchronous here), every thread then waits for the phase.  Emulated word: bit 63 =
+    # parity of the phase in progress, low bits = bytes still expected.
+    "mbar_init": "{ (void)count; __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }",
+    "mbar_fence_init": "{}",
+    "fence_proxy_async": "{}",
+    "mbar_arrive_expect_tx": "{ __atomic_fetch_add(bar, (unsigned long long)bytes, __ATOMIC_SEQ_CST); if (bytes == 0) emu::mbar_complete_if_done(bar); }",
+    "mbar_wait": "{ while (((__atomic_load_n(bar, __ATOMIC_SEQ_CST) >> 63) & 1ull) == (unsigned long long)(parity & 1u)) std::this_thread::yield(); }",
+    "tma_bulk_g2s": "{ memcpy(smem_dst, gmem_src, bytes); __atomic_fetch_sub(bar, (unsigned long long)bytes, __ATOMIC_SEQ_CST); emu::mbar_complete_if_done(bar); }",
+    "red_add_f4": "{ std::lock_guard<std::mutex> g(emu::atomic_mutex); addr[0] += a; addr[1] += b; addr[2] += c; addr[3] += d; }",
+    "lanemask_lt": "{ return (1u << (emu::linear_tid() & 31u)) - 1u; }",
+    "lanemask_le": "{ const unsigned l = emu::linear_tid() & 31u; return ((1u << l) - 1u) | (1u << l); }",
+    # packed pairs: two independent IEEE round-to-nearest operations
+    "ffma2": "{ return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }",
+    "fmul2": "{ return float2{a.x * b.x, a.y * b.y}; }",
+    "fadd2": "{ return float2{a.x + b.x, a.y + b.y}; }",
+}
+
+_FUNC_HEAD = re.compile(r"(?:template\s*<[^>]*>\s*)?__device__\s+__forceinline__\s+[\w\s\*]+?\b(\w+)\s*\(([^)]*)\)\s*\{")
+
+
+def transform_common(src: str) -> str:
+    """sings_b200/csrc/common.cuh with every function whose body is inline PTX given its emulation body."""
+    out, pos, seen = [], 0, set()
+    for m in _FUNC_HEAD.finditer(src):
+        if m.start() < pos:
+            continue
+        depth, k = 1, m.end()
+        while depth:
+            depth += {"{": 1, "}": -1}.get(src[k], 0)
+            k += 1
+        body = src[m.end() - 1:k]
+        if "asm" not in body:
+            continue
+        name = m.group(1)
+        if name not in _EMU_BODIES:
+            raise KeyError(f"common.cuh: no emulation body for the inline-PTX helper {name}()")
+        seen.add(name)
+        out.append(src[pos:m.end() - 1])
+        out.append(_EMU_BODIES[name])
+        pos = k
+    out.append(src[pos:])
+    res = "".join(out)
+    if "asm" in re.sub(r"//[^\n]*", "", res):
+        raise ValueError("common.cuh: an inline-PTX statement survived the transformation")
+    return res
+
+
+# host-side helpers that api.cu defines (kernel attribute caches); single-file builds get these instead
+_HOST_STUBS = """
 namespace sgs {
-// stand-ins for the helpers of the real common.cuh that are PTX there: programmatic dependent launch
-// (ordering only), the streaming load (a cache hint)
-inline void pdl_wait() {}
-inline void pdl_launch_dependents() {}
-inline void pdl_sync() {}
-inline float4 ldg_stream_f4(const float4* p) { return *p; }
-// packed-pair arithmetic (fma / mul / add .rn.f32x2 in the real header): two independent IEEE operations
-inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
-inline float2 fmul2(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
-inline float2 fadd2(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
-inline float2 splat2(float v) { return float2{v, v}; }
-inline float warp_sum(float v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+bool pdl_enabled() { return false; }
+cudaError_t ensure_max_smem(const void*, size_t) { return cudaSuccess; }
+long long resident_ctas(const void*, int, size_t) { return 296; }
 }
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
-    emu::launch(kernel, grid, block, static_cast<KArgs>(args)...);
-    return cudaSuccess;
-}
-}  // namespace sgs
-'''
+"""
 
 _LAUNCH = re.compile(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^<>;]*>)?)\s*<<<\s*([^;]*?)>>>\s*\(")
 
 
 def _rewrite_launches(src: str) -> str:
-    """kernel<T><<<grid, block, smem, stream>>>(args...)  ->  EMU_LAUNCH((kernel<T>), grid, block, args...)"""
+    """kernel<T><<<grid, block, smem, stream>>>(args...)  ->  EMU_LAUNCH((kernel<T>), grid, block, smem, args...)"""
     out, pos = [], 0
     for m in _LAUNCH.finditer(src):
-        cfg = [c.strip() for c in m.group(2).split(",")]
+        cfg, depth, cur = [], 0, ""
+        for ch in m.group(2):                      # split at top-level commas only: <<<min(a, b), 256, 0, stream>>>
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 0:
+                cfg.append(cur.strip()); cur = ""
+            else:
+                cur += ch
+        cfg.append(cur.strip())
         if len(cfg) < 2:
             raise ValueError(f"launch configuration not understood: {m.group(0)}")
         out.append(src[pos:m.start()])
-        out.append(f"EMU_LAUNCH(({m.group(1)}), {cfg[0]}, {cfg[1]}, ")
+        out.append(f"EMU_LAUNCH(({m.group(1)}), {cfg[0]}, {cfg[1]}, {cfg[2] if len(cfg) > 2 else 0}, ")
         pos = m.end()
     out.append(src[pos:])
     return "".join(out)
 
 
-def build(cu_path: str, exports: str) -> ctypes.CDLL:
-    """g++-compile `cu_path` with its launches rewritten plus `exports` (extern "C" wrappers appended to the
-    translation unit) into a shared object and load it."""
-    src = _rewrite_launches(open(cu_path).read()) + "\n" + exports
-    tag = hashlib.sha1((src + open(os.path.join(HERE, "emu.h")).read()).encode()).hexdigest()[:16]
-    d = os.path.join(tempfile.gettempdir(), f"sgs_cuda_emu_{tag}")
+_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
+CSRC = os.path.join(ROOT, "sings_b200", "csrc")
+_GXX = ["g++", "-std=c++17", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w"]
+
+
+def _prepare(text: str, rewrites=()) -> str:
+    for pat, rep in rewrites:
+        text, n = re.subn(pat, rep, text)
+        if n == 0:
+            raise ValueError(f"rewrite {pat!r} matched nothing")
+    text = _DYN_SMEM.sub(r"\1* \2 = reinterpret_cast<\1*>(emu::blk->dyn_smem);", text)
+    return _rewrite_launches(text)
+
+
+def _stage_headers(d: str) -> None:
+    """The library's own headers beside the translation units: common.cuh transformed, the others as they are;
+    <cuda_runtime.h> resolves to the emulation."""
+    open(os.path.join(d, "cuda_runtime.h"), "w").write('#pragma once\n#include "emu.h"\n')
+    for h in sorted(os.listdir(CSRC)):
+        if h.endswith((".h", ".cuh")):
+            text = open(os.path.join(CSRC, h)).read()
+            text = transform_common(text) if h == "common.cuh" else text
+            open(os.path.join(d, h), "w").write(_DYN_SMEM.sub(r"\1* \2 = reinterpret_cast<\1*>(emu::blk->dyn_smem);", text))
+    inc = os.path.join(ROOT, "include", "sings_b200.h")
+    os.makedirs(os.path.join(d, "include"), exist_ok=True)
+    open(os.path.join(d, "include", "sings_b200.h"), "w").write(open(inc).read())
+
+
+def _digest(*texts) -> str:
+    h = hashlib.sha1()
+    for t in texts:
+        h.update(t.encode())
+    for f in sorted(os.listdir(CSRC)) + ["emu.h"]:
+        path = os.path.join(CSRC, f) if f != "emu.h" else os.path.join(HERE, f)
+        if f.endswith((".h", ".cuh")):
+            h.update(open(path).read().encode())
+    h.update(open(os.path.abspath(__file__)).read().encode())
+    return h.hexdigest()[:16]
+
+
+# the three inline-PTX statements lbs.cu defines itself (bulk shared -> global store and its group bookkeeping)
+LBS_REWRITES = [(r'asm volatile\("cp\.async\.bulk\.global\.shared::cta\.bulk_group[^;]*;"[^;]*;', "memcpy(gmem_dst, smem_src, bytes); (void)sa;"),
+                (r'asm volatile\("cp\.async\.bulk\.commit_group;" ::: "memory"\);', "(void)0;"),
+                (r'asm volatile\("cp\.async\.bulk\.wait_group\.read 0;" ::: "memory"\);', "(void)0;")]
+
+
+def build(cu_path: str, exports: str, rewrites=(), headers=()) -> ctypes.CDLL:
+    """g++-compile ONE kernel source (launches rewritten, `extern "C"` wrappers `exports` appended to the
+    translation unit) against the emulation into a shared object and load it.  `rewrites`: (regex, replacement)
+    pairs applied to the source first (for the few inline-PTX statements a file defines itself)."""
+    src = _prepare(open(cu_path).read(), rewrites) + "\n" + _HOST_STUBS + "\n" + exports
+    d = os.path.join(tempfile.gettempdir(), f"sgs_cuda_emu_{_digest(src)}")
     so = os.path.join(d, "kernel_emu.so")
     if not os.path.exists(so):
         os.makedirs(d, exist_ok=True)
-        open(os.path.join(d, "common.cuh"), "w").write(_COMMON)
-        open(os.path.join(d, "kernels.h"), "w").write("#pragma once\n")
+        _stage_headers(d)
         cpp = os.path.join(d, "kernel_emu.cpp")
         open(cpp, "w").write(src)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
-                               "-I", HERE, "-I", d, cpp, "-o", so + ".tmp"])
+        subprocess.check_call(_GXX + ["-shared", "-I", HERE, "-I", d, cpp, "-o", so + ".tmp"])
+        os.replace(so + ".tmp", so)
+    return ctypes.CDLL(so)
+
+
+def build_library() -> ctypes.CDLL:
+    """The WHOLE library -- every .cu of sings_b200/csrc incl. api.cu, i.e. the real C ABI of
+    include/sings_b200.h -- compiled against the emulation: one object per source, linked into one shared
+    object.  CUDA graphs are not available in it (capture returns an error); everything else runs."""
+    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    special = {"lbs.cu": LBS_REWRITES, "api.cu": [(r'#include "\.\./\.\./include/sings_b200\.h"', '#include "include/sings_b200.h"')]}
+    texts = {f: _prepare(open(os.path.join(CSRC, f)).read(), special.get(f, ())) for f in srcs}
+    d = os.path.join(tempfile.gettempdir(), f"sgs_cuda_emu_lib_{_digest(*[texts[f] for f in srcs])}")
+    so = os.path.join(d, "libsings_b200_emu.so")
+    if not os.path.exists(so):
+        os.makedirs(d, exist_ok=True)
+        _stage_headers(d)
+        procs, objs = [], []
+        for f in srcs:
+            cpp = os.path.join(d, f[:-3] + ".cpp")
+            open(cpp, "w").write(texts[f])
+            objs.append(cpp[:-4] + ".o")
+            procs.append((f, subprocess.Popen(_GXX + ["-c", "-I", HERE, "-I", d, cpp, "-o", objs[-1]], stderr=subprocess.PIPE)))
+        for f, pr in procs:
+            err = pr.communicate()[1]
+            if pr.returncode:
+                raise RuntimeError(f"emulated build of {f} failed:\n" + err.decode()[-6000:])
+        subprocess.check_call(["g++", "-shared", "-pthread"] + objs + ["-o", so + ".tmp"])
         os.replace(so + ".tmp", so)
     return ctypes.CDLL(so)
