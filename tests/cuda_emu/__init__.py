@@ -116,7 +116,12 @@ def _rewrite_launches(src: str) -> str:
 
 _DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
 CSRC = os.path.join(ROOT, "sings_b200", "csrc")
-_GXX = ["g++", "-std=c++17", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w"]
+# SGS_EMU_SANITIZE=address|thread: build the emulated kernels with that sanitizer (run the tests with the matching
+# runtime preloaded, tools/emu_sanitize.sh) -- out-of-bounds accesses / data races inside a block in the kernel
+# source are then reported on the CPU
+_SAN = os.environ.get("SGS_EMU_SANITIZE", "")
+_GXX = ["g++", "-std=c++17", "-O1", "-fPIC", "-pthread", "-ffp-contract=off", "-w"] + \
+    ([f"-fsanitize={_SAN}", "-g", "-fno-omit-frame-pointer"] if _SAN else [])
 
 
 def _prepare(text: str, rewrites=()) -> str:
@@ -151,6 +156,7 @@ def _digest(*texts) -> str:
         if f.endswith((".h", ".cuh")):
             h.update(open(path).read().encode())
     h.update(open(os.path.abspath(__file__)).read().encode())
+    h.update(_SAN.encode())
     return h.hexdigest()[:16]
 
 
@@ -199,6 +205,6 @@ def build_library() -> ctypes.CDLL:
             err = pr.communicate()[1]
             if pr.returncode:
                 raise RuntimeError(f"emulated build of {f} failed:\n" + err.decode()[-6000:])
-        subprocess.check_call(["g++", "-shared", "-pthread"] + objs + ["-o", so + ".tmp"])
+        subprocess.check_call(["g++", "-shared", "-pthread"] + ([f"-fsanitize={_SAN}"] if _SAN else []) + objs + ["-o", so + ".tmp"])
         os.replace(so + ".tmp", so)
     return ctypes.CDLL(so)
