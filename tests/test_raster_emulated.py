@@ -15,7 +15,7 @@ from helpers import assert_grad_close, make_scene, oracle_camera
 from oracle import raster_oracle as ro
 
 IMG_TOL, GRAD_TOL = 1e-4, 1e-3
-FLAG_PRECLEARED = 2
+FLAG_PRECLEARED, FLAG_FORWARD_ONLY = 2, 8
 
 
 @pytest.fixture(scope="module")
@@ -57,16 +57,18 @@ def layout(L, P, W, H, L_cap):
 class Frame:
     """One forward through sgs_raster_clear + sgs_raster_forward, buffers kept for the backward."""
 
-    def __init__(self, L, sc, bg, D, colors=None):
+    def __init__(self, L, sc, bg, D, colors=None, L_cap=None, expect_rc=0, flags=0):
         view = sc["view"]
         self.L, self.sc, self.D = L, sc, D
         self.P = P = sc["means3D"].shape[0]
         self.W, self.H = W, H = view.image_width, view.image_height
         self.M = M = 0 if colors is not None else sc["shs"].shape[1]
-        self.L_cap = L_cap = max(4 * P, 1 << 16)
+        self.L_cap = L_cap = L_cap or max(4 * P, 1 << 16)
         s = [C.c_size_t() for _ in range(4)]
         assert L.sgs_raster_sizes(P, W, H, L_cap, *[C.byref(x) for x in s]) == 0
         self.geom, self.binning, self.img, self.acc = (buf(int(x.value)) for x in s)
+        for b_ in (self.geom, self.binning, self.img, self.acc):
+            b_[:] = 0xA5                         # scratch arrives dirty: whatever must be zero is cleared by the library
         self.bg, self.m3, self.opa = c32(bg), c32(sc["means3D"]), c32(sc["opacity"])
         self.sca, self.rot = c32(sc["scales"]), c32(sc["rotations"])
         self.shs, self.col = (None if colors is not None else c32(sc["shs"])), c32(colors)
@@ -81,8 +83,8 @@ class Frame:
         rc = L.sgs_raster_forward(P, D, M, W, H, p(self.bg), p(self.m3), p(self.col), p(self.opa), p(self.sca), 1.0,
                                   p(self.rot), None, p(self.viewm), p(self.proj), p(self.campos), self.tfx, self.tfy,
                                   p(self.shs), 0, L_cap, p(self.geom), p(self.binning), p(self.img), p(self.color),
-                                  p(self.radii), p(self.alpha), p(self.depth), p(self.counters), None, FLAG_PRECLEARED, None)
-        assert rc == 0, L.sgs_error_string(rc)
+                                  p(self.radii), p(self.alpha), p(self.depth), p(self.counters), None, FLAG_PRECLEARED | flags, None)
+        assert rc == expect_rc, L.sgs_error_string(rc)
 
     def state(self):
         info = layout(self.L, self.P, self.W, self.H, self.L_cap)
@@ -135,6 +137,9 @@ def test_rasterizer_forward_backward_through_the_c_abi(L, N, H, W, D):
     assert st.num_rendered > N            # a real workload: several tiles per Gaussian
     fr = Frame(L, sc, bg, D)
     check_forward(fr, st)
+    # animation frames (SGS_FLAG_FORWARD_ONLY: nothing is left for a backward) render the same bits
+    fo = Frame(L, sc, bg, D, flags=FLAG_FORWARD_ONLY)
+    assert np.array_equal(fo.color, fr.color) and np.array_equal(fo.radii, fr.radii) and np.array_equal(fo.alpha, fr.alpha)
     G = np.random.default_rng(1).normal(size=st.color.shape).astype(np.float32)
     got, ref = fr.backward(G), ro.backward(st, G)
     for k, name in (("means3D", "means3D"), ("means2D", "means2D"), ("opacities", "opacities"), ("sh", "sh"),
@@ -271,3 +276,59 @@ def test_knn_and_mark_visible_through_the_c_abi(L):
     vm = view.reshape(4, 4)
     z = pts @ vm[:3, 2] + vm[3, 2]
     assert np.array_equal(present.astype(bool), z > 0.2)
+
+
+def test_edge_cases_through_the_c_abi(L):
+    """No Gaussians, every Gaussian culled, and a pair list that does not fit its capacity (reported, nothing
+    written out of bounds; rendered again with room it equals the oracle) -- on dirty scratch buffers."""
+    bg = np.array([0.1, 0.5, 0.9], np.float32)
+    sc = make_scene(N=400, H=40, W=56, seed=9, scale_range=(0.02, 0.05))
+    # every Gaussian behind the camera
+    hidden = dict(sc)
+    hidden["means3D"] = np.ascontiguousarray(sc["means3D"] - np.array([0, 0, 40], np.float32))
+    fr = Frame(L, hidden, bg, 3)
+    assert int(fr.counters[0]) == 0 and not fr.radii.any()
+    assert np.array_equal(fr.color, np.broadcast_to(bg[:, None, None], fr.color.shape)) and not fr.alpha.any()
+    g = fr.backward(np.ones((3, 40, 56), np.float32))
+    assert all(not np.asarray(v).any() for k, v in g.items() if k not in ("colors", "cov"))
+    # no Gaussians at all
+    empty = dict(sc)
+    for k in ("means3D", "opacity", "shs", "scales", "rotations"):
+        empty[k] = np.ascontiguousarray(sc[k][:0])
+    fr0 = Frame(L, empty, bg, 3)
+    assert np.array_equal(fr0.color, np.broadcast_to(bg[:, None, None], fr0.color.shape))
+    # capacity too small: the needed count comes back with the overflow flag set
+    st = ro.forward(oracle_camera(sc["view"]), sc["means3D"], sc["opacity"], bg, sh_degree=3, shs=sc["shs"],
+                    scales=sc["scales"], rotations=sc["rotations"])
+    assert st.num_rendered > 512
+    small = Frame(L, sc, bg, 3, L_cap=512)
+    assert int(small.counters[1]) == 1 and int(small.counters[0]) == st.num_rendered
+    check_forward(Frame(L, sc, bg, 3, L_cap=int(st.num_rendered * 1.3) + 4096), st)
+
+
+def test_precomputed_colours_and_joint_counts(L):
+    """colors_precomp instead of SH, and the SMPL-H joint count (J = 52) through the fused deform kernel."""
+    from oracle import lbs_oracle as lo
+    from sings_b200 import synthetic as syn
+    import torch
+    sc = make_scene(N=500, H=48, W=48, seed=21)
+    cols = np.random.default_rng(2).uniform(size=(500, 3)).astype(np.float32)
+    bg = np.zeros(3, np.float32)
+    st = ro.forward(oracle_camera(sc["view"]), sc["means3D"], sc["opacity"], bg, sh_degree=0, colors_precomp=cols,
+                    scales=sc["scales"], rotations=sc["rotations"])
+    check_forward(Frame(L, sc, bg, 0, colors=cols), st)
+    N, J = 300, 52
+    av = syn.make_avatar(N, J, seed=4)
+    pose = c32(syn.random_pose(J, seed=6)).reshape(1, J, 3)
+    transl = np.array([[0.1, -0.2, 9.0]], np.float32)
+    A, Gm = np.zeros((1, J, 4, 4), np.float32), np.zeros((1, J, 12), np.float32)
+    xyz, q, s_ = np.zeros((1, N, 3), np.float32), np.zeros((1, N, 4), np.float32), np.zeros((1, N, 3), np.float32)
+    assert L.sgs_pose_lbs_fwd(p(pose), p(c32(av.rest)), p(np.ascontiguousarray(av.parents, np.int32)), p(c32(av.inv_A_t2cano)), 1, N, J,
+                              p(A), p(Gm), p(c32(av.xyz_canon)), p(c32(av.lbs_weights)), p(c32(av.rotmat_canon)), p(c32(av.scales)),
+                              None, p(transl), p(xyz), p(q), p(s_), None) == 0
+    tc = torch.from_numpy
+    A_o = lo.pose_to_A(tc(pose), tc(c32(av.rest)), av.parents, tc(c32(av.inv_A_t2cano)))
+    xo, qo, so, _ = lo.deform(A_o, tc(c32(av.xyz_canon)), tc(c32(av.lbs_weights)), tc(c32(av.scales)), tc(c32(av.rotmat_canon)),
+                              None, tc(transl))
+    assert np.abs(A - A_o.numpy()).max() < 1e-5 and np.abs(xyz - xo.numpy()).max() < 2e-5
+    assert np.abs(s_ - so.numpy()).max() < 1e-6
