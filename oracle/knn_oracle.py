@@ -8,6 +8,9 @@ only tests/ and bench.py's comparison legs may import it).
                   function (no golden vectors can be produced without the package); what anchors
                   it is its definition: tests compare against this brute force.
   GaussiansEdgeLoss.forward    /root/reference/sings/rec/losses/loss_items.py:57-90, statement by statement.
+                  PINNED around knn_points: tests/golden/reg_golden_edge.npz holds the loss and its gradient as the
+                  reference's own class computes them when knn_points is this brute force
+                  (tests/golden/make_reg_golden.py); tests/test_reg_oracle.py checks gaussians_edge_loss against it.
 """
 import torch
 

@@ -3,8 +3,8 @@
 Run in the build container only (needs /root/reference):
     python tests/golden/make_reg_golden.py
 Writes tests/golden/reg_golden_<case>.npz.  Executed reference code:
-  L2Norm, RegionLaplacianLoss_v2 (reset_laplacians, forward, forward_hands), pcd_laplacian_smoothing
-                                      /root/reference/sings/rec/losses/loss_items.py:15-54, 93-190, 205-214
+  L2Norm, GaussiansEdgeLoss, RegionLaplacianLoss_v2 (reset_laplacians, forward, forward_hands), pcd_laplacian_smoothing
+                                      /root/reference/sings/rec/losses/loss_items.py:15-54, 57-90, 93-190, 205-214
   parse_weights                       /root/reference/sings/rec/utils/body_model/smpl_parsing.py:38-44
                                       (reads /root/reference/data/human_models/smpl_parsing/*.json)
 loss_items.py imports pytorch3d.ops at module level; pytorch3d is not installed (and not vendored:
@@ -12,10 +12,11 @@ install_all.sh:21 pulls its default branch).  Stand-ins registered for it:
   laplacian   the published algorithm of pytorch3d/ops/laplacian_matrices.py::laplacian as a torch sparse
               COO tensor (values computed in float32 as there; cast to verts.dtype so that the float64
               runs, which give the gradient truth, can multiply it)
-  knn_points  brute force (only reached through build_edges, which this script does not call)
+  knn_points  brute force: exact K nearest neighbours by squared distance, ascending (reached by GaussiansEdgeLoss)
 Everything the reference's classes do around that function -- region selection, renumbering, weights,
 means, the calls' autograd -- is the reference's own code.
 """
+import collections
 import importlib.util
 import os
 import sys
@@ -61,10 +62,13 @@ def pytorch3d_laplacian(verts, edges):
     return L.coalesce().to(verts.dtype)
 
 
+_KNN = collections.namedtuple("KNN", "dists idx knn")          # pytorch3d returns this named 3-tuple
+
+
 def brute_knn_points(p1, p2, K):
     d = torch.cdist(p1[0].double(), p2[0].double()) ** 2
     dists, idx = torch.topk(d, K, dim=1, largest=False, sorted=True)
-    return types.SimpleNamespace(dists=dists[None], idx=idx[None], knn=None)
+    return _KNN(dists=dists[None].to(p1.dtype), idx=idx[None], knn=None)
 
 
 def load_reference_loss_items():
@@ -169,6 +173,24 @@ def main():
         out.update({f"loss_{tag}": float(l), f"grad_{tag}": gx.numpy()})
     np.savez_compressed(os.path.join(HERE, "reg_golden_pcd.npz"), **out)
     print("pcd", out["loss_f32"], out["loss_f64"])
+
+    # ---------------- scale-edge loss (GaussiansEdgeLoss, loss_items.py:57-90; gs_trainer.py:194, 367) with the brute-force
+    # knn_points stand-in: everything the class does around the neighbour search is the reference's own code
+    N = 400
+    g = torch.Generator().manual_seed(41)
+    pts = torch.rand(N, 3, generator=g) * torch.tensor([0.6, 1.7, 0.3])
+    sc = (0.002 + 0.01 * torch.rand(N, 1, generator=g)).repeat(1, 3)
+    out = dict(xyz_canon=pts.numpy(), scales=sc.numpy())
+    edge = M.GaussiansEdgeLoss()                                         # K = 9 (the point itself + 8 neighbours)
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        x = pts.to(dt).clone().requires_grad_(True)
+        s = sc.to(dt).clone().requires_grad_(True)
+        l = edge({"xyz_canon": x, "scales": s})
+        gs, gx = torch.autograd.grad(l, [s, x], allow_unused=True)
+        assert gx is None or float(gx.abs().max()) == 0.0                # the edge lengths are detached (:79)
+        out.update({f"loss_{tag}": float(l), f"grad_scales_{tag}": gs.numpy()})
+    np.savez_compressed(os.path.join(HERE, "reg_golden_edge.npz"), **out)
+    print("edge", out["loss_f32"], out["loss_f64"])
 
     # ---------------- L2Norm
     cases = [dict(name="l2_a", N=500, cfg=L2_CFG, opacity=True, seed=31, big=True),

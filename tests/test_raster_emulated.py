@@ -267,6 +267,16 @@ def test_knn_and_mark_visible_through_the_c_abi(L):
     assert np.abs(d2 - ref_d2).max() <= 1e-6 * ref_d2.max()
     assert np.array_equal(np.sort(idx, 1), np.sort(order, 1))
     assert np.abs(mean - np.sqrt(ref_d2).mean(1)).max() <= 2e-6 * np.sqrt(ref_d2).mean(1).max()
+    # the scale-edge loss of the reference (GaussiansEdgeLoss run with a brute-force knn_points, reg_golden_edge.npz)
+    # from the library's neighbour distances: ((scale_i - mean edge length_i)^2).mean()
+    zg = np.load(os.path.join(os.path.dirname(__file__), "golden", "reg_golden_edge.npz"))
+    xg = np.ascontiguousarray(zg["xyz_canon"])
+    Ng = xg.shape[0]
+    scratch = buf(int(L.sgs_knn_scratch_bytes(Ng)))
+    mg = np.full(Ng, np.nan, np.float32)
+    assert L.sgs_knn_mean_dist(Ng, p(xg), 8, p(scratch), scratch.nbytes, p(mg), None, None, None) == 0
+    loss = float(((zg["scales"][:, 0].astype(np.float64) - mg) ** 2).mean())
+    assert abs(loss - float(zg["loss_f64"])) <= 1e-5 * float(zg["loss_f64"])
     sc = make_scene(N=300, H=32, W=32, seed=2)
     pts = np.ascontiguousarray(sc["means3D"].copy())
     pts[::3, 2] -= 20.0                                      # a third of the points behind the camera

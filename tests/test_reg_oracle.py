@@ -23,7 +23,7 @@ def load(name):
 
 
 def test_goldens_are_committed():
-    assert len(glob.glob(os.path.join(GOLD, "reg_golden_*.npz"))) == 6
+    assert len(glob.glob(os.path.join(GOLD, "reg_golden_*.npz"))) == 7
 
 
 def test_parse_weights_matches_reference_table():
@@ -136,6 +136,20 @@ def test_sparse_oracle_variant_equals_the_dense_one():
     assert abs(float(a.forward(x)) - float(z["loss_pos_f32"])) <= 1e-6 * float(z["loss_pos_f32"])
     for La, Lb in zip(a.laplacians, b.laplacians):
         np.testing.assert_allclose(La.to_dense().numpy(), Lb.numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag,dt,tol", [("f32", torch.float32, 2e-5), ("f64", torch.float64, 1e-9)])
+def test_scale_edge_loss_oracle_vs_reference(tag, dt, tol):
+    """oracle/knn_oracle.py::gaussians_edge_loss against the reference's GaussiansEdgeLoss (run with a brute-force
+    knn_points): loss and its gradient to the scales."""
+    from oracle import knn_oracle as ko
+    z = load("edge")
+    x = torch.from_numpy(z["xyz_canon"]).to(dt)
+    s = torch.from_numpy(z["scales"]).to(dt).requires_grad_(True)
+    loss = ko.gaussians_edge_loss({"xyz_canon": x, "scales": s}, K=9)
+    g, = torch.autograd.grad(loss, s)
+    assert abs(float(loss) - float(z[f"loss_{tag}"])) <= tol * float(z[f"loss_{tag}"])
+    assert np.abs(g.numpy() - z[f"grad_scales_{tag}"]).max() <= tol * np.abs(z[f"grad_scales_{tag}"]).max()
 
 
 def test_label_checks_and_no_cpu_path():
