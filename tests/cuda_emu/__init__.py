@@ -166,10 +166,38 @@ LBS_REWRITES = [(r'asm volatile\("cp\.async\.bulk\.global\.shared::cta\.bulk_gro
                 (r'asm volatile\("cp\.async\.bulk\.wait_group\.read 0;" ::: "memory"\);', "(void)0;")]
 
 
+_THREADS_OK = None
+
+
+def require_threads(n: int = 300) -> None:
+    """The emulation runs one host thread per CUDA thread of a block (up to 256 + the caller): skip the test
+    (pytest.skip) where the environment cannot start that many, instead of aborting inside std::thread."""
+    global _THREADS_OK
+    if _THREADS_OK is None:
+        import threading
+        gate, started = threading.Event(), []
+        try:
+            for _ in range(n):
+                t = threading.Thread(target=gate.wait)
+                t.start()
+                started.append(t)
+            _THREADS_OK = True
+        except RuntimeError:
+            _THREADS_OK = False
+        finally:
+            gate.set()
+            for t in started:
+                t.join()
+    if not _THREADS_OK:
+        import pytest
+        pytest.skip(f"cannot start {n} threads here (the SIMT emulation needs one per CUDA thread of a block)")
+
+
 def build(cu_path: str, exports: str, rewrites=(), headers=()) -> ctypes.CDLL:
     """g++-compile ONE kernel source (launches rewritten, `extern "C"` wrappers `exports` appended to the
     translation unit) against the emulation into a shared object and load it.  `rewrites`: (regex, replacement)
     pairs applied to the source first (for the few inline-PTX statements a file defines itself)."""
+    require_threads()
     src = _prepare(open(cu_path).read(), rewrites) + "\n" + _HOST_STUBS + "\n" + exports
     d = os.path.join(tempfile.gettempdir(), f"sgs_cuda_emu_{_digest(src)}")
     so = os.path.join(d, "kernel_emu.so")
@@ -187,6 +215,7 @@ def build_library() -> ctypes.CDLL:
     """The WHOLE library -- every .cu of sings_b200/csrc incl. api.cu, i.e. the real C ABI of
     include/sings_b200.h -- compiled against the emulation: one object per source, linked into one shared
     object.  CUDA graphs are not available in it (capture returns an error); everything else runs."""
+    require_threads()
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     special = {"lbs.cu": LBS_REWRITES, "api.cu": [(r'#include "\.\./\.\./include/sings_b200\.h"', '#include "include/sings_b200.h"')]}
     texts = {f: _prepare(open(os.path.join(CSRC, f)).read(), special.get(f, ())) for f in srcs}
