@@ -237,10 +237,16 @@ def test_fused_avatar_path_equals_the_separate_kernels(L, iso):
     assert np.array_equal(f["xyz"], xyz) and np.array_equal(f["rotq"], rotq) and np.array_equal(f["sc"], sc)
     assert np.array_equal(color, sep.color) and np.array_equal(radii, sep.radii)
     g_m2, d_opa, d_shs = z(N, 3), z(N, 1), z(N, M, 3)
+    # densification statistics ride in the same kernel (sings_hybrid.py:1013-1015, gs_trainer.py:487-490): accumulated
+    accum, denom, maxr = np.full(N, 0.5, np.float32), np.full(N, 2.0, np.float32), np.full(N, 3.0, np.float32)
     rc = L.sgs_avatar_backward(C.byref(d), D, M, W, H, p(bg), 1.0, p(sep.viewm), p(sep.proj), p(sep.campos), sep.tfx, sep.tfy,
                                p(shs), p(radii), p(G), L_cap, p(geom), p(binning), p(img), p(acc), p(g_m2), p(d_opa), p(d_shs),
-                               None, None, None, None, FLAG_PRECLEARED, None)
+                               p(accum), p(denom), p(maxr), None, FLAG_PRECLEARED, None)
     assert rc == 0, L.sgs_error_string(rc)
+    vis = radii > 0
+    assert vis.any()
+    np.testing.assert_allclose(accum, 0.5 + vis * np.sqrt(g_m2[:, 0] ** 2 + g_m2[:, 1] ** 2), rtol=2e-6)
+    assert np.array_equal(denom, 2.0 + vis) and np.array_equal(maxr, np.where(vis, np.maximum(3.0, radii), 3.0).astype(np.float32))
     rel = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
     pairs = [("d_xyz_canon", f["d_xyz"], d_xyz), ("d_scales", f["d_scl"], d_scl), ("d_pose", f["d_pose"], d_pose),
              ("d_transl", f["d_tr"], d_tr), ("means2D", g_m2, gs["means2D"]), ("d_opacity", d_opa, gs["opacities"]),
