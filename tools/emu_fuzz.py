@@ -5,6 +5,8 @@ Odd image sizes, every SH degree, tiny and huge Gaussians, opacities at the ends
     python tools/emu_fuzz.py --deform [n_cases] [first_seed]      the deformer: pose -> A, LBS forward / backward (matrix and 6D
                                                                   canonical rotations, isotropic, smpl_scale, transl, ext_tfs, B frames,
                                                                   J = 24 / 52) against the float64 oracle of the reference's lbs_extra path
+    python tools/emu_fuzz.py --stress                             four fixed shapes: long per-tile lists (every Gaussian covers the
+                                                                  image), many tiles, a 1936-pixel-wide strip (121 tile columns), a tall strip
 CPU only; a divergence prints the case's parameters and exits 1."""
 import os
 import sys
@@ -106,14 +108,11 @@ def deform_fuzz(n, first):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--deform":
         return deform_fuzz(int(sys.argv[2]) if len(sys.argv) > 2 else 10, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    from cuda_emu import build_library
-    from sings_b200 import _lib
-    L = build_library()
-    for name, (res, args) in _lib._SIGNATURES.items():
-        fn = getattr(L, name)
-        fn.restype, fn.argtypes = res, args
+    stress = len(sys.argv) > 1 and sys.argv[1] == "--stress"
+    fixed = [(400, 64, 96, 3, 0.2, 0.4), (2500, 144, 208, 1, 0.002, 0.01), (900, 32, 1936, 2, 0.004, 0.03), (700, 1100, 16, 0, 0.004, 0.03)]
+    n = len(fixed) if stress else (int(sys.argv[1]) if len(sys.argv) > 1 else 10)
+    first = 0 if stress else (int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    L = load()
     worst = {}
     for seed in range(first, first + n):
         rng = np.random.default_rng(seed)
@@ -122,6 +121,8 @@ def main():
         D = int(rng.integers(0, 4))
         lo = float(rng.choice([0.001, 0.004, 0.02]))
         hi = lo * float(rng.choice([2.0, 8.0, 40.0]))
+        if stress:
+            N, H, W, D, lo, hi = fixed[seed]
         par = dict(seed=seed, N=N, H=H, W=W, D=D, scale_range=(lo, hi), yaw=float(rng.uniform(0, 6.28)),
                    fill=float(rng.choice([0.5, 0.85, 1.6])), iso=bool(rng.integers(0, 2)))
         sc = make_scene(N=N, H=H, W=W, seed=seed, scale_range=(lo, hi), isotropic=par["iso"], yaw=par["yaw"], fill=par["fill"])
