@@ -123,7 +123,8 @@ int sgs_raster_clear(int P, int W, int H, long long L_cap, void* binning, void* 
  * kernel itself when the memory is mapped into the device's address space (cudaHostAlloc /
  * torch pin_memory under unified addressing), else by an async copy on `stream`; read it after
  * synchronising.  If overflow != 0 the pair list did not fit L_cap: grow the binning buffer and
- * call again.  `debug`: SGS_FLAG_* bits. */
+ * call again.  `debug`: SGS_FLAG_* bits.  Limits: P < 2^24 (a pair-list entry carries the Gaussian id in
+ * 24 bits beside its 8-bit reach mask) and L_cap < 2^30, else SGS_ERR_CAPACITY. */
 int sgs_raster_forward(int P, int D, int M, int W, int H, const float* bg, const float* means3D,
                        const float* colors_precomp, const float* opacities, const float* scales,
                        float scale_modifier, const float* rotations, const float* cov3D_precomp,

@@ -208,6 +208,7 @@ static int fill_geom_args(GeomArgs& a, int P, int D, int M, int W, int H, const 
                           const float* campos, float tanfovx, float tanfovy, const float* shs,
                           int prefiltered) {
     if (P < 0 || W <= 0 || H <= 0) return SGS_ERR_BAD_ARG;
+    if (P >= (1 << 24)) return SGS_ERR_CAPACITY;      // a pair-list entry = Gaussian id (24 bits) | reach mask (8 bits)
     if (P > 0) {
         if ((shs == nullptr) == (colors_precomp == nullptr)) return SGS_ERR_BAD_ARG;
         if ((cov3D_precomp == nullptr) == (scales == nullptr || rotations == nullptr)) return SGS_ERR_BAD_ARG;

@@ -313,6 +313,11 @@ def test_edge_cases_through_the_c_abi(L):
         empty[k] = np.ascontiguousarray(sc[k][:0])
     fr0 = Frame(L, empty, bg, 3)
     assert np.array_equal(fr0.color, np.broadcast_to(bg[:, None, None], fr0.color.shape))
+    # more Gaussians than a list entry can name (id in 24 bits): refused before anything is launched
+    one = np.zeros(16, np.float32)
+    rc = L.sgs_raster_forward(1 << 24, 0, 1, 16, 16, p(one), p(one), None, p(one), p(one), 1.0, p(one), None, p(one), p(one), p(one),
+                              1.0, 1.0, p(one), 0, 1 << 16, p(one), p(one), p(one), p(one), p(one), None, None, None, None, 0, None)
+    assert rc == -5 and b"capacity" in L.sgs_error_string(rc)
     # capacity too small: the needed count comes back with the overflow flag set
     st = ro.forward(oracle_camera(sc["view"]), sc["means3D"], sc["opacity"], bg, sh_degree=3, shs=sc["shs"],
                     scales=sc["scales"], rotations=sc["rotations"])
