@@ -208,7 +208,8 @@ int sgs_hexplane_bwd(int N, const float* pts, const float* aabb_host, int n_scal
  *   idx (N,K) int   neighbours, nearest first (-1 where the set has fewer than K + 1 points; ties in
  *                   arbitrary order)                                (nullable)
  *   dist2 (N,K)     their squared distances, ascending              (nullable)
- * 1 <= K <= 16.  scratch: sgs_knn_scratch_bytes(N) bytes, 256-byte aligned. */
+ * With fewer than K + 1 points the missing neighbours have idx -1 and dist2 3.4e38 (and mean_dist is
+ * meaningless): callers need N > K.  1 <= K <= 16.  scratch: sgs_knn_scratch_bytes(N) bytes, 256-byte aligned. */
 size_t sgs_knn_scratch_bytes(int N);
 int sgs_knn_mean_dist(int N, const float* xyz, int K, void* scratch, size_t scratch_bytes, float* mean_dist,
                       int* idx, float* dist2, sgs_stream_t stream);
