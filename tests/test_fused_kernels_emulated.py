@@ -113,3 +113,29 @@ def test_hexplane_kernels(hexplane, path):
     for i in range(3 * S):
         ref = z[f"d_plane_{i}"][0].transpose(1, 2, 0)
         assert np.abs(d_planes[i] - ref).max() <= 1e-5 * np.abs(ref).max(), i
+
+
+@pytest.mark.parametrize("H,W,masked", [(1, 1, False), (5, 7, True), (11, 3, False), (33, 65, True)])
+def test_image_loss_edge_sizes_vs_oracle(image_loss, H, W, masked):
+    """Images smaller than the 11 x 11 window and ragged against the 32 x 32 tile, against float64 autograd of
+    the oracle (the reference's l1_loss + ssim composed as HumanLoss.forward)."""
+    import torch
+    from oracle import loss_oracle as llo
+    rng = np.random.default_rng(H * 100 + W)
+    pred, gt = rng.random((3, H, W)).astype(np.float32), rng.random((3, H, W)).astype(np.float32)
+    mask = None
+    if masked:
+        mask = (rng.random((H, W)) > 0.3).astype(np.float32)
+        mask[0, 0] = 1.0
+    bg = np.array([1.0, 0.5, 0.2], np.float32)
+    scratch, sums, loss3 = np.full(12 * H * W, np.nan, np.float32), np.full(4, np.nan), np.full(3, np.nan, np.float32)
+    assert image_loss.emu_image_loss_fwd(H, W, p(pred), p(gt), 0, p(mask), p(bg), p(scratch), p(sums), 0.8, 0.2, p(loss3)) == 0
+    grad = np.full((3, H, W), np.nan, np.float32)
+    dl = np.asarray([1.0], np.float32)
+    assert image_loss.emu_image_loss_bwd(H, W, p(pred), p(scratch), p(sums), 0.8, 0.2, p(dl), p(grad), None) == 0
+    pt = torch.from_numpy(pred).double().requires_grad_(True)
+    ref = llo.human_image_loss(pt, torch.from_numpy(gt).double(), None if mask is None else torch.from_numpy(mask).double(),
+                               torch.from_numpy(bg).double())[0]
+    ref.backward()
+    assert abs(float(loss3[0]) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    assert np.abs(grad - pt.grad.numpy()).max() <= 1e-4 * np.abs(pt.grad.numpy()).max()
