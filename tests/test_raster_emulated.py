@@ -57,7 +57,7 @@ def layout(L, P, W, H, L_cap):
 class Frame:
     """One forward through sgs_raster_clear + sgs_raster_forward, buffers kept for the backward."""
 
-    def __init__(self, L, sc, bg, D, colors=None, L_cap=None, expect_rc=0, flags=0):
+    def __init__(self, L, sc, bg, D, colors=None, L_cap=None, expect_rc=0, flags=0, preclear=True):
         view = sc["view"]
         self.L, self.sc, self.D = L, sc, D
         self.P = P = sc["means3D"].shape[0]
@@ -79,11 +79,13 @@ class Frame:
         self.radii = np.full(P, -7, np.int32)
         self.alpha, self.depth = np.full((H, W), np.nan, np.float32), np.full((H, W), np.nan, np.float32)
         self.counters = np.zeros(2, np.int32)
-        assert L.sgs_raster_clear(P, W, H, L_cap, p(self.binning), p(self.acc), None, 0, None) == 0
+        if preclear:
+            assert L.sgs_raster_clear(P, W, H, L_cap, p(self.binning), p(self.acc), None, 0, None) == 0
+            flags |= FLAG_PRECLEARED
         rc = L.sgs_raster_forward(P, D, M, W, H, p(self.bg), p(self.m3), p(self.col), p(self.opa), p(self.sca), 1.0,
                                   p(self.rot), None, p(self.viewm), p(self.proj), p(self.campos), self.tfx, self.tfy,
                                   p(self.shs), 0, L_cap, p(self.geom), p(self.binning), p(self.img), p(self.color),
-                                  p(self.radii), p(self.alpha), p(self.depth), p(self.counters), None, FLAG_PRECLEARED | flags, None)
+                                  p(self.radii), p(self.alpha), p(self.depth), p(self.counters), None, flags, None)
         assert rc == expect_rc, L.sgs_error_string(rc)
 
     def state(self):
@@ -99,7 +101,7 @@ class Frame:
         out["n_contrib"] = im[info["n_contrib"]:info["n_contrib"] + 4 * W * H].view(np.uint32).reshape(H, W).copy()
         return out
 
-    def backward(self, G):
+    def backward(self, G, precleared=True):
         P, M = self.P, self.M
         z = lambda *s: np.full(s, np.nan, np.float32)
         g = dict(means3D=z(P, 3), means2D=z(P, 3), colors=z(P, 3), opacities=z(P, 1), cov=z(P, 6),
@@ -109,7 +111,7 @@ class Frame:
                                         p(self.shs), p(self.radii), p(c32(G)), self.L_cap, p(self.geom), p(self.binning),
                                         p(self.img), p(self.acc), p(g["means3D"]), p(g["means2D"]), p(g["colors"]),
                                         p(g["opacities"]), p(g["cov"]), p(g["sh"]) if M else None, p(g["scales"]),
-                                        p(g["rotations"]), None, None, None, None, FLAG_PRECLEARED, None)
+                                        p(g["rotations"]), None, None, None, None, FLAG_PRECLEARED if precleared else 0, None)
         assert rc == 0, self.L.sgs_error_string(rc)
         return g
 
@@ -137,11 +139,20 @@ def test_rasterizer_forward_backward_through_the_c_abi(L, N, H, W, D):
     assert st.num_rendered > N            # a real workload: several tiles per Gaussian
     fr = Frame(L, sc, bg, D)
     check_forward(fr, st)
+    # without the up-front clear kernel the entry points clear what they need themselves (dirty scratch either way),
+    # and a second backward of the same forward finds the accumulator dirty
+    own = Frame(L, sc, bg, D, preclear=False)
+    check_forward(own, st)
     # animation frames (SGS_FLAG_FORWARD_ONLY: nothing is left for a backward) render the same bits
     fo = Frame(L, sc, bg, D, flags=FLAG_FORWARD_ONLY)
     assert np.array_equal(fo.color, fr.color) and np.array_equal(fo.radii, fr.radii) and np.array_equal(fo.alpha, fr.alpha)
     G = np.random.default_rng(1).normal(size=st.color.shape).astype(np.float32)
     got, ref = fr.backward(G), ro.backward(st, G)
+    again = own.backward(G, precleared=False)
+    second = own.backward(G, precleared=False)
+    for k in ("means3D", "means2D", "opacities", "sh", "scales", "rotations"):
+        assert np.abs(again[k] - got[k]).max() <= 2e-5 * np.abs(got[k]).max(), k
+        assert np.abs(second[k] - got[k]).max() <= 2e-5 * np.abs(got[k]).max(), k
     for k, name in (("means3D", "means3D"), ("means2D", "means2D"), ("opacities", "opacities"), ("sh", "sh"),
                     ("scales", "scales"), ("rotations", "rotations")):
         assert_grad_close(got[k], np.asarray(ref[name]).reshape(got[k].shape), k, tol=GRAD_TOL)
